@@ -1,0 +1,183 @@
+/* rama_b200.h — C ABI of the B200-native (sm_100a) llama2 f32 decode path.
+ *
+ * This is the drop-in boundary for ONE hot path of oliverhu/rama: the per-token decode loop
+ * (engine/src/transformer/infer.rs:8-53 `forward`, engine/src/device/*.rs `Device`,
+ * engine/src/transformer/mod.rs:169-248 `generate`).  Every entry point below names the
+ * reference interface it replaces (paths relative to the reference repo root).  The Rust
+ * binding a maintainer adds (gpu.rs / hbm.rs / build.rs) is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - plain C types only; device memory is passed as `float*` device pointers (rama_dev_alloc).
+ *  - every function returns 0 (RAMA_OK) or a negative rama_status; the message is available
+ *    from rama_last_error() (thread-local).  Nothing throws or aborts across the boundary; the
+ *    Rust shim `.unwrap()`s to keep the reference's panic-on-error behaviour.
+ *  - a rama_ctx is shared and thread-safe for concurrent sessions (reference: `GPU` lives in a
+ *    static OnceLock, engine/src/lib.rs:56); a rama_session is used by one thread at a time
+ *    (reference: one RunState per request task, engine/src/lib.rs:133-153).
+ *  - there is no CPU fallback: without a CUDA device every call fails with RAMA_E_CUDA.
+ */
+#ifndef RAMA_B200_H
+#define RAMA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RAMA_ABI_VERSION 1
+
+typedef enum rama_status {
+  RAMA_OK = 0,
+  RAMA_E_INVALID = -1, /* bad argument / unsupported shape */
+  RAMA_E_CUDA = -2,    /* CUDA runtime error (no device, launch failure, ...) */
+  RAMA_E_IO = -3,      /* checkpoint file problem */
+  RAMA_E_NCCL = -4,    /* NCCL unavailable or failed */
+  RAMA_E_STATE = -5    /* call out of order (no weights loaded, pos >= seq_len, ...) */
+} rama_status;
+
+/* engine/src/transformer/mod.rs:128-138 `Config` (shared_weight: vocab>0 in the file header) */
+typedef struct rama_config {
+  int32_t dim, hidden_dim, n_layers, n_heads, n_kv_heads, vocab_size, seq_len, shared_weight;
+} rama_config;
+
+/* The 14 tensors in llama2.c v0 file order (engine/export/export.py:75-127 ⇔
+ * engine/src/transformer/ram.rs:30-49) ≙ fields of TransformerWeights (state.rs:54-74). */
+enum rama_tensor {
+  RAMA_T_TOKEN_EMBEDDING = 0, RAMA_T_RMS_ATT, RAMA_T_WQ, RAMA_T_WK, RAMA_T_WV, RAMA_T_WO,
+  RAMA_T_RMS_FFN, RAMA_T_W1, RAMA_T_W2, RAMA_T_W3, RAMA_T_RMS_FINAL, RAMA_T_FREQ_REAL,
+  RAMA_T_FREQ_IMAG, RAMA_T_WCLS, RAMA_T_COUNT
+};
+
+/* The 12 RunState buffers (engine/src/transformer/state.rs:4-17). */
+enum rama_state_buf {
+  RAMA_S_X = 0, RAMA_S_XB, RAMA_S_XB2, RAMA_S_HB, RAMA_S_HB2, RAMA_S_Q, RAMA_S_K, RAMA_S_V,
+  RAMA_S_ATT, RAMA_S_LOGITS, RAMA_S_KEY_CACHE, RAMA_S_VALUE_CACHE, RAMA_S_COUNT
+};
+
+/* Tensor-parallel placement of this process (one process per GPU).  NULL ⇒ single GPU.
+ * nccl_id is an ncclUniqueId made by rama_tp_unique_id() on rank 0 and distributed by the
+ * caller (torch.distributed / files / sockets).  New relative to the reference, which has no
+ * multi-GPU path (gpu.rs:215 `CudaDevice::new(0)`). */
+typedef struct rama_tp {
+  int32_t rank, world;
+  uint8_t nccl_id[128];
+} rama_tp;
+
+typedef struct rama_ctx rama_ctx;         /* ≙ `GPU` + `TransformerWeights<Dev>` */
+typedef struct rama_session rama_session; /* ≙ `RunState<Dev>` (+ stream, step graph) */
+
+int rama_abi_version(void);
+const char* rama_last_error(void);
+int rama_device_count(int* n);
+
+/* ---- context: device + weights -------------------------------------------------------- */
+
+/* ≙ GPU::new() (engine/src/device/gpu.rs:213-234).  No NVRTC, no cuBLAS. */
+int rama_ctx_create(int device, const rama_tp* tp, rama_ctx** out);
+int rama_ctx_destroy(rama_ctx* ctx);
+int rama_tp_unique_id(uint8_t out[128]);
+
+/* ≙ Config::from_file + TransformerWeights::from_file + ::from_weight
+ * (mod.rs:140-166, ram.rs:27-51, hbm.rs:55-90): mmap the v0 .bin, stream it through pinned
+ * staging into HBM once, keeping only this rank's shard under TP. */
+int rama_ctx_load_file(rama_ctx* ctx, const char* path);
+/* ≙ TransformerWeights::from_weight(&mut TransformerWeights<Vec<f32>>, &GPU) (hbm.rs:55-90).
+ * tensors[] in rama_tensor order, full (unsharded) host arrays; tensors[WCLS] may be NULL when
+ * cfg->shared_weight (state.rs:111-117: wcls then aliases the embedding). */
+int rama_ctx_load_host(rama_ctx* ctx, const rama_config* cfg, const float* const tensors[RAMA_T_COUNT]);
+/* Bench/test helper: fill the weights in HBM with the counter-based synthetic recipe of
+ * rama_b200/checkpoint.py (bit-identical to the numpy and oracle generators).  scale[i] == 0
+ * with offset[i] == 0 leaves tensor i to the host pointer given (RoPE tables). */
+int rama_ctx_load_synthetic(rama_ctx* ctx, const rama_config* cfg, uint64_t seed,
+                            const float scale[RAMA_T_COUNT], const float offset[RAMA_T_COUNT],
+                            const float* freq_real, const float* freq_imag);
+int rama_ctx_config(const rama_ctx* ctx, rama_config* out);
+/* Copies this rank's shard of a weight tensor back (tests). n = capacity in floats; *n_out = shard size. */
+int rama_ctx_weight_to_host(rama_ctx* ctx, int tensor, float* dst, size_t n, size_t* n_out);
+int rama_ctx_weight_bytes(const rama_ctx* ctx, size_t* bytes);
+
+/* ---- session: RunState on the device --------------------------------------------------- */
+
+/* ≙ RunState::from_config + RunState::from_state (ram.rs:6-23, hbm.rs:19-34), without the
+ * host round trip: buffers (incl. the KV cache) are allocated and zeroed in HBM. */
+int rama_session_create(rama_ctx* ctx, rama_session** out);
+int rama_session_reset(rama_session* s);
+int rama_session_destroy(rama_session* s);
+
+/* ≙ forward(cfg, wv, rsv, token, pos, device) (infer.rs:8-53): one fused, CUDA-graph-replayed
+ * decode step; asynchronous (returns after enqueue on the session stream). */
+int rama_forward(rama_session* s, int32_t token, int32_t pos);
+/* ≙ Device::sample(cfg, rsv, temperature, topp) -> usize (device.rs:16, cpu.rs:155-179,
+ * infer.rs:55-85) run ON THE DEVICE; only the 4-byte token id crosses PCIe.  Synchronous.
+ * As in the reference the logits buffer is overwritten with probabilities when temperature != 0. */
+int rama_sample(rama_session* s, float temperature, float topp, int32_t* next);
+/* ≙ generate(...) token loop (mod.rs:169-206) without tokenizer/printing: BOS at pos 0, prompt
+ * forcing, then sampling; the token fed back never leaves the device.  out_tokens[pos] = `next`
+ * of step pos.  Synchronous; *elapsed_ms (optional) = CUDA-event time of the step loop. */
+int rama_generate(rama_session* s, const int32_t* prompt, int32_t n_prompt, int32_t steps,
+                  float temperature, float topp, int32_t* out_tokens, float* elapsed_ms);
+int rama_session_sync(rama_session* s);
+
+/* ≙ Device::to_cpu / RunState::into_state (device.rs:21, gpu.rs:196-209, hbm.rs:38-51).
+ * buf in rama_state_buf; layouts as the reference's RunState (KV cache [L][T][D]).  Under TP the
+ * sharded buffers (q,k,v,hb,hb2,att,caches) hold this rank's slice.  RAMA_S_ATT is only kept
+ * when rama_session_set_debug(s, 1). */
+int rama_state_to_host(rama_session* s, int buf, float* dst, size_t n, size_t* n_out);
+int rama_logits_to_host(rama_session* s, float* dst, size_t n);
+int rama_session_set_debug(rama_session* s, int keep_att);
+/* number of kernels one step enqueues (bench `gpu_launches`). */
+int rama_session_launches_per_step(const rama_session* s, int* n);
+
+/* Tracing: runs `forward(token,pos)` un-graphed with a CUDA-event pair around every kernel and
+ * returns the summed milliseconds and launch counts per kernel kind. */
+enum rama_kernel_kind {
+  RAMA_K_EMBED = 0, RAMA_K_QKV, RAMA_K_ATTN, RAMA_K_WO, RAMA_K_W13, RAMA_K_W2, RAMA_K_CLS,
+  RAMA_K_SAMPLE, RAMA_K_COMM, RAMA_K_COUNT
+};
+int rama_profile_step(rama_session* s, int32_t token, int32_t pos, float ms[RAMA_K_COUNT],
+                      int32_t launches[RAMA_K_COUNT]);
+
+/* ---- op level: 1:1 with `trait Device<T>` (engine/src/device/device.rs:3-24) -------------
+ * Pointers are device pointers already offset by the view's range.start (a View is
+ * (storage, absolute range), mod.rs:16-51).  Asynchronous on the ctx's op stream;
+ * rama_dev_d2h / rama_ctx_sync synchronise. */
+int rama_dev_alloc(rama_ctx* ctx, size_t n_floats, float** out);          /* hbm.rs:14-16 allocate */
+int rama_dev_free(rama_ctx* ctx, float* p);
+int rama_dev_h2d(rama_ctx* ctx, float* dst, const float* src, size_t n);  /* htod_sync_copy */
+int rama_dev_d2h(rama_ctx* ctx, float* dst, const float* src, size_t n);  /* dtoh_sync_copy_into */
+int rama_ctx_sync(rama_ctx* ctx);
+
+int rama_op_array_add(rama_ctx* ctx, float* target, const float* source, size_t n);   /* device.rs:4 */
+int rama_op_array_mult(rama_ctx* ctx, float* target, const float* source, size_t n);  /* device.rs:5 */
+int rama_op_sinu(rama_ctx* ctx, float* o, size_t n);                                  /* device.rs:6 */
+/* device.rs:7-8; buffers as RunStateView fields; cfg gives dim/n_heads/seq_len. att may be NULL. */
+int rama_op_multi_head_attention(rama_ctx* ctx, float* xb, float* att, const float* q,
+                                 const float* key_cache, const float* value_cache,
+                                 const rama_config* cfg, int32_t layer, int32_t pos);
+int rama_op_copy_from_slice(rama_ctx* ctx, float* target, const float* source, size_t n); /* device.rs:9 */
+int rama_op_rmsnorm(rama_ctx* ctx, float* o, const float* x, const float* weight, size_t n); /* device.rs:10-11 */
+int rama_op_apply_position(rama_ctx* ctx, float* q, float* k, const float* pos_real,
+                           const float* pos_img, size_t head_size);                  /* device.rs:12 */
+/* device.rs:13: o[r*o_cols+c] = Σ_i a[r*width+i]·b[i*o_cols+c]; the hot path only uses o_cols=1. */
+int rama_op_matmul(rama_ctx* ctx, float* o, const float* a, const float* b, size_t width,
+                   size_t o_rows, size_t o_cols);
+int rama_op_softmax(rama_ctx* ctx, float* x, size_t n);                               /* device.rs:14 */
+/* device.rs:16 on raw logits (in place, like the reference). */
+int rama_op_sample(rama_ctx* ctx, float* logits, size_t vocab_size, float temperature, float topp,
+                   int32_t* next);
+
+/* Synthetic fill of a device buffer (bench/test data): elements [start, start+n) of tensor_id. */
+int rama_synth_fill(rama_ctx* ctx, float* dst, size_t n, uint64_t seed, uint64_t tensor_id,
+                    uint64_t start, float scale, float offset);
+
+/* Micro-benchmark hook used by bench.py / tools: runs the plain GEMV kernel `iters` times on
+ * device buffers and returns the average milliseconds per launch (CUDA events on its stream). */
+int rama_bench_gemv(rama_ctx* ctx, float* o, const float* w, const float* x, size_t rows, size_t width,
+                    int variant, int iters, float* avg_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAMA_B200_H */

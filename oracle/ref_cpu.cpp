@@ -548,7 +548,10 @@ int ref_tok_decode(const RefTok* t, int id, char* out, int cap) {
   if (s.find("<s>") != std::string::npos) {
     r = "";
   } else if (!s.empty() && s.front() == '<' && s.back() == '>' && s.size() >= 5) {
-    unsigned c = (unsigned)strtoul(s.substr(3, 2).c_str(), nullptr, 16);
+    char* endp = nullptr;
+    const std::string hex = s.substr(3, 2);
+    unsigned c = (unsigned)strtoul(hex.c_str(), &endp, 16);
+    if (endp != hex.c_str() + 2) return -2;  // u8::from_str_radix(..).unwrap() panics (e.g. "<unk>")
     if (c < 0x80) r.push_back((char)c);
     else { r.push_back((char)(0xC0 | (c >> 6))); r.push_back((char)(0x80 | (c & 0x3F))); }
   } else {

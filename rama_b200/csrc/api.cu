@@ -1,0 +1,1169 @@
+// api.cu — host side of the C ABI (include/rama_b200.h): context (device + sharded weights),
+// session (RunState in HBM, per-session stream, captured step graph), loaders, NCCL tensor
+// parallelism and the op-level Device entry points.  No cuBLAS, no NVRTC, no CPU fallback.
+#include "../../include/rama_b200.h"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "attention.cuh"
+#include "common.cuh"
+#include "gemv.cuh"
+#include "misc_kernels.cuh"
+
+using namespace rama;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return fail(RAMA_E_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+  } while (0)
+#define RK(call)                     \
+  do {                               \
+    int r_ = (call);                 \
+    if (r_ != RAMA_OK) return r_;    \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// NCCL, resolved at run time (only when tp->world > 1) so that the single-GPU path has no
+// dependency on it and the process shares whatever libnccl.so.2 is already loaded.
+// ------------------------------------------------------------------------------------------------
+struct NcclId { char internal[128]; };
+typedef void* NcclComm;
+struct NcclApi {
+  void* h = nullptr;
+  int (*GetUniqueId)(NcclId*) = nullptr;
+  int (*CommInitRank)(NcclComm*, int, NcclId, int) = nullptr;
+  int (*CommDestroy)(NcclComm) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, NcclComm, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static std::mutex g_nccl_mu;
+constexpr int kNcclFloat32 = 7, kNcclSum = 0;
+
+static int nccl_load() {
+  std::lock_guard<std::mutex> lk(g_nccl_mu);
+  if (g_nccl.h) return RAMA_OK;
+  const char* names[] = {getenv("RAMA_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+  void* h = nullptr;
+  for (const char* n : names) {
+    if (!n) continue;
+    h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (h) break;
+  }
+  if (!h) return fail(RAMA_E_NCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+#define SYM(field, name)                                               \
+  *(void**)(&g_nccl.field) = dlsym(h, name);                           \
+  if (!g_nccl.field) return fail(RAMA_E_NCCL, "libnccl lacks %s", name);
+  SYM(GetUniqueId, "ncclGetUniqueId")
+  SYM(CommInitRank, "ncclCommInitRank")
+  SYM(CommDestroy, "ncclCommDestroy")
+  SYM(AllReduce, "ncclAllReduce")
+  SYM(AllGather, "ncclAllGather")
+  SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+  g_nccl.h = h;
+  return RAMA_OK;
+}
+#define NK(call)                                                                                   \
+  do {                                                                                             \
+    int e_ = (call);                                                                               \
+    if (e_ != 0) return fail(RAMA_E_NCCL, "%s:%d %s: %s", __FILE__, __LINE__, #call, g_nccl.GetErrorString(e_)); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// structures
+// ------------------------------------------------------------------------------------------------
+struct TensorPlan {  // local window [Lc][Rl][Cl] of the global tensor [Lc][R][C] at (r0, c0)
+  size_t Lc = 1, R = 0, C = 0, r0 = 0, Rl = 0, c0 = 0, Cl = 0;
+  size_t local_elems() const { return Lc * Rl * Cl; }
+  size_t global_elems() const { return Lc * R * C; }
+};
+
+struct rama_ctx {
+  int device = 0, sm_count = 148;
+  int rank = 0, world = 1;
+  NcclComm comm = nullptr;
+  bool loaded = false;
+  rama_config cfg{};
+  int D = 0, F = 0, L = 0, H = 0, V = 0, T = 0, hs = 0;  // global
+  int Dq = 0, Fl = 0, Hl = 0, Vl = 0, v0 = 0;            // this rank's shard
+  TensorPlan plan[RAMA_T_COUNT];
+  float* w[RAMA_T_COUNT] = {nullptr};
+  const float* wcls = nullptr;  // this rank's classifier rows (own tensor, or a window of the embedding)
+  cudaStream_t op_stream = nullptr;
+  int use_pdl = 0;
+  int variant_override = -1;
+  std::mutex mu;
+};
+
+struct rama_session {
+  rama_ctx* ctx = nullptr;
+  cudaStream_t stream = nullptr;
+  float *x0 = nullptr, *x1 = nullptr, *xfinal = nullptr, *xb = nullptr, *xb2 = nullptr, *w2out = nullptr;
+  float *hb = nullptr, *hb2 = nullptr, *q = nullptr, *k = nullptr, *v = nullptr, *att = nullptr;
+  float *logits = nullptr;  // [V]; this rank's rows live at logits + v0
+  float *key_cache = nullptr, *value_cache = nullptr;
+  float* attn_ws = nullptr;
+  unsigned int* tickets = nullptr;
+  ArgPart* part = nullptr;      // [world * sm_count]
+  unsigned long long* sort_keys = nullptr;
+  StepCtrl* ctrl = nullptr;     // device
+  int32_t *d_prompt = nullptr, *d_out = nullptr;
+  StepCtrl* h_ring = nullptr;   // pinned ring for host-driven (token,pos)
+  int ring_i = 0;
+  int32_t* h_ret = nullptr;     // pinned {next, error}
+  cudaGraphExec_t g_fwd = nullptr, g_step[2] = {nullptr, nullptr};  // [0] greedy, [1] sampled
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int keep_att = 0;
+  int n_split = 1;
+  int host_mode_set = 0;
+  int launches = 0;
+  bool logits_gathered = false;
+};
+
+// ------------------------------------------------------------------------------------------------
+// GEMV dispatch
+// ------------------------------------------------------------------------------------------------
+constexpr int kNumVariants = 8;
+struct Variant { int WK, RP, U; };
+static const Variant kVariants[kNumVariants] = {{16, 2, 2}, {8, 2, 4}, {4, 2, 4}, {1, 2, 4},
+                                                {16, 4, 2}, {8, 4, 2}, {2, 2, 4}, {16, 1, 4}};
+constexpr size_t kMaxDynSmem = 200 * 1024;
+
+template <int WK, int RP, int U, class Pro, class Rows, class Epi>
+static cudaError_t launch_gemv_t(int grid, cudaStream_t st, int pdl, const Pro& pro, const Rows& rows,
+                                 const Epi& epi, int K4, int n_pairs) {
+  auto kern = gemv_fused_kernel<WK, RP, U, Pro, Rows, Epi>;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [&] {
+    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
+  });
+  if (attr_err != cudaSuccess) return attr_err;
+  const size_t smem = gemv_smem_bytes(K4, n_pairs, grid, WK);
+  if (smem > kMaxDynSmem) return cudaErrorInvalidValue;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kGemvThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  if (pdl) {
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+  }
+  return cudaLaunchKernelEx(&cfg, kern, pro, rows, epi, K4, n_pairs, pdl);
+}
+
+template <class Pro, class Rows, class Epi>
+static cudaError_t launch_gemv(int variant, int grid, cudaStream_t st, int pdl, const Pro& pro,
+                               const Rows& rows, const Epi& epi, int K4, int n_pairs) {
+  switch (variant) {
+    case 0: return launch_gemv_t<16, 2, 2>(grid, st, pdl, pro, rows, epi, K4, n_pairs);
+    case 1: return launch_gemv_t<8, 2, 4>(grid, st, pdl, pro, rows, epi, K4, n_pairs);
+    case 2: return launch_gemv_t<4, 2, 4>(grid, st, pdl, pro, rows, epi, K4, n_pairs);
+    case 3: return launch_gemv_t<1, 2, 4>(grid, st, pdl, pro, rows, epi, K4, n_pairs);
+    case 4: return launch_gemv_t<16, 4, 2>(grid, st, pdl, pro, rows, epi, K4, n_pairs);
+    case 5: return launch_gemv_t<8, 4, 2>(grid, st, pdl, pro, rows, epi, K4, n_pairs);
+    case 6: return launch_gemv_t<2, 2, 4>(grid, st, pdl, pro, rows, epi, K4, n_pairs);
+    case 7: return launch_gemv_t<16, 1, 4>(grid, st, pdl, pro, rows, epi, K4, n_pairs);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+static int pick_variant(const rama_ctx* c, int K4) {
+  if (c->variant_override >= 0 && c->variant_override < kNumVariants) return c->variant_override;
+  if (K4 >= 1024) return 1;
+  if (K4 >= 512) return 2;
+  if (K4 >= 128) return 6;
+  return 3;
+}
+static int pick_grid(const rama_ctx* c, int variant, int n_pairs) {
+  const int rp = kVariants[variant].RP;
+  return std::max(1, std::min(c->sm_count, (n_pairs + rp - 1) / rp));
+}
+
+// ------------------------------------------------------------------------------------------------
+// misc API
+// ------------------------------------------------------------------------------------------------
+extern "C" int rama_abi_version(void) { return RAMA_ABI_VERSION; }
+extern "C" const char* rama_last_error(void) { return g_err; }
+extern "C" int rama_device_count(int* n) {
+  if (!n) return fail(RAMA_E_INVALID, "n is NULL");
+  CK(cudaGetDeviceCount(n));
+  return RAMA_OK;
+}
+extern "C" int rama_tp_unique_id(uint8_t out[128]) {
+  if (!out) return fail(RAMA_E_INVALID, "out is NULL");
+  RK(nccl_load());
+  NcclId id;
+  NK(g_nccl.GetUniqueId(&id));
+  memcpy(out, &id, 128);
+  return RAMA_OK;
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
+
+extern "C" int rama_ctx_create(int device, const rama_tp* tp, rama_ctx** out) {
+  if (!out) return fail(RAMA_E_INVALID, "out is NULL");
+  int n = 0;
+  CK(cudaGetDeviceCount(&n));
+  if (device < 0 || device >= n) return fail(RAMA_E_CUDA, "device %d not present (%d CUDA devices)", device, n);
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return fail(RAMA_E_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                prop.major, prop.minor);
+  rama_ctx* c = new rama_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  c->use_pdl = env_int("RAMA_PDL", 1);
+  c->variant_override = env_int("RAMA_GEMV_VARIANT", -1);
+  if (tp && tp->world > 1) {
+    if (tp->rank < 0 || tp->rank >= tp->world) { delete c; return fail(RAMA_E_INVALID, "bad tp rank"); }
+    int r = nccl_load();
+    if (r != RAMA_OK) { delete c; return r; }
+    NcclId id;
+    memcpy(&id, tp->nccl_id, 128);
+    int e = g_nccl.CommInitRank(&c->comm, tp->world, id, tp->rank);
+    if (e != 0) { delete c; return fail(RAMA_E_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString(e)); }
+    c->rank = tp->rank;
+    c->world = tp->world;
+  }
+  cudaError_t e = cudaStreamCreateWithFlags(&c->op_stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { delete c; return fail(RAMA_E_CUDA, "stream: %s", cudaGetErrorString(e)); }
+  *out = c;
+  return RAMA_OK;
+}
+
+static void free_weights(rama_ctx* c) {
+  for (int i = 0; i < RAMA_T_COUNT; ++i) {
+    if (c->w[i]) cudaFree(c->w[i]);
+    c->w[i] = nullptr;
+  }
+  c->wcls = nullptr;
+  c->loaded = false;
+}
+
+extern "C" int rama_ctx_destroy(rama_ctx* c) {
+  if (!c) return RAMA_OK;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  free_weights(c);
+  if (c->comm) g_nccl.CommDestroy(c->comm);
+  if (c->op_stream) cudaStreamDestroy(c->op_stream);
+  delete c;
+  return RAMA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// weights: validation, shard plan, loaders
+// ------------------------------------------------------------------------------------------------
+static int set_config(rama_ctx* c, const rama_config* cfg) {
+  const int P = c->world;
+  if (cfg->dim <= 0 || cfg->hidden_dim <= 0 || cfg->n_layers <= 0 || cfg->n_heads <= 0 ||
+      cfg->vocab_size <= 1 || cfg->seq_len <= 0)
+    return fail(RAMA_E_INVALID, "non-positive dimension in config");
+  if (cfg->dim % cfg->n_heads) return fail(RAMA_E_INVALID, "dim %% n_heads != 0");
+  const int hs = cfg->dim / cfg->n_heads;
+  // The reference's forward ignores n_kv_heads (K/V are dim wide, infer.rs:22-23,31-33) while its
+  // cache is sized by it (ram.rs:8,20-21): only n_kv_heads == n_heads is consistent there.
+  if (cfg->n_kv_heads != cfg->n_heads)
+    return fail(RAMA_E_INVALID, "n_kv_heads (%d) != n_heads (%d): not supported by the reference forward",
+                cfg->n_kv_heads, cfg->n_heads);
+  if (hs % 4 || hs > kAttnMaxHs) return fail(RAMA_E_INVALID, "head_size %d must be a multiple of 4 and <= %d", hs, kAttnMaxHs);
+  if (cfg->dim % 4 || cfg->hidden_dim % 4)
+    return fail(RAMA_E_INVALID, "dim and hidden_dim must be multiples of 4 (reference matmul, cpu.rs:142)");
+  if (cfg->n_heads % P || cfg->hidden_dim % P || cfg->vocab_size % P || (cfg->hidden_dim / P) % 4)
+    return fail(RAMA_E_INVALID, "n_heads/hidden_dim/vocab_size not divisible by tp world %d", P);
+  c->cfg = *cfg;
+  c->D = cfg->dim; c->F = cfg->hidden_dim; c->L = cfg->n_layers; c->H = cfg->n_heads;
+  c->V = cfg->vocab_size; c->T = cfg->seq_len; c->hs = hs;
+  c->Hl = c->H / P; c->Dq = c->Hl * hs; c->Fl = c->F / P; c->Vl = c->V / P; c->v0 = c->rank * c->Vl;
+  const size_t D = c->D, F = c->F, L = c->L, V = c->V, T = c->T;
+  const size_t Dq = c->Dq, Fl = c->Fl, r = c->rank;
+  auto full = [](size_t Lc, size_t R, size_t C) { TensorPlan p; p.Lc = Lc; p.R = R; p.C = C; p.Rl = R; p.Cl = C; return p; };
+  auto rows = [](size_t Lc, size_t R, size_t C, size_t r0, size_t Rl) { TensorPlan p; p.Lc = Lc; p.R = R; p.C = C; p.r0 = r0; p.Rl = Rl; p.Cl = C; return p; };
+  auto cols = [](size_t Lc, size_t R, size_t C, size_t c0, size_t Cl) { TensorPlan p; p.Lc = Lc; p.R = R; p.C = C; p.Rl = R; p.c0 = c0; p.Cl = Cl; return p; };
+  c->plan[RAMA_T_TOKEN_EMBEDDING] = full(1, V, D);
+  c->plan[RAMA_T_RMS_ATT] = full(1, L, D);
+  c->plan[RAMA_T_WQ] = rows(L, D, D, r * Dq, Dq);   // column-parallel: this rank's heads
+  c->plan[RAMA_T_WK] = rows(L, D, D, r * Dq, Dq);
+  c->plan[RAMA_T_WV] = rows(L, D, D, r * Dq, Dq);
+  c->plan[RAMA_T_WO] = cols(L, D, D, r * Dq, Dq);   // row-parallel: repacked to [D][Dq]
+  c->plan[RAMA_T_RMS_FFN] = full(1, L, D);
+  c->plan[RAMA_T_W1] = rows(L, F, D, r * Fl, Fl);
+  c->plan[RAMA_T_W2] = cols(L, D, F, r * Fl, Fl);   // row-parallel: repacked to [D][Fl]
+  c->plan[RAMA_T_W3] = rows(L, F, D, r * Fl, Fl);
+  c->plan[RAMA_T_RMS_FINAL] = full(1, 1, D);
+  c->plan[RAMA_T_FREQ_REAL] = full(1, T, hs / 2);
+  c->plan[RAMA_T_FREQ_IMAG] = full(1, T, hs / 2);
+  if (cfg->shared_weight) c->plan[RAMA_T_WCLS] = TensorPlan();
+  else c->plan[RAMA_T_WCLS] = rows(1, V, D, (size_t)c->v0, (size_t)c->Vl);
+  return RAMA_OK;
+}
+
+static int alloc_weights(rama_ctx* c) {
+  free_weights(c);
+  for (int i = 0; i < RAMA_T_COUNT; ++i) {
+    const size_t n = c->plan[i].local_elems();
+    if (!n) continue;
+    cudaError_t e = cudaMalloc(&c->w[i], n * sizeof(float));
+    if (e != cudaSuccess) {
+      free_weights(c);
+      return fail(RAMA_E_CUDA, "cudaMalloc of tensor %d (%zu floats): %s", i, n, cudaGetErrorString(e));
+    }
+  }
+  c->wcls = c->cfg.shared_weight ? c->w[RAMA_T_TOKEN_EMBEDDING] + (size_t)c->v0 * c->D : c->w[RAMA_T_WCLS];
+  return RAMA_OK;
+}
+
+// One pass host → HBM of this rank's window of tensor i (src = full global tensor on the host).
+static int upload_tensor(rama_ctx* c, int i, const float* src, cudaStream_t st) {
+  const TensorPlan& p = c->plan[i];
+  if (!p.local_elems()) return RAMA_OK;
+  if (!src) return fail(RAMA_E_INVALID, "tensor %d is NULL", i);
+  for (size_t l = 0; l < p.Lc; ++l) {
+    float* dst = c->w[i] + l * p.Rl * p.Cl;
+    const float* s = src + (l * p.R + p.r0) * p.C + p.c0;
+    if (p.Cl == p.C) CK(cudaMemcpyAsync(dst, s, p.Rl * p.C * sizeof(float), cudaMemcpyHostToDevice, st));
+    else CK(cudaMemcpy2DAsync(dst, p.Cl * sizeof(float), s, p.C * sizeof(float), p.Cl * sizeof(float), p.Rl,
+                              cudaMemcpyHostToDevice, st));
+  }
+  return RAMA_OK;
+}
+
+extern "C" int rama_ctx_load_host(rama_ctx* c, const rama_config* cfg, const float* const tensors[RAMA_T_COUNT]) {
+  if (!c || !cfg || !tensors) return fail(RAMA_E_INVALID, "NULL argument");
+  std::lock_guard<std::mutex> lk(c->mu);
+  CK(cudaSetDevice(c->device));
+  RK(set_config(c, cfg));
+  RK(alloc_weights(c));
+  for (int i = 0; i < RAMA_T_COUNT; ++i) {
+    int r = upload_tensor(c, i, tensors[i], c->op_stream);
+    if (r != RAMA_OK) { free_weights(c); return r; }
+  }
+  CK(cudaStreamSynchronize(c->op_stream));
+  c->loaded = true;
+  return RAMA_OK;
+}
+
+extern "C" int rama_ctx_load_file(rama_ctx* c, const char* path) {
+  if (!c || !path) return fail(RAMA_E_INVALID, "NULL argument");
+  int fd = open(path, O_RDONLY);
+  if (fd < 0) return fail(RAMA_E_IO, "cannot open %s", path);
+  struct stat st;
+  if (fstat(fd, &st) != 0 || st.st_size < 28) { close(fd); return fail(RAMA_E_IO, "%s: too short for a v0 header", path); }
+  void* map = mmap(nullptr, st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+  close(fd);
+  if (map == MAP_FAILED) return fail(RAMA_E_IO, "mmap of %s failed", path);
+  madvise(map, st.st_size, MADV_SEQUENTIAL);
+  // header: 7 LE i32; vocab > 0 ⇒ shared classifier (mod.rs:140-166)
+  const int32_t* h = (const int32_t*)map;
+  rama_config cfg{h[0], h[1], h[2], h[3], h[4], h[5] > 0 ? h[5] : -h[5], h[6], h[5] > 0 ? 1 : 0};
+  int rc;
+  {
+    std::lock_guard<std::mutex> lk(c->mu);
+    cudaSetDevice(c->device);
+    rc = set_config(c, &cfg);
+    if (rc == RAMA_OK) {
+      size_t need = 28;
+      for (int i = 0; i < RAMA_T_COUNT; ++i) need += c->plan[i].global_elems() * 4;
+      if ((size_t)st.st_size < need) rc = fail(RAMA_E_IO, "%s: %lld bytes, config needs %zu", path, (long long)st.st_size, need);
+    }
+    if (rc == RAMA_OK) rc = alloc_weights(c);
+    if (rc == RAMA_OK) {
+      const float* f = (const float*)((const char*)map + 28);
+      for (int i = 0; i < RAMA_T_COUNT && rc == RAMA_OK; ++i) {
+        rc = upload_tensor(c, i, f, c->op_stream);
+        f += c->plan[i].global_elems();
+      }
+      if (rc == RAMA_OK && cudaStreamSynchronize(c->op_stream) != cudaSuccess) rc = fail(RAMA_E_CUDA, "sync after upload");
+      if (rc != RAMA_OK) free_weights(c); else c->loaded = true;
+    }
+  }
+  munmap(map, st.st_size);
+  return rc;
+}
+
+extern "C" int rama_ctx_load_synthetic(rama_ctx* c, const rama_config* cfg, uint64_t seed,
+                                       const float scale[RAMA_T_COUNT], const float offset[RAMA_T_COUNT],
+                                       const float* freq_real, const float* freq_imag) {
+  if (!c || !cfg || !scale || !offset || !freq_real || !freq_imag) return fail(RAMA_E_INVALID, "NULL argument");
+  std::lock_guard<std::mutex> lk(c->mu);
+  CK(cudaSetDevice(c->device));
+  RK(set_config(c, cfg));
+  RK(alloc_weights(c));
+  for (int i = 0; i < RAMA_T_COUNT; ++i) {
+    const TensorPlan& p = c->plan[i];
+    const size_t n = p.local_elems();
+    if (!n) continue;
+    if (i == RAMA_T_FREQ_REAL || i == RAMA_T_FREQ_IMAG) {
+      CK(cudaMemcpyAsync(c->w[i], i == RAMA_T_FREQ_REAL ? freq_real : freq_imag, n * sizeof(float),
+                         cudaMemcpyHostToDevice, c->op_stream));
+      continue;
+    }
+    // key = splitmix64(seed ^ tensor_id * 0xD1B54A32D192ED03)  (rama_b200/checkpoint.py)
+    unsigned long long z = seed ^ ((unsigned long long)i * 0xD1B54A32D192ED03ull);
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z = z ^ (z >> 31);
+    ShardMap m{p.R, p.C, p.r0, p.Rl, p.c0, p.Cl};
+    synth_fill_kernel<<<c->sm_count * 8, 256, 0, c->op_stream>>>(c->w[i], n, z, m, 0ull, scale[i], offset[i]);
+    CK(cudaGetLastError());
+  }
+  CK(cudaStreamSynchronize(c->op_stream));
+  c->loaded = true;
+  return RAMA_OK;
+}
+
+extern "C" int rama_ctx_config(const rama_ctx* c, rama_config* out) {
+  if (!c || !out) return fail(RAMA_E_INVALID, "NULL argument");
+  if (!c->loaded) return fail(RAMA_E_STATE, "no weights loaded");
+  *out = c->cfg;
+  return RAMA_OK;
+}
+
+extern "C" int rama_ctx_weight_to_host(rama_ctx* c, int tensor, float* dst, size_t n, size_t* n_out) {
+  if (!c || tensor < 0 || tensor >= RAMA_T_COUNT) return fail(RAMA_E_INVALID, "bad argument");
+  if (!c->loaded) return fail(RAMA_E_STATE, "no weights loaded");
+  const size_t have = c->plan[tensor].local_elems();
+  if (n_out) *n_out = have;
+  if (!dst) return RAMA_OK;
+  if (n < have) return fail(RAMA_E_INVALID, "buffer too small: %zu < %zu", n, have);
+  CK(cudaSetDevice(c->device));
+  if (have) CK(cudaMemcpy(dst, c->w[tensor], have * sizeof(float), cudaMemcpyDeviceToHost));
+  return RAMA_OK;
+}
+
+extern "C" int rama_ctx_weight_bytes(const rama_ctx* c, size_t* bytes) {
+  if (!c || !bytes) return fail(RAMA_E_INVALID, "NULL argument");
+  size_t t = 0;
+  for (int i = 0; i < RAMA_T_COUNT; ++i) t += c->plan[i].local_elems() * 4;
+  *bytes = t;
+  return RAMA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// session
+// ------------------------------------------------------------------------------------------------
+template <class Tp>
+static cudaError_t dalloc(Tp** p, size_t n) {
+  cudaError_t e = cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(Tp));
+  if (e == cudaSuccess) e = cudaMemset(*p, 0, std::max<size_t>(n, 1) * sizeof(Tp));
+  return e;
+}
+
+static void session_free(rama_session* s) {
+  if (!s) return;
+  cudaSetDevice(s->ctx->device);
+  if (s->stream) cudaStreamSynchronize(s->stream);
+  if (s->g_fwd) cudaGraphExecDestroy(s->g_fwd);
+  for (auto& g : s->g_step) if (g) cudaGraphExecDestroy(g);
+  void* bufs[] = {s->x0, s->x1, s->xfinal, s->xb, s->xb2, s->w2out, s->hb, s->hb2, s->q, s->k, s->v, s->att,
+                  s->logits, s->key_cache, s->value_cache, s->attn_ws, s->tickets, s->part, s->sort_keys,
+                  s->ctrl, s->d_prompt, s->d_out};
+  for (void* b : bufs) if (b) cudaFree(b);
+  if (s->h_ring) cudaFreeHost(s->h_ring);
+  if (s->h_ret) cudaFreeHost(s->h_ret);
+  if (s->ev0) cudaEventDestroy(s->ev0);
+  if (s->ev1) cudaEventDestroy(s->ev1);
+  if (s->stream) cudaStreamDestroy(s->stream);
+  delete s;
+}
+
+constexpr int kRing = 64;
+
+extern "C" int rama_session_create(rama_ctx* c, rama_session** out) {
+  if (!c || !out) return fail(RAMA_E_INVALID, "NULL argument");
+  if (!c->loaded) return fail(RAMA_E_STATE, "no weights loaded");
+  CK(cudaSetDevice(c->device));
+  rama_session* s = new rama_session();
+  s->ctx = c;
+  s->n_split = (c->T + kAttnChunk - 1) / kAttnChunk;
+  const size_t D = c->D, Dq = c->Dq, Fl = c->Fl, V = c->V, T = c->T, L = c->L;
+  size_t vp2 = 1;
+  while (vp2 < V) vp2 <<= 1;
+  cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+#define A(call) if (e == cudaSuccess) e = (call)
+  A(dalloc(&s->x0, D)); A(dalloc(&s->x1, D)); A(dalloc(&s->xfinal, D));
+  A(dalloc(&s->xb, Dq)); A(dalloc(&s->xb2, D)); A(dalloc(&s->w2out, D));
+  A(dalloc(&s->hb, Fl)); A(dalloc(&s->hb2, Fl));
+  A(dalloc(&s->q, Dq)); A(dalloc(&s->k, Dq)); A(dalloc(&s->v, Dq));
+  A(dalloc(&s->att, (size_t)c->Hl * T));
+  A(dalloc(&s->logits, V));
+  A(dalloc(&s->key_cache, L * T * Dq)); A(dalloc(&s->value_cache, L * T * Dq));
+  A(dalloc(&s->attn_ws, (size_t)c->Hl * s->n_split * (c->hs + 2)));
+  A(dalloc(&s->tickets, (size_t)c->Hl));
+  A(dalloc(&s->part, (size_t)c->world * c->sm_count));
+  A(dalloc(&s->sort_keys, vp2));
+  A(dalloc(&s->ctrl, 1));
+  A(dalloc(&s->d_prompt, T)); A(dalloc(&s->d_out, T));
+  A(cudaHostAlloc((void**)&s->h_ring, kRing * sizeof(StepCtrl), cudaHostAllocDefault));
+  A(cudaHostAlloc((void**)&s->h_ret, 4 * sizeof(int32_t), cudaHostAllocDefault));
+  A(cudaEventCreate(&s->ev0)); A(cudaEventCreate(&s->ev1));
+#undef A
+  if (e != cudaSuccess) {
+    session_free(s);
+    return fail(RAMA_E_CUDA, "session allocation: %s", cudaGetErrorString(e));
+  }
+  *out = s;
+  return RAMA_OK;
+}
+
+extern "C" int rama_session_destroy(rama_session* s) {
+  session_free(s);
+  return RAMA_OK;
+}
+
+extern "C" int rama_session_sync(rama_session* s) {
+  if (!s) return fail(RAMA_E_INVALID, "NULL session");
+  CK(cudaSetDevice(s->ctx->device));
+  CK(cudaStreamSynchronize(s->stream));
+  return RAMA_OK;
+}
+
+extern "C" int rama_session_reset(rama_session* s) {
+  if (!s) return fail(RAMA_E_INVALID, "NULL session");
+  rama_ctx* c = s->ctx;
+  CK(cudaSetDevice(c->device));
+  const size_t kv = (size_t)c->L * c->T * c->Dq * sizeof(float);
+  CK(cudaMemsetAsync(s->key_cache, 0, kv, s->stream));
+  CK(cudaMemsetAsync(s->value_cache, 0, kv, s->stream));
+  CK(cudaMemsetAsync(s->ctrl, 0, sizeof(StepCtrl), s->stream));
+  CK(cudaMemsetAsync(s->tickets, 0, c->Hl * sizeof(unsigned int), s->stream));
+  s->host_mode_set = 0;
+  CK(cudaStreamSynchronize(s->stream));
+  return RAMA_OK;
+}
+
+extern "C" int rama_session_set_debug(rama_session* s, int keep_att) {
+  if (!s) return fail(RAMA_E_INVALID, "NULL session");
+  CK(cudaSetDevice(s->ctx->device));
+  CK(cudaStreamSynchronize(s->stream));
+  if (s->keep_att != keep_att) {  // the captured graphs bake the att pointer in
+    if (s->g_fwd) { cudaGraphExecDestroy(s->g_fwd); s->g_fwd = nullptr; }
+    for (auto& g : s->g_step) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+  }
+  s->keep_att = keep_att;
+  return RAMA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the decode step
+// ------------------------------------------------------------------------------------------------
+struct StepTrace {  // optional per-kernel CUDA-event timing (rama_profile_step)
+  std::vector<cudaEvent_t> ev;
+  std::vector<int> kind;
+};
+
+struct StepEnq {
+  rama_session* s;
+  cudaStream_t st;
+  StepTrace* tr;
+  int launches = 0;
+  int pdl;
+  cudaError_t err = cudaSuccess;
+  int nccl_err = 0;
+  void pre(int kind) {
+    if (tr) {
+      cudaEvent_t a;
+      cudaEventCreate(&a);
+      cudaEventRecord(a, st);
+      tr->ev.push_back(a);
+      tr->kind.push_back(kind);
+    }
+  }
+  void post(cudaError_t e) {
+    if (err == cudaSuccess && e != cudaSuccess) err = e;
+    if (err == cudaSuccess) { cudaError_t l = cudaGetLastError(); if (l != cudaSuccess) err = l; }
+    ++launches;
+    if (tr) {
+      cudaEvent_t b;
+      cudaEventCreate(&b);
+      cudaEventRecord(b, st);
+      tr->ev.push_back(b);
+    }
+  }
+};
+
+template <class F>
+static void launch_plain(StepEnq& q, int kind, F&& f) {
+  q.pre(kind);
+  f();
+  q.post(cudaSuccess);
+}
+
+// mode: 0 = forward only (logits + greedy partials), 1 = + chained greedy sampler, 2 = + chained top-p
+static int enqueue_step(rama_session* s, cudaStream_t st, int mode, StepTrace* tr, int* n_launch) {
+  rama_ctx* c = s->ctx;
+  StepEnq q{s, st, tr};
+  // PDL edges are only used inside captured graphs / plain streams without event timing
+  q.pdl = tr ? 0 : c->use_pdl;
+  const int D = c->D, Dq = c->Dq, Fl = c->Fl, T = c->T, hs = c->hs, L = c->L;
+  const float* W[RAMA_T_COUNT];
+  for (int i = 0; i < RAMA_T_COUNT; ++i) W[i] = c->w[i];
+
+  // x0 ← embedding row of ctrl->token (infer.rs:13)
+  q.pre(RAMA_K_EMBED);
+  {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(std::max(1, std::min(8, D / 4 / 256)));
+    cfg.blockDim = dim3(256);
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    if (q.pdl) {
+      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+    }
+    q.post(cudaLaunchKernelEx(&cfg, step_begin_kernel, s->ctrl, W[RAMA_T_TOKEN_EMBEDDING], s->x0, D, c->V, q.pdl));
+  }
+
+  for (int l = 0; l < L; ++l) {
+    // ---- rmsnorm → [wq|wk|wv] → RoPE → KV write (infer.rs:19-33) ----
+    {
+      ProNorm pro{s->x0, l == 0 ? nullptr : s->w2out, s->x1, W[RAMA_T_RMS_ATT] + (size_t)l * D, nullptr};
+      RowsQKV rows{W[RAMA_T_WQ] + (size_t)l * Dq * D, W[RAMA_T_WK] + (size_t)l * Dq * D,
+                   W[RAMA_T_WV] + (size_t)l * Dq * D, D, Dq / 2};
+      EpiQKV epi{s->q, s->k, s->v, s->key_cache + (size_t)l * T * Dq, s->value_cache + (size_t)l * T * Dq,
+                 W[RAMA_T_FREQ_REAL], W[RAMA_T_FREQ_IMAG], s->ctrl, Dq / 2, hs / 2, Dq};
+      const int np = 3 * Dq / 2, var = pick_variant(c, D / 4);
+      q.pre(RAMA_K_QKV);
+      q.post(launch_gemv(var, pick_grid(c, var, np), st, q.pdl, pro, rows, epi, D / 4, np));
+    }
+    // ---- attention (infer.rs:34) ----
+    {
+      AttnParams ap{s->q, s->key_cache + (size_t)l * T * Dq, s->value_cache + (size_t)l * T * Dq, s->xb,
+                    s->keep_att ? s->att : nullptr, s->attn_ws, s->tickets, s->ctrl, -1, T, Dq, hs, s->n_split};
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(c->Hl, s->n_split);
+      cfg.blockDim = dim3(kAttnThreads);
+      cfg.stream = st;
+      cudaLaunchAttribute at[1];
+      if (q.pdl) {
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+      }
+      q.pre(RAMA_K_ATTN);
+      q.post(cudaLaunchKernelEx(&cfg, attn_decode_kernel, ap, q.pdl));
+    }
+    // ---- wo (infer.rs:35); the residual add (:37) is folded into the next prologue ----
+    {
+      ProPlain pro{s->xb};
+      RowsPlain rows{W[RAMA_T_WO] + (size_t)l * D * Dq, Dq, D};
+      EpiStore epi{s->xb2, D};
+      const int np = D / 2, var = pick_variant(c, Dq / 4);
+      q.pre(RAMA_K_WO);
+      q.post(launch_gemv(var, pick_grid(c, var, np), st, q.pdl, pro, rows, epi, Dq / 4, np));
+    }
+    if (c->world > 1) {
+      q.pre(RAMA_K_COMM);
+      int e = g_nccl.AllReduce(s->xb2, s->xb2, D, kNcclFloat32, kNcclSum, c->comm, st);
+      if (e && !q.nccl_err) q.nccl_err = e;
+      q.post(cudaSuccess);
+    }
+    // ---- x += xb2; rmsnorm → [w1|w3] → SwiGLU (infer.rs:37-45) ----
+    {
+      ProNorm pro{s->x1, s->xb2, s->x0, W[RAMA_T_RMS_FFN] + (size_t)l * D, nullptr};
+      RowsW13 rows{W[RAMA_T_W1] + (size_t)l * Fl * D, W[RAMA_T_W3] + (size_t)l * Fl * D, D};
+      EpiSwiGLU epi{s->hb, s->hb2};
+      const int np = Fl, var = pick_variant(c, D / 4);
+      q.pre(RAMA_K_W13);
+      q.post(launch_gemv(var, pick_grid(c, var, np), st, q.pdl, pro, rows, epi, D / 4, np));
+    }
+    // ---- w2 (infer.rs:46); residual add (:47) folded into the next prologue ----
+    {
+      ProPlain pro{s->hb};
+      RowsPlain rows{W[RAMA_T_W2] + (size_t)l * D * Fl, Fl, D};
+      EpiStore epi{s->w2out, D};
+      const int np = D / 2, var = pick_variant(c, Fl / 4);
+      q.pre(RAMA_K_W2);
+      q.post(launch_gemv(var, pick_grid(c, var, np), st, q.pdl, pro, rows, epi, Fl / 4, np));
+    }
+    if (c->world > 1) {
+      q.pre(RAMA_K_COMM);
+      int e = g_nccl.AllReduce(s->w2out, s->w2out, D, kNcclFloat32, kNcclSum, c->comm, st);
+      if (e && !q.nccl_err) q.nccl_err = e;
+      q.post(cudaSuccess);
+    }
+  }
+  // ---- x += w2out; final rmsnorm → wcls → logits (+ greedy partials) (infer.rs:49-51) ----
+  int cls_grid;
+  {
+    ProNorm pro{s->x0, s->w2out, s->x1, W[RAMA_T_RMS_FINAL], s->xfinal};
+    RowsPlain rows{c->wcls, D, c->Vl};
+    EpiCls epi{s->logits + c->v0, s->part + (size_t)c->rank * c->sm_count, c->Vl, c->v0, -INFINITY, -1};
+    const int np = (c->Vl + 1) / 2, var = pick_variant(c, D / 4);
+    cls_grid = pick_grid(c, var, np);
+    q.pre(RAMA_K_CLS);
+    q.post(launch_gemv(var, cls_grid, st, q.pdl, pro, rows, epi, D / 4, np));
+  }
+  int n_part = cls_grid;
+  if (c->world > 1) {
+    // every rank learns every rank's per-CTA (value, index) partials: 8 B × SMs per rank
+    q.pre(RAMA_K_COMM);
+    int e = g_nccl.AllGather(s->part + (size_t)c->rank * c->sm_count, s->part, (size_t)c->sm_count * 2,
+                             kNcclFloat32, c->comm, st);
+    if (e && !q.nccl_err) q.nccl_err = e;
+    q.post(cudaSuccess);
+    n_part = c->world * c->sm_count;
+    if (mode == 2) {
+      q.pre(RAMA_K_COMM);
+      e = g_nccl.AllGather(s->logits + c->v0, s->logits, (size_t)c->Vl, kNcclFloat32, c->comm, st);
+      if (e && !q.nccl_err) q.nccl_err = e;
+      q.post(cudaSuccess);
+    }
+  }
+  if (mode >= 1) {
+    SampleParams sp{s->logits, s->part, n_part, c->V, s->ctrl, s->d_prompt, s->d_out, s->sort_keys, 0.f, 0.f, 1};
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(1);
+    cfg.blockDim = dim3(kSampleThreads);
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    if (q.pdl) {
+      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+    }
+    q.pre(RAMA_K_SAMPLE);
+    q.post(cudaLaunchKernelEx(&cfg, sample_kernel, sp, q.pdl));
+  }
+  if (n_launch) *n_launch = q.launches;
+  if (q.nccl_err) return fail(RAMA_E_NCCL, "nccl collective in step: %s", g_nccl.GetErrorString(q.nccl_err));
+  if (q.err != cudaSuccess) return fail(RAMA_E_CUDA, "kernel launch in step: %s", cudaGetErrorString(q.err));
+  return RAMA_OK;
+}
+
+// unused partial slots (a CTA-less tail when the classifier grid < sm_count) must read as "empty"
+static int init_parts(rama_session* s) {
+  rama_ctx* c = s->ctx;
+  std::vector<ArgPart> h((size_t)c->world * c->sm_count, ArgPart{-INFINITY, -1});
+  CK(cudaMemcpyAsync(s->part, h.data(), h.size() * sizeof(ArgPart), cudaMemcpyHostToDevice, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  return RAMA_OK;
+}
+
+static int capture(rama_session* s, int mode, cudaGraphExec_t* out) {
+  RK(init_parts(s));
+  cudaGraph_t g = nullptr;
+  CK(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeRelaxed));
+  int n = 0;
+  int rc = enqueue_step(s, s->stream, mode, nullptr, &n);
+  cudaError_t e = cudaStreamEndCapture(s->stream, &g);
+  if (rc != RAMA_OK) { if (g) cudaGraphDestroy(g); return rc; }
+  if (e != cudaSuccess) return fail(RAMA_E_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+  e = cudaGraphInstantiate(out, g, 0);
+  cudaGraphDestroy(g);
+  if (e != cudaSuccess) return fail(RAMA_E_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+  s->launches = n;
+  return RAMA_OK;
+}
+
+extern "C" int rama_session_launches_per_step(const rama_session* s, int* n) {
+  if (!s || !n) return fail(RAMA_E_INVALID, "NULL argument");
+  const rama_ctx* c = s->ctx;
+  // embed + L·(qkv, attn, wo, w13, w2) + cls + sample (+ collectives under TP)
+  *n = 1 + 5 * c->L + 1 + 1 + (c->world > 1 ? 2 * c->L + 1 : 0);
+  return RAMA_OK;
+}
+
+extern "C" int rama_forward(rama_session* s, int32_t token, int32_t pos) {
+  if (!s) return fail(RAMA_E_INVALID, "NULL session");
+  rama_ctx* c = s->ctx;
+  if (pos < 0 || pos >= c->T)  // the reference panics on the cache slice (infer.rs:32)
+    return fail(RAMA_E_STATE, "pos %d outside [0, seq_len=%d)", pos, c->T);
+  if (token < 0 || token >= c->V) return fail(RAMA_E_INVALID, "token %d outside the vocabulary", token);
+  CK(cudaSetDevice(c->device));
+  if (!s->g_fwd) RK(capture(s, 0, &s->g_fwd));
+  StepCtrl* h = &s->h_ring[s->ring_i];
+  if (++s->ring_i == kRing) {  // never overwrite a slot a pending copy may still read
+    s->ring_i = 0;
+    CK(cudaStreamSynchronize(s->stream));
+  }
+  memset(h, 0, sizeof(*h));
+  h->pos = pos;
+  h->token = token;
+  h->chained = 0;
+  CK(cudaMemcpyAsync(s->ctrl, h, sizeof(StepCtrl), cudaMemcpyHostToDevice, s->stream));
+  CK(cudaGraphLaunch(s->g_fwd, s->stream));
+  s->logits_gathered = false;
+  return RAMA_OK;
+}
+
+static int gather_logits(rama_session* s) {
+  rama_ctx* c = s->ctx;
+  if (c->world > 1 && !s->logits_gathered) {
+    NK(g_nccl.AllGather(s->logits + c->v0, s->logits, (size_t)c->Vl, kNcclFloat32, c->comm, s->stream));
+    s->logits_gathered = true;
+  }
+  return RAMA_OK;
+}
+
+static int read_ret(rama_session* s, int32_t* next) {
+  CK(cudaMemcpyAsync(s->h_ret, &s->ctrl->next, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  if (s->h_ret[1] == 1) return fail(RAMA_E_STATE, "token id outside the vocabulary reached the device step");
+  if (s->h_ret[1] == 2) return fail(RAMA_E_STATE, "top-p candidate list is empty (the reference panics here, infer.rs:66)");
+  if (next) *next = s->h_ret[0];
+  return RAMA_OK;
+}
+
+extern "C" int rama_sample(rama_session* s, float temperature, float topp, int32_t* next) {
+  if (!s || !next) return fail(RAMA_E_INVALID, "NULL argument");
+  rama_ctx* c = s->ctx;
+  CK(cudaSetDevice(c->device));
+  const bool greedy = temperature == 0.0f;
+  if (!greedy) RK(gather_logits(s));
+  const int n_part = c->world > 1 ? c->world * c->sm_count : c->sm_count;
+  SampleParams sp{s->logits, s->part, n_part, c->V, s->ctrl, s->d_prompt, s->d_out, s->sort_keys,
+                  temperature, topp, 0};
+  sample_kernel<<<1, kSampleThreads, 0, s->stream>>>(sp, 0);
+  CK(cudaGetLastError());
+  return read_ret(s, next);
+}
+
+extern "C" int rama_generate(rama_session* s, const int32_t* prompt, int32_t n_prompt, int32_t steps,
+                             float temperature, float topp, int32_t* out_tokens, float* elapsed_ms) {
+  if (!s || (n_prompt > 0 && !prompt) || !out_tokens) return fail(RAMA_E_INVALID, "NULL argument");
+  rama_ctx* c = s->ctx;
+  if (steps < 0 || steps > c->T)  // mod.rs has no guard: the reference panics past seq_len
+    return fail(RAMA_E_STATE, "steps %d exceeds seq_len %d", steps, c->T);
+  if (n_prompt < 0) return fail(RAMA_E_INVALID, "n_prompt < 0");
+  for (int i = 0; i < n_prompt; ++i)
+    if (prompt[i] < 0 || prompt[i] >= c->V) return fail(RAMA_E_INVALID, "prompt token %d outside the vocabulary", prompt[i]);
+  CK(cudaSetDevice(c->device));
+  const int gi = temperature == 0.0f ? 0 : 1;
+  if (!s->g_step[gi]) RK(capture(s, gi + 1, &s->g_step[gi]));
+  const int np = std::min<int>(n_prompt, c->T);
+  if (np) CK(cudaMemcpyAsync(s->d_prompt, prompt, np * sizeof(int32_t), cudaMemcpyHostToDevice, s->stream));
+  StepCtrl* h = &s->h_ring[s->ring_i];
+  if (++s->ring_i == kRing) { s->ring_i = 0; CK(cudaStreamSynchronize(s->stream)); }
+  memset(h, 0, sizeof(*h));
+  h->pos = 0;
+  h->token = 1;  // BOS (mod.rs:182)
+  h->chained = 1;
+  h->n_prompt = n_prompt;
+  h->temperature = temperature;
+  h->topp = topp;
+  CK(cudaMemcpyAsync(s->ctrl, h, sizeof(StepCtrl), cudaMemcpyHostToDevice, s->stream));
+  CK(cudaEventRecord(s->ev0, s->stream));
+  for (int i = 0; i < steps; ++i) CK(cudaGraphLaunch(s->g_step[gi], s->stream));
+  CK(cudaEventRecord(s->ev1, s->stream));
+  if (steps) CK(cudaMemcpyAsync(out_tokens, s->d_out, steps * sizeof(int32_t), cudaMemcpyDeviceToHost, s->stream));
+  s->logits_gathered = gi == 1;
+  RK(read_ret(s, nullptr));
+  if (elapsed_ms) CK(cudaEventElapsedTime(elapsed_ms, s->ev0, s->ev1));
+  return RAMA_OK;
+}
+
+extern "C" int rama_profile_step(rama_session* s, int32_t token, int32_t pos, float ms[RAMA_K_COUNT],
+                                 int32_t launches[RAMA_K_COUNT]) {
+  if (!s || !ms || !launches) return fail(RAMA_E_INVALID, "NULL argument");
+  rama_ctx* c = s->ctx;
+  if (pos < 0 || pos >= c->T) return fail(RAMA_E_STATE, "pos %d outside [0, seq_len=%d)", pos, c->T);
+  if (token < 0 || token >= c->V) return fail(RAMA_E_INVALID, "token outside the vocabulary");
+  CK(cudaSetDevice(c->device));
+  RK(init_parts(s));
+  StepCtrl* h = &s->h_ring[s->ring_i];
+  if (++s->ring_i == kRing) { s->ring_i = 0; CK(cudaStreamSynchronize(s->stream)); }
+  memset(h, 0, sizeof(*h));
+  h->pos = pos; h->token = token; h->chained = 0;
+  CK(cudaMemcpyAsync(s->ctrl, h, sizeof(StepCtrl), cudaMemcpyHostToDevice, s->stream));
+  StepTrace tr;
+  int n = 0;
+  int rc = enqueue_step(s, s->stream, 0, &tr, &n);
+  cudaError_t e = cudaStreamSynchronize(s->stream);
+  for (int i = 0; i < RAMA_K_COUNT; ++i) { ms[i] = 0.f; launches[i] = 0; }
+  for (size_t i = 0; i < tr.kind.size(); ++i) {
+    float t = 0.f;
+    if (rc == RAMA_OK && e == cudaSuccess) cudaEventElapsedTime(&t, tr.ev[2 * i], tr.ev[2 * i + 1]);
+    ms[tr.kind[i]] += t;
+    launches[tr.kind[i]] += 1;
+  }
+  for (cudaEvent_t ev : tr.ev) cudaEventDestroy(ev);
+  s->logits_gathered = false;
+  if (rc != RAMA_OK) return rc;
+  if (e != cudaSuccess) return fail(RAMA_E_CUDA, "profile step: %s", cudaGetErrorString(e));
+  return RAMA_OK;
+}
+
+extern "C" int rama_logits_to_host(rama_session* s, float* dst, size_t n) {
+  if (!s || !dst) return fail(RAMA_E_INVALID, "NULL argument");
+  rama_ctx* c = s->ctx;
+  if (n < (size_t)c->V) return fail(RAMA_E_INVALID, "buffer too small");
+  CK(cudaSetDevice(c->device));
+  RK(gather_logits(s));
+  CK(cudaMemcpyAsync(dst, s->logits, (size_t)c->V * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  return RAMA_OK;
+}
+
+extern "C" int rama_state_to_host(rama_session* s, int buf, float* dst, size_t n, size_t* n_out) {
+  if (!s) return fail(RAMA_E_INVALID, "NULL session");
+  rama_ctx* c = s->ctx;
+  CK(cudaSetDevice(c->device));
+  const float* src = nullptr;
+  size_t have = 0;
+  switch (buf) {
+    case RAMA_S_X: src = s->xfinal; have = c->D; break;     // after forward: final rmsnorm output (infer.rs:50)
+    case RAMA_S_XB: src = s->x1; have = c->D; break;        // pre-norm residual copy (infer.rs:49)
+    case RAMA_S_XB2: src = s->xb2; have = c->D; break;
+    case RAMA_S_HB: src = s->hb; have = c->Fl; break;
+    case RAMA_S_HB2: src = s->hb2; have = c->Fl; break;
+    case RAMA_S_Q: src = s->q; have = c->Dq; break;
+    case RAMA_S_K: src = s->k; have = c->Dq; break;
+    case RAMA_S_V: src = s->v; have = c->Dq; break;
+    case RAMA_S_ATT: src = s->att; have = (size_t)c->Hl * c->T; break;
+    case RAMA_S_LOGITS: RK(gather_logits(s)); src = s->logits; have = c->V; break;
+    case RAMA_S_KEY_CACHE: src = s->key_cache; have = (size_t)c->L * c->T * c->Dq; break;
+    case RAMA_S_VALUE_CACHE: src = s->value_cache; have = (size_t)c->L * c->T * c->Dq; break;
+    default: return fail(RAMA_E_INVALID, "unknown state buffer %d", buf);
+  }
+  if (n_out) *n_out = have;
+  if (!dst) return RAMA_OK;
+  if (n < have) return fail(RAMA_E_INVALID, "buffer too small: %zu < %zu", n, have);
+  CK(cudaMemcpyAsync(dst, src, have * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  return RAMA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// op level (Device trait)
+// ------------------------------------------------------------------------------------------------
+extern "C" int rama_dev_alloc(rama_ctx* c, size_t n, float** out) {
+  if (!c || !out) return fail(RAMA_E_INVALID, "NULL argument");
+  CK(cudaSetDevice(c->device));
+  CK(cudaMalloc((void**)out, std::max<size_t>(n, 1) * sizeof(float)));
+  CK(cudaMemset(*out, 0, std::max<size_t>(n, 1) * sizeof(float)));  // RunState::from_config zero-fills (ram.rs:7-23)
+  return RAMA_OK;
+}
+extern "C" int rama_dev_free(rama_ctx* c, float* p) {
+  if (!c) return fail(RAMA_E_INVALID, "NULL ctx");
+  CK(cudaSetDevice(c->device));
+  CK(cudaFree(p));
+  return RAMA_OK;
+}
+extern "C" int rama_dev_h2d(rama_ctx* c, float* dst, const float* src, size_t n) {
+  if (!c || (!dst && n) || (!src && n)) return fail(RAMA_E_INVALID, "NULL argument");
+  CK(cudaSetDevice(c->device));
+  CK(cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyHostToDevice, c->op_stream));
+  CK(cudaStreamSynchronize(c->op_stream));
+  return RAMA_OK;
+}
+extern "C" int rama_dev_d2h(rama_ctx* c, float* dst, const float* src, size_t n) {
+  if (!c || (!dst && n) || (!src && n)) return fail(RAMA_E_INVALID, "NULL argument");
+  CK(cudaSetDevice(c->device));
+  CK(cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyDeviceToHost, c->op_stream));
+  CK(cudaStreamSynchronize(c->op_stream));
+  return RAMA_OK;
+}
+extern "C" int rama_ctx_sync(rama_ctx* c) {
+  if (!c) return fail(RAMA_E_INVALID, "NULL ctx");
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->op_stream));
+  return RAMA_OK;
+}
+
+static int ew_grid(const rama_ctx* c, size_t n) {
+  return (int)std::max<size_t>(1, std::min<size_t>((n + 255) / 256, (size_t)c->sm_count * 8));
+}
+#define OP_PRE(c)                                         \
+  if (!(c)) return fail(RAMA_E_INVALID, "NULL ctx");      \
+  CK(cudaSetDevice((c)->device));
+
+extern "C" int rama_op_array_add(rama_ctx* c, float* t, const float* s, size_t n) {
+  OP_PRE(c);
+  if (n) op_array_add_kernel<<<ew_grid(c, n), 256, 0, c->op_stream>>>(t, s, n);
+  CK(cudaGetLastError());
+  return RAMA_OK;
+}
+extern "C" int rama_op_array_mult(rama_ctx* c, float* t, const float* s, size_t n) {
+  OP_PRE(c);
+  if (n) op_array_mult_kernel<<<ew_grid(c, n), 256, 0, c->op_stream>>>(t, s, n);
+  CK(cudaGetLastError());
+  return RAMA_OK;
+}
+extern "C" int rama_op_sinu(rama_ctx* c, float* o, size_t n) {
+  OP_PRE(c);
+  if (n) op_sinu_kernel<<<ew_grid(c, n), 256, 0, c->op_stream>>>(o, n);
+  CK(cudaGetLastError());
+  return RAMA_OK;
+}
+extern "C" int rama_op_copy_from_slice(rama_ctx* c, float* t, const float* s, size_t n) {
+  OP_PRE(c);
+  if (n) op_copy_kernel<<<ew_grid(c, n), 256, 0, c->op_stream>>>(t, s, n);
+  CK(cudaGetLastError());
+  return RAMA_OK;
+}
+extern "C" int rama_op_rmsnorm(rama_ctx* c, float* o, const float* x, const float* w, size_t n) {
+  OP_PRE(c);
+  if (!n) return fail(RAMA_E_INVALID, "rmsnorm of an empty vector");
+  op_rmsnorm_kernel<<<1, 1024, 0, c->op_stream>>>(o, x, w, (int)n);
+  CK(cudaGetLastError());
+  return RAMA_OK;
+}
+extern "C" int rama_op_apply_position(rama_ctx* c, float* q, float* k, const float* pr, const float* pi,
+                                      size_t head_size) {
+  OP_PRE(c);
+  const int hs2 = (int)(head_size / 2);
+  if (hs2) op_apply_position_kernel<<<(hs2 + 127) / 128, 128, 0, c->op_stream>>>(q, k, pr, pi, hs2);
+  CK(cudaGetLastError());
+  return RAMA_OK;
+}
+extern "C" int rama_op_softmax(rama_ctx* c, float* x, size_t n) {
+  OP_PRE(c);
+  if (!n) return fail(RAMA_E_INVALID, "softmax of an empty vector");
+  op_softmax_kernel<<<1, 1024, 0, c->op_stream>>>(x, (int)n);
+  CK(cudaGetLastError());
+  return RAMA_OK;
+}
+
+static int matvec(rama_ctx* c, float* o, const float* a, const float* b, size_t width, size_t o_rows,
+                  int variant, cudaStream_t st) {
+  if (width % 4) return fail(RAMA_E_INVALID, "width %% 4 != 0 (the reference steps k by 4, cpu.rs:142)");
+  if (((uintptr_t)a | (uintptr_t)b) & 15) return fail(RAMA_E_INVALID, "matmul operands must be 16-byte aligned");
+  ProPlain pro{b};
+  RowsPlain rows{a, (int)width, (int)o_rows};
+  EpiStore epi{o, (int)o_rows};
+  const int np = (int)((o_rows + 1) / 2), K4 = (int)(width / 4);
+  const int var = variant >= 0 ? variant : pick_variant(c, K4);
+  cudaError_t e = launch_gemv(var, pick_grid(c, var, np), st, 0, pro, rows, epi, K4, np);
+  if (e != cudaSuccess) return fail(RAMA_E_CUDA, "gemv launch: %s", cudaGetErrorString(e));
+  CK(cudaGetLastError());
+  return RAMA_OK;
+}
+
+extern "C" int rama_op_matmul(rama_ctx* c, float* o, const float* a, const float* b, size_t width,
+                              size_t o_rows, size_t o_cols) {
+  OP_PRE(c);
+  if (!width || !o_rows || !o_cols) return fail(RAMA_E_INVALID, "empty matmul");
+  if (o_cols == 1) return matvec(c, o, a, b, width, o_rows, -1, c->op_stream);
+  const size_t n = o_rows * o_cols;
+  op_matmul_general_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->op_stream>>>(o, a, b, (int)width, (int)o_rows, (int)o_cols);
+  CK(cudaGetLastError());
+  return RAMA_OK;
+}
+
+extern "C" int rama_op_multi_head_attention(rama_ctx* c, float* xb, float* att, const float* q,
+                                            const float* key_cache, const float* value_cache,
+                                            const rama_config* cfg, int32_t layer, int32_t pos) {
+  OP_PRE(c);
+  if (!cfg) return fail(RAMA_E_INVALID, "NULL cfg");
+  const int D = cfg->dim, H = cfg->n_heads, T = cfg->seq_len;
+  if (H <= 0 || D % H) return fail(RAMA_E_INVALID, "dim %% n_heads != 0");
+  const int hs = D / H;
+  if (hs % 4 || hs > kAttnMaxHs) return fail(RAMA_E_INVALID, "head_size %d unsupported", hs);
+  if (pos < 0 || pos >= T || layer < 0 || layer >= cfg->n_layers) return fail(RAMA_E_STATE, "layer/pos out of range");
+  const int n_split = (T + kAttnChunk - 1) / kAttnChunk;
+  float* ws = nullptr;
+  unsigned int* tickets = nullptr;
+  CK(cudaMallocAsync((void**)&ws, (size_t)H * n_split * (hs + 2) * sizeof(float), c->op_stream));
+  CK(cudaMallocAsync((void**)&tickets, H * sizeof(unsigned int), c->op_stream));
+  CK(cudaMemsetAsync(tickets, 0, H * sizeof(unsigned int), c->op_stream));
+  const size_t lo = (size_t)layer * T * D;
+  AttnParams ap{q, key_cache + lo, value_cache + lo, xb, att, ws, tickets, nullptr, pos, T, D, hs, n_split};
+  attn_decode_kernel<<<dim3(H, n_split), kAttnThreads, 0, c->op_stream>>>(ap, 0);
+  CK(cudaGetLastError());
+  CK(cudaFreeAsync(ws, c->op_stream));
+  CK(cudaFreeAsync(tickets, c->op_stream));
+  return RAMA_OK;
+}
+
+extern "C" int rama_op_sample(rama_ctx* c, float* logits, size_t vocab_size, float temperature, float topp,
+                              int32_t* next) {
+  OP_PRE(c);
+  if (!logits || !next || vocab_size < 2) return fail(RAMA_E_INVALID, "bad argument");
+  size_t vp2 = 1;
+  while (vp2 < vocab_size) vp2 <<= 1;
+  StepCtrl* ctrl = nullptr;
+  unsigned long long* keys = nullptr;
+  CK(cudaMallocAsync((void**)&ctrl, sizeof(StepCtrl), c->op_stream));
+  CK(cudaMemsetAsync(ctrl, 0, sizeof(StepCtrl), c->op_stream));
+  CK(cudaMallocAsync((void**)&keys, vp2 * sizeof(unsigned long long), c->op_stream));
+  SampleParams sp{logits, nullptr, 0, (int)vocab_size, ctrl, nullptr, nullptr, keys, temperature, topp, 0};
+  sample_kernel<<<1, kSampleThreads, 0, c->op_stream>>>(sp, 0);
+  CK(cudaGetLastError());
+  int32_t ret[2] = {0, 0};
+  CK(cudaMemcpyAsync(ret, &ctrl->next, sizeof(ret), cudaMemcpyDeviceToHost, c->op_stream));
+  CK(cudaFreeAsync(ctrl, c->op_stream));
+  CK(cudaFreeAsync(keys, c->op_stream));
+  CK(cudaStreamSynchronize(c->op_stream));
+  if (ret[1] == 2) return fail(RAMA_E_STATE, "top-p candidate list is empty (the reference panics here, infer.rs:66)");
+  *next = ret[0];
+  return RAMA_OK;
+}
+
+extern "C" int rama_synth_fill(rama_ctx* c, float* dst, size_t n, uint64_t seed, uint64_t tensor_id,
+                               uint64_t start, float scale, float offset) {
+  OP_PRE(c);
+  unsigned long long z = seed ^ ((unsigned long long)tensor_id * 0xD1B54A32D192ED03ull);
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  ShardMap m{1, n, 0, 1, 0, n};
+  if (n) synth_fill_kernel<<<c->sm_count * 8, 256, 0, c->op_stream>>>(dst, n, z, m, start, scale, offset);
+  CK(cudaGetLastError());
+  return RAMA_OK;
+}
+
+extern "C" int rama_bench_gemv(rama_ctx* c, float* o, const float* w, const float* x, size_t rows, size_t width,
+                               int variant, int iters, float* avg_ms) {
+  OP_PRE(c);
+  if (!avg_ms || iters <= 0) return fail(RAMA_E_INVALID, "bad argument");
+  if (variant >= kNumVariants) return fail(RAMA_E_INVALID, "variant %d out of range", variant);
+  cudaEvent_t a, b;
+  CK(cudaEventCreate(&a));
+  CK(cudaEventCreate(&b));
+  for (int i = 0; i < 3; ++i) RK(matvec(c, o, w, x, width, rows, variant, c->op_stream));
+  CK(cudaEventRecord(a, c->op_stream));
+  for (int i = 0; i < iters; ++i) RK(matvec(c, o, w, x, width, rows, variant, c->op_stream));
+  CK(cudaEventRecord(b, c->op_stream));
+  CK(cudaStreamSynchronize(c->op_stream));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, a, b));
+  *avg_ms = ms / iters;
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  return RAMA_OK;
+}

@@ -1,0 +1,84 @@
+// common.cuh — device helpers shared by the sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rama {
+
+constexpr int kWarp = 32;
+
+// Device-resident step control block (one per session).  Kernels read pos/token from here so
+// that one captured CUDA graph can be replayed for every position.
+struct StepCtrl {
+  int32_t pos;          // position of the step being computed
+  int32_t token;        // input token of the step
+  int32_t chained;      // 1: device-resident generate loop (token feedback on device)
+  int32_t n_prompt;     // chained mode: prompt length
+  float temperature;    // chained mode sampling parameters
+  float topp;
+  int32_t next;         // output of the sampler
+  int32_t error;        // sticky device-side error flag (e.g. empty top-p candidate list)
+};
+
+// 128-bit streaming load: read-only path, do not allocate in L1 (weights are read once per token).
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ float dot4(const float4& a, const float4& b, float acc) {
+  acc = fmaf(a.x, b.x, acc);
+  acc = fmaf(a.y, b.y, acc);
+  acc = fmaf(a.z, b.z, acc);
+  acc = fmaf(a.w, b.w, acc);
+  return acc;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Block-wide sum with a fixed association (deterministic run to run). red: >= 32 floats smem.
+template <int NT>
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  constexpr int NW = NT / kWarp;
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();  // protect red from a previous use
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  float t = (l < NW) ? red[l] : 0.f;
+  t = warp_sum(t);
+  return t;  // every thread holds the total
+}
+
+// Programmatic dependent launch (PDL): let the next kernel in the stream start its
+// weight-prefetch prologue while this one drains; wait before touching activations.
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// L2 prefetch of a contiguous byte range (bytes % 16 == 0, 16-byte aligned), issued by one thread.
+__device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+// (value, index) argmax merge with the reference's tie rule: later index wins on ties
+// (cpu.rs:165-167: `if v1 > v2 {a} else {b}` in a left fold).
+__device__ __forceinline__ void argmax_merge(float& bv, int& bi, float v, int i) {
+  // (bv,bi) and (v,i) are partial results over disjoint index sets.
+  if (v > bv || (v == bv && i > bi)) { bv = v; bi = i; }
+}
+
+}  // namespace rama

@@ -1,0 +1,343 @@
+// gemv.cuh — the batch-1 f32 GEMV family (HBM-bound) with fused prologues / epilogues.
+//
+// Replaces, for the decode step, the reference's cuBLAS sgemm m=1 calls (gpu.rs:175-189; 8·L+1
+// per token) plus the rmsnorm / apply_position / copy_from_slice / sinu / array_mult /
+// array_add launches around them (math.cu:17-49,117-136): SURVEY.md §2.3.
+//
+// Shape of one launch: W is row-major [rows][K] (llama2.c layout), x has K floats.
+//   * Work unit = a PAIR of rows (RoPE rotates output pairs (2i,2i+1); SwiGLU pairs w1 row j
+//     with w3 row j), so every epilogue sees both members of its pair in one thread.
+//   * One persistent CTA per SM (512 threads); CTA b owns a contiguous, balanced range of
+//     pairs ⇒ each SM streams one contiguous slab of W (coalesced 128-bit ld.global.nc with
+//     L1::no_allocate), ≤1 pair of imbalance across the grid.
+//   * Inside the CTA the 16 warps form WR×WK: WK warps split K of a row, WR warps take different
+//     pair groups.  Each warp keeps 2·RP·U independent 128-bit loads in flight.
+//   * x (after the fused prologue: residual add + rmsnorm, or plain copy) lives in shared memory,
+//     read as conflict-free LDS.128; partial sums of the WK k-slices meet in shared memory and are
+//     combined in a fixed order (deterministic), then the fused epilogue runs.
+#pragma once
+#include "common.cuh"
+
+namespace rama {
+
+constexpr int kGemvThreads = 512;
+constexpr int kGemvWarps = kGemvThreads / kWarp;
+constexpr int kPdlPrefetchBytes = 192 * 1024;  // per CTA: ≈ what HBM delivers to one SM in ~4 µs
+
+struct ArgPart {  // greedy partial: best value and its global vocabulary index
+  float v;
+  int i;
+};
+
+// ---- prologues: fill xs[0..K4) (float4) ---------------------------------------------------
+
+// xs = x                                      (wo: attention output; w2: SwiGLU output)
+struct ProPlain {
+  const float* x;
+  __device__ __forceinline__ void operator()(float4* xs, int K4, float* red) const {
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    for (int i = threadIdx.x; i < K4; i += kGemvThreads) xs[i] = x4[i];
+    (void)red;
+  }
+};
+
+// v = xin (+ add);  [CTA 0: xout = v];  xs = w * (rsqrt_scale * v)   [CTA 0: xnorm = xs]
+// ≙ array_add (cpu.rs:16-21) folded in front of rmsnorm (cpu.rs:99-117):
+//   scale = 1/sqrt(Σv²/n + 1e-5);  o[i] = w[i] * (scale * v[i])
+struct ProNorm {
+  const float* xin;    // residual stream (D)
+  const float* add;    // pending residual contribution (wo / w2 output) or nullptr
+  float* xout;         // updated residual stream (ping-pong buffer ≠ xin)
+  const float* w;      // norm weight (D)
+  float* xnorm;        // optional: normalised vector out (final rmsnorm → RunState.x) or nullptr
+  __device__ __forceinline__ void operator()(float4* xs, int K4, float* red) const {
+    const float4* x4 = reinterpret_cast<const float4*>(xin);
+    const float4* a4 = reinterpret_cast<const float4*>(add);
+    float ss = 0.f;
+    for (int i = threadIdx.x; i < K4; i += kGemvThreads) {
+      float4 v = x4[i];
+      if (add) {
+        const float4 a = a4[i];
+        v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+      }
+      xs[i] = v;
+      ss = dot4(v, v, ss);
+      if (blockIdx.x == 0) reinterpret_cast<float4*>(xout)[i] = v;
+    }
+    ss = block_sum<kGemvThreads>(ss, red);
+    const float scale = 1.0f / sqrtf(ss / (float)(K4 * 4) + 1e-5f);
+    const float4* w4 = reinterpret_cast<const float4*>(w);
+    for (int i = threadIdx.x; i < K4; i += kGemvThreads) {  // same i as above: no sync needed
+      float4 v = xs[i];
+      const float4 g = w4[i];
+      v.x = g.x * (scale * v.x); v.y = g.y * (scale * v.y);
+      v.z = g.z * (scale * v.z); v.w = g.w * (scale * v.w);
+      xs[i] = v;
+      if (xnorm && blockIdx.x == 0) reinterpret_cast<float4*>(xnorm)[i] = v;
+    }
+  }
+};
+
+// ---- row addressing: pair p → two row pointers ----------------------------------------------
+
+struct RowsPlain {  // rows 2p, 2p+1 of one matrix
+  const float* w;
+  int K, n_rows;
+  static constexpr int kStreams = 1;
+  // contiguous byte range that pairs [p0, p0+np) read from stream s (for the PDL L2 prefetch)
+  __device__ __forceinline__ void slab(int p0, int np, int, const float*& ptr, size_t& bytes) const {
+    ptr = w + (size_t)(2 * p0) * K;
+    bytes = (size_t)min(2 * np, n_rows - 2 * p0) * K * 4;
+  }
+  __device__ __forceinline__ void operator()(int p, const float4*& r0, const float4*& r1) const {
+    const size_t a = (size_t)(2 * p) * K;
+    r0 = reinterpret_cast<const float4*>(w + a);
+    r1 = (2 * p + 1 < n_rows) ? reinterpret_cast<const float4*>(w + a + K) : r0;
+  }
+};
+
+struct RowsQKV {  // virtual matrix [wq; wk; wv] of this layer, each `rows_per` rows (even)
+  const float* wq;
+  const float* wk;
+  const float* wv;
+  int K, pairs_per;  // pairs per section = rows_per / 2
+  static constexpr int kStreams = 1;
+  __device__ __forceinline__ void slab(int p0, int np, int, const float*& ptr, size_t& bytes) const {
+    const int sec = p0 / pairs_per, i = p0 - sec * pairs_per;
+    const float* b = sec == 0 ? wq : (sec == 1 ? wk : wv);
+    ptr = b + (size_t)(2 * i) * K;
+    bytes = (size_t)(2 * min(np, pairs_per - i)) * K * 4;  // up to the end of this section
+  }
+  __device__ __forceinline__ void operator()(int p, const float4*& r0, const float4*& r1) const {
+    const int sec = p / pairs_per, i = p - sec * pairs_per;
+    const float* b = sec == 0 ? wq : (sec == 1 ? wk : wv);
+    r0 = reinterpret_cast<const float4*>(b + (size_t)(2 * i) * K);
+    r1 = r0 + (K >> 2);
+  }
+};
+
+struct RowsW13 {  // pair p = (w1 row p, w3 row p)
+  const float* w1;
+  const float* w3;
+  int K;
+  static constexpr int kStreams = 2;
+  __device__ __forceinline__ void slab(int p0, int np, int s, const float*& ptr, size_t& bytes) const {
+    ptr = (s == 0 ? w1 : w3) + (size_t)p0 * K;
+    bytes = (size_t)np * K * 4;
+  }
+  __device__ __forceinline__ void operator()(int p, const float4*& r0, const float4*& r1) const {
+    r0 = reinterpret_cast<const float4*>(w1 + (size_t)p * K);
+    r1 = reinterpret_cast<const float4*>(w3 + (size_t)p * K);
+  }
+};
+
+// ---- epilogues: (pair index, dot0, dot1) ------------------------------------------------------
+
+struct EpiStore {  // o[2p], o[2p+1]    (wo → xb2, w2 → residual contribution, op-level matmul)
+  float* o;
+  int n_rows;
+  __device__ __forceinline__ void operator()(int p, float v0, float v1) {
+    o[2 * p] = v0;
+    if (2 * p + 1 < n_rows) o[2 * p + 1] = v1;
+  }
+  __device__ __forceinline__ void finish(float*) {}
+};
+
+// RoPE (cpu.rs:74-97, simultaneous pair update, unfused mul/sub as in the reference) on q and k,
+// then the KV-cache row write (infer.rs:31-33) — replaces H·L apply_position launches and
+// 2·L copy_from_slice launches per token.
+struct EpiQKV {
+  float* q;
+  float* k;
+  float* v;
+  float* key_cache;    // this layer's [T][Dq] block
+  float* value_cache;
+  const float* freq_real;  // [T][hs/2]
+  const float* freq_imag;
+  const StepCtrl* ctrl;
+  int pairs_per, hs2, Dq;  // pairs per section, head_size/2, row stride of the cache
+  __device__ __forceinline__ void operator()(int p, float v0, float v1) {
+    const int pos = ctrl->pos;
+    const int sec = p / pairs_per, i = p - sec * pairs_per;
+    if (sec < 2) {
+      const int f = pos * hs2 + (i % hs2);
+      const float c = freq_real[f], s = freq_imag[f];
+      const float o0 = __fsub_rn(__fmul_rn(v0, c), __fmul_rn(v1, s));
+      const float o1 = __fadd_rn(__fmul_rn(v0, s), __fmul_rn(v1, c));
+      if (sec == 0) {
+        reinterpret_cast<float2*>(q)[i] = make_float2(o0, o1);
+      } else {
+        reinterpret_cast<float2*>(k)[i] = make_float2(o0, o1);
+        reinterpret_cast<float2*>(key_cache + (size_t)pos * Dq)[i] = make_float2(o0, o1);
+      }
+    } else {
+      reinterpret_cast<float2*>(v)[i] = make_float2(v0, v1);
+      reinterpret_cast<float2*>(value_cache + (size_t)pos * Dq)[i] = make_float2(v0, v1);
+    }
+  }
+  __device__ __forceinline__ void finish(float*) {}
+};
+
+// SwiGLU (cpu.rs:54-64): hb = (h1 * (1/(1+exp(-h1)))) * h3 — replaces sinu + array_mult.
+struct EpiSwiGLU {
+  float* hb;
+  float* hb2;
+  __device__ __forceinline__ void operator()(int p, float h1, float h3) {
+    const float a = h1 * (1.0f / (1.0f + expf(-h1)));
+    hb[p] = a * h3;
+    hb2[p] = h3;
+  }
+  __device__ __forceinline__ void finish(float*) {}
+};
+
+// Classifier: logits + per-CTA greedy argmax partial (ties → higher index, cpu.rs:165-167).
+struct EpiCls {
+  float* logits;       // local logits [n_rows]
+  ArgPart* part;       // [gridDim.x]: this CTA's best (value, global vocab index)
+  int n_rows, row_offset;
+  float bv;
+  int bi;
+  __device__ __forceinline__ void operator()(int p, float v0, float v1) {
+    logits[2 * p] = v0;
+    argmax_merge(bv, bi, v0, row_offset + 2 * p);
+    if (2 * p + 1 < n_rows) {
+      logits[2 * p + 1] = v1;
+      argmax_merge(bv, bi, v1, row_offset + 2 * p + 1);
+    }
+  }
+  __device__ __forceinline__ void finish(float* red) {
+    // block argmax: warp shuffle then 16 warps through shared memory
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      argmax_merge(bv, bi, ov, oi);
+    }
+    int* redi = reinterpret_cast<int*>(red + kGemvWarps);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) { red[w] = bv; redi[w] = bi; }
+    __syncthreads();
+    if (w == 0) {
+      float tv = l < kGemvWarps ? red[l] : -INFINITY;
+      int ti = l < kGemvWarps ? redi[l] : -1;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, tv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, ti, o);
+        argmax_merge(tv, ti, ov, oi);
+      }
+      if (l == 0) { part[blockIdx.x].v = tv; part[blockIdx.x].i = ti; }
+    }
+  }
+};
+
+// ---- the streaming core ---------------------------------------------------------------------
+
+template <int WK, int RP, int U, class Rows>
+__device__ __forceinline__ void gemv_pairs(const Rows& rows, int K4, int p0, int np,
+                                           const float4* __restrict__ xs, float* __restrict__ part) {
+  constexpr int WR = kGemvWarps / WK;
+  constexpr int R = 2 * RP;
+  constexpr int stride = kWarp * WK;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wr = warp / WK, wk = warp % WK;
+
+  for (int base = wr * RP; base < np; base += WR * RP) {
+    const float4* rp[R];
+#pragma unroll
+    for (int j = 0; j < RP; ++j) {
+      const int p = min(base + j, np - 1);  // clamp: a duplicate is computed but never stored
+      rows(p0 + p, rp[2 * j], rp[2 * j + 1]);
+    }
+    float acc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r] = 0.f;
+
+    int c = wk * kWarp + lane;
+    for (; c + (U - 1) * stride < K4; c += U * stride) {
+      float4 w[U][R];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int r = 0; r < R; ++r) w[u][r] = ldg_stream(rp[r] + c + u * stride);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const float4 xv = xs[c + u * stride];
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = dot4(w[u][r], xv, acc[r]);
+      }
+    }
+    for (; c < K4; c += stride) {
+      float4 w[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) w[r] = ldg_stream(rp[r] + c);
+      const float4 xv = xs[c];
+#pragma unroll
+      for (int r = 0; r < R; ++r) acc[r] = dot4(w[r], xv, acc[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r] = warp_sum(acc[r]);
+    if (lane == 0) {
+#pragma unroll
+      for (int j = 0; j < RP; ++j) {
+        if (base + j < np) {
+          part[((base + j) * 2 + 0) * WK + wk] = acc[2 * j];
+          part[((base + j) * 2 + 1) * WK + wk] = acc[2 * j + 1];
+        }
+      }
+    }
+  }
+}
+
+// Shared memory: float4 xs[K4] | float part[max_pairs_per_cta * 2 * WK]
+__host__ __device__ inline size_t gemv_smem_bytes(int K4, int n_pairs, int grid, int WK) {
+  const int maxp = (n_pairs + grid - 1) / grid;
+  return (size_t)K4 * 16 + (size_t)maxp * 2 * WK * 4;
+}
+
+template <int WK, int RP, int U, class Pro, class Rows, class Epi>
+__global__ void __launch_bounds__(kGemvThreads, 1)
+gemv_fused_kernel(const Pro pro, const Rows rows, const Epi epi_in, int K4, int n_pairs, int use_pdl) {
+  extern __shared__ float4 gemv_smem[];
+  __shared__ float red[2 * kWarp];
+  float4* xs = gemv_smem;
+  float* part = reinterpret_cast<float*>(xs + K4);
+
+  const int per = n_pairs / gridDim.x, rem = n_pairs % gridDim.x;
+  const int p0 = blockIdx.x * per + min((int)blockIdx.x, rem);
+  const int np = per + ((int)blockIdx.x < rem ? 1 : 0);
+
+  if (use_pdl) {
+    // Weights never depend on the previous kernel: pull the head of this CTA's slab into L2
+    // while the previous kernel drains, then wait for its activations.
+    pdl_launch_dependents();
+    if (np > 0 && threadIdx.x < Rows::kStreams) {
+      const float* ptr;
+      size_t bytes;
+      rows.slab(p0, np, threadIdx.x, ptr, bytes);
+      bytes = min(bytes, (size_t)kPdlPrefetchBytes / Rows::kStreams);
+      if (bytes >= 16) l2_prefetch_bulk(ptr, (uint32_t)(bytes & ~(size_t)15));
+    }
+    pdl_wait();
+  }
+
+  pro(xs, K4, red);
+  __syncthreads();
+  gemv_pairs<WK, RP, U>(rows, K4, p0, np, xs, part);
+  __syncthreads();
+
+  Epi epi = epi_in;
+  for (int i = threadIdx.x; i < np; i += kGemvThreads) {
+    float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+    for (int k = 0; k < WK; ++k) {
+      v0 += part[(i * 2 + 0) * WK + k];
+      v1 += part[(i * 2 + 1) * WK + k];
+    }
+    epi(p0 + i, v0, v1);
+  }
+  epi.finish(red);
+}
+
+}  // namespace rama

@@ -1,0 +1,172 @@
+"""Op-level parity: every `Device` trait method (device.rs:3-24) through the C ABI vs the oracle."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import ref
+from rama_b200 import _lib, checkpoint as ck
+from rama_b200.engine import GPU, DeviceBuffer, View
+from util import rand, rel_err
+
+pytestmark = pytest.mark.gpu
+
+SIZES = [4, 288, 768, 2048, 4096, 11008, 32000]
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    g = GPU(0)
+    yield g
+    g.close()
+
+
+def dev(gpu, a):
+    return View(DeviceBuffer(gpu, a.size, a))
+
+
+@pytest.mark.parametrize("n", SIZES)
+def test_elementwise_ops_bit_exact(gpu, n):
+    a, b = rand(n, 1), rand(n, 2)
+    for op, rop in (("array_add", "ref_array_add"), ("array_mult", "ref_array_mult")):
+        want = a.copy()
+        getattr(ref.lib(), rop)(ref.fptr(want), ref.fptr(b), n)
+        t = dev(gpu, a)
+        getattr(gpu, op)(t, dev(gpu, b), n)
+        assert t.data.to_host().tobytes() == want.tobytes(), op
+    t = dev(gpu, np.zeros(n, np.float32))
+    gpu.copy_from_slice(t, dev(gpu, a), n)
+    assert t.data.to_host().tobytes() == a.tobytes()
+
+
+@pytest.mark.parametrize("n", SIZES)
+def test_sinu(gpu, n):
+    a = rand(n, 3, 3.0)
+    want = a.copy()
+    ref.lib().ref_sinu(ref.fptr(want), n)
+    t = dev(gpu, a)
+    gpu.sinu(t, n)
+    np.testing.assert_allclose(t.data.to_host(), want, rtol=2e-6, atol=1e-7)  # expf: ≤2 ulp apart
+
+
+@pytest.mark.parametrize("n", [4, 288, 768, 4096])
+def test_rmsnorm(gpu, n):
+    x, w = rand(n, 4, 2.0), 1.0 + rand(n, 5, 0.2)
+    want = np.empty(n, np.float32)
+    ref.lib().ref_rmsnorm(ref.fptr(want), ref.fptr(x), ref.fptr(w), n)
+    o = dev(gpu, np.zeros(n, np.float32))
+    gpu.rmsnorm(o, dev(gpu, x), dev(gpu, w), n)
+    np.testing.assert_allclose(o.data.to_host(), want, rtol=3e-6, atol=1e-7)
+    xi = dev(gpu, x)  # in place, as infer.rs:50 uses it (o != x there, but aliasing must be safe)
+    gpu.rmsnorm(xi, xi, dev(gpu, w), n)
+    np.testing.assert_allclose(xi.data.to_host(), want, rtol=3e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("hs", [16, 48, 64, 128])
+def test_apply_position_bit_exact(gpu, hs):
+    q, k = rand(hs, 6), rand(hs, 7)
+    ang = rand(hs // 2, 8, 3.0)
+    pr, pi = np.cos(ang).astype(np.float32), np.sin(ang).astype(np.float32)
+    wq, wk = q.copy(), k.copy()
+    ref.lib().ref_apply_position(ref.fptr(wq), ref.fptr(wk), ref.fptr(pr), ref.fptr(pi), hs)
+    dq, dk = dev(gpu, q), dev(gpu, k)
+    gpu.apply_position(dq, dk, dev(gpu, pr), dev(gpu, pi), hs)
+    assert dq.data.to_host().tobytes() == wq.tobytes()
+    assert dk.data.to_host().tobytes() == wk.tobytes()
+
+
+@pytest.mark.parametrize("n", [1, 7, 257, 32000])
+def test_softmax(gpu, n):
+    x = rand(n, 9, 4.0)
+    want = x.copy()
+    ref.lib().ref_softmax(ref.fptr(want), n)
+    d = dev(gpu, x)
+    gpu.softmax(d, n)
+    got = d.data.to_host()
+    np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-9)
+    assert abs(float(got.sum(dtype=np.float64)) - 1.0) < 1e-5
+
+
+# (rows, width): the hot-path shapes of stories15M / stories110M / llama2-7B
+# plus ragged ones (odd row count, width not a multiple of the warp tile).
+MATMUL_SHAPES = [(288, 288), (768, 288), (288, 768), (32000, 288), (768, 768), (2048, 768), (768, 2048),
+                 (4096, 4096), (11008, 4096), (4096, 11008), (32000, 4096), (4096, 512), (4096, 1376),
+                 (1, 4), (3, 8), (301, 100), (17, 4100)]
+
+
+@pytest.mark.parametrize("rows,width", MATMUL_SHAPES)
+def test_matmul_vs_oracle(gpu, rows, width):
+    w = ref.synth_fill(rows * width, 11, 2, float(ck.synth_scale(width ** -0.5)))
+    x = rand(width, 12)
+    want = np.empty(rows, np.float32)
+    ref.lib().ref_matmul(ref.fptr(want), ref.fptr(w), ref.fptr(x), width, rows, 1)
+    dw, dx = dev(gpu, w), dev(gpu, x)
+    o = dev(gpu, np.zeros(rows, np.float32))
+    gpu.matmul(o, dw, dx, width, rows, 1)
+    assert rel_err(o.data.to_host(), want) < 2e-5
+
+
+@pytest.mark.parametrize("variant", range(8))
+@pytest.mark.parametrize("rows,width", [(4096, 4096), (301, 100), (4096, 11008), (64, 288)])
+def test_every_gemv_variant(gpu, variant, rows, width):
+    w = ref.synth_fill(rows * width, 13, 3, float(ck.synth_scale(width ** -0.5)))
+    x = rand(width, 14)
+    want = np.empty(rows, np.float32)
+    ref.lib().ref_matmul(ref.fptr(want), ref.fptr(w), ref.fptr(x), width, rows, 1)
+    dw, dx = dev(gpu, w), dev(gpu, x)
+    o = dev(gpu, np.zeros(rows, np.float32))
+    ms = C.c_float()
+    _lib.check(_lib.lib().rama_bench_gemv(gpu.h, o.ptr(), dw.ptr(), dx.ptr(), rows, width, variant, 2, C.byref(ms)))
+    assert rel_err(o.data.to_host(), want) < 2e-5
+    assert ms.value > 0
+
+
+def test_matmul_general_o_cols(gpu):
+    rows, width, cols = 5, 12, 3
+    a, b = rand(rows * width, 15), rand(width * cols, 16)
+    want = np.empty(rows * cols, np.float32)
+    ref.lib().ref_matmul(ref.fptr(want), ref.fptr(a), ref.fptr(b), width, rows * cols, cols)
+    o = dev(gpu, np.zeros(rows * cols, np.float32))
+    gpu.matmul(o, dev(gpu, a), dev(gpu, b), width, rows, cols)
+    assert rel_err(o.data.to_host(), want) < 1e-5
+
+
+def test_matmul_rejects_what_the_reference_cannot_do(gpu):
+    o, a, b = dev(gpu, np.zeros(4, np.float32)), dev(gpu, rand(24, 1)), dev(gpu, rand(6, 2))
+    with pytest.raises(_lib.RamaError):
+        gpu.matmul(o, a, b, 6, 4, 1)  # width % 4 != 0: the reference would slice-panic (cpu.rs:143)
+
+
+class _RS:
+    pass
+
+
+@pytest.mark.parametrize("name,layer,positions", [
+    ("stories15M", 3, [0, 1, 63, 64, 65, 255]),           # hs 48
+    ("stories110M", 1, [0, 127, 128, 500, 1023]),         # hs 64
+    ("l7-2layer", 1, [0, 5, 64, 700, 2047]),              # hs 128, 7B cache geometry
+])
+def test_multi_head_attention_vs_oracle(gpu, name, layer, positions):
+    cfg = ck.CONFIGS[name]
+    if name == "stories110M":
+        cfg = ck.Config(cfg.dim, cfg.hidden_dim, 2, cfg.n_heads, cfg.n_kv_heads, cfg.vocab_size, cfg.seq_len, True)
+    D, H, T, L = cfg.dim, cfg.n_heads, cfg.seq_len, cfg.n_layers
+    kc, vc = rand(L * T * D, 21, 0.3), rand(L * T * D, 22)
+    rs = _RS()
+    rs.key_cache, rs.value_cache = dev(gpu, kc), dev(gpu, vc)
+    rs.att, rs.xb = dev(gpu, np.zeros(H * T, np.float32)), dev(gpu, np.zeros(D, np.float32))
+    cc = ref.cconfig(cfg)
+    for pos in positions:
+        q = rand(D, 100 + pos)
+        rs.q = dev(gpu, q)
+        want_xb, want_att = np.zeros(D, np.float32), np.zeros(H * T, np.float32)
+        ref.lib().ref_multi_head_attention(ref.fptr(want_xb), ref.fptr(want_att), ref.fptr(q), ref.fptr(kc),
+                                           ref.fptr(vc), C.byref(cc), layer, pos)
+        gpu.multi_head_attention(rs, cfg, layer, pos)
+        got_xb = rs.xb.data.to_host()
+        got_att = rs.att.data.to_host().reshape(H, T)[:, : pos + 1]
+        assert rel_err(got_xb, want_xb) < 2e-5, pos
+        np.testing.assert_allclose(got_att, want_att.reshape(H, T)[:, : pos + 1], rtol=2e-4, atol=1e-7)
+        # att=None path (what the fused step uses) gives the same xb
+        gpu.multi_head_attention(rs, cfg, layer, pos, keep_att=False)
+        assert rs.xb.data.to_host().tobytes() == got_xb.tobytes()
