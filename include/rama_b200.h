@@ -172,10 +172,11 @@ int rama_op_sample(rama_ctx* ctx, float* logits, size_t vocab_size, float temper
 int rama_synth_fill(rama_ctx* ctx, float* dst, size_t n, uint64_t seed, uint64_t tensor_id,
                     uint64_t start, float scale, float offset);
 
-/* Micro-benchmark hook used by bench.py / tools: runs the plain GEMV kernel `iters` times on
- * device buffers and returns the average milliseconds per launch (CUDA events on its stream). */
+/* Micro-benchmark hook used by tools/gemv_sweep.py: runs the plain GEMV kernel `iters` times and
+ * returns the average milliseconds per launch (CUDA events on its stream).  `w` holds n_mats
+ * matrices back to back; launch i reads matrix i % n_mats, so a set larger than L2 stays cold. */
 int rama_bench_gemv(rama_ctx* ctx, float* o, const float* w, const float* x, size_t rows, size_t width,
-                    int variant, int iters, float* avg_ms);
+                    size_t n_mats, int variant, int iters, float* avg_ms);
 
 #ifdef __cplusplus
 }

@@ -1148,16 +1148,17 @@ extern "C" int rama_synth_fill(rama_ctx* c, float* dst, size_t n, uint64_t seed,
 }
 
 extern "C" int rama_bench_gemv(rama_ctx* c, float* o, const float* w, const float* x, size_t rows, size_t width,
-                               int variant, int iters, float* avg_ms) {
+                               size_t n_mats, int variant, int iters, float* avg_ms) {
   OP_PRE(c);
-  if (!avg_ms || iters <= 0) return fail(RAMA_E_INVALID, "bad argument");
+  if (!avg_ms || iters <= 0 || n_mats == 0) return fail(RAMA_E_INVALID, "bad argument");
   if (variant >= kNumVariants) return fail(RAMA_E_INVALID, "variant %d out of range", variant);
   cudaEvent_t a, b;
   CK(cudaEventCreate(&a));
   CK(cudaEventCreate(&b));
-  for (int i = 0; i < 3; ++i) RK(matvec(c, o, w, x, width, rows, variant, c->op_stream));
+  for (int i = 0; i < 3; ++i) RK(matvec(c, o, w + (i % n_mats) * rows * width, x, width, rows, variant, c->op_stream));
   CK(cudaEventRecord(a, c->op_stream));
-  for (int i = 0; i < iters; ++i) RK(matvec(c, o, w, x, width, rows, variant, c->op_stream));
+  for (int i = 0; i < iters; ++i)
+    RK(matvec(c, o, w + ((i + 3) % n_mats) * rows * width, x, width, rows, variant, c->op_stream));
   CK(cudaEventRecord(b, c->op_stream));
   CK(cudaStreamSynchronize(c->op_stream));
   float ms = 0.f;

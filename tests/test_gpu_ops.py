@@ -116,7 +116,7 @@ def test_every_gemv_variant(gpu, variant, rows, width):
     dw, dx = dev(gpu, w), dev(gpu, x)
     o = dev(gpu, np.zeros(rows, np.float32))
     ms = C.c_float()
-    _lib.check(_lib.lib().rama_bench_gemv(gpu.h, o.ptr(), dw.ptr(), dx.ptr(), rows, width, variant, 2, C.byref(ms)))
+    _lib.check(_lib.lib().rama_bench_gemv(gpu.h, o.ptr(), dw.ptr(), dx.ptr(), rows, width, 1, variant, 2, C.byref(ms)))
     assert rel_err(o.data.to_host(), want) < 2e-5
     assert ms.value > 0
 
