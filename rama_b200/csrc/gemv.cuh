@@ -308,10 +308,11 @@ gemv_fused_kernel(const Pro pro, const Rows rows, const Epi epi_in, int K4, int 
   const int p0 = blockIdx.x * per + min((int)blockIdx.x, rem);
   const int np = per + ((int)blockIdx.x < rem ? 1 : 0);
 
-  if (use_pdl) {
-    // Weights never depend on the previous kernel: pull the head of this CTA's slab into L2
-    // while the previous kernel drains, then wait for its activations.
-    pdl_launch_dependents();
+  // Weights never depend on the previous kernel: pull the head of this CTA's slab into L2 while
+  // the previous kernel drains (PDL) and while the prologue below computes the norm, then wait
+  // for the previous kernel's activations.
+  if (use_pdl) pdl_launch_dependents();
+  {
     if (np > 0 && threadIdx.x < Rows::kStreams) {
       const float* ptr;
       size_t bytes;
@@ -319,8 +320,8 @@ gemv_fused_kernel(const Pro pro, const Rows rows, const Epi epi_in, int K4, int 
       bytes = min(bytes, (size_t)kPdlPrefetchBytes / Rows::kStreams);
       if (bytes >= 16) l2_prefetch_bulk(ptr, (uint32_t)(bytes & ~(size_t)15));
     }
-    pdl_wait();
   }
+  if (use_pdl) pdl_wait();
 
   pro(xs, K4, red);
   __syncthreads();

@@ -83,7 +83,12 @@ def test_softmax(gpu, n):
     d = dev(gpu, x)
     gpu.softmax(d, n)
     got = d.data.to_host()
-    np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-9)
+    # the oracle sums 32000 terms sequentially in f32 (its own error ~1e-5·√n-ish); rayon's sum in the
+    # reference is a different association again — compare against f64 truth as well
+    np.testing.assert_allclose(got, want, rtol=3e-4 if n > 1000 else 1e-5, atol=1e-9)
+    x64 = x.astype(np.float64)
+    truth = np.exp(x64 - x64.max()); truth /= truth.sum()
+    np.testing.assert_allclose(got, truth, rtol=2e-5, atol=1e-12)
     assert abs(float(got.sum(dtype=np.float64)) - 1.0) < 1e-5
 
 
