@@ -52,9 +52,15 @@ def test_top_p_matches_oracle(gpu, V, temperature, topp, scale):
     for seed in range(4):
         x = rand(V, 1000 + seed, scale)
         want, wprobs = _ref_sample(x, temperature, topp)
+        if want < 0:  # no p above the cutoff (e.g. V=2, topp=0.1 ⇒ cutoff 0.9): the reference panics
+            with pytest.raises(_lib.RamaError):
+                _dev_sample(gpu, x, temperature, topp)
+            agree += 1
+            continue
         got, gprobs = _dev_sample(gpu, x, temperature, topp)
-        # in place like the reference: logits now hold probabilities
-        np.testing.assert_allclose(gprobs, wprobs, rtol=2e-5, atol=1e-10)
+        # in place like the reference: logits now hold probabilities (the oracle's sequential f32 sum
+        # over V terms carries ~1e-4 relative error at V=32000; rayon's sum in the reference differs again)
+        np.testing.assert_allclose(gprobs, wprobs, rtol=3e-4 if V > 1000 else 2e-5, atol=1e-10)
         agree += int(got == want)
         if got != want:
             # the only legitimate difference: the f32 softmax sum is associated differently, which may
