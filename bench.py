@@ -251,9 +251,15 @@ def main():
         for k, (ms, n) in sess.profile_step(int(toks[pos - 1]) if pos else 1, pos).items():
             a = prof.setdefault(k, [0.0, 0])
             a[0] += ms; a[1] += n
-    if rank != 0:
+    def teardown():
+        # symmetric on every rank: the library's communicator is destroyed collectively
+        sess.close(); gpu.close()
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
+
+    if rank != 0:
+        teardown()
         return
 
     peak, peak_src = measured_peaks()
@@ -304,10 +310,8 @@ def main():
                             "memory and 8 B D2H per token inside the timed region"},
             "gpu_launches": args.steps * tokens * sess.launches_per_step(),
             "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu}
-    print(json.dumps(line))
-    sess.close(); gpu.close()
-    if world > 1:
-        dist.destroy_process_group()
+    print(json.dumps(line), flush=True)
+    teardown()
 
 
 if __name__ == "__main__":

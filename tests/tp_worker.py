@@ -20,14 +20,14 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("gloo")  # only to hand out the NCCL id; the data path is the library's NCCL
-    ids = [GPU.unique_id() if rank == 0 else None]
-    dist.broadcast_object_list(ids, src=0)
     for name, steps in (("tiny", 40), ("tiny-sep", 30), ("l7-2layer", 12)):
         cfg = ck.CONFIGS[name]
         if cfg.n_heads % world:
             continue
         spec = ck.SynthSpec(seed=77, rms_jitter=0.1)
         tensors = ref.synth_tensors(cfg, spec)
+        ids = [GPU.unique_id() if rank == 0 else None]  # one ncclUniqueId per communicator
+        dist.broadcast_object_list(ids, src=0)
         gpu = GPU(local, (rank, world, ids[0]))
         gpu.load_host(cfg, tensors)
         for t in ("wq", "wo", "w1", "w2", "wcls", "token_embedding_table"):  # shards = production plan
@@ -43,10 +43,13 @@ def main():
         lg = sess.logits()  # all-gathered across ranks
         err = float(np.max(np.abs(lg - want_logits[steps - 1])) / max(1.0, float(np.max(np.abs(want_logits[steps - 1])))))
         assert err < 1e-3, (name, rank, err)
+        sess.close()
         # synthetic loader generates each rank's shard in place: same bits as the host recipe
-        g2 = GPU(local, None)
-        g2.close()
-        sess.close(); gpu.close()
+        gpu.load_synthetic(cfg, spec)
+        for t in ("wq", "wo", "w2", "rms_att_weight"):
+            assert gpu.weight_shard(t).tobytes() == shard_tensor(cfg, t, tensors[t], rank, world).tobytes(), t
+        dist.barrier()
+        gpu.close()
         dist.barrier()
     if rank == 0:
         print("TP-OK")
