@@ -298,6 +298,9 @@ def main():
             "warmup": args.warmup, "ms_per_step": round(dev_ms / args.steps, 4), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload, "parallelism": f"tp{world}", "seed": args.seed,
+                       "tp_exchange": None if world == 1 else os.environ.get("RAMA_TP_COMM", "p2p") +
+                       (" (one-shot all-reduce over peer memory fused into the wo/w2 GEMV epilogue + next prologue)"
+                        if os.environ.get("RAMA_TP_COMM", "p2p") == "p2p" else " (ncclAllReduce in the graph)"),
                        "l2": "weights streamed per token exceed L2 (no flush needed)" if cfg.weight_bytes_per_token() / world > 200e6
                              else "working set near/below the 126 MB L2: numbers are L2-assisted, reported as is",
                        "timing": "CUDA events around each 256-token graph-replay loop, summed over steps, max over ranks",

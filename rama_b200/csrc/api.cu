@@ -123,6 +123,7 @@ struct rama_ctx {
   cudaStream_t op_stream = nullptr;
   int use_pdl = 0;
   int variant_override = -1;
+  int p2p = 0;  // TP exchange: 1 = fused peer-memory all-reduce (default), 0 = NCCL collectives
   std::mutex mu;
 };
 
@@ -135,7 +136,13 @@ struct rama_session {
   float *key_cache = nullptr, *value_cache = nullptr;
   float* attn_ws = nullptr;
   unsigned int* tickets = nullptr;
-  ArgPart* part = nullptr;      // [world * sm_count]
+  ArgPart* part = nullptr;      // [world * sm_count] (inside peer_mem in p2p mode)
+  // fused TP exchange: one IPC-exported block per session {flags[3][P] | parts[P][SMs] | inbox[2][P][D]}
+  char* peer_mem = nullptr;
+  char* peer_base[kMaxPeers] = {nullptr};  // every rank's block, peer-mapped (own block at [rank])
+  size_t off_parts = 0, off_inbox = 0, peer_bytes = 0;
+  bool p2p = false;
+  bool parts_ready = false;
   unsigned long long* sort_keys = nullptr;
   StepCtrl* ctrl = nullptr;     // device
   int32_t *d_prompt = nullptr, *d_out = nullptr;
@@ -255,6 +262,10 @@ extern "C" int rama_ctx_create(int device, const rama_tp* tp, rama_ctx** out) {
   c->sm_count = prop.multiProcessorCount;
   c->use_pdl = env_int("RAMA_PDL", 1);
   c->variant_override = env_int("RAMA_GEMV_VARIANT", -1);
+  {
+    const char* m = getenv("RAMA_TP_COMM");
+    c->p2p = !(m && strcmp(m, "nccl") == 0);
+  }
   if (tp && tp->world > 1) {
     if (tp->rank < 0 || tp->rank >= tp->world) { delete c; return fail(RAMA_E_INVALID, "bad tp rank"); }
     int r = nccl_load();
@@ -497,6 +508,18 @@ static void session_free(rama_session* s) {
   if (s->stream) cudaStreamSynchronize(s->stream);
   if (s->g_fwd) cudaGraphExecDestroy(s->g_fwd);
   for (auto& g : s->g_step) if (g) cudaGraphExecDestroy(g);
+  if (s->p2p) {
+    rama_ctx* c = s->ctx;
+    for (int r = 0; r < c->world; ++r)
+      if (r != c->rank && s->peer_base[r]) cudaIpcCloseMemHandle(s->peer_base[r]);
+    // every rank must have unmapped this block before its owner frees it: barrier through NCCL
+    if (c->comm && s->xb2) {
+      g_nccl.AllReduce(s->xb2, s->xb2, 1, kNcclFloat32, kNcclSum, c->comm, s->stream);
+      cudaStreamSynchronize(s->stream);
+    }
+    if (s->peer_mem) cudaFree(s->peer_mem);
+    s->part = nullptr;
+  }
   void* bufs[] = {s->x0, s->x1, s->xfinal, s->xb, s->xb2, s->w2out, s->hb, s->hb2, s->q, s->k, s->v, s->att,
                   s->logits, s->key_cache, s->value_cache, s->attn_ws, s->tickets, s->part, s->sort_keys,
                   s->ctrl, s->d_prompt, s->d_out};
@@ -510,6 +533,90 @@ static void session_free(rama_session* s) {
 }
 
 constexpr int kRing = 64;
+
+// Collective over the TP group: allocate this session's exchange block, swap CUDA IPC handles through
+// NCCL and map every peer's block (NVLink P2P).  Layout: u64 flags[3][P] | ArgPart parts[P][SMs] |
+// float inbox[2][P][D].
+static int setup_peer_exchange(rama_session* s) {
+  rama_ctx* c = s->ctx;
+  const int P = c->world;
+  if (P > kMaxPeers) return fail(RAMA_E_INVALID, "tp world %d > %d", P, kMaxPeers);
+  s->off_parts = 256;
+  s->off_inbox = (s->off_parts + (size_t)P * c->sm_count * sizeof(ArgPart) + 255) / 256 * 256;
+  s->peer_bytes = s->off_inbox + (size_t)2 * P * c->D * sizeof(float);
+  CK(cudaMalloc((void**)&s->peer_mem, s->peer_bytes));
+  CK(cudaMemset(s->peer_mem, 0, s->peer_bytes));
+  s->part = reinterpret_cast<ArgPart*>(s->peer_mem + s->off_parts);
+  cudaIpcMemHandle_t mine;
+  CK(cudaIpcGetMemHandle(&mine, s->peer_mem));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  char* d_h = nullptr;
+  CK(cudaMalloc((void**)&d_h, 64 * (size_t)P));
+  CK(cudaMemcpy(d_h + 64 * (size_t)c->rank, &mine, 64, cudaMemcpyHostToDevice));
+  int e = g_nccl.AllGather(d_h + 64 * (size_t)c->rank, d_h, 16, kNcclFloat32, c->comm, s->stream);
+  if (e) { cudaFree(d_h); return fail(RAMA_E_NCCL, "handle all-gather: %s", g_nccl.GetErrorString(e)); }
+  CK(cudaStreamSynchronize(s->stream));
+  std::vector<cudaIpcMemHandle_t> all(P);
+  CK(cudaMemcpy(all.data(), d_h, 64 * (size_t)P, cudaMemcpyDeviceToHost));
+  CK(cudaFree(d_h));
+  for (int r = 0; r < P; ++r) {
+    if (r == c->rank) { s->peer_base[r] = s->peer_mem; continue; }
+    void* p = nullptr;
+    cudaError_t ce = cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess);
+    if (ce != cudaSuccess)
+      return fail(RAMA_E_CUDA, "cudaIpcOpenMemHandle(rank %d): %s (set RAMA_TP_COMM=nccl to fall back)", r,
+                  cudaGetErrorString(ce));
+    s->peer_base[r] = (char*)p;
+  }
+  // nobody may write into a peer block before its owner has zeroed it: barrier
+  e = g_nccl.AllReduce(s->xb2, s->xb2, 1, kNcclFloat32, kNcclSum, c->comm, s->stream);
+  if (e) return fail(RAMA_E_NCCL, "barrier: %s", g_nccl.GetErrorString(e));
+  CK(cudaStreamSynchronize(s->stream));
+  CK(cudaMemsetAsync(s->xb2, 0, sizeof(float), s->stream));
+  return RAMA_OK;
+}
+
+static PeerOut peer_out(const rama_session* s, int stage) {  // stage 0 = wo, 1 = w2
+  PeerOut po{};
+  const rama_ctx* c = s->ctx;
+  if (!s->p2p) return po;
+  po.P = c->world;
+  for (int r = 0; r < c->world; ++r) {
+    po.inbox[r] = reinterpret_cast<float*>(s->peer_base[r] + s->off_inbox) + ((size_t)stage * c->world + c->rank) * c->D;
+    po.flag[r] = reinterpret_cast<unsigned long long*>(s->peer_base[r]) + (size_t)stage * c->world + c->rank;
+  }
+  return po;
+}
+static PeerIn peer_in(const rama_session* s, int stage) {
+  PeerIn pi{};
+  const rama_ctx* c = s->ctx;
+  if (!s->p2p) return pi;
+  pi.inbox = reinterpret_cast<const float*>(s->peer_mem + s->off_inbox) + (size_t)stage * c->world * c->D;
+  pi.flags = reinterpret_cast<const unsigned long long*>(s->peer_mem) + (size_t)stage * c->world;
+  pi.error = &s->ctrl->error;
+  pi.P = c->world; pi.me = c->rank; pi.n = c->D;
+  return pi;
+}
+static PeerOut peer_out_parts(const rama_session* s) {  // stage 2: classifier partials
+  PeerOut po{};
+  const rama_ctx* c = s->ctx;
+  if (!s->p2p) return po;
+  po.P = c->world;
+  for (int r = 0; r < c->world; ++r) {
+    po.inbox[r] = reinterpret_cast<float*>(reinterpret_cast<ArgPart*>(s->peer_base[r] + s->off_parts) + (size_t)c->rank * c->sm_count);
+    po.flag[r] = reinterpret_cast<unsigned long long*>(s->peer_base[r]) + (size_t)2 * c->world + c->rank;
+  }
+  return po;
+}
+static PeerIn peer_in_parts(const rama_session* s) {
+  PeerIn pi{};
+  const rama_ctx* c = s->ctx;
+  if (!s->p2p) return pi;
+  pi.flags = reinterpret_cast<const unsigned long long*>(s->peer_mem) + (size_t)2 * c->world;
+  pi.error = &s->ctrl->error;
+  pi.P = c->world; pi.me = c->rank; pi.n = 0;
+  return pi;
+}
 
 extern "C" int rama_session_create(rama_ctx* c, rama_session** out) {
   if (!c || !out) return fail(RAMA_E_INVALID, "NULL argument");
@@ -532,7 +639,8 @@ extern "C" int rama_session_create(rama_ctx* c, rama_session** out) {
   A(dalloc(&s->key_cache, L * T * Dq)); A(dalloc(&s->value_cache, L * T * Dq));
   A(dalloc(&s->attn_ws, (size_t)c->Hl * s->n_split * (c->hs + 2)));
   A(dalloc(&s->tickets, (size_t)c->Hl));
-  A(dalloc(&s->part, (size_t)c->world * c->sm_count));
+  s->p2p = c->world > 1 && c->p2p;
+  if (!s->p2p) A(dalloc(&s->part, (size_t)c->world * c->sm_count));
   A(dalloc(&s->sort_keys, vp2));
   A(dalloc(&s->ctrl, 1));
   A(dalloc(&s->d_prompt, T)); A(dalloc(&s->d_out, T));
@@ -543,6 +651,14 @@ extern "C" int rama_session_create(rama_ctx* c, rama_session** out) {
   if (e != cudaSuccess) {
     session_free(s);
     return fail(RAMA_E_CUDA, "session allocation: %s", cudaGetErrorString(e));
+  }
+  if (s->p2p) {
+    int rc = setup_peer_exchange(s);
+    if (rc != RAMA_OK) {
+      s->p2p = false;
+      session_free(s);
+      return rc;
+    }
   }
   *out = s;
   return RAMA_OK;
@@ -660,7 +776,7 @@ static int enqueue_step(rama_session* s, cudaStream_t st, int mode, StepTrace* t
   for (int l = 0; l < L; ++l) {
     // ---- rmsnorm → [wq|wk|wv] → RoPE → KV write (infer.rs:19-33) ----
     {
-      ProNorm pro{s->x0, l == 0 ? nullptr : s->w2out, s->x1, W[RAMA_T_RMS_ATT] + (size_t)l * D, nullptr};
+      ProNorm pro{s->x0, l == 0 ? nullptr : s->w2out, s->x1, W[RAMA_T_RMS_ATT] + (size_t)l * D, nullptr, peer_in(s, 1)};
       RowsQKV rows{W[RAMA_T_WQ] + (size_t)l * Dq * D, W[RAMA_T_WK] + (size_t)l * Dq * D,
                    W[RAMA_T_WV] + (size_t)l * Dq * D, D, Dq / 2};
       EpiQKV epi{s->q, s->k, s->v, s->key_cache + (size_t)l * T * Dq, s->value_cache + (size_t)l * T * Dq,
@@ -690,12 +806,12 @@ static int enqueue_step(rama_session* s, cudaStream_t st, int mode, StepTrace* t
     {
       ProPlain pro{s->xb};
       RowsPlain rows{W[RAMA_T_WO] + (size_t)l * D * Dq, Dq, D};
-      EpiStore epi{s->xb2, D};
+      EpiStore epi{s->xb2, D, peer_out(s, 0)};
       const int np = D / 2, var = pick_variant(c, Dq / 4);
       q.pre(RAMA_K_WO);
       q.post(launch_gemv(var, pick_grid(c, var, np), st, q.pdl, pro, rows, epi, Dq / 4, np));
     }
-    if (c->world > 1) {
+    if (c->world > 1 && !s->p2p) {
       q.pre(RAMA_K_COMM);
       int e = g_nccl.AllReduce(s->xb2, s->xb2, D, kNcclFloat32, kNcclSum, c->comm, st);
       if (e && !q.nccl_err) q.nccl_err = e;
@@ -703,7 +819,7 @@ static int enqueue_step(rama_session* s, cudaStream_t st, int mode, StepTrace* t
     }
     // ---- x += xb2; rmsnorm → [w1|w3] → SwiGLU (infer.rs:37-45) ----
     {
-      ProNorm pro{s->x1, s->xb2, s->x0, W[RAMA_T_RMS_FFN] + (size_t)l * D, nullptr};
+      ProNorm pro{s->x1, s->xb2, s->x0, W[RAMA_T_RMS_FFN] + (size_t)l * D, nullptr, peer_in(s, 0)};
       RowsW13 rows{W[RAMA_T_W1] + (size_t)l * Fl * D, W[RAMA_T_W3] + (size_t)l * Fl * D, D};
       EpiSwiGLU epi{s->hb, s->hb2};
       const int np = Fl, var = pick_variant(c, D / 4);
@@ -714,12 +830,12 @@ static int enqueue_step(rama_session* s, cudaStream_t st, int mode, StepTrace* t
     {
       ProPlain pro{s->hb};
       RowsPlain rows{W[RAMA_T_W2] + (size_t)l * D * Fl, Fl, D};
-      EpiStore epi{s->w2out, D};
+      EpiStore epi{s->w2out, D, peer_out(s, 1)};
       const int np = D / 2, var = pick_variant(c, Fl / 4);
       q.pre(RAMA_K_W2);
       q.post(launch_gemv(var, pick_grid(c, var, np), st, q.pdl, pro, rows, epi, Fl / 4, np));
     }
-    if (c->world > 1) {
+    if (c->world > 1 && !s->p2p) {
       q.pre(RAMA_K_COMM);
       int e = g_nccl.AllReduce(s->w2out, s->w2out, D, kNcclFloat32, kNcclSum, c->comm, st);
       if (e && !q.nccl_err) q.nccl_err = e;
@@ -729,9 +845,10 @@ static int enqueue_step(rama_session* s, cudaStream_t st, int mode, StepTrace* t
   // ---- x += w2out; final rmsnorm → wcls → logits (+ greedy partials) (infer.rs:49-51) ----
   int cls_grid;
   {
-    ProNorm pro{s->x0, s->w2out, s->x1, W[RAMA_T_RMS_FINAL], s->xfinal};
+    ProNorm pro{s->x0, s->w2out, s->x1, W[RAMA_T_RMS_FINAL], s->xfinal, peer_in(s, 1)};
     RowsPlain rows{c->wcls, D, c->Vl};
-    EpiCls epi{s->logits + c->v0, s->part + (size_t)c->rank * c->sm_count, c->Vl, c->v0, -INFINITY, -1};
+    EpiCls epi{s->logits + c->v0, s->part + (size_t)c->rank * c->sm_count, c->Vl, c->v0, -INFINITY, -1,
+               peer_out_parts(s)};
     const int np = (c->Vl + 1) / 2, var = pick_variant(c, D / 4);
     cls_grid = pick_grid(c, var, np);
     q.pre(RAMA_K_CLS);
@@ -740,11 +857,15 @@ static int enqueue_step(rama_session* s, cudaStream_t st, int mode, StepTrace* t
   int n_part = cls_grid;
   if (c->world > 1) {
     // every rank learns every rank's per-CTA (value, index) partials: 8 B × SMs per rank
-    q.pre(RAMA_K_COMM);
-    int e = g_nccl.AllGather(s->part + (size_t)c->rank * c->sm_count, s->part, (size_t)c->sm_count * 2,
-                             kNcclFloat32, c->comm, st);
-    if (e && !q.nccl_err) q.nccl_err = e;
-    q.post(cudaSuccess);
+    // (p2p mode: the classifier epilogue already wrote them into every rank's array)
+    int e = 0;
+    if (!s->p2p) {
+      q.pre(RAMA_K_COMM);
+      e = g_nccl.AllGather(s->part + (size_t)c->rank * c->sm_count, s->part, (size_t)c->sm_count * 2,
+                           kNcclFloat32, c->comm, st);
+      if (e && !q.nccl_err) q.nccl_err = e;
+      q.post(cudaSuccess);
+    }
     n_part = c->world * c->sm_count;
     if (mode == 2) {
       q.pre(RAMA_K_COMM);
@@ -754,7 +875,8 @@ static int enqueue_step(rama_session* s, cudaStream_t st, int mode, StepTrace* t
     }
   }
   if (mode >= 1) {
-    SampleParams sp{s->logits, s->part, n_part, c->V, s->ctrl, s->d_prompt, s->d_out, s->sort_keys, 0.f, 0.f, 1};
+    SampleParams sp{s->logits, s->part, n_part, c->V, s->ctrl, s->d_prompt, s->d_out, s->sort_keys, 0.f, 0.f, 1,
+                    peer_in_parts(s)};
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(1);
     cfg.blockDim = dim3(kSampleThreads);
@@ -777,9 +899,19 @@ static int enqueue_step(rama_session* s, cudaStream_t st, int mode, StepTrace* t
 // unused partial slots (a CTA-less tail when the classifier grid < sm_count) must read as "empty"
 static int init_parts(rama_session* s) {
   rama_ctx* c = s->ctx;
+  if (s->p2p) {
+    // peers write into this array: initialise only once, before any step ran (all slots "empty");
+    // later calls must not race with a peer's classifier epilogue
+    if (s->parts_ready) return RAMA_OK;
+    s->parts_ready = true;
+  }
   std::vector<ArgPart> h((size_t)c->world * c->sm_count, ArgPart{-INFINITY, -1});
   CK(cudaMemcpyAsync(s->part, h.data(), h.size() * sizeof(ArgPart), cudaMemcpyHostToDevice, s->stream));
   CK(cudaStreamSynchronize(s->stream));
+  if (s->p2p) {  // every rank initialised before anyone steps
+    NK(g_nccl.AllReduce(s->xb2, s->xb2, 1, kNcclFloat32, kNcclSum, c->comm, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+  }
   return RAMA_OK;
 }
 
@@ -803,7 +935,7 @@ extern "C" int rama_session_launches_per_step(const rama_session* s, int* n) {
   if (!s || !n) return fail(RAMA_E_INVALID, "NULL argument");
   const rama_ctx* c = s->ctx;
   // embed + L·(qkv, attn, wo, w13, w2) + cls + sample (+ collectives under TP)
-  *n = 1 + 5 * c->L + 1 + 1 + (c->world > 1 ? 2 * c->L + 1 : 0);
+  *n = 1 + 5 * c->L + 1 + 1 + (c->world > 1 && !s->p2p ? 2 * c->L + 1 : 0);
   return RAMA_OK;
 }
 
@@ -844,6 +976,7 @@ static int read_ret(rama_session* s, int32_t* next) {
   CK(cudaStreamSynchronize(s->stream));
   if (s->h_ret[1] == 1) return fail(RAMA_E_STATE, "token id outside the vocabulary reached the device step");
   if (s->h_ret[1] == 2) return fail(RAMA_E_STATE, "top-p candidate list is empty (the reference panics here, infer.rs:66)");
+  if (s->h_ret[1] == 3) return fail(RAMA_E_NCCL, "timed out waiting for a tensor-parallel peer's partial results");
   if (next) *next = s->h_ret[0];
   return RAMA_OK;
 }
@@ -856,7 +989,7 @@ extern "C" int rama_sample(rama_session* s, float temperature, float topp, int32
   if (!greedy) RK(gather_logits(s));
   const int n_part = c->world > 1 ? c->world * c->sm_count : c->sm_count;
   SampleParams sp{s->logits, s->part, n_part, c->V, s->ctrl, s->d_prompt, s->d_out, s->sort_keys,
-                  temperature, topp, 0};
+                  temperature, topp, 0, peer_in_parts(s)};
   sample_kernel<<<1, kSampleThreads, 0, s->stream>>>(sp, 0);
   CK(cudaGetLastError());
   return read_ret(s, next);
@@ -1064,7 +1197,7 @@ static int matvec(rama_ctx* c, float* o, const float* a, const float* b, size_t 
   if (((uintptr_t)a | (uintptr_t)b) & 15) return fail(RAMA_E_INVALID, "matmul operands must be 16-byte aligned");
   ProPlain pro{b};
   RowsPlain rows{a, (int)width, (int)o_rows};
-  EpiStore epi{o, (int)o_rows};
+  EpiStore epi{o, (int)o_rows, PeerOut{}};
   const int np = (int)((o_rows + 1) / 2), K4 = (int)(width / 4);
   const int var = variant >= 0 ? variant : pick_variant(c, K4);
   cudaError_t e = launch_gemv(var, pick_grid(c, var, np), st, 0, pro, rows, epi, K4, np);
@@ -1120,7 +1253,7 @@ extern "C" int rama_op_sample(rama_ctx* c, float* logits, size_t vocab_size, flo
   CK(cudaMallocAsync((void**)&ctrl, sizeof(StepCtrl), c->op_stream));
   CK(cudaMemsetAsync(ctrl, 0, sizeof(StepCtrl), c->op_stream));
   CK(cudaMallocAsync((void**)&keys, vp2 * sizeof(unsigned long long), c->op_stream));
-  SampleParams sp{logits, nullptr, 0, (int)vocab_size, ctrl, nullptr, nullptr, keys, temperature, topp, 0};
+  SampleParams sp{logits, nullptr, 0, (int)vocab_size, ctrl, nullptr, nullptr, keys, temperature, topp, 0, PeerIn{}};
   sample_kernel<<<1, kSampleThreads, 0, c->op_stream>>>(sp, 0);
   CK(cudaGetLastError());
   int32_t ret[2] = {0, 0};

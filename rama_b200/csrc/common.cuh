@@ -74,6 +74,39 @@ __device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) 
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
+// ---- peer-memory exchange (tensor parallelism over NVLink; see gemv.cuh PeerOut/PeerIn) -----------
+constexpr int kMaxPeers = 8;
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+// release-increment of a (possibly remote, peer-mapped) counter
+__device__ __forceinline__ void red_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("red.release.sys.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Spin until *flag >= target (another GPU's kernel increments it).  Bounded: after ~4 s the sticky
+// error flag is raised instead of hanging the GPU (a peer process died).
+__device__ __forceinline__ void wait_flag(const unsigned long long* flag, unsigned long long target,
+                                          int32_t* error) {
+  if (ld_acquire_sys(flag) >= target) return;
+  if (*reinterpret_cast<volatile int32_t*>(error) == 3) return;  // already failed: do not stall every stage
+  const unsigned long long t0 = globaltimer_ns();
+  while (ld_acquire_sys(flag) < target) {
+    __nanosleep(64);
+    if (globaltimer_ns() - t0 > 4000000000ull) {
+      *error = 3;
+      break;
+    }
+  }
+}
+
 // (value, index) argmax merge with the reference's tie rule: later index wins on ties
 // (cpu.rs:165-167: `if v1 > v2 {a} else {b}` in a left fold).
 __device__ __forceinline__ void argmax_merge(float& bv, int& bi, float v, int i) {

@@ -29,6 +29,48 @@ struct ArgPart {  // greedy partial: best value and its global vocabulary index
   int i;
 };
 
+// ---- tensor-parallel exchange fused into the GEMVs (one-shot all-reduce over peer memory) -------
+// Row-parallel wo / w2 leave a D-float PARTIAL on every rank.  Instead of a separate collective,
+// the producing GEMV's epilogue stores each of its outputs straight into EVERY rank's inbox slot
+// [stage][src rank][D] (peer-mapped HBM over NVLink) and release-increments that rank's arrival
+// counter once per CTA; the consuming GEMV's prologue (which already adds the pending residual)
+// waits until every source's counter reached its own rank's count (all ranks run the same launch
+// sequence, and the local producer kernel has completed by stream order, so the local counter IS
+// the target), then sums the P partials in rank order — bit-identical on every rank.
+// Slot reuse is safe without double buffering because the two stages (wo, w2) alternate and each
+// consumer waits for all ranks.
+struct PeerOut {
+  float* inbox[kMaxPeers];                // rank r's slot for (stage, src = me), peer-mapped
+  unsigned long long* flag[kMaxPeers];    // rank r's arrival counter for (stage, src = me)
+  int P;                                  // 0 ⇒ no exchange (single GPU / NCCL mode)
+  // select with static indices (a runtime index would spill the table to local memory)
+  __device__ __forceinline__ unsigned long long* flag_of(int r) const {
+    unsigned long long* f = flag[0];
+#pragma unroll
+    for (int i = 1; i < kMaxPeers; ++i) f = (r == i) ? flag[i] : f;
+    return f;
+  }
+  __device__ __forceinline__ float* inbox_of(int r) const {
+    float* f = inbox[0];
+#pragma unroll
+    for (int i = 1; i < kMaxPeers; ++i) f = (r == i) ? inbox[i] : f;
+    return f;
+  }
+};
+struct PeerIn {
+  const float* inbox;                     // local [P][n] partials of this stage
+  const unsigned long long* flags;        // local [P] arrival counters of this stage
+  int32_t* error;                         // StepCtrl.error
+  int P, me, n;                           // n = floats per partial (row stride of inbox)
+  __device__ __forceinline__ void wait() const {
+    if (threadIdx.x < P && threadIdx.x != me) {
+      const unsigned long long target = ld_acquire_sys(flags + me);
+      wait_flag(flags + threadIdx.x, target, error);
+    }
+    __syncthreads();
+  }
+};
+
 // ---- prologues: fill xs[0..K4) (float4) ---------------------------------------------------
 
 // xs = x                                      (wo: attention output; w2: SwiGLU output)
@@ -50,13 +92,24 @@ struct ProNorm {
   float* xout;         // updated residual stream (ping-pong buffer ≠ xin)
   const float* w;      // norm weight (D)
   float* xnorm;        // optional: normalised vector out (final rmsnorm → RunState.x) or nullptr
+  PeerIn pin;          // pin.P > 0: the pending contribution is the sum of P peer partials instead of `add`
   __device__ __forceinline__ void operator()(float4* xs, int K4, float* red) const {
     const float4* x4 = reinterpret_cast<const float4*>(xin);
     const float4* a4 = reinterpret_cast<const float4*>(add);
+    const bool peers = pin.P > 0 && add != nullptr;
+    if (peers) pin.wait();
     float ss = 0.f;
     for (int i = threadIdx.x; i < K4; i += kGemvThreads) {
       float4 v = x4[i];
-      if (add) {
+      if (peers) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = 0; r < pin.P; ++r) {  // rank order: same association on every rank
+          const float4 t = __ldcg(reinterpret_cast<const float4*>(pin.inbox + (size_t)r * pin.n) + i);
+          a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+        }
+        v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+        if (blockIdx.x == 0) reinterpret_cast<float4*>(const_cast<float*>(add))[i] = a;  // RunState.xb2 / xb
+      } else if (add) {
         const float4 a = a4[i];
         v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
       }
@@ -136,11 +189,30 @@ struct RowsW13 {  // pair p = (w1 row p, w3 row p)
 struct EpiStore {  // o[2p], o[2p+1]    (wo → xb2, w2 → residual contribution, op-level matmul)
   float* o;
   int n_rows;
+  PeerOut po;      // po.P > 0: the outputs are a TP partial → stored into every rank's inbox instead
   __device__ __forceinline__ void operator()(int p, float v0, float v1) {
+    if (po.P > 0) {
+#pragma unroll
+      for (int r = 0; r < kMaxPeers; ++r) {  // static indexing keeps the pointer table in param space
+        if (r < po.P) {
+          po.inbox[r][2 * p] = v0;
+          if (2 * p + 1 < n_rows) po.inbox[r][2 * p + 1] = v1;
+        }
+      }
+      return;
+    }
     o[2 * p] = v0;
     if (2 * p + 1 < n_rows) o[2 * p + 1] = v1;
   }
-  __device__ __forceinline__ void finish(float*) {}
+  __device__ __forceinline__ void finish(float*) {
+    if (po.P > 0) {  // one arrival per CTA per destination, after all of the CTA's stores
+      __syncthreads();
+      if (threadIdx.x < po.P) {
+        __threadfence_system();
+        red_release_sys(po.flag_of(threadIdx.x), 1ull);
+      }
+    }
+  }
 };
 
 // RoPE (cpu.rs:74-97, simultaneous pair update, unfused mul/sub as in the reference) on q and k,
@@ -197,6 +269,7 @@ struct EpiCls {
   int n_rows, row_offset;
   float bv;
   int bi;
+  PeerOut po;          // po.P > 0: the partial goes to every rank's part array (po.inbox[r] = its slot base)
   __device__ __forceinline__ void operator()(int p, float v0, float v1) {
     logits[2 * p] = v0;
     argmax_merge(bv, bi, v0, row_offset + 2 * p);
@@ -227,7 +300,18 @@ struct EpiCls {
         const int oi = __shfl_xor_sync(0xffffffffu, ti, o);
         argmax_merge(tv, ti, ov, oi);
       }
-      if (l == 0) { part[blockIdx.x].v = tv; part[blockIdx.x].i = ti; }
+      if (po.P > 0) {
+        if (l < po.P) {
+          ArgPart* dst = reinterpret_cast<ArgPart*>(po.inbox_of(l)) + blockIdx.x;
+          dst->v = tv;
+          dst->i = ti;
+          __threadfence_system();
+          red_release_sys(po.flag_of(l), 1ull);
+        }
+      } else if (l == 0) {
+        part[blockIdx.x].v = tv;
+        part[blockIdx.x].i = ti;
+      }
     }
   }
 };

@@ -44,6 +44,7 @@ struct SampleParams {
   unsigned long long* keys; // scratch [2][V] composite sort keys (top-p path)
   float temperature, topp;  // used when !ctrl->chained (host-driven rama_sample)
   int use_ctrl_params;      // 1: take temperature/topp from ctrl (chained generate)
+  PeerIn pin;               // pin.P > 0: wait for every rank's classifier partials (peer-written)
 };
 
 __device__ __forceinline__ unsigned long long sample_key(float p, int idx) {
@@ -120,12 +121,17 @@ __global__ void __launch_bounds__(kSampleThreads) sample_kernel(const SamplePara
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
   int* redi = reinterpret_cast<int*>(red + kWarp);
 
+  if (p.pin.P > 0) p.pin.wait();
   if (temperature == 0.0f) {
     float bv = -INFINITY;
     int bi = -1;
     if (p.part) {
       for (int i = threadIdx.x; i < p.n_part; i += kSampleThreads)
-        if (p.part[i].i >= 0) argmax_merge(bv, bi, p.part[i].v, p.part[i].i);
+      {
+        const float pv = __ldcg(&p.part[i].v);
+        const int pi = __ldcg(&p.part[i].i);
+        if (pi >= 0) argmax_merge(bv, bi, pv, pi);
+      }
     } else {
       for (int i = threadIdx.x; i < V; i += kSampleThreads) argmax_merge(bv, bi, p.logits[i], i);
     }
