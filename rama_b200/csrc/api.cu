@@ -136,13 +136,14 @@ struct rama_session {
   float *key_cache = nullptr, *value_cache = nullptr;
   float* attn_ws = nullptr;
   unsigned int* tickets = nullptr;
-  ArgPart* part = nullptr;      // [world * sm_count] (inside peer_mem in p2p mode)
+  ArgPart* part = nullptr;      // [world * sm_count] greedy partials (single GPU / NCCL mode)
+  unsigned* seq = nullptr;      // device step counter (epoch source of the fused TP exchange)
+  int cls_grid = 0;             // CTAs of the classifier launch (slots that get written)
   // fused TP exchange: one IPC-exported block per session {flags[3][P] | parts[P][SMs] | inbox[2][P][D]}
   char* peer_mem = nullptr;
   char* peer_base[kMaxPeers] = {nullptr};  // every rank's block, peer-mapped (own block at [rank])
   size_t off_parts = 0, off_inbox = 0, peer_bytes = 0;
   bool p2p = false;
-  bool parts_ready = false;
   unsigned long long* sort_keys = nullptr;
   StepCtrl* ctrl = nullptr;     // device
   int32_t *d_prompt = nullptr, *d_out = nullptr;
@@ -518,11 +519,10 @@ static void session_free(rama_session* s) {
       cudaStreamSynchronize(s->stream);
     }
     if (s->peer_mem) cudaFree(s->peer_mem);
-    s->part = nullptr;
   }
   void* bufs[] = {s->x0, s->x1, s->xfinal, s->xb, s->xb2, s->w2out, s->hb, s->hb2, s->q, s->k, s->v, s->att,
                   s->logits, s->key_cache, s->value_cache, s->attn_ws, s->tickets, s->part, s->sort_keys,
-                  s->ctrl, s->d_prompt, s->d_out};
+                  s->ctrl, s->d_prompt, s->d_out, s->seq};
   for (void* b : bufs) if (b) cudaFree(b);
   if (s->h_ring) cudaFreeHost(s->h_ring);
   if (s->h_ret) cudaFreeHost(s->h_ret);
@@ -535,18 +535,17 @@ static void session_free(rama_session* s) {
 constexpr int kRing = 64;
 
 // Collective over the TP group: allocate this session's exchange block, swap CUDA IPC handles through
-// NCCL and map every peer's block (NVLink P2P).  Layout: u64 flags[3][P] | ArgPart parts[P][SMs] |
-// float inbox[2][P][D].
+// NCCL and map every peer's block (NVLink P2P).  Layout (LL elements = {payload, epoch} uint2):
+//   uint2 parts[P][SMs][2] | uint2 inbox[2 stages][P][D]
 static int setup_peer_exchange(rama_session* s) {
   rama_ctx* c = s->ctx;
   const int P = c->world;
   if (P > kMaxPeers) return fail(RAMA_E_INVALID, "tp world %d > %d", P, kMaxPeers);
-  s->off_parts = 256;
-  s->off_inbox = (s->off_parts + (size_t)P * c->sm_count * sizeof(ArgPart) + 255) / 256 * 256;
-  s->peer_bytes = s->off_inbox + (size_t)2 * P * c->D * sizeof(float);
+  s->off_parts = 0;
+  s->off_inbox = ((size_t)P * c->sm_count * 2 * sizeof(uint2) + 255) / 256 * 256;
+  s->peer_bytes = s->off_inbox + (size_t)2 * P * c->D * sizeof(uint2);
   CK(cudaMalloc((void**)&s->peer_mem, s->peer_bytes));
-  CK(cudaMemset(s->peer_mem, 0, s->peer_bytes));
-  s->part = reinterpret_cast<ArgPart*>(s->peer_mem + s->off_parts);
+  CK(cudaMemset(s->peer_mem, 0, s->peer_bytes));  // epoch 0 is never used
   cudaIpcMemHandle_t mine;
   CK(cudaIpcGetMemHandle(&mine, s->peer_mem));
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
@@ -576,45 +575,40 @@ static int setup_peer_exchange(rama_session* s) {
   return RAMA_OK;
 }
 
-static PeerOut peer_out(const rama_session* s, int stage) {  // stage 0 = wo, 1 = w2
+static PeerOut peer_out(const rama_session* s, int stage, int layer) {  // stage 0 = wo, 1 = w2
   PeerOut po{};
   const rama_ctx* c = s->ctx;
   if (!s->p2p) return po;
-  po.P = c->world;
-  for (int r = 0; r < c->world; ++r) {
-    po.inbox[r] = reinterpret_cast<float*>(s->peer_base[r] + s->off_inbox) + ((size_t)stage * c->world + c->rank) * c->D;
-    po.flag[r] = reinterpret_cast<unsigned long long*>(s->peer_base[r]) + (size_t)stage * c->world + c->rank;
-  }
+  po.P = c->world; po.seq = s->seq; po.L = c->L + 1; po.layer = layer;
+  for (int r = 0; r < c->world; ++r)
+    po.inbox[r] = reinterpret_cast<uint2*>(s->peer_base[r] + s->off_inbox) + ((size_t)stage * c->world + c->rank) * c->D;
   return po;
 }
-static PeerIn peer_in(const rama_session* s, int stage) {
+static PeerIn peer_in(const rama_session* s, int stage, int layer) {
   PeerIn pi{};
   const rama_ctx* c = s->ctx;
   if (!s->p2p) return pi;
-  pi.inbox = reinterpret_cast<const float*>(s->peer_mem + s->off_inbox) + (size_t)stage * c->world * c->D;
-  pi.flags = reinterpret_cast<const unsigned long long*>(s->peer_mem) + (size_t)stage * c->world;
-  pi.error = &s->ctrl->error;
-  pi.P = c->world; pi.me = c->rank; pi.n = c->D;
+  pi.inbox = reinterpret_cast<const uint2*>(s->peer_mem + s->off_inbox) + (size_t)stage * c->world * c->D;
+  pi.seq = s->seq; pi.error = &s->ctrl->error;
+  pi.P = c->world; pi.n = c->D; pi.L = c->L + 1; pi.layer = layer;
   return pi;
 }
-static PeerOut peer_out_parts(const rama_session* s) {  // stage 2: classifier partials
+static PeerOut peer_out_parts(const rama_session* s) {  // classifier partials, "layer" L
   PeerOut po{};
   const rama_ctx* c = s->ctx;
   if (!s->p2p) return po;
-  po.P = c->world;
-  for (int r = 0; r < c->world; ++r) {
-    po.inbox[r] = reinterpret_cast<float*>(reinterpret_cast<ArgPart*>(s->peer_base[r] + s->off_parts) + (size_t)c->rank * c->sm_count);
-    po.flag[r] = reinterpret_cast<unsigned long long*>(s->peer_base[r]) + (size_t)2 * c->world + c->rank;
-  }
+  po.P = c->world; po.seq = s->seq; po.L = c->L + 1; po.layer = c->L;
+  for (int r = 0; r < c->world; ++r)
+    po.inbox[r] = reinterpret_cast<uint2*>(s->peer_base[r] + s->off_parts) + (size_t)c->rank * c->sm_count * 2;
   return po;
 }
 static PeerIn peer_in_parts(const rama_session* s) {
   PeerIn pi{};
   const rama_ctx* c = s->ctx;
   if (!s->p2p) return pi;
-  pi.flags = reinterpret_cast<const unsigned long long*>(s->peer_mem) + (size_t)2 * c->world;
-  pi.error = &s->ctrl->error;
-  pi.P = c->world; pi.me = c->rank; pi.n = 0;
+  pi.inbox = reinterpret_cast<const uint2*>(s->peer_mem + s->off_parts);
+  pi.seq = s->seq; pi.error = &s->ctrl->error;
+  pi.P = c->world; pi.n = c->sm_count; pi.L = c->L + 1; pi.layer = c->L;
   return pi;
 }
 
@@ -625,6 +619,10 @@ extern "C" int rama_session_create(rama_ctx* c, rama_session** out) {
   rama_session* s = new rama_session();
   s->ctx = c;
   s->n_split = (c->T + kAttnChunk - 1) / kAttnChunk;
+  {
+    const int var = pick_variant(c, c->D / 4);
+    s->cls_grid = pick_grid(c, var, (c->Vl + 1) / 2);
+  }
   const size_t D = c->D, Dq = c->Dq, Fl = c->Fl, V = c->V, T = c->T, L = c->L;
   size_t vp2 = 1;
   while (vp2 < V) vp2 <<= 1;
@@ -640,7 +638,8 @@ extern "C" int rama_session_create(rama_ctx* c, rama_session** out) {
   A(dalloc(&s->attn_ws, (size_t)c->Hl * s->n_split * (c->hs + 2)));
   A(dalloc(&s->tickets, (size_t)c->Hl));
   s->p2p = c->world > 1 && c->p2p;
-  if (!s->p2p) A(dalloc(&s->part, (size_t)c->world * c->sm_count));
+  A(dalloc(&s->part, (size_t)c->world * c->sm_count));
+  A(dalloc(&s->seq, 1));
   A(dalloc(&s->sort_keys, vp2));
   A(dalloc(&s->ctrl, 1));
   A(dalloc(&s->d_prompt, T)); A(dalloc(&s->d_out, T));
@@ -770,13 +769,13 @@ static int enqueue_step(rama_session* s, cudaStream_t st, int mode, StepTrace* t
       at[0].val.programmaticStreamSerializationAllowed = 1;
       cfg.attrs = at; cfg.numAttrs = 1;
     }
-    q.post(cudaLaunchKernelEx(&cfg, step_begin_kernel, s->ctrl, W[RAMA_T_TOKEN_EMBEDDING], s->x0, D, c->V, q.pdl));
+    q.post(cudaLaunchKernelEx(&cfg, step_begin_kernel, s->ctrl, s->seq, W[RAMA_T_TOKEN_EMBEDDING], s->x0, D, c->V, q.pdl));
   }
 
   for (int l = 0; l < L; ++l) {
     // ---- rmsnorm → [wq|wk|wv] → RoPE → KV write (infer.rs:19-33) ----
     {
-      ProNorm pro{s->x0, l == 0 ? nullptr : s->w2out, s->x1, W[RAMA_T_RMS_ATT] + (size_t)l * D, nullptr, peer_in(s, 1)};
+      ProNorm pro{s->x0, l == 0 ? nullptr : s->w2out, s->x1, W[RAMA_T_RMS_ATT] + (size_t)l * D, nullptr, peer_in(s, 1, l - 1)};
       RowsQKV rows{W[RAMA_T_WQ] + (size_t)l * Dq * D, W[RAMA_T_WK] + (size_t)l * Dq * D,
                    W[RAMA_T_WV] + (size_t)l * Dq * D, D, Dq / 2};
       EpiQKV epi{s->q, s->k, s->v, s->key_cache + (size_t)l * T * Dq, s->value_cache + (size_t)l * T * Dq,
@@ -806,7 +805,7 @@ static int enqueue_step(rama_session* s, cudaStream_t st, int mode, StepTrace* t
     {
       ProPlain pro{s->xb};
       RowsPlain rows{W[RAMA_T_WO] + (size_t)l * D * Dq, Dq, D};
-      EpiStore epi{s->xb2, D, peer_out(s, 0)};
+      EpiStore epi{s->xb2, D, peer_out(s, 0, l)};
       const int np = D / 2, var = pick_variant(c, Dq / 4);
       q.pre(RAMA_K_WO);
       q.post(launch_gemv(var, pick_grid(c, var, np), st, q.pdl, pro, rows, epi, Dq / 4, np));
@@ -819,7 +818,7 @@ static int enqueue_step(rama_session* s, cudaStream_t st, int mode, StepTrace* t
     }
     // ---- x += xb2; rmsnorm → [w1|w3] → SwiGLU (infer.rs:37-45) ----
     {
-      ProNorm pro{s->x1, s->xb2, s->x0, W[RAMA_T_RMS_FFN] + (size_t)l * D, nullptr, peer_in(s, 0)};
+      ProNorm pro{s->x1, s->xb2, s->x0, W[RAMA_T_RMS_FFN] + (size_t)l * D, nullptr, peer_in(s, 0, l)};
       RowsW13 rows{W[RAMA_T_W1] + (size_t)l * Fl * D, W[RAMA_T_W3] + (size_t)l * Fl * D, D};
       EpiSwiGLU epi{s->hb, s->hb2};
       const int np = Fl, var = pick_variant(c, D / 4);
@@ -830,7 +829,7 @@ static int enqueue_step(rama_session* s, cudaStream_t st, int mode, StepTrace* t
     {
       ProPlain pro{s->hb};
       RowsPlain rows{W[RAMA_T_W2] + (size_t)l * D * Fl, Fl, D};
-      EpiStore epi{s->w2out, D, peer_out(s, 1)};
+      EpiStore epi{s->w2out, D, peer_out(s, 1, l)};
       const int np = D / 2, var = pick_variant(c, Fl / 4);
       q.pre(RAMA_K_W2);
       q.post(launch_gemv(var, pick_grid(c, var, np), st, q.pdl, pro, rows, epi, Fl / 4, np));
@@ -845,7 +844,7 @@ static int enqueue_step(rama_session* s, cudaStream_t st, int mode, StepTrace* t
   // ---- x += w2out; final rmsnorm → wcls → logits (+ greedy partials) (infer.rs:49-51) ----
   int cls_grid;
   {
-    ProNorm pro{s->x0, s->w2out, s->x1, W[RAMA_T_RMS_FINAL], s->xfinal, peer_in(s, 1)};
+    ProNorm pro{s->x0, s->w2out, s->x1, W[RAMA_T_RMS_FINAL], s->xfinal, peer_in(s, 1, L - 1)};
     RowsPlain rows{c->wcls, D, c->Vl};
     EpiCls epi{s->logits + c->v0, s->part + (size_t)c->rank * c->sm_count, c->Vl, c->v0, -INFINITY, -1,
                peer_out_parts(s)};
@@ -875,8 +874,8 @@ static int enqueue_step(rama_session* s, cudaStream_t st, int mode, StepTrace* t
     }
   }
   if (mode >= 1) {
-    SampleParams sp{s->logits, s->part, n_part, c->V, s->ctrl, s->d_prompt, s->d_out, s->sort_keys, 0.f, 0.f, 1,
-                    peer_in_parts(s)};
+    SampleParams sp{s->logits, s->part, n_part, s->cls_grid, c->V, s->ctrl, s->d_prompt, s->d_out, s->sort_keys,
+                    0.f, 0.f, 1, peer_in_parts(s)};
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(1);
     cfg.blockDim = dim3(kSampleThreads);
@@ -899,19 +898,9 @@ static int enqueue_step(rama_session* s, cudaStream_t st, int mode, StepTrace* t
 // unused partial slots (a CTA-less tail when the classifier grid < sm_count) must read as "empty"
 static int init_parts(rama_session* s) {
   rama_ctx* c = s->ctx;
-  if (s->p2p) {
-    // peers write into this array: initialise only once, before any step ran (all slots "empty");
-    // later calls must not race with a peer's classifier epilogue
-    if (s->parts_ready) return RAMA_OK;
-    s->parts_ready = true;
-  }
   std::vector<ArgPart> h((size_t)c->world * c->sm_count, ArgPart{-INFINITY, -1});
   CK(cudaMemcpyAsync(s->part, h.data(), h.size() * sizeof(ArgPart), cudaMemcpyHostToDevice, s->stream));
   CK(cudaStreamSynchronize(s->stream));
-  if (s->p2p) {  // every rank initialised before anyone steps
-    NK(g_nccl.AllReduce(s->xb2, s->xb2, 1, kNcclFloat32, kNcclSum, c->comm, s->stream));
-    CK(cudaStreamSynchronize(s->stream));
-  }
   return RAMA_OK;
 }
 
@@ -988,7 +977,7 @@ extern "C" int rama_sample(rama_session* s, float temperature, float topp, int32
   const bool greedy = temperature == 0.0f;
   if (!greedy) RK(gather_logits(s));
   const int n_part = c->world > 1 ? c->world * c->sm_count : c->sm_count;
-  SampleParams sp{s->logits, s->part, n_part, c->V, s->ctrl, s->d_prompt, s->d_out, s->sort_keys,
+  SampleParams sp{s->logits, s->part, n_part, s->cls_grid, c->V, s->ctrl, s->d_prompt, s->d_out, s->sort_keys,
                   temperature, topp, 0, peer_in_parts(s)};
   sample_kernel<<<1, kSampleThreads, 0, s->stream>>>(sp, 0);
   CK(cudaGetLastError());
@@ -1253,7 +1242,7 @@ extern "C" int rama_op_sample(rama_ctx* c, float* logits, size_t vocab_size, flo
   CK(cudaMallocAsync((void**)&ctrl, sizeof(StepCtrl), c->op_stream));
   CK(cudaMemsetAsync(ctrl, 0, sizeof(StepCtrl), c->op_stream));
   CK(cudaMallocAsync((void**)&keys, vp2 * sizeof(unsigned long long), c->op_stream));
-  SampleParams sp{logits, nullptr, 0, (int)vocab_size, ctrl, nullptr, nullptr, keys, temperature, topp, 0, PeerIn{}};
+  SampleParams sp{logits, nullptr, 0, 0, (int)vocab_size, ctrl, nullptr, nullptr, keys, temperature, topp, 0, PeerIn{}};
   sample_kernel<<<1, kSampleThreads, 0, c->op_stream>>>(sp, 0);
   CK(cudaGetLastError());
   int32_t ret[2] = {0, 0};

@@ -75,36 +75,44 @@ __device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) 
 }
 
 // ---- peer-memory exchange (tensor parallelism over NVLink; see gemv.cuh PeerOut/PeerIn) -----------
+// Low-latency "LL" protocol: every 4-byte payload travels in ONE 8-byte store together with a 32-bit
+// epoch, so arrival of the epoch proves arrival of the payload — no fences, no atomics, no flags;
+// the reader spins per element on the epoch (normally already there).
 constexpr int kMaxPeers = 8;
 
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
+__device__ __forceinline__ void st_ll(void* p, unsigned payload, unsigned epoch) {
+  asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(payload), "r"(epoch) : "memory");
 }
-// release-increment of a (possibly remote, peer-mapped) counter
-__device__ __forceinline__ void red_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("red.release.sys.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+__device__ __forceinline__ uint4 ld_ll2(const void* p) {  // two adjacent {payload, epoch} elements
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
 }
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-// Spin until *flag >= target (another GPU's kernel increments it).  Bounded: after ~4 s the sticky
-// error flag is raised instead of hanging the GPU (a peer process died).
-__device__ __forceinline__ void wait_flag(const unsigned long long* flag, unsigned long long target,
-                                          int32_t* error) {
-  if (ld_acquire_sys(flag) >= target) return;
-  if (*reinterpret_cast<volatile int32_t*>(error) == 3) return;  // already failed: do not stall every stage
+// Reads two LL elements, spinning until both carry `epoch`.  Bounded: after ~4 s the sticky error
+// flag is raised instead of hanging the GPU (a peer process died).
+__device__ __forceinline__ uint4 ld_ll2_wait(const void* p, unsigned epoch, int32_t* error) {
+  uint4 v = ld_ll2(p);
+  if (v.y == epoch && v.w == epoch) return v;
+  if (*reinterpret_cast<volatile int32_t*>(error) == 3) return v;
   const unsigned long long t0 = globaltimer_ns();
-  while (ld_acquire_sys(flag) < target) {
-    __nanosleep(64);
-    if (globaltimer_ns() - t0 > 4000000000ull) {
+  unsigned spins = 0;
+  for (;;) {
+    v = ld_ll2(p);
+    if (v.y == epoch && v.w == epoch) break;
+    if ((++spins & 1023u) == 0 && globaltimer_ns() - t0 > 4000000000ull) {
       *error = 3;
       break;
     }
   }
+  return v;
 }
 
 // (value, index) argmax merge with the reference's tie rule: later index wins on ties

@@ -32,43 +32,34 @@ struct ArgPart {  // greedy partial: best value and its global vocabulary index
 // ---- tensor-parallel exchange fused into the GEMVs (one-shot all-reduce over peer memory) -------
 // Row-parallel wo / w2 leave a D-float PARTIAL on every rank.  Instead of a separate collective,
 // the producing GEMV's epilogue stores each of its outputs straight into EVERY rank's inbox slot
-// [stage][src rank][D] (peer-mapped HBM over NVLink) and release-increments that rank's arrival
-// counter once per CTA; the consuming GEMV's prologue (which already adds the pending residual)
-// waits until every source's counter reached its own rank's count (all ranks run the same launch
-// sequence, and the local producer kernel has completed by stream order, so the local counter IS
-// the target), then sums the P partials in rank order — bit-identical on every rank.
+// [stage][src rank][D] (peer-mapped HBM over NVLink) as {value, epoch} 8-byte elements; the
+// consuming GEMV's prologue (which already adds the pending residual) reads the P partials, spinning
+// per element until the epoch of this (step, layer) shows, and sums them in rank order —
+// bit-identical on every rank.  epoch = step_seq·L + layer + 1, where step_seq is a per-session
+// device counter bumped by step_begin_kernel (all ranks run the same launch sequence).
 // Slot reuse is safe without double buffering because the two stages (wo, w2) alternate and each
-// consumer waits for all ranks.
+// consumer waits for all ranks before the next producer of that slot can run.
 struct PeerOut {
-  float* inbox[kMaxPeers];                // rank r's slot for (stage, src = me), peer-mapped
-  unsigned long long* flag[kMaxPeers];    // rank r's arrival counter for (stage, src = me)
-  int P;                                  // 0 ⇒ no exchange (single GPU / NCCL mode)
+  uint2* inbox[kMaxPeers];   // rank r's slot for (stage, src = me), peer-mapped
+  const unsigned* seq;       // step counter (device)
+  int P;                     // 0 ⇒ no exchange (single GPU / NCCL mode)
+  int L, layer;
+  __device__ __forceinline__ unsigned epoch() const { return *seq * (unsigned)L + (unsigned)layer + 1u; }
   // select with static indices (a runtime index would spill the table to local memory)
-  __device__ __forceinline__ unsigned long long* flag_of(int r) const {
-    unsigned long long* f = flag[0];
-#pragma unroll
-    for (int i = 1; i < kMaxPeers; ++i) f = (r == i) ? flag[i] : f;
-    return f;
-  }
-  __device__ __forceinline__ float* inbox_of(int r) const {
-    float* f = inbox[0];
+  __device__ __forceinline__ uint2* inbox_of(int r) const {
+    uint2* f = inbox[0];
 #pragma unroll
     for (int i = 1; i < kMaxPeers; ++i) f = (r == i) ? inbox[i] : f;
     return f;
   }
 };
 struct PeerIn {
-  const float* inbox;                     // local [P][n] partials of this stage
-  const unsigned long long* flags;        // local [P] arrival counters of this stage
-  int32_t* error;                         // StepCtrl.error
-  int P, me, n;                           // n = floats per partial (row stride of inbox)
-  __device__ __forceinline__ void wait() const {
-    if (threadIdx.x < P && threadIdx.x != me) {
-      const unsigned long long target = ld_acquire_sys(flags + me);
-      wait_flag(flags + threadIdx.x, target, error);
-    }
-    __syncthreads();
-  }
+  const uint2* inbox;        // local [P][n] LL elements of this stage
+  const unsigned* seq;
+  int32_t* error;            // StepCtrl.error
+  int P, n;                  // n = elements per partial (row stride of inbox)
+  int L, layer;
+  __device__ __forceinline__ unsigned epoch() const { return *seq * (unsigned)L + (unsigned)layer + 1u; }
 };
 
 // ---- prologues: fill xs[0..K4) (float4) ---------------------------------------------------
@@ -97,15 +88,17 @@ struct ProNorm {
     const float4* x4 = reinterpret_cast<const float4*>(xin);
     const float4* a4 = reinterpret_cast<const float4*>(add);
     const bool peers = pin.P > 0 && add != nullptr;
-    if (peers) pin.wait();
+    const unsigned ep = peers ? pin.epoch() : 0u;
     float ss = 0.f;
     for (int i = threadIdx.x; i < K4; i += kGemvThreads) {
       float4 v = x4[i];
       if (peers) {
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int r = 0; r < pin.P; ++r) {  // rank order: same association on every rank
-          const float4 t = __ldcg(reinterpret_cast<const float4*>(pin.inbox + (size_t)r * pin.n) + i);
-          a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+          const uint2* e = pin.inbox + (size_t)r * pin.n + 4 * i;
+          const uint4 lo = ld_ll2_wait(e, ep, pin.error), hi = ld_ll2_wait(e + 2, ep, pin.error);
+          a.x += __uint_as_float(lo.x); a.y += __uint_as_float(lo.z);
+          a.z += __uint_as_float(hi.x); a.w += __uint_as_float(hi.z);
         }
         v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
         if (blockIdx.x == 0) reinterpret_cast<float4*>(const_cast<float*>(add))[i] = a;  // RunState.xb2 / xb
@@ -192,11 +185,12 @@ struct EpiStore {  // o[2p], o[2p+1]    (wo → xb2, w2 → residual contributio
   PeerOut po;      // po.P > 0: the outputs are a TP partial → stored into every rank's inbox instead
   __device__ __forceinline__ void operator()(int p, float v0, float v1) {
     if (po.P > 0) {
+      const unsigned ep = po.epoch();
 #pragma unroll
       for (int r = 0; r < kMaxPeers; ++r) {  // static indexing keeps the pointer table in param space
         if (r < po.P) {
-          po.inbox[r][2 * p] = v0;
-          if (2 * p + 1 < n_rows) po.inbox[r][2 * p + 1] = v1;
+          st_ll(po.inbox[r] + 2 * p, __float_as_uint(v0), ep);
+          if (2 * p + 1 < n_rows) st_ll(po.inbox[r] + 2 * p + 1, __float_as_uint(v1), ep);
         }
       }
       return;
@@ -204,15 +198,7 @@ struct EpiStore {  // o[2p], o[2p+1]    (wo → xb2, w2 → residual contributio
     o[2 * p] = v0;
     if (2 * p + 1 < n_rows) o[2 * p + 1] = v1;
   }
-  __device__ __forceinline__ void finish(float*) {
-    if (po.P > 0) {  // one arrival per CTA per destination, after all of the CTA's stores
-      __syncthreads();
-      if (threadIdx.x < po.P) {
-        __threadfence_system();
-        red_release_sys(po.flag_of(threadIdx.x), 1ull);
-      }
-    }
-  }
+  __device__ __forceinline__ void finish(float*) {}
 };
 
 // RoPE (cpu.rs:74-97, simultaneous pair update, unfused mul/sub as in the reference) on q and k,
@@ -301,12 +287,11 @@ struct EpiCls {
         argmax_merge(tv, ti, ov, oi);
       }
       if (po.P > 0) {
-        if (l < po.P) {
-          ArgPart* dst = reinterpret_cast<ArgPart*>(po.inbox_of(l)) + blockIdx.x;
-          dst->v = tv;
-          dst->i = ti;
-          __threadfence_system();
-          red_release_sys(po.flag_of(l), 1ull);
+        if (l < po.P) {  // {value, epoch}, {index, epoch} into rank l's array
+          uint2* dst = po.inbox_of(l) + 2 * blockIdx.x;
+          const unsigned ep = po.epoch();
+          st_ll(dst, __float_as_uint(tv), ep);
+          st_ll(dst + 1, (unsigned)ti, ep);
         }
       } else if (l == 0) {
         part[blockIdx.x].v = tv;

@@ -7,10 +7,12 @@
 namespace rama {
 
 // ---- step begin: x ← token_embedding_table[token] (infer.rs:13) ---------------------------------
-__global__ void __launch_bounds__(256) step_begin_kernel(StepCtrl* ctrl, const float* __restrict__ emb,
+__global__ void __launch_bounds__(256) step_begin_kernel(StepCtrl* ctrl, unsigned* seq,
+                                                         const float* __restrict__ emb,
                                                          float* __restrict__ x, int D, int vocab,
                                                          int use_pdl) {
   if (use_pdl) { pdl_launch_dependents(); pdl_wait(); }
+  if (blockIdx.x == 0 && threadIdx.x == 0) *seq += 1u;  // step counter: epoch source of the TP exchange
   int token = ctrl->token;
   if (token < 0 || token >= vocab) {  // the reference would panic on the slice (infer.rs:13)
     if (threadIdx.x == 0 && blockIdx.x == 0) ctrl->error = 1;
@@ -36,7 +38,8 @@ constexpr float kRefU = 0.2721174359321594f;  // f32 bits 0x3e8b52fa
 struct SampleParams {
   float* logits;            // [V] (full vocabulary on this rank)
   const ArgPart* part;      // optional greedy partials from the classifier kernel(s)
-  int n_part;
+  int n_part;               // number of partial slots (P * SMs under TP)
+  int n_live;               // TP: classifier CTAs per rank that actually write a slot
   int V;
   StepCtrl* ctrl;
   const int32_t* prompt;    // chained mode
@@ -44,7 +47,7 @@ struct SampleParams {
   unsigned long long* keys; // scratch [2][V] composite sort keys (top-p path)
   float temperature, topp;  // used when !ctrl->chained (host-driven rama_sample)
   int use_ctrl_params;      // 1: take temperature/topp from ctrl (chained generate)
-  PeerIn pin;               // pin.P > 0: wait for every rank's classifier partials (peer-written)
+  PeerIn pin;               // pin.P > 0: part is an LL array [P*n_per][2] written by every rank's classifier
 };
 
 __device__ __forceinline__ unsigned long long sample_key(float p, int idx) {
@@ -121,11 +124,18 @@ __global__ void __launch_bounds__(kSampleThreads) sample_kernel(const SamplePara
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
   int* redi = reinterpret_cast<int*>(red + kWarp);
 
-  if (p.pin.P > 0) p.pin.wait();
   if (temperature == 0.0f) {
     float bv = -INFINITY;
     int bi = -1;
-    if (p.part) {
+    if (p.pin.P > 0) {
+      // peer-written {value,epoch},{index,epoch} pairs; slots of CTAs that do not exist keep epoch 0
+      const unsigned ep = p.pin.epoch();
+      for (int i = threadIdx.x; i < p.n_part; i += kSampleThreads) {
+        if ((i % p.pin.n) >= p.n_live) continue;
+        const uint4 e = ld_ll2_wait(p.pin.inbox + 2 * (size_t)i, ep, p.pin.error);
+        if ((int)e.z >= 0) argmax_merge(bv, bi, __uint_as_float(e.x), (int)e.z);
+      }
+    } else if (p.part) {
       for (int i = threadIdx.x; i < p.n_part; i += kSampleThreads)
       {
         const float pv = __ldcg(&p.part[i].v);
