@@ -787,7 +787,9 @@ static int enqueue_step(rama_session* s, cudaStream_t st, int mode, StepTrace* t
     // ---- attention (infer.rs:34) ----
     {
       AttnParams ap{s->q, s->key_cache + (size_t)l * T * Dq, s->value_cache + (size_t)l * T * Dq, s->xb,
-                    s->keep_att ? s->att : nullptr, s->attn_ws, s->tickets, s->ctrl, -1, T, Dq, hs, s->n_split};
+                    s->keep_att ? s->att : nullptr, s->attn_ws, s->tickets, s->ctrl, -1, T, Dq, hs, s->n_split,
+                    // HBM idles during attention: pull this layer's wo (≤ 64 MB, fits L2) in meanwhile
+                    W[RAMA_T_WO] + (size_t)l * D * Dq, std::min((size_t)D * Dq * sizeof(float), (size_t)96 << 20)};
       cudaLaunchConfig_t cfg{};
       cfg.gridDim = dim3(c->Hl, s->n_split);
       cfg.blockDim = dim3(kAttnThreads);
@@ -1223,7 +1225,7 @@ extern "C" int rama_op_multi_head_attention(rama_ctx* c, float* xb, float* att, 
   CK(cudaMallocAsync((void**)&tickets, H * sizeof(unsigned int), c->op_stream));
   CK(cudaMemsetAsync(tickets, 0, H * sizeof(unsigned int), c->op_stream));
   const size_t lo = (size_t)layer * T * D;
-  AttnParams ap{q, key_cache + lo, value_cache + lo, xb, att, ws, tickets, nullptr, pos, T, D, hs, n_split};
+  AttnParams ap{q, key_cache + lo, value_cache + lo, xb, att, ws, tickets, nullptr, pos, T, D, hs, n_split, nullptr, 0};
   attn_decode_kernel<<<dim3(H, n_split), kAttnThreads, 0, c->op_stream>>>(ap, 0);
   CK(cudaGetLastError());
   CK(cudaFreeAsync(ws, c->op_stream));

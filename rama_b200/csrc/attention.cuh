@@ -4,20 +4,26 @@
 // bug at 7B — SURVEY App. C) ≙ Device::multi_head_attention (cpu.rs:23-52):
 //     score_t = (q·k_t) / sqrt(hs);  p = softmax(score_0..pos);  xb = Σ_t p_t · v_t
 //
-// Grid (heads, splits): CTA (h, c) owns timesteps [c·TC, (c+1)·TC) of head h, keeps a running
-// (max, sum, acc[hs]) per warp (online softmax), merges its 4 warps in shared memory and writes
-// one partial to the workspace.  The last CTA of a head to finish (atomic ticket) merges the
-// partials in split order (deterministic) and writes xb — no second launch.
+// Grid (heads, splits): CTA (h, c) owns timesteps [c·TC, (c+1)·TC) of head h.  The kernel is
+// latency-bound at short contexts (a few KB per head), so it is organised for memory-level
+// parallelism: 8 warps × 4 timesteps each; every lane issues its 4 K-row and 4 V-row 128-bit loads
+// back to back before the first dot product.  Each warp folds its 4 timesteps into a running
+// (max, sum, acc[hs]) (online softmax), the 8 warps merge through shared memory and the CTA writes
+// one partial; the last CTA of a head to finish (atomic ticket) merges the partials in split order
+// (deterministic) and writes xb — no second launch.
 // KV cache layout is the reference's [T][Dq] per layer (head h at column h·hs): each timestep's
 // head row is hs·4 contiguous bytes (512 B at 7B) ⇒ one coalesced 128-bit load per lane.
+// While it runs, HBM is otherwise idle: every CTA (also the ones beyond `pos` that exit at once)
+// prefetches its slice of the NEXT kernel's weights (wo of this layer) into L2.
 #pragma once
 #include "common.cuh"
 
 namespace rama {
 
-constexpr int kAttnThreads = 128;
+constexpr int kAttnThreads = 256;
 constexpr int kAttnWarps = kAttnThreads / kWarp;
-constexpr int kAttnChunk = 64;       // timesteps per CTA
+constexpr int kAttnPerWarp = 4;                          // timesteps per warp
+constexpr int kAttnChunk = kAttnWarps * kAttnPerWarp;    // 32 timesteps per CTA
 constexpr int kAttnMaxHs = 128;
 
 struct AttnParams {
@@ -31,6 +37,8 @@ struct AttnParams {
   const StepCtrl* ctrl;      // pos read from here unless pos_override >= 0
   int pos_override;
   int T, Dq, hs, n_split;
+  const float* prefetch;     // next kernel's weights (or nullptr)
+  size_t prefetch_bytes;
 };
 
 __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnParams p, int use_pdl) {
@@ -38,7 +46,17 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnPar
   __shared__ __align__(16) float s_acc[kAttnWarps][kAttnMaxHs];
   __shared__ unsigned int s_ticket;
 
-  if (use_pdl) { pdl_launch_dependents(); pdl_wait(); }
+  if (use_pdl) pdl_launch_dependents();
+  if (p.prefetch && threadIdx.x == 0) {  // weights do not depend on the previous kernel
+    const size_t n_cta = (size_t)gridDim.x * gridDim.y, me = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+    const size_t per = ((p.prefetch_bytes + n_cta - 1) / n_cta + 15) & ~(size_t)15;
+    const size_t off = me * per;
+    if (off < p.prefetch_bytes) {
+      const size_t n = min(per, p.prefetch_bytes - off) & ~(size_t)15;
+      if (n) l2_prefetch_bulk(reinterpret_cast<const char*>(p.prefetch) + off, (uint32_t)n);
+    }
+  }
+  if (use_pdl) pdl_wait();
 
   const int pos = p.pos_override >= 0 ? p.pos_override : p.ctrl->pos;
   const int n = pos + 1;
@@ -49,54 +67,50 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnPar
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int hs = p.hs, hs4 = hs >> 2;
   const bool active = lane < hs4;
-  const float inv_div = sqrtf((float)hs);
-
-  const float4 q4 = active ? reinterpret_cast<const float4*>(p.q + (size_t)h * hs)[lane]
-                           : make_float4(0.f, 0.f, 0.f, 0.f);
-  const int t0 = chunk * kAttnChunk, t1 = min(n, t0 + kAttnChunk);
+  const float div = sqrtf((float)hs);
   const size_t col = (size_t)h * hs;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  // this warp's timesteps: t0 + j, j < kAttnPerWarp
+  const int t0 = chunk * kAttnChunk + warp * kAttnPerWarp;
+  float4 kk[kAttnPerWarp], vv[kAttnPerWarp];
+#pragma unroll
+  for (int j = 0; j < kAttnPerWarp; ++j) {
+    const bool ok = active && (t0 + j) < n;
+    kk[j] = ok ? reinterpret_cast<const float4*>(p.key_cache + (size_t)(t0 + j) * p.Dq + col)[lane] : zero4;
+  }
+#pragma unroll
+  for (int j = 0; j < kAttnPerWarp; ++j) {
+    const bool ok = active && (t0 + j) < n;
+    vv[j] = ok ? reinterpret_cast<const float4*>(p.value_cache + (size_t)(t0 + j) * p.Dq + col)[lane] : zero4;
+  }
+  const float4 q4 = active ? reinterpret_cast<const float4*>(p.q + col)[lane] : zero4;
+
+  float sc[kAttnPerWarp];
+#pragma unroll
+  for (int j = 0; j < kAttnPerWarp; ++j) sc[j] = dot4(q4, kk[j], 0.f);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int j = 0; j < kAttnPerWarp; ++j) sc[j] += __shfl_xor_sync(0xffffffffu, sc[j], o);
 
   float m = -INFINITY, l = 0.f;
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-
-  // two timesteps per iteration per warp for memory-level parallelism
-  for (int t = t0 + warp; t < t1; t += 2 * kAttnWarps) {
-    const int tb = t + kAttnWarps;
-    const bool hb = tb < t1;
-    float4 ka = make_float4(0.f, 0.f, 0.f, 0.f), kb = ka, va = ka, vb = ka;
-    if (active) {
-      ka = reinterpret_cast<const float4*>(p.key_cache + (size_t)t * p.Dq + col)[lane];
-      va = reinterpret_cast<const float4*>(p.value_cache + (size_t)t * p.Dq + col)[lane];
-      if (hb) {
-        kb = reinterpret_cast<const float4*>(p.key_cache + (size_t)tb * p.Dq + col)[lane];
-        vb = reinterpret_cast<const float4*>(p.value_cache + (size_t)tb * p.Dq + col)[lane];
-      }
-    }
-    float sa = warp_sum(dot4(q4, ka, 0.f)) / inv_div;   // divide, as cpu.rs:41
-    float sb = warp_sum(dot4(q4, kb, 0.f)) / inv_div;
-    if (p.att && lane == 0) {
-      p.att[(size_t)h * p.T + t] = sa;                  // raw score; normalised by the merger
-      if (hb) p.att[(size_t)h * p.T + tb] = sb;
-    }
-    {
-      const float mn = fmaxf(m, sa);
-      const float sc = expf(m - mn), pe = expf(sa - mn);
-      l = l * sc + pe;
-      acc.x = acc.x * sc + pe * va.x; acc.y = acc.y * sc + pe * va.y;
-      acc.z = acc.z * sc + pe * va.z; acc.w = acc.w * sc + pe * va.w;
-      m = mn;
-    }
-    if (hb) {
-      const float mn = fmaxf(m, sb);
-      const float sc = expf(m - mn), pe = expf(sb - mn);
-      l = l * sc + pe;
-      acc.x = acc.x * sc + pe * vb.x; acc.y = acc.y * sc + pe * vb.y;
-      acc.z = acc.z * sc + pe * vb.z; acc.w = acc.w * sc + pe * vb.w;
+  float4 acc = zero4;
+#pragma unroll
+  for (int j = 0; j < kAttnPerWarp; ++j) {
+    if (t0 + j < n) {                                  // warp-uniform
+      const float s = sc[j] / div;                     // divide, as cpu.rs:41
+      if (p.att && lane == 0) p.att[(size_t)h * p.T + t0 + j] = s;  // raw score; normalised by the merger
+      const float mn = fmaxf(m, s);
+      const float f = expf(m - mn), pe = expf(s - mn);
+      l = l * f + pe;
+      acc.x = acc.x * f + pe * vv[j].x; acc.y = acc.y * f + pe * vv[j].y;
+      acc.z = acc.z * f + pe * vv[j].z; acc.w = acc.w * f + pe * vv[j].w;
       m = mn;
     }
   }
 
-  // merge the 4 warps of this CTA (fixed order)
+  // merge the warps of this CTA (fixed order)
   if (lane == 0) { s_m[warp] = m; s_l[warp] = l; }
   if (active) reinterpret_cast<float4*>(s_acc[warp])[lane] = acc;
   __syncthreads();
@@ -105,7 +119,8 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnPar
     float M = -INFINITY;
 #pragma unroll
     for (int w = 0; w < kAttnWarps; ++w) M = fmaxf(M, s_m[w]);
-    // a warp that saw no timestep has m = -inf, l = 0: exp(-inf - M) = 0 contributes nothing
+    // a warp that saw no timestep has m = -inf, l = 0, acc = 0: exp(-inf - M) = 0 contributes nothing
+    // (warp 0 always has one, so M is finite)
     for (int i = threadIdx.x; i < hs; i += kAttnThreads) {
       float a = 0.f;
 #pragma unroll
@@ -137,6 +152,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnPar
     L += __ldcg(wh + (size_t)c * (hs + 2) + 1) * expf(__ldcg(wh + (size_t)c * (hs + 2)) - M);
   for (int i = threadIdx.x; i < hs; i += kAttnThreads) {
     float a = 0.f;
+#pragma unroll 4
     for (int c = 0; c < n_chunks; ++c)
       a += __ldcg(wh + (size_t)c * (hs + 2) + 2 + i) * expf(__ldcg(wh + (size_t)c * (hs + 2)) - M);
     p.out[(size_t)h * hs + i] = a / L;

@@ -93,12 +93,27 @@ struct ProNorm {
     for (int i = threadIdx.x; i < K4; i += kGemvThreads) {
       float4 v = x4[i];
       if (peers) {
+        // issue every rank's two 16-byte LL loads first (independent), then validate the epochs;
+        // only an element that has not arrived yet falls into the spinning reload
+        uint4 lo[kMaxPeers], hi[kMaxPeers];
+#pragma unroll
+        for (int r = 0; r < kMaxPeers; ++r) {
+          if (r < pin.P) {
+            const uint2* e = pin.inbox + (size_t)r * pin.n + 4 * i;
+            lo[r] = ld_ll2(e);
+            hi[r] = ld_ll2(e + 2);
+          }
+        }
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int r = 0; r < pin.P; ++r) {  // rank order: same association on every rank
-          const uint2* e = pin.inbox + (size_t)r * pin.n + 4 * i;
-          const uint4 lo = ld_ll2_wait(e, ep, pin.error), hi = ld_ll2_wait(e + 2, ep, pin.error);
-          a.x += __uint_as_float(lo.x); a.y += __uint_as_float(lo.z);
-          a.z += __uint_as_float(hi.x); a.w += __uint_as_float(hi.z);
+#pragma unroll
+        for (int r = 0; r < kMaxPeers; ++r) {  // rank order: same association on every rank
+          if (r < pin.P) {
+            const uint2* e = pin.inbox + (size_t)r * pin.n + 4 * i;
+            if (lo[r].y != ep || lo[r].w != ep) lo[r] = ld_ll2_wait(e, ep, pin.error);
+            if (hi[r].y != ep || hi[r].w != ep) hi[r] = ld_ll2_wait(e + 2, ep, pin.error);
+            a.x += __uint_as_float(lo[r].x); a.y += __uint_as_float(lo[r].z);
+            a.z += __uint_as_float(hi[r].x); a.w += __uint_as_float(hi[r].z);
+          }
         }
         v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
         if (blockIdx.x == 0) reinterpret_cast<float4*>(const_cast<float*>(add))[i] = a;  // RunState.xb2 / xb

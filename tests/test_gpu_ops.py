@@ -147,8 +147,8 @@ class _RS:
 
 
 @pytest.mark.parametrize("name,layer,positions", [
-    ("stories15M", 3, [0, 1, 63, 64, 65, 255]),           # hs 48
-    ("stories110M", 1, [0, 127, 128, 500, 1023]),         # hs 64
+    ("stories15M", 3, [0, 1, 3, 4, 31, 32, 33, 63, 64, 65, 255]),           # hs 48
+    ("stories110M", 1, [0, 30, 127, 128, 500, 1023]),         # hs 64
     ("l7-2layer", 1, [0, 5, 64, 700, 2047]),              # hs 128, 7B cache geometry
 ])
 def test_multi_head_attention_vs_oracle(gpu, name, layer, positions):
