@@ -546,12 +546,14 @@ static int setup_peer_exchange(rama_session* s) {
   s->peer_bytes = s->off_inbox + (size_t)2 * P * c->D * sizeof(uint2);
   CK(cudaMalloc((void**)&s->peer_mem, s->peer_bytes));
   CK(cudaMemset(s->peer_mem, 0, s->peer_bytes));  // epoch 0 is never used
+  CK(cudaDeviceSynchronize());
   cudaIpcMemHandle_t mine;
   CK(cudaIpcGetMemHandle(&mine, s->peer_mem));
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
   char* d_h = nullptr;
   CK(cudaMalloc((void**)&d_h, 64 * (size_t)P));
   CK(cudaMemcpy(d_h + 64 * (size_t)c->rank, &mine, 64, cudaMemcpyHostToDevice));
+  CK(cudaDeviceSynchronize());  // s->stream is non-blocking: make the staged copy land first
   int e = g_nccl.AllGather(d_h + 64 * (size_t)c->rank, d_h, 16, kNcclFloat32, c->comm, s->stream);
   if (e) { cudaFree(d_h); return fail(RAMA_E_NCCL, "handle all-gather: %s", g_nccl.GetErrorString(e)); }
   CK(cudaStreamSynchronize(s->stream));
@@ -646,6 +648,7 @@ extern "C" int rama_session_create(rama_ctx* c, rama_session** out) {
   A(cudaHostAlloc((void**)&s->h_ring, kRing * sizeof(StepCtrl), cudaHostAllocDefault));
   A(cudaHostAlloc((void**)&s->h_ret, 4 * sizeof(int32_t), cudaHostAllocDefault));
   A(cudaEventCreate(&s->ev0)); A(cudaEventCreate(&s->ev1));
+  A(cudaDeviceSynchronize());  // the zero-fills above ran on the default stream; session streams are non-blocking
 #undef A
   if (e != cudaSuccess) {
     session_free(s);
@@ -1098,7 +1101,10 @@ extern "C" int rama_dev_alloc(rama_ctx* c, size_t n, float** out) {
   if (!c || !out) return fail(RAMA_E_INVALID, "NULL argument");
   CK(cudaSetDevice(c->device));
   CK(cudaMalloc((void**)out, std::max<size_t>(n, 1) * sizeof(float)));
-  CK(cudaMemset(*out, 0, std::max<size_t>(n, 1) * sizeof(float)));  // RunState::from_config zero-fills (ram.rs:7-23)
+  // RunState::from_config zero-fills (ram.rs:7-23).  On the op stream (non-blocking: it does not
+  // synchronise with the legacy default stream, so a default-stream memset could land after later copies).
+  CK(cudaMemsetAsync(*out, 0, std::max<size_t>(n, 1) * sizeof(float), c->op_stream));
+  CK(cudaStreamSynchronize(c->op_stream));
   return RAMA_OK;
 }
 extern "C" int rama_dev_free(rama_ctx* c, float* p) {
