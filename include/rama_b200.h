@@ -168,6 +168,20 @@ int rama_op_softmax(rama_ctx* ctx, float* x, size_t n);                         
 int rama_op_sample(rama_ctx* ctx, float* logits, size_t vocab_size, float temperature, float topp,
                    int32_t* next);
 
+/* Dense contraction on the tensor cores (tcgen05.mma kind::tf32, 3xTF32 split for f32 accuracy):
+ *   out[M][N] = a[M][K] · b[N][K]^T          (both operands row-major with K contiguous)
+ * The shape the reference's Device::matmul (device.rs:13, cpu.rs:127-153) takes when a whole prompt or a
+ * batch of sequences goes through one weight matrix instead of o_cols = 1 per token (mod.rs:187-192,
+ * lib.rs:127-160).  variant selects the tile configuration (tests sweep them); flags bit 0: keep the raw
+ * f32 tile as the hi operand (hardware truncation) instead of rounding it; bit 1: store out^T, i.e.
+ * out[N][M] (batched decode orientation: a = weights, b = activations). */
+int rama_op_matmul_nt(rama_ctx* ctx, float* out, const float* a, const float* b, size_t M, size_t N, size_t K,
+                      int variant, int flags);
+
+/* Micro-benchmark hook used by tools/gemm_sweep.py: average milliseconds per rama_op_matmul_nt launch. */
+int rama_bench_matmul_nt(rama_ctx* ctx, float* out, const float* a, const float* b, size_t M, size_t N, size_t K,
+                         int variant, int flags, int iters, float* avg_ms);
+
 /* Synthetic fill of a device buffer (bench/test data): elements [start, start+n) of tensor_id. */
 int rama_synth_fill(rama_ctx* ctx, float* dst, size_t n, uint64_t seed, uint64_t tensor_id,
                     uint64_t start, float scale, float offset);

@@ -22,6 +22,7 @@
 
 #include "attention.cuh"
 #include "common.cuh"
+#include "gemm_host.cuh"
 #include "gemv.cuh"
 #include "misc_kernels.cuh"
 
@@ -1296,5 +1297,59 @@ extern "C" int rama_bench_gemv(rama_ctx* c, float* o, const float* w, const floa
   *avg_ms = ms / iters;
   cudaEventDestroy(a);
   cudaEventDestroy(b);
+  return RAMA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// tensor-core contraction (tcgen05, 3xTF32): C[M][N] = A[M][K] · B[N][K]^T
+// ------------------------------------------------------------------------------------------------
+extern "C" int rama_op_matmul_nt(rama_ctx* c, float* out, const float* a, const float* b, size_t M, size_t N,
+                                 size_t K, int variant, int flags) {
+  OP_PRE(c);
+  if (!out || !a || !b || !M || !N || !K) return fail(RAMA_E_INVALID, "empty matmul_nt");
+  if (K % 4) return fail(RAMA_E_INVALID, "K %% 4 != 0 (TMA needs 16-byte row pitch; the reference steps k by 4, cpu.rs:142)");
+  const int hi_raw = flags & 1;
+  const bool transposed = (flags & 2) != 0;
+  GemmOperand A{a, M, K}, B{b, N, K};
+  cudaError_t e;
+  if (transposed) {
+    EpiStoreT epi{out, (int)M, (int)N};
+    switch (variant) {
+      case 0: e = launch_gemm_tf32x3<64, 32, 4, 4>(c->op_stream, A, &B, 1, (int)M, (int)N, (int)K, hi_raw, epi); break;
+      case 1: e = launch_gemm_tf32x3<64, 16, 6, 8>(c->op_stream, A, &B, 1, (int)M, (int)N, (int)K, hi_raw, epi); break;
+      default: return fail(RAMA_E_INVALID, "matmul_nt: unknown transposed variant %d", variant);
+    }
+  } else {
+    EpiStoreNT epi{out, (int)N, (int)N, 0};
+    switch (variant) {
+      case 0: e = launch_gemm_tf32x3<128, 32, 3, 4>(c->op_stream, A, &B, 1, (int)M, (int)N, (int)K, hi_raw, epi); break;
+      case 1: e = launch_gemm_tf32x3<128, 16, 6, 8>(c->op_stream, A, &B, 1, (int)M, (int)N, (int)K, hi_raw, epi); break;
+      case 2: e = launch_gemm_tf32x3<128, 32, 3, 2>(c->op_stream, A, &B, 1, (int)M, (int)N, (int)K, hi_raw, epi); break;
+      case 3: e = launch_gemm_tf32x3<128, 32, 3, 8>(c->op_stream, A, &B, 1, (int)M, (int)N, (int)K, hi_raw, epi); break;
+      default: return fail(RAMA_E_INVALID, "matmul_nt: unknown variant %d", variant);
+    }
+  }
+  if (e != cudaSuccess) return fail(RAMA_E_CUDA, "gemm_tf32x3 launch: %s", cudaGetErrorString(e));
+  return RAMA_OK;
+}
+
+// Micro-benchmark hook (tools/gemm_sweep.py): average milliseconds of rama_op_matmul_nt over `iters` launches.
+extern "C" int rama_bench_matmul_nt(rama_ctx* c, float* out, const float* a, const float* b, size_t M, size_t N,
+                                    size_t K, int variant, int flags, int iters, float* avg_ms) {
+  OP_PRE(c);
+  if (!avg_ms || iters <= 0) return fail(RAMA_E_INVALID, "bad argument");
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  for (int i = 0; i < 3; ++i) RK(rama_op_matmul_nt(c, out, a, b, M, N, K, variant, flags));
+  CK(cudaEventRecord(e0, c->op_stream));
+  for (int i = 0; i < iters; ++i) RK(rama_op_matmul_nt(c, out, a, b, M, N, K, variant, flags));
+  CK(cudaEventRecord(e1, c->op_stream));
+  CK(cudaStreamSynchronize(c->op_stream));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  *avg_ms = ms / iters;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
   return RAMA_OK;
 }

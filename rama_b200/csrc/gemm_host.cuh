@@ -1,0 +1,76 @@
+// gemm_host.cuh — host side of the tcgen05 3xTF32 GEMM: TMA descriptor creation (driver entry point
+// resolved at run time, no link-time libcuda dependency) and the templated launcher.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <mutex>
+
+#include "gemm_tf32x3.cuh"
+
+namespace rama {
+
+typedef CUresult (*TmapEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline TmapEncodeTiledFn tmap_encode_fn() {
+  static TmapEncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<TmapEncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// f32 matrix [rows][K] with row pitch `ld` floats; box = box_rows × BK, swizzle = BK·4 bytes; out-of-bounds → 0
+inline bool make_tmap_2d(CUtensorMap* m, const float* base, size_t rows, size_t K, size_t ld, int box_rows, int BK) {
+  TmapEncodeTiledFn f = tmap_encode_fn();
+  if (!f) return false;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld * 4) % 16 || box_rows > 256 || box_rows < 1) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapSwizzle sw = BK == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  return f(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+           CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+struct GemmOperand {  // a K-major f32 matrix [rows][K], row pitch ld
+  const float* p;
+  size_t rows, ld;
+};
+
+// C (per group g < n_groups) = A · B[g]ᵀ;  for a dual epilogue B[0] and B[1] are stacked inside one tile.
+template <int BN, int BK, int STAGES, int CH, class Epi>
+cudaError_t launch_gemm_tf32x3(cudaStream_t st, const GemmOperand& A, const GemmOperand* B, int n_b, int M, int N,
+                               int K, int hi_raw, const Epi& epi) {
+  using SM = GemmSmem<BN, BK, STAGES>;
+  static_assert(SM::kTotal <= 227 * 1024, "tile does not fit shared memory");
+  auto kern = gemm_tf32x3_kernel<BN, BK, STAGES, CH, Epi>;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal); });
+  if (attr_err != cudaSuccess) return attr_err;
+  if (M <= 0 || N <= 0 || K <= 0 || K % 4 || n_b < 1 || n_b > 3) return cudaErrorInvalidValue;
+  GemmMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  if (!make_tmap_2d(&maps.a, A.p, A.rows, (size_t)K, A.ld, kGemmBM, BK)) return cudaErrorInvalidValue;
+  constexpr int box_n = Epi::kDual ? BN / 2 : BN;
+  for (int i = 0; i < n_b; ++i)
+    if (!make_tmap_2d(&maps.b[i], B[i].p, B[i].rows, (size_t)K, B[i].ld, box_n, BK)) return cudaErrorInvalidValue;
+  for (int i = n_b; i < 3; ++i) maps.b[i] = maps.b[0];
+  GemmShape shp{M, N, K, hi_raw};
+  const int groups = Epi::kDual ? 1 : n_b;
+  dim3 grid((N + box_n - 1) / box_n, (M + kGemmBM - 1) / kGemmBM, groups);
+  kern<<<grid, kGemmThreads, SM::kTotal, st>>>(maps, shp, epi);
+  return cudaGetLastError();
+}
+
+}  // namespace rama

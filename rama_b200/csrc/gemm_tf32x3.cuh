@@ -1,0 +1,402 @@
+// gemm_tf32x3.cuh — f32-accurate dense contraction on the 5th-gen tensor cores (tcgen05, sm_100a).
+//
+//     C[M][N] = A[M][K] · B[N][K]ᵀ          (both operands K-major = the llama2.c weight layout)
+//
+// Used where the decode path stops being a GEMV: prompt prefill (A = the prompt's activations,
+// B = a weight matrix) and multi-sequence batched decode (A = a 128-row weight slab, B = the
+// batch's activations) — SURVEY §8(f) rows 1-2; the reference has only Device::matmul with
+// o_cols = 1 (cpu.rs:127-153) called once per token (mod.rs:187-192).
+//
+// f32 accuracy on tf32 tensor cores ("3xTF32"): every f32 operand element a is split into
+//     hi = rna_tf32(a)   (11 significant bits, exactly representable in tf32)
+//     lo = a − hi        (exact in f32; ≤ 13 significant bits, |lo| ≤ 2⁻¹¹|a|)
+// and the product is accumulated in f32 as  lo·hi' + hi·lo' + hi·hi'  (the lo·lo' term, ≤ 2⁻²² relative,
+// is dropped; small terms are added first).  The split is done IN THE KERNEL on the shared-memory tile
+// that TMA delivered, so weights are still read from HBM exactly once as plain f32.
+//
+// Structure (one 128×BN output tile per CTA, 10 warps):
+//   warp 0      TMA producer: cp.async.bulk.tensor.2d of the raw A/B k-blocks (SWIZZLE_64B/128B)
+//   warp 1      TMEM allocation + MMA issue: one elected lane issues tcgen05.mma.kind::tf32
+//               (3 per 8-wide k-step), tcgen05.commit releases the stage / publishes the accumulator
+//   warps 2-9   split workers: hi/lo conversion of each landed stage (generic proxy →
+//               fence.proxy.async → mbarrier), then the epilogue: tcgen05.ld of the accumulator
+//               (each warp its TMEM lane quarter) and the fused epilogue functor
+//   mbarriers per stage: full (TMA bytes) → ready (split done) → empty (MMA finished reading).
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace rama {
+
+constexpr int kGemmBM = 128;
+constexpr int kGemmWorkerWarps = 8;
+constexpr int kGemmThreads = (2 + kGemmWorkerWarps) * kWarp;  // 320
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst) {  // whole warp
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "n"(COLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {  // whole warp
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+// D[tmem] (+)= A[smem desc] · B[smem desc], kind::tf32, issued by ONE thread
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrive when all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 32 TMEM lanes (this warp's quarter) × 32 consecutive 32-bit columns → 32 registers per thread
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major shared-memory matrix descriptor (sm_100 format): rows of BK·4 bytes, 8-row groups of
+// 8·BK·4 bytes back to back, swizzle = row bytes (64 B or 128 B).  `addr` is the tile base
+// (1024-byte aligned) plus the k-step offset inside the swizzle row.
+template <int BK>
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t addr) {
+  constexpr uint64_t row_bytes = BK * 4;
+  static_assert(row_bytes == 64 || row_bytes == 128, "BK must be 16 or 32 floats");
+  constexpr uint64_t layout = row_bytes == 128 ? 2 : 4;  // SWIZZLE_128B = 2, SWIZZLE_64B = 4
+  constexpr uint64_t sbo = (8 * row_bytes) >> 4;         // stride between 8-row groups
+  return (uint64_t)((addr & 0x3FFFF) >> 4) | (1ull << 16) /* LBO (unused for swizzled K-major) */ | (sbo << 32) |
+         (1ull << 46) /* descriptor version: Blackwell */ | (layout << 61);
+}
+
+template <int BN>
+__host__ __device__ constexpr uint32_t umma_idesc_tf32() {
+  // c_format F32 (bit 4), a/b_format TF32 = 2 (bits 7-9, 10-12), both K-major, N>>3 at 17, M>>4 at 24
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kGemmBM >> 4) << 24);
+}
+
+// ---- kernel parameters ------------------------------------------------------------------------------
+struct GemmMaps {  // TMA descriptors: A and up to three B operands (grouped / dual launches)
+  CUtensorMap a;
+  CUtensorMap b[3];
+};
+
+struct GemmShape {
+  int M, N, K;   // logical problem (per group); rows ≥ M / cols ≥ N of a tile are masked
+  int hi_raw;    // 1: leave the raw f32 tile as the "hi" operand (hardware truncation), lo = a − trunc(a)
+};
+
+template <int BN, int BK, int STAGES>
+struct GemmSmem {
+  static constexpr int kRawBytes = (kGemmBM + BN) * BK * 4;     // [A_hi | B_hi] as delivered by TMA
+  static constexpr int kStageBytes = 2 * kRawBytes;             // + [A_lo | B_lo]
+  static constexpr int kABytes = kGemmBM * BK * 4;
+  static constexpr int kBarOff = STAGES * kStageBytes;
+  static constexpr int kNumBars = 3 * STAGES + 4;               // full/ready/empty per stage, accfull[2], accfree[2]
+  static constexpr int kTotal = kBarOff + kNumBars * 8 + 16 + 1024 /* alignment slack */;
+};
+
+// Accumulation.  The tensor core adds into its f32 TMEM accumulator with truncation, which drifts
+// linearly with the chain length (measured: 1.4e-4 relative at K = 4096 in one chain — far outside f32).
+// So the chain is kept short and the long sum is done by CUDA cores in round-to-nearest:
+//   * hi·hi products (the only ones whose rounding matters) accumulate over a CHUNK of CH k-blocks into
+//     one of two ping-pong TMEM accumulators; at the end of a chunk the workers tcgen05.ld it and add it
+//     into per-thread f32 registers while the tensor core already fills the other one;
+//   * the two cross terms (≤ 2⁻¹¹ of the result) share a third TMEM accumulator for the whole K loop.
+// TMEM columns: [0,BN) main 0 | [BN,2BN) main 1 | [2BN,3BN) cross terms.
+
+// Epilogue functor interface (device):
+//   static constexpr bool kDual        — the B tile stacks BN/2 rows of b[0] on BN/2 rows of b[1]; the epilogue
+//                                        receives both accumulator chunks of a column (SwiGLU)
+//   void operator()(int m, int n, const float (&v)[32], int group)               (!kDual)
+//   void operator()(int m, int n, const float (&v0)[32], const float (&v1)[32])  (kDual)
+// where m is the global row, n the first global column of the 32-column chunk.
+
+template <int BN, int BK, int STAGES, int CH, class Epi>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, const Epi epi_in) {
+  using SM = GemmSmem<BN, BK, STAGES>;
+  static_assert(BN == 64 || BN == 128, "BN: three accumulators must fit 512 TMEM columns");
+  static_assert(!Epi::kDual || BN == 128, "dual epilogue needs BN = 128");
+  constexpr int kTmemCols = BN == 128 ? 512 : 256;
+  constexpr int NSEG = BN / 64;  // 32-column segments per epilogue warp
+  extern __shared__ uint8_t gemm_smem_raw[];
+  const uint32_t base = (smem_u32(gemm_smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_full = base + SM::kBarOff;            // [STAGES] TMA bytes landed
+  const uint32_t bar_ready = bar_full + 8 * STAGES;        // [STAGES] hi/lo split done
+  const uint32_t bar_empty = bar_ready + 8 * STAGES;       // [STAGES] MMAs finished reading
+  const uint32_t bar_accfull = bar_empty + 8 * STAGES;     // [2] chunk accumulated in main[b]
+  const uint32_t bar_accfree = bar_accfull + 16;           // [2] main[b] drained into registers
+  const uint32_t tmem_slot = bar_accfree + 16;
+  uint8_t* gen_base = gemm_smem_raw + (base - smem_u32(gemm_smem_raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int group = blockIdx.z;
+  const int m0 = blockIdx.y * kGemmBM;
+  const int tile_n = blockIdx.x;
+  const int num_kb = (shp.K + BK - 1) / BK;
+  const int num_ch = (num_kb + CH - 1) / CH;
+  constexpr int kBoxN = Epi::kDual ? BN / 2 : BN;  // rows per B box
+  const CUtensorMap* mapB0 = &maps.b[Epi::kDual ? 0 : group];
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.a);
+    tma_prefetch_desc(mapB0);
+    if (Epi::kDual) tma_prefetch_desc(&maps.b[1]);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_ready + 8 * s, kGemmWorkerWarps);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_accfull + 8 * b, 1);
+      mbar_init(bar_accfree + 8 * b, kGemmWorkerWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen_base + SM::kBarOff + SM::kNumBars * 8);
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(bar_empty + 8 * s, ph ^ 1);
+        const uint32_t st = base + s * SM::kStageBytes;
+        mbar_arrive_expect_tx(bar_full + 8 * s, SM::kRawBytes);
+        tma_load_2d(st, &maps.a, bar_full + 8 * s, kb * BK, m0);
+        if (Epi::kDual) {
+          tma_load_2d(st + SM::kABytes, &maps.b[0], bar_full + 8 * s, kb * BK, tile_n * kBoxN);
+          tma_load_2d(st + SM::kABytes + kBoxN * BK * 4, &maps.b[1], bar_full + 8 * s, kb * BK, tile_n * kBoxN);
+        } else {
+          tma_load_2d(st + SM::kABytes, mapB0, bar_full + 8 * s, kb * BK, tile_n * BN);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_tf32<BN>();
+      const uint32_t cross = tmem + 2 * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        const int ch = kb / CH;
+        const bool first = kb % CH == 0, last = (kb % CH == CH - 1) || kb == num_kb - 1;
+        const uint32_t main = tmem + (ch & 1) * BN;
+        mbar_wait(bar_ready + 8 * s, ph);
+        tc_fence_after();
+        const uint32_t st = base + s * SM::kStageBytes;
+        const uint32_t a_hi = st, b_hi = st + SM::kABytes, a_lo = st + SM::kRawBytes, b_lo = a_lo + SM::kABytes;
+#pragma unroll
+        for (int ks = 0; ks < BK / 8; ++ks) {  // cross terms first: they never wait for a drain
+          const uint32_t off = ks * 32;        // 8 tf32 = 32 bytes inside the swizzle row
+          umma_tf32(cross, umma_smem_desc<BK>(a_lo + off), umma_smem_desc<BK>(b_hi + off), idesc, (kb | ks) != 0);
+          umma_tf32(cross, umma_smem_desc<BK>(a_hi + off), umma_smem_desc<BK>(b_lo + off), idesc, 1);
+        }
+        if (first && ch >= 2) {  // main[ch&1] still holds chunk ch-2 until the workers have drained it
+          mbar_wait(bar_accfree + 8 * (ch & 1), ((ch >> 1) - 1) & 1);
+          tc_fence_after();
+        }
+#pragma unroll
+        for (int ks = 0; ks < BK / 8; ++ks) {
+          const uint32_t off = ks * 32;
+          umma_tf32(main, umma_smem_desc<BK>(a_hi + off), umma_smem_desc<BK>(b_hi + off), idesc, !(first && ks == 0));
+        }
+        umma_commit(bar_empty + 8 * s);  // stage reusable once these MMAs have read it
+        if (last) umma_commit(bar_accfull + 8 * (ch & 1));
+      }
+    }
+  } else {
+    // ===== split workers + second-level accumulation, then epilogue =====
+    const int wt = threadIdx.x - 2 * kWarp;  // 0 .. 255
+    const int quarter = warp & 3;            // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;        // which half of the tile's columns
+    const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16);
+    // column (inside the tile) of this warp's segment j
+    auto seg_col = [&](int j) { return Epi::kDual ? j * (BN / 2) + 32 * half : half * (BN / 2) + 32 * j; };
+    float acc[NSEG][32];
+#pragma unroll
+    for (int j = 0; j < NSEG; ++j)
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc[j][i] = 0.f;
+
+    int drained = 0;
+    auto drain = [&](int c) {  // acc += main[c&1] (chunk c), then hand the buffer back
+      const int b = c & 1;
+      mbar_wait(bar_accfull + 8 * b, (c >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int j = 0; j < NSEG; ++j) {
+        float v[32];
+        tmem_ld_32x32(trow + b * BN + seg_col(j), v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[j][i] += v[i];
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_accfree + 8 * b);
+    };
+
+    constexpr int kVec = SM::kRawBytes / 16;
+    constexpr int kLag = STAGES > 2 ? 1 : 0;  // k-blocks split beyond a chunk's end before draining it
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb % STAGES;
+      const uint32_t ph = (kb / STAGES) & 1;
+      mbar_wait(bar_full + 8 * s, ph);
+      float4* raw = reinterpret_cast<float4*>(gen_base + s * SM::kStageBytes);
+      float4* lo = reinterpret_cast<float4*>(gen_base + s * SM::kStageBytes + SM::kRawBytes);
+#pragma unroll 4
+      for (int i = wt; i < kVec; i += kGemmWorkerWarps * kWarp) {
+        const float4 a = raw[i];
+        float4 h, l;
+        if (shp.hi_raw) {
+          h.x = __uint_as_float(__float_as_uint(a.x) & 0xFFFFE000u); h.y = __uint_as_float(__float_as_uint(a.y) & 0xFFFFE000u);
+          h.z = __uint_as_float(__float_as_uint(a.z) & 0xFFFFE000u); h.w = __uint_as_float(__float_as_uint(a.w) & 0xFFFFE000u);
+        } else {
+          uint32_t hx, hy, hz, hw;
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hx) : "f"(a.x));
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hy) : "f"(a.y));
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hz) : "f"(a.z));
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hw) : "f"(a.w));
+          h = make_float4(__uint_as_float(hx), __uint_as_float(hy), __uint_as_float(hz), __uint_as_float(hw));
+          raw[i] = h;
+        }
+        l.x = a.x - h.x; l.y = a.y - h.y; l.z = a.z - h.z; l.w = a.w - h.w;
+        lo[i] = l;
+      }
+      fence_proxy_async_smem();  // generic-proxy writes → visible to the tensor core's async proxy
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_ready + 8 * s);
+      // chunk c ends with k-block min((c+1)·CH, num_kb) − 1; drain it once kLag further blocks are split
+      while (drained < num_ch && min((drained + 1) * CH, num_kb) - 1 + kLag <= kb) drain(drained++);
+    }
+    while (drained < num_ch) drain(drained++);
+
+    // cross terms: complete once the last chunk's commit has fired (tcgen05.commit covers all prior MMAs)
+#pragma unroll
+    for (int j = 0; j < NSEG; ++j) {
+      float v[32];
+      tmem_ld_32x32(trow + 2 * BN + seg_col(j), v);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc[j][i] += v[i];
+    }
+    tc_fence_before();
+
+    Epi epi = epi_in;
+    const int m = m0 + quarter * 32 + lane;
+    if (m < shp.M) {
+      if constexpr (Epi::kDual) {
+        epi(m, tile_n * (BN / 2) + 32 * half, acc[0], acc[1]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < NSEG; ++j) epi(m, tile_n * BN + seg_col(j), acc[j], group);
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem);
+  }
+}
+
+// ---- epilogues ------------------------------------------------------------------------------------------
+
+// C[m][n] row-major with leading dimension ldc (per group: base + group·group_stride)
+struct EpiStoreNT {
+  static constexpr bool kDual = false;
+  float* c;
+  int ldc, N;
+  size_t group_stride;
+  __device__ __forceinline__ void operator()(int m, int n, const float (&v)[32], int group) const {
+    float* row = c + group * group_stride + (size_t)m * ldc + n;
+    if (n + 32 <= N && ((reinterpret_cast<uintptr_t>(row) & 15) == 0)) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        reinterpret_cast<float4*>(row)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (n + j < N) row[j] = v[j];
+    }
+  }
+};
+
+// Cᵀ store: out[n][m] (batched decode: the tile rows are weight rows r = m, columns are sequences b = n;
+// consecutive lanes hold consecutive r ⇒ coalesced rows of out[b][·])
+struct EpiStoreT {
+  static constexpr bool kDual = false;
+  float* c;      // out[b][ldc]
+  int ldc, N;    // N = number of sequences
+  __device__ __forceinline__ void operator()(int m, int n, const float (&v)[32], int) const {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (n + j < N) c[(size_t)(n + j) * ldc + m] = v[j];
+  }
+};
+
+}  // namespace rama

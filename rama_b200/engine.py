@@ -214,6 +214,10 @@ class GPU:
     def matmul(self, o: View, a: View, b: View, width: int, o_rows: int, o_cols: int):
         check(_lib.lib().rama_op_matmul(self.h, o.ptr(), a.ptr(), b.ptr(), width, o_rows, o_cols))
 
+    def matmul_nt(self, o: View, a: View, b: View, M: int, N: int, K: int, variant: int = 0, flags: int = 0):
+        """o[M][N] = a[M][K] · b[N][K]^T on the tensor cores (3xTF32); flags & 2 stores o^T."""
+        check(_lib.lib().rama_op_matmul_nt(self.h, o.ptr(), a.ptr(), b.ptr(), M, N, K, variant, flags))
+
     def softmax(self, x: View, n: int):
         check(_lib.lib().rama_op_softmax(self.h, x.ptr(), n))
 
