@@ -120,6 +120,21 @@ int rama_generate(rama_session* s, const int32_t* prompt, int32_t n_prompt, int3
                   float temperature, float topp, int32_t* out_tokens, float* elapsed_ms);
 int rama_session_sync(rama_session* s);
 
+/* Prompt prefill on the tensor cores: processes tokens[0..n) at positions [pos0, pos0+n) in one pass —
+ * every weight matrix is read once per prompt, the contractions run as tcgen05 3xTF32 GEMMs, attention is
+ * causal over the KV cache.  The reference has no such entry point: generate() feeds the prompt through
+ * forward() one token at a time and discards the logits (mod.rs:187-192).  Afterwards the session is in the
+ * state those n forward() calls would have left: KV-cache rows pos0..pos0+n-1 of every layer (infer.rs:31-33)
+ * and the logits of the last position (infer.rs:51), so rama_sample / rama_forward(token, pos0+n) continue
+ * from it.  Synchronous.  elapsed_ms (optional): CUDA-event time; ms_kind (optional): per-kind event times
+ * (slower: events around every launch); n_launch (optional): kernels launched. */
+enum rama_prefill_kind { RAMA_PK_GEMM = 0, RAMA_PK_ATTN, RAMA_PK_NORM, RAMA_PK_COMM, RAMA_PK_OTHER, RAMA_PK_COUNT };
+int rama_prefill(rama_session* s, const int32_t* tokens, int32_t n, int32_t pos0, float* elapsed_ms,
+                 float ms_kind[RAMA_PK_COUNT], int32_t* n_launch);
+/* rama_generate prefills prompts of at least min_rows rows (BOS included; default 16; 0 = never: every
+ * prompt token goes through the per-token step like the reference loop). */
+int rama_session_set_prefill(rama_session* s, int32_t min_rows);
+
 /* ≙ Device::to_cpu / RunState::into_state (device.rs:21, gpu.rs:196-209, hbm.rs:38-51).
  * buf in rama_state_buf; layouts as the reference's RunState (KV cache [L][T][D]).  Under TP the
  * sharded buffers (q,k,v,hb,hb2,att,caches) hold this rank's slice.  RAMA_S_ATT is only kept

@@ -13,6 +13,8 @@ SO_PATH = os.path.join(_HERE, "librama_b200.so")
 
 T_COUNT = 14
 K_COUNT = 9
+PK_COUNT = 5
+PREFILL_KINDS = ["gemm", "attn", "norm", "comm", "other"]
 KERNEL_KINDS = ["embed", "qkv", "attn", "wo", "w13", "w2", "cls", "sample", "comm"]
 STATE = ["x", "xb", "xb2", "hb", "hb2", "q", "k", "v", "att", "logits", "key_cache", "value_cache"]
 
@@ -59,6 +61,8 @@ _SIGS = {
     "rama_sample": ([vp, C.c_float, C.c_float, ip], C.c_int),
     "rama_generate": ([vp, ip, C.c_int32, C.c_int32, C.c_float, C.c_float, ip, fp], C.c_int),
     "rama_session_sync": ([vp], C.c_int),
+    "rama_prefill": ([vp, ip, C.c_int32, C.c_int32, fp, fp, ip], C.c_int),
+    "rama_session_set_prefill": ([vp, C.c_int32], C.c_int),
     "rama_state_to_host": ([vp, C.c_int, fp, sz, C.POINTER(sz)], C.c_int),
     "rama_logits_to_host": ([vp, fp, sz], C.c_int),
     "rama_session_set_debug": ([vp, C.c_int], C.c_int),

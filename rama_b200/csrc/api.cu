@@ -25,6 +25,7 @@
 #include "gemm_host.cuh"
 #include "gemv.cuh"
 #include "misc_kernels.cuh"
+#include "prefill.cuh"
 
 using namespace rama;
 
@@ -158,6 +159,11 @@ struct rama_session {
   int host_mode_set = 0;
   int launches = 0;
   bool logits_gathered = false;
+  // prefill workspace (allocated on first use): activations of one chunk of prompt rows
+  int pf_cap = 0;                // rows per chunk
+  int pf_min = 16;               // rama_generate: prompts of at least this many rows (BOS included) are prefilled
+  float *pf_x = nullptr, *pf_xn = nullptr, *pf_q = nullptr, *pf_att = nullptr, *pf_y = nullptr, *pf_h = nullptr;
+  int32_t* pf_tokens = nullptr;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -523,7 +529,8 @@ static void session_free(rama_session* s) {
   }
   void* bufs[] = {s->x0, s->x1, s->xfinal, s->xb, s->xb2, s->w2out, s->hb, s->hb2, s->q, s->k, s->v, s->att,
                   s->logits, s->key_cache, s->value_cache, s->attn_ws, s->tickets, s->part, s->sort_keys,
-                  s->ctrl, s->d_prompt, s->d_out, s->seq};
+                  s->ctrl, s->d_prompt, s->d_out, s->seq, s->pf_x, s->pf_xn, s->pf_q, s->pf_att, s->pf_y, s->pf_h,
+                  s->pf_tokens};
   for (void* b : bufs) if (b) cudaFree(b);
   if (s->h_ring) cudaFreeHost(s->h_ring);
   if (s->h_ret) cudaFreeHost(s->h_ret);
@@ -990,6 +997,9 @@ extern "C" int rama_sample(rama_session* s, float temperature, float topp, int32
   return read_ret(s, next);
 }
 
+static int prefill_run(rama_session* s, const int32_t* tokens, int32_t n, int32_t pos0, float ms_kind[RAMA_PK_COUNT],
+                       int32_t* n_launch);
+
 extern "C" int rama_generate(rama_session* s, const int32_t* prompt, int32_t n_prompt, int32_t steps,
                              float temperature, float topp, int32_t* out_tokens, float* elapsed_ms) {
   if (!s || (n_prompt > 0 && !prompt) || !out_tokens) return fail(RAMA_E_INVALID, "NULL argument");
@@ -1013,9 +1023,31 @@ extern "C" int rama_generate(rama_session* s, const int32_t* prompt, int32_t n_p
   h->n_prompt = n_prompt;
   h->temperature = temperature;
   h->topp = topp;
-  CK(cudaMemcpyAsync(s->ctrl, h, sizeof(StepCtrl), cudaMemcpyHostToDevice, s->stream));
-  CK(cudaEventRecord(s->ev0, s->stream));
-  for (int i = 0; i < steps; ++i) CK(cudaGraphLaunch(s->g_step[gi], s->stream));
+  // Long prompts: one tensor-core prefill pass over [BOS, prompt...] instead of n_prompt+1 per-token steps
+  // (the reference loop feeds them one by one and throws the logits away, mod.rs:187-192).
+  const bool use_prefill = s->pf_min > 0 && n_prompt + 1 >= s->pf_min && steps > n_prompt && n_prompt < c->T;
+  int first_step = 0;
+  if (use_prefill) {
+    std::vector<int32_t> rows((size_t)n_prompt + 1);
+    rows[0] = 1;  // BOS (mod.rs:182)
+    for (int i = 0; i < n_prompt; ++i) rows[i + 1] = prompt[i];
+    h->pos = n_prompt;  // the step whose logits prefill leaves behind
+    CK(cudaMemcpyAsync(s->ctrl, h, sizeof(StepCtrl), cudaMemcpyHostToDevice, s->stream));
+    CK(cudaMemcpyAsync(s->d_out, prompt, (size_t)n_prompt * sizeof(int32_t), cudaMemcpyHostToDevice, s->stream));
+    CK(cudaEventRecord(s->ev0, s->stream));
+    RK(prefill_run(s, rows.data(), n_prompt + 1, 0, nullptr, nullptr));
+    if (gi == 1) RK(gather_logits(s));
+    const int n_part = c->world > 1 ? c->world * c->sm_count : c->sm_count;
+    SampleParams sp{s->logits, s->part, n_part, s->cls_grid, c->V, s->ctrl, s->d_prompt, s->d_out, s->sort_keys,
+                    0.f, 0.f, 1, peer_in_parts(s)};
+    sample_kernel<<<1, kSampleThreads, 0, s->stream>>>(sp, 0);  // samples step n_prompt, feeds the token back
+    CK(cudaGetLastError());
+    first_step = n_prompt + 1;
+  } else {
+    CK(cudaMemcpyAsync(s->ctrl, h, sizeof(StepCtrl), cudaMemcpyHostToDevice, s->stream));
+    CK(cudaEventRecord(s->ev0, s->stream));
+  }
+  for (int i = first_step; i < steps; ++i) CK(cudaGraphLaunch(s->g_step[gi], s->stream));
   CK(cudaEventRecord(s->ev1, s->stream));
   if (steps) CK(cudaMemcpyAsync(out_tokens, s->d_out, steps * sizeof(int32_t), cudaMemcpyDeviceToHost, s->stream));
   s->logits_gathered = gi == 1;
@@ -1092,6 +1124,206 @@ extern "C" int rama_state_to_host(rama_session* s, int buf, float* dst, size_t n
   if (n < have) return fail(RAMA_E_INVALID, "buffer too small: %zu < %zu", n, have);
   CK(cudaMemcpyAsync(dst, src, have * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
   CK(cudaStreamSynchronize(s->stream));
+  return RAMA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// prompt prefill (tensor cores): ≙ the prompt part of generate()'s loop, mod.rs:187-192
+// ------------------------------------------------------------------------------------------------
+constexpr int kPrefillChunk = 512;
+
+static int ensure_prefill_ws(rama_session* s) {
+  if (s->pf_cap) return RAMA_OK;
+  rama_ctx* c = s->ctx;
+  const size_t cap = std::min(c->T, kPrefillChunk);
+  cudaError_t e = cudaSuccess;
+#define A(call) if (e == cudaSuccess) e = (call)
+  A(cudaMalloc((void**)&s->pf_x, cap * c->D * sizeof(float)));
+  A(cudaMalloc((void**)&s->pf_xn, cap * c->D * sizeof(float)));
+  A(cudaMalloc((void**)&s->pf_q, cap * c->Dq * sizeof(float)));
+  A(cudaMalloc((void**)&s->pf_att, cap * c->Dq * sizeof(float)));
+  A(cudaMalloc((void**)&s->pf_y, cap * c->D * sizeof(float)));
+  A(cudaMalloc((void**)&s->pf_h, cap * c->Fl * sizeof(float)));
+  A(cudaMalloc((void**)&s->pf_tokens, cap * sizeof(int32_t)));
+#undef A
+  if (e != cudaSuccess) return fail(RAMA_E_CUDA, "prefill workspace: %s", cudaGetErrorString(e));
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [&] {
+    attr_err = cudaFuncSetAttribute(prefill_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)prefill_attn_smem_bytes(kPfMaxHs));
+  });
+  if (attr_err != cudaSuccess) return fail(RAMA_E_CUDA, "prefill attention smem: %s", cudaGetErrorString(attr_err));
+  s->pf_cap = (int)cap;
+  return RAMA_OK;
+}
+
+struct PfTrace {  // optional per-launch CUDA-event timing by kind (rama_prefill's ms_kind)
+  cudaStream_t st;
+  bool on;
+  std::vector<cudaEvent_t> ev;
+  std::vector<int> kind;
+  void pre(int k) {
+    if (!on) return;
+    cudaEvent_t a; cudaEventCreate(&a); cudaEventRecord(a, st); ev.push_back(a); kind.push_back(k);
+  }
+  void post() {
+    if (!on) return;
+    cudaEvent_t b; cudaEventCreate(&b); cudaEventRecord(b, st); ev.push_back(b);
+  }
+};
+
+// one chunk of M ≤ pf_cap rows at positions [pos0, pos0+M); `last`: also produce the logits of the final row
+static int prefill_chunk(rama_session* s, const int32_t* tokens, int M, int pos0, bool last, PfTrace& tr, int* n_launch) {
+  rama_ctx* c = s->ctx;
+  cudaStream_t st = s->stream;
+  const int D = c->D, Dq = c->Dq, Fl = c->Fl, T = c->T, hs = c->hs, L = c->L;
+  const float* const* W = c->w;
+  int launches = 0;
+#define GK(kind, call)                                                                                         \
+  do {                                                                                                         \
+    tr.pre(kind);                                                                                              \
+    cudaError_t e_ = (call);                                                                                   \
+    if (e_ == cudaSuccess) e_ = cudaGetLastError();                                                            \
+    tr.post();                                                                                                 \
+    ++launches;                                                                                                \
+    if (e_ != cudaSuccess) return fail(RAMA_E_CUDA, "prefill launch %s: %s", #call, cudaGetErrorString(e_));   \
+  } while (0)
+  CK(cudaMemcpyAsync(s->pf_tokens, tokens, (size_t)M * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  tr.pre(RAMA_PK_OTHER);
+  prefill_embed_kernel<<<M, 256, 0, st>>>(s->pf_tokens, W[RAMA_T_TOKEN_EMBEDDING], s->pf_x, D, c->V, &s->ctrl->error, s->seq);
+  tr.post(); ++launches;
+  CK(cudaGetLastError());
+  for (int l = 0; l < L; ++l) {
+    float* kc = s->key_cache + (size_t)l * T * Dq;
+    float* vc = s->value_cache + (size_t)l * T * Dq;
+    // x += pending w2 output; xn = rmsnorm(x)·w_att   (infer.rs:19)
+    tr.pre(RAMA_PK_NORM);
+    prefill_addnorm_kernel<<<M, 256, 0, st>>>(s->pf_x, l == 0 ? nullptr : s->pf_y, W[RAMA_T_RMS_ATT] + (size_t)l * D, s->pf_xn, D);
+    tr.post(); ++launches;
+    // [wq;wk;wv] → RoPE → Q, KV-cache rows   (infer.rs:20-33)
+    {
+      GemmOperand A{s->pf_xn, (size_t)M, (size_t)D};
+      GemmOperand B[3] = {{W[RAMA_T_WQ] + (size_t)l * Dq * D, (size_t)Dq, (size_t)D},
+                          {W[RAMA_T_WK] + (size_t)l * Dq * D, (size_t)Dq, (size_t)D},
+                          {W[RAMA_T_WV] + (size_t)l * Dq * D, (size_t)Dq, (size_t)D}};
+      EpiQKVPrefill epi{s->pf_q, kc, vc, W[RAMA_T_FREQ_REAL], W[RAMA_T_FREQ_IMAG], pos0, Dq, hs / 2};
+      GK(RAMA_PK_GEMM, (launch_gemm_tf32x3<128, 4, 4>(st, A, B, 3, M, Dq, D, 0, epi)));
+    }
+    // causal attention of every prompt row over the cache   (infer.rs:34)
+    {
+      PrefillAttnParams ap{s->pf_q, kc, vc, s->pf_att, M, pos0, Dq, hs};
+      tr.pre(RAMA_PK_ATTN);
+      prefill_attn_kernel<<<dim3((M + kPfBQ - 1) / kPfBQ, c->Hl), kPfThreads, prefill_attn_smem_bytes(hs), st>>>(ap);
+      tr.post(); ++launches;
+    }
+    // wo   (infer.rs:35); the residual add is the next addnorm
+    {
+      GemmOperand A{s->pf_att, (size_t)M, (size_t)Dq};
+      GemmOperand B{W[RAMA_T_WO] + (size_t)l * D * Dq, (size_t)D, (size_t)Dq};
+      EpiStoreNT epi{s->pf_y, D, D, 0};
+      GK(RAMA_PK_GEMM, (launch_gemm_tf32x3<128, 4, 4>(st, A, &B, 1, M, D, Dq, 0, epi)));
+    }
+    if (c->world > 1) {
+      tr.pre(RAMA_PK_COMM);
+      NK(g_nccl.AllReduce(s->pf_y, s->pf_y, (size_t)M * D, kNcclFloat32, kNcclSum, c->comm, st));
+      tr.post(); ++launches;
+    }
+    tr.pre(RAMA_PK_NORM);
+    prefill_addnorm_kernel<<<M, 256, 0, st>>>(s->pf_x, s->pf_y, W[RAMA_T_RMS_FFN] + (size_t)l * D, s->pf_xn, D);
+    tr.post(); ++launches;
+    // [w1|w3] → SwiGLU   (infer.rs:39-45)
+    {
+      GemmOperand A{s->pf_xn, (size_t)M, (size_t)D};
+      GemmOperand B[2] = {{W[RAMA_T_W1] + (size_t)l * Fl * D, (size_t)Fl, (size_t)D},
+                          {W[RAMA_T_W3] + (size_t)l * Fl * D, (size_t)Fl, (size_t)D}};
+      EpiSwiGLUPrefill epi{s->pf_h, Fl};
+      GK(RAMA_PK_GEMM, (launch_gemm_tf32x3<128, 4, 4>(st, A, B, 2, M, Fl, D, 0, epi)));
+    }
+    // w2   (infer.rs:46)
+    {
+      GemmOperand A{s->pf_h, (size_t)M, (size_t)Fl};
+      GemmOperand B{W[RAMA_T_W2] + (size_t)l * D * Fl, (size_t)D, (size_t)Fl};
+      EpiStoreNT epi{s->pf_y, D, D, 0};
+      GK(RAMA_PK_GEMM, (launch_gemm_tf32x3<128, 4, 4>(st, A, &B, 1, M, D, Fl, 0, epi)));
+    }
+    if (c->world > 1) {
+      tr.pre(RAMA_PK_COMM);
+      NK(g_nccl.AllReduce(s->pf_y, s->pf_y, (size_t)M * D, kNcclFloat32, kNcclSum, c->comm, st));
+      tr.post(); ++launches;
+    }
+  }
+  CK(cudaGetLastError());
+  if (last) {
+    // only the last row's logits exist after the reference's prompt loop: x0 = x + y of that row, then the
+    // decode path's fused final-rmsnorm → classifier GEMV (infer.rs:49-51)
+    tr.pre(RAMA_PK_OTHER);
+    prefill_last_row_kernel<<<std::max(1, D / 256), 256, 0, st>>>(s->pf_x + (size_t)(M - 1) * D, s->pf_y + (size_t)(M - 1) * D, s->x0, D);
+    tr.post(); ++launches;
+    RK(init_parts(s));
+    ProNorm pro{s->x0, nullptr, s->x1, W[RAMA_T_RMS_FINAL], s->xfinal, PeerIn{}};
+    RowsPlain rows{c->wcls, D, c->Vl};
+    EpiCls epi{s->logits + c->v0, s->part + (size_t)c->rank * c->sm_count, c->Vl, c->v0, -INFINITY, -1, peer_out_parts(s)};
+    const int np = (c->Vl + 1) / 2, var = pick_variant(c, D / 4);
+    GK(RAMA_PK_OTHER, launch_gemv(var, pick_grid(c, var, np), st, 0, pro, rows, epi, D / 4, np));
+    if (c->world > 1 && !s->p2p) {
+      NK(g_nccl.AllGather(s->part + (size_t)c->rank * c->sm_count, s->part, (size_t)c->sm_count * 2, kNcclFloat32, c->comm, st));
+      ++launches;
+    }
+  }
+#undef GK
+  if (n_launch) *n_launch += launches;
+  return RAMA_OK;
+}
+
+static int prefill_run(rama_session* s, const int32_t* tokens, int32_t n, int32_t pos0, float ms_kind[RAMA_PK_COUNT],
+                       int32_t* n_launch) {
+  rama_ctx* c = s->ctx;
+  if (n <= 0 || pos0 < 0 || (long long)pos0 + n > c->T)  // the reference panics past seq_len (infer.rs:32)
+    return fail(RAMA_E_STATE, "prefill rows [%d, %d) outside [0, seq_len=%d)", pos0, pos0 + n, c->T);
+  for (int i = 0; i < n; ++i)
+    if (tokens[i] < 0 || tokens[i] >= c->V) return fail(RAMA_E_INVALID, "prompt token %d outside the vocabulary", tokens[i]);
+  CK(cudaSetDevice(c->device));
+  RK(ensure_prefill_ws(s));
+  PfTrace tr{s->stream, ms_kind != nullptr, {}, {}};
+  int launches = 0, rc = RAMA_OK;
+  for (int c0 = 0; c0 < n && rc == RAMA_OK; c0 += s->pf_cap) {
+    const int M = std::min(s->pf_cap, n - c0);
+    rc = prefill_chunk(s, tokens + c0, M, pos0 + c0, c0 + M == n, tr, &launches);
+  }
+  cudaError_t e = cudaSuccess;
+  if (tr.on) {
+    e = cudaStreamSynchronize(s->stream);
+    for (int i = 0; i < RAMA_PK_COUNT; ++i) ms_kind[i] = 0.f;
+    for (size_t i = 0; i < tr.kind.size() && 2 * i + 1 < tr.ev.size(); ++i) {
+      float t = 0.f;
+      if (rc == RAMA_OK && e == cudaSuccess) cudaEventElapsedTime(&t, tr.ev[2 * i], tr.ev[2 * i + 1]);
+      ms_kind[tr.kind[i]] += t;
+    }
+    for (cudaEvent_t ev : tr.ev) cudaEventDestroy(ev);
+  }
+  if (n_launch) *n_launch = launches;
+  s->logits_gathered = false;
+  if (rc != RAMA_OK) return rc;
+  if (e != cudaSuccess) return fail(RAMA_E_CUDA, "prefill: %s", cudaGetErrorString(e));
+  return RAMA_OK;
+}
+
+extern "C" int rama_prefill(rama_session* s, const int32_t* tokens, int32_t n, int32_t pos0, float* elapsed_ms,
+                            float ms_kind[RAMA_PK_COUNT], int32_t* n_launch) {
+  if (!s || !tokens) return fail(RAMA_E_INVALID, "NULL argument");
+  CK(cudaSetDevice(s->ctx->device));
+  CK(cudaEventRecord(s->ev0, s->stream));
+  RK(prefill_run(s, tokens, n, pos0, ms_kind, n_launch));
+  CK(cudaEventRecord(s->ev1, s->stream));
+  RK(read_ret(s, nullptr));  // synchronises; surfaces device-side errors
+  if (elapsed_ms) CK(cudaEventElapsedTime(elapsed_ms, s->ev0, s->ev1));
+  return RAMA_OK;
+}
+
+extern "C" int rama_session_set_prefill(rama_session* s, int32_t min_rows) {
+  if (!s) return fail(RAMA_E_INVALID, "NULL session");
+  s->pf_min = min_rows;
   return RAMA_OK;
 }
 
@@ -1308,24 +1540,26 @@ extern "C" int rama_op_matmul_nt(rama_ctx* c, float* out, const float* a, const 
   OP_PRE(c);
   if (!out || !a || !b || !M || !N || !K) return fail(RAMA_E_INVALID, "empty matmul_nt");
   if (K % 4) return fail(RAMA_E_INVALID, "K %% 4 != 0 (TMA needs 16-byte row pitch; the reference steps k by 4, cpu.rs:142)");
-  const int hi_raw = flags & 1;
+  const int hi_round = flags & 1;
   const bool transposed = (flags & 2) != 0;
   GemmOperand A{a, M, K}, B{b, N, K};
   cudaError_t e;
+  const int m = (int)M, n = (int)N, k = (int)K;
   if (transposed) {
-    EpiStoreT epi{out, (int)M, (int)N};
+    EpiStoreT epi{out, m, n};
     switch (variant) {
-      case 0: e = launch_gemm_tf32x3<64, 32, 4, 4>(c->op_stream, A, &B, 1, (int)M, (int)N, (int)K, hi_raw, epi); break;
-      case 1: e = launch_gemm_tf32x3<64, 16, 6, 8>(c->op_stream, A, &B, 1, (int)M, (int)N, (int)K, hi_raw, epi); break;
+      case 0: e = launch_gemm_tf32x3<64, 6, 2>(c->op_stream, A, &B, 1, m, n, k, hi_round, epi); break;
+      case 1: e = launch_gemm_tf32x3<64, 6, 4>(c->op_stream, A, &B, 1, m, n, k, hi_round, epi); break;
+      case 2: e = launch_gemm_tf32x3<64, 4, 2>(c->op_stream, A, &B, 1, m, n, k, hi_round, epi); break;
       default: return fail(RAMA_E_INVALID, "matmul_nt: unknown transposed variant %d", variant);
     }
   } else {
-    EpiStoreNT epi{out, (int)N, (int)N, 0};
+    EpiStoreNT epi{out, n, n, 0};
     switch (variant) {
-      case 0: e = launch_gemm_tf32x3<128, 32, 3, 4>(c->op_stream, A, &B, 1, (int)M, (int)N, (int)K, hi_raw, epi); break;
-      case 1: e = launch_gemm_tf32x3<128, 16, 6, 8>(c->op_stream, A, &B, 1, (int)M, (int)N, (int)K, hi_raw, epi); break;
-      case 2: e = launch_gemm_tf32x3<128, 32, 3, 2>(c->op_stream, A, &B, 1, (int)M, (int)N, (int)K, hi_raw, epi); break;
-      case 3: e = launch_gemm_tf32x3<128, 32, 3, 8>(c->op_stream, A, &B, 1, (int)M, (int)N, (int)K, hi_raw, epi); break;
+      case 0: e = launch_gemm_tf32x3<128, 4, 2>(c->op_stream, A, &B, 1, m, n, k, hi_round, epi); break;
+      case 1: e = launch_gemm_tf32x3<128, 4, 4>(c->op_stream, A, &B, 1, m, n, k, hi_round, epi); break;
+      case 2: e = launch_gemm_tf32x3<128, 3, 2>(c->op_stream, A, &B, 1, m, n, k, hi_round, epi); break;
+      case 3: e = launch_gemm_tf32x3<64, 6, 2>(c->op_stream, A, &B, 1, m, n, k, hi_round, epi); break;
       default: return fail(RAMA_E_INVALID, "matmul_nt: unknown variant %d", variant);
     }
   }

@@ -48,12 +48,13 @@ struct GemmOperand {  // a K-major f32 matrix [rows][K], row pitch ld
 };
 
 // C (per group g < n_groups) = A · B[g]ᵀ;  for a dual epilogue B[0] and B[1] are stacked inside one tile.
-template <int BN, int BK, int STAGES, int CH, class Epi>
+template <int BN, int STAGES, int CH, class Epi>
 cudaError_t launch_gemm_tf32x3(cudaStream_t st, const GemmOperand& A, const GemmOperand* B, int n_b, int M, int N,
-                               int K, int hi_raw, const Epi& epi) {
-  using SM = GemmSmem<BN, BK, STAGES>;
+                               int K, int hi_round, const Epi& epi) {
+  using SM = GemmSmem<BN, STAGES>;
+  constexpr int BK = kGemmBK;
   static_assert(SM::kTotal <= 227 * 1024, "tile does not fit shared memory");
-  auto kern = gemm_tf32x3_kernel<BN, BK, STAGES, CH, Epi>;
+  auto kern = gemm_tf32x3_kernel<BN, STAGES, CH, Epi>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal); });
@@ -66,7 +67,7 @@ cudaError_t launch_gemm_tf32x3(cudaStream_t st, const GemmOperand& A, const Gemm
   for (int i = 0; i < n_b; ++i)
     if (!make_tmap_2d(&maps.b[i], B[i].p, B[i].rows, (size_t)K, B[i].ld, box_n, BK)) return cudaErrorInvalidValue;
   for (int i = n_b; i < 3; ++i) maps.b[i] = maps.b[0];
-  GemmShape shp{M, N, K, hi_raw};
+  GemmShape shp{M, N, K, hi_round};
   const int groups = Epi::kDual ? 1 : n_b;
   dim3 grid((N + box_n - 1) / box_n, (M + kGemmBM - 1) / kGemmBM, groups);
   kern<<<grid, kGemmThreads, SM::kTotal, st>>>(maps, shp, epi);

@@ -15,13 +15,19 @@
 // that TMA delivered, so weights are still read from HBM exactly once as plain f32.
 //
 // Structure (one 128×BN output tile per CTA, 10 warps):
-//   warp 0      TMA producer: cp.async.bulk.tensor.2d of the raw A/B k-blocks (SWIZZLE_64B/128B)
+//   warp 0      TMA producer: cp.async.bulk.tensor.2d of the raw A/B k-blocks (SWIZZLE_128B)
 //   warp 1      TMEM allocation + MMA issue: one elected lane issues tcgen05.mma.kind::tf32
-//               (3 per 8-wide k-step), tcgen05.commit releases the stage / publishes the accumulator
-//   warps 2-9   split workers: hi/lo conversion of each landed stage (generic proxy →
-//               fence.proxy.async → mbarrier), then the epilogue: tcgen05.ld of the accumulator
-//               (each warp its TMEM lane quarter) and the fused epilogue functor
+//               (3 per 8-wide k-step), tcgen05.commit releases the stage / publishes an accumulator
+//   warps 2-9   workers: per landed stage they (a) read their row of the A tile from shared memory,
+//               split it and tcgen05.st BOTH halves into TMEM — the MMA takes A from TMEM, so the
+//               128-row operand is read from shared memory once instead of six times —, (b) write the
+//               lo half of the B tile next to the raw one (the raw f32 tile itself is the hi operand: the
+//               tensor core ignores the 13 low mantissa bits, verified against an explicit split);
+//               and they own the second-level accumulation (below) and the fused epilogue
 //   mbarriers per stage: full (TMA bytes) → ready (split done) → empty (MMA finished reading).
+// Shared-memory bandwidth, not the tensor pipe, is what bounds an f32-split GEMM (every k-block is written by
+// TMA, read and partly re-written by the split, then read by 3 MMAs per k-step); the A-through-TMEM path cuts
+// that traffic from 192 KB to 128 KB per k-block at BN = 128 and from 144 KB to 80 KB at BN = 64.
 #pragma once
 #include <cuda.h>
 
@@ -92,6 +98,27 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same with the A operand in tensor memory (lane = row, 8 consecutive 32-bit columns = the k-step)
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// registers → 32 TMEM lanes (this warp's quarter) × 16 consecutive columns
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // mbarrier arrive when all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -141,27 +168,32 @@ struct GemmMaps {  // TMA descriptors: A and up to three B operands (grouped / d
 
 struct GemmShape {
   int M, N, K;   // logical problem (per group); rows ≥ M / cols ≥ N of a tile are masked
-  int hi_raw;    // 1: leave the raw f32 tile as the "hi" operand (hardware truncation), lo = a − trunc(a)
+  int hi_round;  // 1: also rewrite the B tile's hi half rounded to nearest (default 0: raw tile = hi by truncation)
 };
 
-template <int BN, int BK, int STAGES>
+constexpr int kGemmBK = 32;  // floats per k-block = one 128-byte swizzle row
+
+template <int BN, int STAGES>
 struct GemmSmem {
-  static constexpr int kRawBytes = (kGemmBM + BN) * BK * 4;     // [A_hi | B_hi] as delivered by TMA
-  static constexpr int kStageBytes = 2 * kRawBytes;             // + [A_lo | B_lo]
-  static constexpr int kABytes = kGemmBM * BK * 4;
+  static constexpr int kABytes = kGemmBM * kGemmBK * 4;         // raw A k-block (only the workers read it)
+  static constexpr int kBBytes = BN * kGemmBK * 4;              // raw B k-block = hi operand
+  static constexpr int kTxBytes = kABytes + kBBytes;
+  static constexpr int kStageBytes = kABytes + 2 * kBBytes;     // + B lo
   static constexpr int kBarOff = STAGES * kStageBytes;
   static constexpr int kNumBars = 3 * STAGES + 4;               // full/ready/empty per stage, accfull[2], accfree[2]
   static constexpr int kTotal = kBarOff + kNumBars * 8 + 16 + 1024 /* alignment slack */;
+  // TMEM: [0,BN) acc 0 | [BN,2BN) acc 1 | then per stage 32 columns A hi + 32 columns A lo
+  static constexpr int kTmemCols = 512;
+  static_assert(2 * BN + 64 * STAGES <= 512, "accumulators + A stages exceed tensor memory");
 };
 
 // Accumulation.  The tensor core adds into its f32 TMEM accumulator with truncation, which drifts
 // linearly with the chain length (measured: 1.4e-4 relative at K = 4096 in one chain — far outside f32).
-// So the chain is kept short and the long sum is done by CUDA cores in round-to-nearest:
-//   * hi·hi products (the only ones whose rounding matters) accumulate over a CHUNK of CH k-blocks into
-//     one of two ping-pong TMEM accumulators; at the end of a chunk the workers tcgen05.ld it and add it
-//     into per-thread f32 registers while the tensor core already fills the other one;
-//   * the two cross terms (≤ 2⁻¹¹ of the result) share a third TMEM accumulator for the whole K loop.
-// TMEM columns: [0,BN) main 0 | [BN,2BN) main 1 | [2BN,3BN) cross terms.
+// So the chain is kept short and the long sum is done by CUDA cores in round-to-nearest: a CHUNK of CH
+// k-blocks accumulates into one of two ping-pong TMEM accumulators; at the end of a chunk the workers
+// tcgen05.ld it and add it into per-thread f32 registers while the tensor core already fills the other.
+// Chunk partials have random signs, so the truncation bias (≈ 3·CH·4·½ ulp of a partial) no longer adds up
+// coherently: CH = 2 (64 k) keeps the result within ~1.5e-6 relative, the class of an f32 FMA GEMM.
 
 // Epilogue functor interface (device):
 //   static constexpr bool kDual        — the B tile stacks BN/2 rows of b[0] on BN/2 rows of b[1]; the epilogue
@@ -170,21 +202,21 @@ struct GemmSmem {
 //   void operator()(int m, int n, const float (&v0)[32], const float (&v1)[32])  (kDual)
 // where m is the global row, n the first global column of the 32-column chunk.
 
-template <int BN, int BK, int STAGES, int CH, class Epi>
+template <int BN, int STAGES, int CH, class Epi>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, const Epi epi_in) {
-  using SM = GemmSmem<BN, BK, STAGES>;
-  static_assert(BN == 64 || BN == 128, "BN: three accumulators must fit 512 TMEM columns");
+  using SM = GemmSmem<BN, STAGES>;
+  constexpr int BK = kGemmBK;
+  static_assert(BN == 64 || BN == 128, "BN");
   static_assert(!Epi::kDual || BN == 128, "dual epilogue needs BN = 128");
-  constexpr int kTmemCols = BN == 128 ? 512 : 256;
   constexpr int NSEG = BN / 64;  // 32-column segments per epilogue warp
   extern __shared__ uint8_t gemm_smem_raw[];
   const uint32_t base = (smem_u32(gemm_smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_full = base + SM::kBarOff;            // [STAGES] TMA bytes landed
-  const uint32_t bar_ready = bar_full + 8 * STAGES;        // [STAGES] hi/lo split done
+  const uint32_t bar_ready = bar_full + 8 * STAGES;        // [STAGES] split done (A in TMEM, B lo in smem)
   const uint32_t bar_empty = bar_ready + 8 * STAGES;       // [STAGES] MMAs finished reading
-  const uint32_t bar_accfull = bar_empty + 8 * STAGES;     // [2] chunk accumulated in main[b]
-  const uint32_t bar_accfree = bar_accfull + 16;           // [2] main[b] drained into registers
+  const uint32_t bar_accfull = bar_empty + 8 * STAGES;     // [2] chunk accumulated in acc[b]
+  const uint32_t bar_accfree = bar_accfull + 16;           // [2] acc[b] drained into registers
   const uint32_t tmem_slot = bar_accfree + 16;
   uint8_t* gen_base = gemm_smem_raw + (base - smem_u32(gemm_smem_raw));
 
@@ -212,11 +244,12 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, c
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+  if (warp == 1) tmem_alloc<SM::kTmemCols>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen_base + SM::kBarOff + SM::kNumBars * 8);
+  const uint32_t tmem_a = tmem + 2 * BN;  // A stages: stage s at +64·s (hi), +64·s+32 (lo)
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -226,7 +259,7 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, c
         const uint32_t ph = (kb / STAGES) & 1;
         mbar_wait(bar_empty + 8 * s, ph ^ 1);
         const uint32_t st = base + s * SM::kStageBytes;
-        mbar_arrive_expect_tx(bar_full + 8 * s, SM::kRawBytes);
+        mbar_arrive_expect_tx(bar_full + 8 * s, SM::kTxBytes);
         tma_load_2d(st, &maps.a, bar_full + 8 * s, kb * BK, m0);
         if (Epi::kDual) {
           tma_load_2d(st + SM::kABytes, &maps.b[0], bar_full + 8 * s, kb * BK, tile_n * kBoxN);
@@ -240,41 +273,36 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, c
     // ===== MMA issuer =====
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_tf32<BN>();
-      const uint32_t cross = tmem + 2 * BN;
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
         const int ch = kb / CH;
         const bool first = kb % CH == 0, last = (kb % CH == CH - 1) || kb == num_kb - 1;
-        const uint32_t main = tmem + (ch & 1) * BN;
-        mbar_wait(bar_ready + 8 * s, ph);
-        tc_fence_after();
-        const uint32_t st = base + s * SM::kStageBytes;
-        const uint32_t a_hi = st, b_hi = st + SM::kABytes, a_lo = st + SM::kRawBytes, b_lo = a_lo + SM::kABytes;
-#pragma unroll
-        for (int ks = 0; ks < BK / 8; ++ks) {  // cross terms first: they never wait for a drain
-          const uint32_t off = ks * 32;        // 8 tf32 = 32 bytes inside the swizzle row
-          umma_tf32(cross, umma_smem_desc<BK>(a_lo + off), umma_smem_desc<BK>(b_hi + off), idesc, (kb | ks) != 0);
-          umma_tf32(cross, umma_smem_desc<BK>(a_hi + off), umma_smem_desc<BK>(b_lo + off), idesc, 1);
-        }
-        if (first && ch >= 2) {  // main[ch&1] still holds chunk ch-2 until the workers have drained it
+        const uint32_t acc = tmem + (ch & 1) * BN;
+        if (first && ch >= 2) {  // acc[ch&1] still holds chunk ch-2 until the workers have drained it
           mbar_wait(bar_accfree + 8 * (ch & 1), ((ch >> 1) - 1) & 1);
           tc_fence_after();
         }
+        mbar_wait(bar_ready + 8 * s, ph);
+        tc_fence_after();
+        const uint32_t b_hi = base + s * SM::kStageBytes + SM::kABytes, b_lo = b_hi + SM::kBBytes;
+        const uint32_t a_hi = tmem_a + 64 * s, a_lo = a_hi + 32;
 #pragma unroll
         for (int ks = 0; ks < BK / 8; ++ks) {
-          const uint32_t off = ks * 32;
-          umma_tf32(main, umma_smem_desc<BK>(a_hi + off), umma_smem_desc<BK>(b_hi + off), idesc, !(first && ks == 0));
+          const uint64_t dbh = umma_smem_desc<BK>(b_hi + ks * 32), dbl = umma_smem_desc<BK>(b_lo + ks * 32);
+          umma_tf32_ts(acc, a_lo + 8 * ks, dbh, idesc, !(first && ks == 0));  // small terms first
+          umma_tf32_ts(acc, a_hi + 8 * ks, dbl, idesc, 1);
+          umma_tf32_ts(acc, a_hi + 8 * ks, dbh, idesc, 1);
         }
-        umma_commit(bar_empty + 8 * s);  // stage reusable once these MMAs have read it
+        umma_commit(bar_empty + 8 * s);  // smem stage + TMEM A stage reusable once these MMAs have read them
         if (last) umma_commit(bar_accfull + 8 * (ch & 1));
       }
     }
   } else {
-    // ===== split workers + second-level accumulation, then epilogue =====
+    // ===== workers: operand split, second-level accumulation, epilogue =====
     const int wt = threadIdx.x - 2 * kWarp;  // 0 .. 255
     const int quarter = warp & 3;            // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;        // which half of the tile's columns
+    const int half = (warp - 2) >> 2;        // which half of the k-block (split) / of the tile's columns (drain)
     const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16);
     // column (inside the tile) of this warp's segment j
     auto seg_col = [&](int j) { return Epi::kDual ? j * (BN / 2) + 32 * half : half * (BN / 2) + 32 * j; };
@@ -285,7 +313,7 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, c
       for (int i = 0; i < 32; ++i) acc[j][i] = 0.f;
 
     int drained = 0;
-    auto drain = [&](int c) {  // acc += main[c&1] (chunk c), then hand the buffer back
+    auto drain = [&](int c) {  // acc += acc_tmem[c&1] (chunk c), then hand the buffer back
       const int b = c & 1;
       mbar_wait(bar_accfull + 8 * b, (c >> 1) & 1);
       tc_fence_after();
@@ -301,50 +329,69 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, c
       if (lane == 0) mbar_arrive(bar_accfree + 8 * b);
     };
 
-    constexpr int kVec = SM::kRawBytes / 16;
-    constexpr int kLag = STAGES > 2 ? 1 : 0;  // k-blocks split beyond a chunk's end before draining it
+    // A: this thread owns row (quarter·32 + lane) of the tile and 16-byte chunks [4·half, 4·half+4) of its
+    // 128-byte row; SWIZZLE_128B puts chunk c of row r at r·128 + ((c ^ (r & 7)) · 16)
+    const int arow = quarter * 32 + lane;
+    const uint32_t arow_off = arow * 128;
+    constexpr int kBVec = SM::kBBytes / 16;
+    constexpr int kLag = 1;  // k-blocks split beyond a chunk's end before draining it
     for (int kb = 0; kb < num_kb; ++kb) {
       const int s = kb % STAGES;
       const uint32_t ph = (kb / STAGES) & 1;
       mbar_wait(bar_full + 8 * s, ph);
-      float4* raw = reinterpret_cast<float4*>(gen_base + s * SM::kStageBytes);
-      float4* lo = reinterpret_cast<float4*>(gen_base + s * SM::kStageBytes + SM::kRawBytes);
-#pragma unroll 4
-      for (int i = wt; i < kVec; i += kGemmWorkerWarps * kWarp) {
-        const float4 a = raw[i];
-        float4 h, l;
-        if (shp.hi_raw) {
-          h.x = __uint_as_float(__float_as_uint(a.x) & 0xFFFFE000u); h.y = __uint_as_float(__float_as_uint(a.y) & 0xFFFFE000u);
-          h.z = __uint_as_float(__float_as_uint(a.z) & 0xFFFFE000u); h.w = __uint_as_float(__float_as_uint(a.w) & 0xFFFFE000u);
-        } else {
-          uint32_t hx, hy, hz, hw;
-          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hx) : "f"(a.x));
-          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hy) : "f"(a.y));
-          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hz) : "f"(a.z));
-          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hw) : "f"(a.w));
-          h = make_float4(__uint_as_float(hx), __uint_as_float(hy), __uint_as_float(hz), __uint_as_float(hw));
-          raw[i] = h;
+      const uint8_t* st = gen_base + s * SM::kStageBytes;
+      {
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int chunk = 4 * half + c;
+          const float4 a = *reinterpret_cast<const float4*>(st + arow_off + ((chunk ^ (arow & 7)) << 4));
+          const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            uint32_t h;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(av[e]));
+            hi[4 * c + e] = h;
+            lo[4 * c + e] = __float_as_uint(av[e] - __uint_as_float(h));
+          }
         }
-        l.x = a.x - h.x; l.y = a.y - h.y; l.z = a.z - h.z; l.w = a.w - h.w;
-        lo[i] = l;
+        const uint32_t ta = trow + 2 * BN + 64 * s + 16 * half;
+        tmem_st_32x16(ta, hi);
+        tmem_st_32x16(ta + 32, lo);
+      }
+      {
+        const float4* braw = reinterpret_cast<const float4*>(st + SM::kABytes);
+        float4* bhi = reinterpret_cast<float4*>(const_cast<uint8_t*>(st) + SM::kABytes);
+        float4* blo = reinterpret_cast<float4*>(const_cast<uint8_t*>(st) + SM::kABytes + SM::kBBytes);
+#pragma unroll
+        for (int i = wt; i < kBVec; i += kGemmWorkerWarps * kWarp) {
+          const float4 a = braw[i];
+          float4 h, l;
+          if (shp.hi_round) {
+            uint32_t hx, hy, hz, hw;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hx) : "f"(a.x));
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hy) : "f"(a.y));
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hz) : "f"(a.z));
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hw) : "f"(a.w));
+            h = make_float4(__uint_as_float(hx), __uint_as_float(hy), __uint_as_float(hz), __uint_as_float(hw));
+            bhi[i] = h;
+          } else {  // what the tensor core will see of the raw tile
+            h.x = __uint_as_float(__float_as_uint(a.x) & 0xFFFFE000u); h.y = __uint_as_float(__float_as_uint(a.y) & 0xFFFFE000u);
+            h.z = __uint_as_float(__float_as_uint(a.z) & 0xFFFFE000u); h.w = __uint_as_float(__float_as_uint(a.w) & 0xFFFFE000u);
+          }
+          l.x = a.x - h.x; l.y = a.y - h.y; l.z = a.z - h.z; l.w = a.w - h.w;
+          blo[i] = l;
+        }
       }
       fence_proxy_async_smem();  // generic-proxy writes → visible to the tensor core's async proxy
+      tmem_st_wait();            // A halves have landed in TMEM
+      tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_ready + 8 * s);
       // chunk c ends with k-block min((c+1)·CH, num_kb) − 1; drain it once kLag further blocks are split
       while (drained < num_ch && min((drained + 1) * CH, num_kb) - 1 + kLag <= kb) drain(drained++);
     }
     while (drained < num_ch) drain(drained++);
-
-    // cross terms: complete once the last chunk's commit has fired (tcgen05.commit covers all prior MMAs)
-#pragma unroll
-    for (int j = 0; j < NSEG; ++j) {
-      float v[32];
-      tmem_ld_32x32(trow + 2 * BN + seg_col(j), v);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) acc[j][i] += v[i];
-    }
-    tc_fence_before();
 
     Epi epi = epi_in;
     const int m = m0 + quarter * 32 + lane;
@@ -360,7 +407,7 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, c
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<kTmemCols>(tmem);
+    tmem_dealloc<SM::kTmemCols>(tmem);
   }
 }
 

@@ -328,6 +328,22 @@ class Session:
     def sync(self):
         check(_lib.lib().rama_session_sync(self.h))
 
+    def prefill(self, tokens: Sequence[int], pos0: int = 0, profile: bool = False):
+        """Tensor-core prefill of `tokens` at positions [pos0, pos0+len): leaves the KV cache and the last
+        position's logits as len(tokens) forward() calls would (mod.rs:187-192).  Returns
+        (elapsed_ms, {kind: ms} or None, kernel launches)."""
+        t = np.asarray(list(tokens), dtype=np.int32)
+        ms = C.c_float()
+        kinds = (C.c_float * _lib.PK_COUNT)()
+        nl = C.c_int32()
+        check(_lib.lib().rama_prefill(self.h, t.ctypes.data_as(ip), t.size, pos0, C.byref(ms),
+                                      kinds if profile else None, C.byref(nl)))
+        return ms.value, ({k: kinds[i] for i, k in enumerate(_lib.PREFILL_KINDS)} if profile else None), nl.value
+
+    def set_prefill(self, min_rows: int):
+        """generate(): prompts of at least min_rows rows (BOS included) use prefill; 0 = never."""
+        check(_lib.lib().rama_session_set_prefill(self.h, min_rows))
+
     def generate(self, prompt: Sequence[int], steps: int, temperature: float = 0.0, topp: float = 0.9):
         """Device-resident loop. Returns (tokens[steps], elapsed_ms of the step loop)."""
         pr = np.asarray(list(prompt), dtype=np.int32)

@@ -44,19 +44,21 @@ def test_matmul_nt_f32_accuracy(gpu, shape, variant):
     M, N, K = shape
     err, ref_err = run(gpu, M, N, K, variant, 0)
     # 3xTF32 drops the lo·lo term (2^-22 relative per product): allow a few times the f32 GEMM error
-    assert err < max(8 * ref_err, 2e-6), (err, ref_err)
+    assert err < max(8 * ref_err, 6e-6), (err, ref_err)
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 @pytest.mark.parametrize("shape", [(4096, 64, 4096), (11008, 64, 4096), (4096, 64, 11008), (288, 3, 288), (1000, 17, 64)])
 def test_matmul_nt_transposed_store(gpu, shape, variant):
     M, N, K = shape
     err, ref_err = run(gpu, M, N, K, variant, 2)
-    assert err < max(8 * ref_err, 2e-6), (err, ref_err)
+    assert err < max(8 * ref_err, 6e-6), (err, ref_err)
 
 
-def test_matmul_nt_hi_raw_mode(gpu):
-    """flags bit 0: hi operand = raw f32 (relies on the tensor core ignoring the low 13 mantissa bits)."""
+def test_matmul_nt_hi_round_mode(gpu):
+    """flags bit 0: the B tile's hi half is rewritten rounded-to-nearest instead of relying on the tensor
+    core ignoring the 13 low mantissa bits of the raw tile (the default).  Both must be f32-accurate."""
     err, ref_err = run(gpu, 256, 512, 2048, 0, 1)
-    print("hi_raw err", err, "f32 gemm err", ref_err)
-    assert err < 1e-3  # recorded, not relied upon: the default rounds hi explicitly
+    err0, _ = run(gpu, 256, 512, 2048, 0, 0)
+    print("hi_round err", err, "raw-hi err", err0, "f32 gemm err", ref_err)
+    assert err < max(8 * ref_err, 2e-6) and err0 < max(8 * ref_err, 2e-6)
