@@ -44,6 +44,16 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_tensor_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["bf16_tflops"]), "measured"
+        except Exception:
+            pass
+    return 1590.0, "fallback"
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -143,6 +153,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-tokens", type=int, default=0, help="tokens of the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-prefill", action="store_true", help="skip the prompt-prefill (tensor core) measurement")
     ap.add_argument("--seed", type=int, default=1234)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -245,6 +256,36 @@ def main():
     value = total_tokens / (dev_ms * 1e-3)
     e2e_value = total_tokens / (e2e_ms * 1e-3)
 
+    # ---- prompt prefill (BASELINE config 4): 512 prompt rows in one tensor-core pass ----
+    pf = None
+    if not args.no_prefill:
+        n_pf = min(512, cfg.seq_len)
+        rng_tokens = [1] + [(7919 * i + 13) % cfg.vocab_size for i in range(1, n_pf)]
+        psess = Session(gpu)
+        for _ in range(3):
+            psess.prefill(rng_tokens, 0)
+        barrier()
+        pf_ms = [psess.prefill(rng_tokens, 0)[0] for _ in range(5)]
+        barrier()
+        _, pf_kinds, pf_launches = psess.prefill(rng_tokens, 0, profile=True)
+        pt = torch.tensor([sum(pf_ms) / len(pf_ms)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(pt, op=dist.ReduceOp.MAX)
+        pf_avg = float(pt.item())
+        D, F, L, V = cfg.dim, cfg.hidden_dim, cfg.n_layers, cfg.vocab_size
+        gemm_flops = 2.0 * n_pf * L * (4 * D * D + 3 * D * F) / world      # per GPU, f32-equivalent (2MNK)
+        attn_flops = 2.0 * 2 * L * D * n_pf * (n_pf + 1) / 2 / world       # causal QK^T + PV
+        psess.close()
+        pf = {"rows": n_pf, "ms": round(pf_avg, 3), "tok_per_s": round(n_pf / (pf_avg * 1e-3), 1),
+              "speedup_vs_per_token_steps": None, "launches": pf_launches,
+              "gemm_f32_equiv_tflops_per_gpu": round(gemm_flops / (pf_kinds["gemm"] * 1e-3) / 1e12, 1),
+              "gemm_tf32_tflops_issued_per_gpu": round(3 * gemm_flops / (pf_kinds["gemm"] * 1e-3) / 1e12, 1),
+              "attn_f32_tflops_per_gpu": round(attn_flops / max(pf_kinds["attn"], 1e-6) / 1e9, 2),
+              "ms_by_kind": {k: round(v, 3) for k, v in pf_kinds.items()},
+              "what": "rama_prefill: tcgen05 kind::tf32 GEMMs with in-kernel hi/lo split (3 MMAs per k-step, f32-accurate), "
+                      "fused RoPE/KV-write and SwiGLU epilogues, causal f32 attention; ms_by_kind from CUDA events "
+                      "around every launch"}
+
     # ---- per-kernel event timing (un-graphed) at a few positions: dominant-kernel roofline ----
     prof = {}
     for pos in sorted({0, tokens // 4, tokens // 2, 3 * tokens // 4, tokens - 1}):
@@ -313,6 +354,14 @@ def main():
                             "memory and 8 B D2H per token inside the timed region"},
             "gpu_launches": args.steps * tokens * sess.launches_per_step(),
             "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu}
+    if pf is not None:
+        pf["speedup_vs_per_token_steps"] = round(pf["tok_per_s"] / value, 1)
+        bf16, _ = measured_tensor_peak()
+        pf["tensor_roofline"] = {"bound": "tensor", "achieved": pf["gemm_tf32_tflops_issued_per_gpu"], "unit": "TFLOP/s",
+                                 "peak": round(bf16 / 2, 1), "frac": round(pf["gemm_tf32_tflops_issued_per_gpu"] / (bf16 / 2), 4),
+                                 "peak_source": "half of the measured cuBLAS bf16 burst (tf32 runs at half the bf16 rate; "
+                                                "MEASURED_PEAKS.json has no tf32 figure)"}
+        line["prefill"] = pf
     print(json.dumps(line), flush=True)
     teardown()
 

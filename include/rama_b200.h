@@ -135,6 +135,28 @@ int rama_prefill(rama_session* s, const int32_t* tokens, int32_t n, int32_t pos0
  * prompt token goes through the per-token step like the reference loop). */
 int rama_session_set_prefill(rama_session* s, int32_t min_rows);
 
+/* ---- batched multi-sequence decode (server path) ------------------------------------------------
+ * The reference server runs one RunState and one forward()/sample() loop per request task
+ * (engine/src/lib.rs:127-160; the batcher in server/src/batcher.rs:8-38 is dead code), so n concurrent
+ * requests stream the weights n times per step.  rama_forward_batch is n concurrent forward() calls in one
+ * pass: the n token vectors go through every weight matrix together on the tensor cores (weights read once
+ * per step), each sequence at its own position with its own session's KV cache.  Afterwards every
+ * session's logits buffer holds its logits, exactly as after rama_forward(session, token, pos), so
+ * rama_sample / rama_logits_to_host work per session; rama_sample_batch samples all of them in one launch.
+ * A batch object owns the workspace and the stream; sessions in a batch must not be used concurrently
+ * through their own entry points.  Single GPU in this version. */
+typedef struct rama_batch rama_batch;
+int rama_batch_create(rama_ctx* ctx, int32_t max_seqs /* ≤ 64 */, rama_batch** out);
+int rama_batch_destroy(rama_batch* b);
+/* asynchronous on the batch's stream */
+int rama_forward_batch(rama_batch* b, rama_session* const* sessions, const int32_t* tokens, const int32_t* pos,
+                       int32_t n);
+/* ≙ Device::sample for each of the n sessions (same temperature/topp), one launch; synchronous */
+int rama_sample_batch(rama_batch* b, rama_session* const* sessions, int32_t n, float temperature, float topp,
+                      int32_t* next);
+int rama_batch_sync(rama_batch* b);
+int rama_batch_launches_per_step(const rama_batch* b, int32_t* n);
+
 /* ≙ Device::to_cpu / RunState::into_state (device.rs:21, gpu.rs:196-209, hbm.rs:38-51).
  * buf in rama_state_buf; layouts as the reference's RunState (KV cache [L][T][D]).  Under TP the
  * sharded buffers (q,k,v,hb,hb2,att,caches) hold this rank's slice.  RAMA_S_ATT is only kept

@@ -61,6 +61,12 @@ _SIGS = {
     "rama_sample": ([vp, C.c_float, C.c_float, ip], C.c_int),
     "rama_generate": ([vp, ip, C.c_int32, C.c_int32, C.c_float, C.c_float, ip, fp], C.c_int),
     "rama_session_sync": ([vp], C.c_int),
+    "rama_batch_create": ([vp, C.c_int32, C.POINTER(vp)], C.c_int),
+    "rama_batch_destroy": ([vp], C.c_int),
+    "rama_forward_batch": ([vp, C.POINTER(vp), ip, ip, C.c_int32], C.c_int),
+    "rama_sample_batch": ([vp, C.POINTER(vp), C.c_int32, C.c_float, C.c_float, ip], C.c_int),
+    "rama_batch_sync": ([vp], C.c_int),
+    "rama_batch_launches_per_step": ([vp, ip], C.c_int),
     "rama_prefill": ([vp, ip, C.c_int32, C.c_int32, fp, fp, ip], C.c_int),
     "rama_session_set_prefill": ([vp, C.c_int32], C.c_int),
     "rama_state_to_host": ([vp, C.c_int, fp, sz, C.POINTER(sz)], C.c_int),

@@ -26,6 +26,7 @@
 #include "gemv.cuh"
 #include "misc_kernels.cuh"
 #include "prefill.cuh"
+#include "batch.cuh"
 
 using namespace rama;
 
@@ -159,6 +160,7 @@ struct rama_session {
   int host_mode_set = 0;
   int launches = 0;
   bool logits_gathered = false;
+  bool parts_valid = true;       // the classifier GEMV's per-CTA argmax partials describe the current logits
   // prefill workspace (allocated on first use): activations of one chunk of prompt rows
   int pf_cap = 0;                // rows per chunk
   int pf_min = 16;               // rama_generate: prompts of at least this many rows (BOS included) are prefilled
@@ -961,6 +963,7 @@ extern "C" int rama_forward(rama_session* s, int32_t token, int32_t pos) {
   CK(cudaMemcpyAsync(s->ctrl, h, sizeof(StepCtrl), cudaMemcpyHostToDevice, s->stream));
   CK(cudaGraphLaunch(s->g_fwd, s->stream));
   s->logits_gathered = false;
+  s->parts_valid = true;
   return RAMA_OK;
 }
 
@@ -992,6 +995,9 @@ extern "C" int rama_sample(rama_session* s, float temperature, float topp, int32
   const int n_part = c->world > 1 ? c->world * c->sm_count : c->sm_count;
   SampleParams sp{s->logits, s->part, n_part, s->cls_grid, c->V, s->ctrl, s->d_prompt, s->d_out, s->sort_keys,
                   temperature, topp, 0, peer_in_parts(s)};
+  if (!s->parts_valid) {  // logits written by a batched step: no per-CTA partials, scan the logits
+    sp.part = nullptr; sp.n_part = 0; sp.pin = PeerIn{};
+  }
   sample_kernel<<<1, kSampleThreads, 0, s->stream>>>(sp, 0);
   CK(cudaGetLastError());
   return read_ret(s, next);
@@ -1208,7 +1214,7 @@ static int prefill_chunk(rama_session* s, const int32_t* tokens, int M, int pos0
                           {W[RAMA_T_WK] + (size_t)l * Dq * D, (size_t)Dq, (size_t)D},
                           {W[RAMA_T_WV] + (size_t)l * Dq * D, (size_t)Dq, (size_t)D}};
       EpiQKVPrefill epi{s->pf_q, kc, vc, W[RAMA_T_FREQ_REAL], W[RAMA_T_FREQ_IMAG], pos0, Dq, hs / 2};
-      GK(RAMA_PK_GEMM, (launch_gemm_tf32x3<128, 4, 4>(st, A, B, 3, M, Dq, D, 0, epi)));
+      GK(RAMA_PK_GEMM, (launch_gemm_tf32x3<128, 4, 4>(st, &A, 1, B, 3, M, Dq, D, 0, 1, epi)));
     }
     // causal attention of every prompt row over the cache   (infer.rs:34)
     {
@@ -1222,7 +1228,7 @@ static int prefill_chunk(rama_session* s, const int32_t* tokens, int M, int pos0
       GemmOperand A{s->pf_att, (size_t)M, (size_t)Dq};
       GemmOperand B{W[RAMA_T_WO] + (size_t)l * D * Dq, (size_t)D, (size_t)Dq};
       EpiStoreNT epi{s->pf_y, D, D, 0};
-      GK(RAMA_PK_GEMM, (launch_gemm_tf32x3<128, 4, 4>(st, A, &B, 1, M, D, Dq, 0, epi)));
+      GK(RAMA_PK_GEMM, (launch_gemm_tf32x3<128, 4, 4>(st, &A, 1, &B, 1, M, D, Dq, 0, 1, epi)));
     }
     if (c->world > 1) {
       tr.pre(RAMA_PK_COMM);
@@ -1238,14 +1244,14 @@ static int prefill_chunk(rama_session* s, const int32_t* tokens, int M, int pos0
       GemmOperand B[2] = {{W[RAMA_T_W1] + (size_t)l * Fl * D, (size_t)Fl, (size_t)D},
                           {W[RAMA_T_W3] + (size_t)l * Fl * D, (size_t)Fl, (size_t)D}};
       EpiSwiGLUPrefill epi{s->pf_h, Fl};
-      GK(RAMA_PK_GEMM, (launch_gemm_tf32x3<128, 4, 4>(st, A, B, 2, M, Fl, D, 0, epi)));
+      GK(RAMA_PK_GEMM, (launch_gemm_tf32x3<128, 4, 4>(st, &A, 1, B, 2, M, Fl, D, 0, 1, epi)));
     }
     // w2   (infer.rs:46)
     {
       GemmOperand A{s->pf_h, (size_t)M, (size_t)Fl};
       GemmOperand B{W[RAMA_T_W2] + (size_t)l * D * Fl, (size_t)D, (size_t)Fl};
       EpiStoreNT epi{s->pf_y, D, D, 0};
-      GK(RAMA_PK_GEMM, (launch_gemm_tf32x3<128, 4, 4>(st, A, &B, 1, M, D, Fl, 0, epi)));
+      GK(RAMA_PK_GEMM, (launch_gemm_tf32x3<128, 4, 4>(st, &A, 1, &B, 1, M, D, Fl, 0, 1, epi)));
     }
     if (c->world > 1) {
       tr.pre(RAMA_PK_COMM);
@@ -1304,6 +1310,7 @@ static int prefill_run(rama_session* s, const int32_t* tokens, int32_t n, int32_
   }
   if (n_launch) *n_launch = launches;
   s->logits_gathered = false;
+  s->parts_valid = true;
   if (rc != RAMA_OK) return rc;
   if (e != cudaSuccess) return fail(RAMA_E_CUDA, "prefill: %s", cudaGetErrorString(e));
   return RAMA_OK;
@@ -1324,6 +1331,281 @@ extern "C" int rama_prefill(rama_session* s, const int32_t* tokens, int32_t n, i
 extern "C" int rama_session_set_prefill(rama_session* s, int32_t min_rows) {
   if (!s) return fail(RAMA_E_INVALID, "NULL session");
   s->pf_min = min_rows;
+  return RAMA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// batched multi-sequence decode (server path, lib.rs:127-160): one step for n sessions
+// ------------------------------------------------------------------------------------------------
+extern "C" int rama_batch_destroy(rama_batch* b);
+constexpr int kBatchMax = 64;    // one 64-column MMA tile of sequences
+constexpr int kBatchRing = 8;
+
+struct rama_batch {
+  rama_ctx* ctx = nullptr;
+  int cap = 0, n_split = 1;
+  cudaStream_t stream = nullptr;
+  float *x = nullptr, *xn = nullptr, *q = nullptr, *att = nullptr, *h = nullptr, *part = nullptr, *attn_ws = nullptr;
+  unsigned int* tickets = nullptr;
+  size_t part_floats = 0;
+  BatchSeq* d_seqs = nullptr;
+  BatchSeq* h_seqs = nullptr;        // pinned ring [kBatchRing][cap]
+  SampleParams* d_sp = nullptr;
+  SampleParams* h_sp = nullptr;      // pinned [cap]
+  int32_t* d_next = nullptr;
+  int32_t* h_next = nullptr;         // pinned [2·cap]
+  int ring_i = 0;
+  std::vector<cudaGraphExec_t> graphs;  // by batch size
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int launches = 0;
+};
+
+// split-K factor: fill the SMs (tiles·S close to a multiple of the SM count), keep ≥ 8 k-blocks per split
+static int pick_ksplit(const rama_ctx* c, int tiles, int K) {
+  const int total_kb = (K + kGemmBK - 1) / kGemmBK;
+  int best = 1;
+  double best_eff = 0.0;
+  for (int S = 1; S <= 16; ++S) {
+    if (S > 1 && total_kb / S < 8) break;
+    const int units = tiles * S, waves = (units + c->sm_count - 1) / c->sm_count;
+    const double eff = (double)units / ((double)waves * c->sm_count);
+    if (eff > best_eff + 0.02) { best_eff = eff; best = S; }
+  }
+  return best;
+}
+
+extern "C" int rama_batch_create(rama_ctx* c, int32_t max_seqs, rama_batch** out) {
+  if (!c || !out) return fail(RAMA_E_INVALID, "NULL argument");
+  if (!c->loaded) return fail(RAMA_E_STATE, "no weights loaded");
+  if (max_seqs < 1 || max_seqs > kBatchMax) return fail(RAMA_E_INVALID, "max_seqs must be in [1, %d]", kBatchMax);
+  if (c->world > 1) return fail(RAMA_E_INVALID, "batched decode is single-GPU in this version (tensor parallelism: batch-1 and prefill)");
+  CK(cudaSetDevice(c->device));
+  rama_batch* b = new rama_batch();
+  b->ctx = c;
+  b->cap = max_seqs;
+  b->n_split = (c->T + kAttnChunk - 1) / kAttnChunk;
+  const size_t B = max_seqs, D = c->D, Dq = c->Dq, Fl = c->Fl;
+  // partial buffer: the largest of [3][S][B][Dq], [S][B][D], [2][S][B][Fl], [S][B][Vl] over the chosen split factors
+  auto tiles = [](int rows) { return (rows + kGemmBM - 1) / kGemmBM; };
+  size_t pf = 0;
+  pf = std::max(pf, (size_t)3 * pick_ksplit(c, 3 * tiles(c->Dq), c->D) * B * Dq);
+  pf = std::max(pf, (size_t)pick_ksplit(c, tiles(c->D), c->Dq) * B * D);
+  pf = std::max(pf, (size_t)2 * pick_ksplit(c, 2 * tiles(c->Fl), c->D) * B * Fl);
+  pf = std::max(pf, (size_t)pick_ksplit(c, tiles(c->D), c->Fl) * B * D);
+  pf = std::max(pf, (size_t)pick_ksplit(c, tiles(c->Vl), c->D) * B * c->Vl);
+  b->part_floats = pf;
+  cudaError_t e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
+#define A(call) if (e == cudaSuccess) e = (call)
+  A(dalloc(&b->x, B * D)); A(dalloc(&b->xn, B * D)); A(dalloc(&b->q, B * Dq)); A(dalloc(&b->att, B * Dq));
+  A(dalloc(&b->h, B * Fl)); A(dalloc(&b->part, pf));
+  A(dalloc(&b->attn_ws, B * c->Hl * b->n_split * (c->hs + 2)));
+  A(dalloc(&b->tickets, B * c->Hl));
+  A(dalloc(&b->d_seqs, B)); A(dalloc(&b->d_sp, B)); A(dalloc(&b->d_next, 2 * B));
+  A(cudaHostAlloc((void**)&b->h_seqs, kBatchRing * B * sizeof(BatchSeq), cudaHostAllocDefault));
+  A(cudaHostAlloc((void**)&b->h_sp, B * sizeof(SampleParams), cudaHostAllocDefault));
+  A(cudaHostAlloc((void**)&b->h_next, 2 * B * sizeof(int32_t), cudaHostAllocDefault));
+  A(cudaEventCreate(&b->ev0)); A(cudaEventCreate(&b->ev1));
+  A(cudaDeviceSynchronize());
+#undef A
+  if (e != cudaSuccess) {
+    rama_batch_destroy(b);
+    return fail(RAMA_E_CUDA, "batch allocation: %s", cudaGetErrorString(e));
+  }
+  b->graphs.assign(max_seqs + 1, nullptr);
+  *out = b;
+  return RAMA_OK;
+}
+
+extern "C" int rama_batch_destroy(rama_batch* b) {
+  if (!b) return RAMA_OK;
+  cudaSetDevice(b->ctx->device);
+  if (b->stream) cudaStreamSynchronize(b->stream);
+  for (auto g : b->graphs) if (g) cudaGraphExecDestroy(g);
+  void* bufs[] = {b->x, b->xn, b->q, b->att, b->h, b->part, b->attn_ws, b->tickets, b->d_seqs, b->d_sp, b->d_next};
+  for (void* p : bufs) if (p) cudaFree(p);
+  if (b->h_seqs) cudaFreeHost(b->h_seqs);
+  if (b->h_sp) cudaFreeHost(b->h_sp);
+  if (b->h_next) cudaFreeHost(b->h_next);
+  if (b->ev0) cudaEventDestroy(b->ev0);
+  if (b->ev1) cudaEventDestroy(b->ev1);
+  if (b->stream) cudaStreamDestroy(b->stream);
+  delete b;
+  return RAMA_OK;
+}
+
+// enqueue one batched step for n sequences (everything per-sequence is read from b->d_seqs on the device,
+// so the captured graph of a batch size serves every step)
+static int enqueue_batch_step(rama_batch* b, int n, int* n_launch) {
+  rama_ctx* c = b->ctx;
+  cudaStream_t st = b->stream;
+  const int D = c->D, Dq = c->Dq, Fl = c->Fl, T = c->T, hs = c->hs, L = c->L, Vl = c->Vl;
+  const float* const* W = c->w;
+  int launches = 0;
+  auto tiles = [](int rows) { return (rows + kGemmBM - 1) / kGemmBM; };
+#define LK(call)                                                                                              \
+  do {                                                                                                        \
+    cudaError_t e_ = (call);                                                                                  \
+    if (e_ == cudaSuccess) e_ = cudaGetLastError();                                                           \
+    ++launches;                                                                                               \
+    if (e_ != cudaSuccess) return fail(RAMA_E_CUDA, "batched step launch %s: %s", #call, cudaGetErrorString(e_)); \
+  } while (0)
+  batch_embed_kernel<<<n, 256, 0, st>>>(b->d_seqs, W[RAMA_T_TOKEN_EMBEDDING], b->x, D, c->V);
+  LK(cudaSuccess);
+  GemmOperand X{b->xn, (size_t)n, (size_t)D};
+  int S_prev = 0;  // split factor of the pending residual partials in b->part (0: none)
+  for (int l = 0; l < L; ++l) {
+    const size_t layer_off = (size_t)l * T * Dq;
+    // x += pending w2 output; xn = rmsnorm(x)   (infer.rs:19, :47 of the previous layer)
+    batch_addnorm_kernel<<<n, 256, 0, st>>>(b->x, S_prev ? b->part : nullptr, S_prev, (size_t)n * D,
+                                            W[RAMA_T_RMS_ATT] + (size_t)l * D, b->xn, D);
+    LK(cudaSuccess);
+    {  // [wq;wk;wv] (weights = the 128-row operand, the batch = the 64-column operand)   (infer.rs:20-23)
+      GemmOperand A[3] = {{W[RAMA_T_WQ] + (size_t)l * Dq * D, (size_t)Dq, (size_t)D},
+                          {W[RAMA_T_WK] + (size_t)l * Dq * D, (size_t)Dq, (size_t)D},
+                          {W[RAMA_T_WV] + (size_t)l * Dq * D, (size_t)Dq, (size_t)D}};
+      const int S = pick_ksplit(c, 3 * tiles(Dq), D);
+      EpiStoreT epi{b->part, Dq, n, S, (size_t)n * Dq};
+      LK((launch_gemm_tf32x3<64, 4, 2>(st, A, 3, &X, 1, Dq, n, D, 0, S, epi)));
+      batch_qkv_finish_kernel<<<dim3(n, (Dq / 2 + 255) / 256), 256, 0, st>>>(
+          b->part, S, (size_t)n * Dq, b->d_seqs, layer_off, b->q, W[RAMA_T_FREQ_REAL], W[RAMA_T_FREQ_IMAG], Dq, hs / 2);
+      LK(cudaSuccess);
+    }
+    {  // attention per sequence   (infer.rs:34)
+      AttnBatchParams ap{b->d_seqs, b->q, b->att, b->attn_ws, b->tickets, layer_off, T, Dq, hs, b->n_split, c->Hl};
+      attn_decode_batch_kernel<<<dim3(c->Hl, b->n_split, n), kAttnThreads, 0, st>>>(ap);
+      LK(cudaSuccess);
+    }
+    int S_wo;
+    {  // wo   (infer.rs:35)
+      GemmOperand A{W[RAMA_T_WO] + (size_t)l * D * Dq, (size_t)D, (size_t)Dq};
+      GemmOperand Bm{b->att, (size_t)n, (size_t)Dq};
+      S_wo = pick_ksplit(c, tiles(D), Dq);
+      EpiStoreT epi{b->part, D, n, S_wo, (size_t)n * D};
+      LK((launch_gemm_tf32x3<64, 4, 2>(st, &A, 1, &Bm, 1, D, n, Dq, 0, S_wo, epi)));
+    }
+    // x += wo output; xn = rmsnorm(x)   (infer.rs:37-38)
+    batch_addnorm_kernel<<<n, 256, 0, st>>>(b->x, b->part, S_wo, (size_t)n * D, W[RAMA_T_RMS_FFN] + (size_t)l * D, b->xn, D);
+    LK(cudaSuccess);
+    {  // [w1;w3] → SwiGLU   (infer.rs:39-45)
+      GemmOperand A[2] = {{W[RAMA_T_W1] + (size_t)l * Fl * D, (size_t)Fl, (size_t)D},
+                          {W[RAMA_T_W3] + (size_t)l * Fl * D, (size_t)Fl, (size_t)D}};
+      const int S = pick_ksplit(c, 2 * tiles(Fl), D);
+      EpiStoreT epi{b->part, Fl, n, S, (size_t)n * Fl};
+      LK((launch_gemm_tf32x3<64, 4, 2>(st, A, 2, &X, 1, Fl, n, D, 0, S, epi)));
+      batch_swiglu_finish_kernel<<<std::min(c->sm_count * 4, (n * Fl + 255) / 256), 256, 0, st>>>(b->part, S, (size_t)n * Fl, b->h, Fl, n);
+      LK(cudaSuccess);
+    }
+    {  // w2   (infer.rs:46)
+      GemmOperand A{W[RAMA_T_W2] + (size_t)l * D * Fl, (size_t)D, (size_t)Fl};
+      GemmOperand Bm{b->h, (size_t)n, (size_t)Fl};
+      S_prev = pick_ksplit(c, tiles(D), Fl);
+      EpiStoreT epi{b->part, D, n, S_prev, (size_t)n * D};
+      LK((launch_gemm_tf32x3<64, 4, 2>(st, &A, 1, &Bm, 1, D, n, Fl, 0, S_prev, epi)));
+    }
+  }
+  // x += w2 output; final rmsnorm; classifier → each session's logits   (infer.rs:49-51)
+  batch_addnorm_kernel<<<n, 256, 0, st>>>(b->x, b->part, S_prev, (size_t)n * D, W[RAMA_T_RMS_FINAL], b->xn, D);
+  LK(cudaSuccess);
+  {
+    GemmOperand A{c->wcls, (size_t)Vl, (size_t)D};
+    const int S = pick_ksplit(c, tiles(Vl), D);
+    EpiStoreT epi{b->part, Vl, n, S, (size_t)n * Vl};
+    LK((launch_gemm_tf32x3<64, 4, 2>(st, &A, 1, &X, 1, Vl, n, D, 0, S, epi)));
+    batch_cls_finish_kernel<<<dim3(std::min(64, (Vl + 255) / 256), n), 256, 0, st>>>(b->part, S, (size_t)n * Vl, b->d_seqs, Vl, c->v0);
+    LK(cudaSuccess);
+  }
+#undef LK
+  if (n_launch) *n_launch = launches;
+  return RAMA_OK;
+}
+
+static int batch_check_sessions(rama_batch* b, rama_session* const* sessions, int32_t n) {
+  if (n < 1 || n > b->cap) return fail(RAMA_E_INVALID, "batch of %d sequences outside [1, %d]", n, b->cap);
+  for (int i = 0; i < n; ++i) {
+    if (!sessions[i] || sessions[i]->ctx != b->ctx) return fail(RAMA_E_INVALID, "session %d is NULL or belongs to another context", i);
+    for (int j = 0; j < i; ++j)
+      if (sessions[j] == sessions[i]) return fail(RAMA_E_INVALID, "session %d appears twice in the batch", i);
+  }
+  return RAMA_OK;
+}
+
+extern "C" int rama_forward_batch(rama_batch* b, rama_session* const* sessions, const int32_t* tokens,
+                                  const int32_t* pos, int32_t n) {
+  if (!b || !sessions || !tokens || !pos) return fail(RAMA_E_INVALID, "NULL argument");
+  rama_ctx* c = b->ctx;
+  RK(batch_check_sessions(b, sessions, n));
+  for (int i = 0; i < n; ++i) {
+    if (pos[i] < 0 || pos[i] >= c->T) return fail(RAMA_E_STATE, "pos %d of sequence %d outside [0, seq_len=%d)", pos[i], i, c->T);
+    if (tokens[i] < 0 || tokens[i] >= c->V) return fail(RAMA_E_INVALID, "token %d of sequence %d outside the vocabulary", tokens[i], i);
+  }
+  CK(cudaSetDevice(c->device));
+  BatchSeq* hs = b->h_seqs + (size_t)b->ring_i * b->cap;
+  if (++b->ring_i == kBatchRing) { b->ring_i = 0; CK(cudaStreamSynchronize(b->stream)); }
+  for (int i = 0; i < n; ++i) {
+    rama_session* s = sessions[i];
+    hs[i] = BatchSeq{s->key_cache, s->value_cache, s->logits, s->ctrl, pos[i], tokens[i]};
+    s->logits_gathered = false;
+    s->parts_valid = false;
+  }
+  CK(cudaMemcpyAsync(b->d_seqs, hs, (size_t)n * sizeof(BatchSeq), cudaMemcpyHostToDevice, b->stream));
+  if (!b->graphs[n]) {
+    cudaGraph_t g = nullptr;
+    CK(cudaStreamBeginCapture(b->stream, cudaStreamCaptureModeRelaxed));
+    int nl = 0;
+    int rc = enqueue_batch_step(b, n, &nl);
+    cudaError_t e = cudaStreamEndCapture(b->stream, &g);
+    if (rc != RAMA_OK) { if (g) cudaGraphDestroy(g); return rc; }
+    if (e != cudaSuccess) return fail(RAMA_E_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&b->graphs[n], g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) return fail(RAMA_E_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+    b->launches = nl;
+  }
+  CK(cudaGraphLaunch(b->graphs[n], b->stream));
+  return RAMA_OK;
+}
+
+extern "C" int rama_sample_batch(rama_batch* b, rama_session* const* sessions, int32_t n, float temperature,
+                                 float topp, int32_t* next) {
+  if (!b || !sessions || !next) return fail(RAMA_E_INVALID, "NULL argument");
+  rama_ctx* c = b->ctx;
+  RK(batch_check_sessions(b, sessions, n));
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(b->stream));  // h_sp / h_next are single-buffered
+  BatchSeq* hs = b->h_seqs + (size_t)b->ring_i * b->cap;
+  if (++b->ring_i == kBatchRing) b->ring_i = 0;
+  for (int i = 0; i < n; ++i) {
+    rama_session* s = sessions[i];
+    b->h_sp[i] = SampleParams{s->logits, nullptr, 0, 0, c->V, s->ctrl, nullptr, nullptr, s->sort_keys, temperature, topp, 0, PeerIn{}};
+    hs[i] = BatchSeq{s->key_cache, s->value_cache, s->logits, s->ctrl, 0, 0};
+  }
+  CK(cudaMemcpyAsync(b->d_sp, b->h_sp, (size_t)n * sizeof(SampleParams), cudaMemcpyHostToDevice, b->stream));
+  // d_seqs still describes this batch when sample follows forward; rewrite only if the caller passes other sessions
+  CK(cudaMemcpyAsync(b->d_seqs, hs, (size_t)n * sizeof(BatchSeq), cudaMemcpyHostToDevice, b->stream));
+  sample_batch_kernel<<<n, kSampleThreads, 0, b->stream>>>(b->d_sp);
+  CK(cudaGetLastError());
+  batch_collect_kernel<<<1, 64, 0, b->stream>>>(b->d_seqs, b->d_next, n);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(b->h_next, b->d_next, (size_t)2 * n * sizeof(int32_t), cudaMemcpyDeviceToHost, b->stream));
+  CK(cudaStreamSynchronize(b->stream));
+  for (int i = 0; i < n; ++i) {
+    if (b->h_next[2 * i + 1] == 1) return fail(RAMA_E_STATE, "token id outside the vocabulary reached the device step (sequence %d)", i);
+    if (b->h_next[2 * i + 1] == 2) return fail(RAMA_E_STATE, "top-p candidate list is empty (the reference panics here, infer.rs:66) (sequence %d)", i);
+    next[i] = b->h_next[2 * i];
+  }
+  return RAMA_OK;
+}
+
+extern "C" int rama_batch_sync(rama_batch* b) {
+  if (!b) return fail(RAMA_E_INVALID, "NULL batch");
+  CK(cudaSetDevice(b->ctx->device));
+  CK(cudaStreamSynchronize(b->stream));
+  return RAMA_OK;
+}
+
+extern "C" int rama_batch_launches_per_step(const rama_batch* b, int32_t* n) {
+  if (!b || !n) return fail(RAMA_E_INVALID, "NULL argument");
+  *n = b->launches;
   return RAMA_OK;
 }
 
@@ -1542,24 +1824,37 @@ extern "C" int rama_op_matmul_nt(rama_ctx* c, float* out, const float* a, const 
   if (K % 4) return fail(RAMA_E_INVALID, "K %% 4 != 0 (TMA needs 16-byte row pitch; the reference steps k by 4, cpu.rs:142)");
   const int hi_round = flags & 1;
   const bool transposed = (flags & 2) != 0;
+  const int ksplit = std::max(1, (flags >> 8) & 0xff);
   GemmOperand A{a, M, K}, B{b, N, K};
   cudaError_t e;
   const int m = (int)M, n = (int)N, k = (int)K;
   if (transposed) {
-    EpiStoreT epi{out, m, n};
+    // split-K partials land in a scratch [ksplit][N][M]; a reduction kernel sums them into out
+    float* dst = out;
+    if (ksplit > 1) CK(cudaMallocAsync((void**)&dst, (size_t)ksplit * N * M * sizeof(float), c->op_stream));
+    EpiStoreT epi{dst, m, n, ksplit, (size_t)N * M};
     switch (variant) {
-      case 0: e = launch_gemm_tf32x3<64, 6, 2>(c->op_stream, A, &B, 1, m, n, k, hi_round, epi); break;
-      case 1: e = launch_gemm_tf32x3<64, 6, 4>(c->op_stream, A, &B, 1, m, n, k, hi_round, epi); break;
-      case 2: e = launch_gemm_tf32x3<64, 4, 2>(c->op_stream, A, &B, 1, m, n, k, hi_round, epi); break;
+      case 0: e = launch_gemm_tf32x3<64, 6, 2>(c->op_stream, &A, 1, &B, 1, m, n, k, hi_round, ksplit, epi); break;
+      case 1: e = launch_gemm_tf32x3<64, 6, 4>(c->op_stream, &A, 1, &B, 1, m, n, k, hi_round, ksplit, epi); break;
+      case 2: e = launch_gemm_tf32x3<64, 4, 2>(c->op_stream, &A, 1, &B, 1, m, n, k, hi_round, ksplit, epi); break;
+      case 3: e = launch_gemm_tf32x3<64, 4, 4>(c->op_stream, &A, 1, &B, 1, m, n, k, hi_round, ksplit, epi); break;
       default: return fail(RAMA_E_INVALID, "matmul_nt: unknown transposed variant %d", variant);
     }
+    if (ksplit > 1) {
+      if (e == cudaSuccess) {
+        sum_partials_kernel<<<c->sm_count * 4, 256, 0, c->op_stream>>>(out, dst, (size_t)N * M, ksplit);
+        e = cudaGetLastError();
+      }
+      CK(cudaFreeAsync(dst, c->op_stream));
+    }
   } else {
+    if (ksplit > 1) return fail(RAMA_E_INVALID, "matmul_nt: split-K only in the transposed (batched decode) orientation");
     EpiStoreNT epi{out, n, n, 0};
     switch (variant) {
-      case 0: e = launch_gemm_tf32x3<128, 4, 2>(c->op_stream, A, &B, 1, m, n, k, hi_round, epi); break;
-      case 1: e = launch_gemm_tf32x3<128, 4, 4>(c->op_stream, A, &B, 1, m, n, k, hi_round, epi); break;
-      case 2: e = launch_gemm_tf32x3<128, 3, 2>(c->op_stream, A, &B, 1, m, n, k, hi_round, epi); break;
-      case 3: e = launch_gemm_tf32x3<64, 6, 2>(c->op_stream, A, &B, 1, m, n, k, hi_round, epi); break;
+      case 0: e = launch_gemm_tf32x3<128, 4, 2>(c->op_stream, &A, 1, &B, 1, m, n, k, hi_round, 1, epi); break;
+      case 1: e = launch_gemm_tf32x3<128, 4, 4>(c->op_stream, &A, 1, &B, 1, m, n, k, hi_round, 1, epi); break;
+      case 2: e = launch_gemm_tf32x3<128, 3, 2>(c->op_stream, &A, 1, &B, 1, m, n, k, hi_round, 1, epi); break;
+      case 3: e = launch_gemm_tf32x3<64, 6, 2>(c->op_stream, &A, 1, &B, 1, m, n, k, hi_round, 1, epi); break;
       default: return fail(RAMA_E_INVALID, "matmul_nt: unknown variant %d", variant);
     }
   }

@@ -41,24 +41,11 @@ struct AttnParams {
   size_t prefetch_bytes;
 };
 
-__global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnParams p, int use_pdl) {
+// one (head = blockIdx.x, split = blockIdx.y) CTA of the flash-decode pass for the sequence described by p
+__device__ __forceinline__ void attn_decode_body(const AttnParams& p, int pos) {
   __shared__ float s_m[kAttnWarps], s_l[kAttnWarps];
   __shared__ __align__(16) float s_acc[kAttnWarps][kAttnMaxHs];
   __shared__ unsigned int s_ticket;
-
-  if (use_pdl) pdl_launch_dependents();
-  if (p.prefetch && threadIdx.x == 0) {  // weights do not depend on the previous kernel
-    const size_t n_cta = (size_t)gridDim.x * gridDim.y, me = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
-    const size_t per = ((p.prefetch_bytes + n_cta - 1) / n_cta + 15) & ~(size_t)15;
-    const size_t off = me * per;
-    if (off < p.prefetch_bytes) {
-      const size_t n = min(per, p.prefetch_bytes - off) & ~(size_t)15;
-      if (n) l2_prefetch_bulk(reinterpret_cast<const char*>(p.prefetch) + off, (uint32_t)n);
-    }
-  }
-  if (use_pdl) pdl_wait();
-
-  const int pos = p.pos_override >= 0 ? p.pos_override : p.ctrl->pos;
   const int n = pos + 1;
   const int n_chunks = (n + kAttnChunk - 1) / kAttnChunk;
   const int h = blockIdx.x, chunk = blockIdx.y;
@@ -164,6 +151,21 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnPar
     }
   }
   if (threadIdx.x == 0) p.tickets[h] = 0u;  // ready for the next launch
+}
+
+__global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnParams p, int use_pdl) {
+  if (use_pdl) pdl_launch_dependents();
+  if (p.prefetch && threadIdx.x == 0) {  // weights do not depend on the previous kernel
+    const size_t n_cta = (size_t)gridDim.x * gridDim.y, me = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+    const size_t per = ((p.prefetch_bytes + n_cta - 1) / n_cta + 15) & ~(size_t)15;
+    const size_t off = me * per;
+    if (off < p.prefetch_bytes) {
+      const size_t n = min(per, p.prefetch_bytes - off) & ~(size_t)15;
+      if (n) l2_prefetch_bulk(reinterpret_cast<const char*>(p.prefetch) + off, (uint32_t)n);
+    }
+  }
+  if (use_pdl) pdl_wait();
+  attn_decode_body(p, p.pos_override >= 0 ? p.pos_override : p.ctrl->pos);
 }
 
 }  // namespace rama

@@ -4,6 +4,8 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
+#include <cstring>
 #include <mutex>
 
 #include "gemm_tf32x3.cuh"
@@ -47,10 +49,11 @@ struct GemmOperand {  // a K-major f32 matrix [rows][K], row pitch ld
   size_t rows, ld;
 };
 
-// C (per group g < n_groups) = A · B[g]ᵀ;  for a dual epilogue B[0] and B[1] are stacked inside one tile.
+// C (per group g) = A[ga] · B[gb]ᵀ.  n_a > 1: groups differ in A (weights as the 128-row operand, batched decode);
+// n_b > 1: groups differ in B (prefill QKV); a dual epilogue stacks B[0] on B[1] inside one tile.
 template <int BN, int STAGES, int CH, class Epi>
-cudaError_t launch_gemm_tf32x3(cudaStream_t st, const GemmOperand& A, const GemmOperand* B, int n_b, int M, int N,
-                               int K, int hi_round, const Epi& epi) {
+cudaError_t launch_gemm_tf32x3(cudaStream_t st, const GemmOperand* A, int n_a, const GemmOperand* B, int n_b, int M,
+                               int N, int K, int hi_round, int ksplit, const Epi& epi) {
   using SM = GemmSmem<BN, STAGES>;
   constexpr int BK = kGemmBK;
   static_assert(SM::kTotal <= 227 * 1024, "tile does not fit shared memory");
@@ -59,17 +62,20 @@ cudaError_t launch_gemm_tf32x3(cudaStream_t st, const GemmOperand& A, const Gemm
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal); });
   if (attr_err != cudaSuccess) return attr_err;
-  if (M <= 0 || N <= 0 || K <= 0 || K % 4 || n_b < 1 || n_b > 3) return cudaErrorInvalidValue;
+  if (M <= 0 || N <= 0 || K <= 0 || K % 4 || n_a < 1 || n_a > 3 || n_b < 1 || n_b > 3 || ksplit < 1) return cudaErrorInvalidValue;
+  if (n_a > 1 && (n_b > 1 || Epi::kDual)) return cudaErrorInvalidValue;
   GemmMaps maps;
   memset(&maps, 0, sizeof(maps));
-  if (!make_tmap_2d(&maps.a, A.p, A.rows, (size_t)K, A.ld, kGemmBM, BK)) return cudaErrorInvalidValue;
   constexpr int box_n = Epi::kDual ? BN / 2 : BN;
-  for (int i = 0; i < n_b; ++i)
-    if (!make_tmap_2d(&maps.b[i], B[i].p, B[i].rows, (size_t)K, B[i].ld, box_n, BK)) return cudaErrorInvalidValue;
-  for (int i = n_b; i < 3; ++i) maps.b[i] = maps.b[0];
-  GemmShape shp{M, N, K, hi_round};
-  const int groups = Epi::kDual ? 1 : n_b;
-  dim3 grid((N + box_n - 1) / box_n, (M + kGemmBM - 1) / kGemmBM, groups);
+  for (int i = 0; i < 3; ++i) {
+    const GemmOperand& a = A[i < n_a ? i : 0];
+    const GemmOperand& b = B[i < n_b ? i : 0];
+    if (!make_tmap_2d(&maps.a[i], a.p, a.rows, (size_t)K, a.ld, kGemmBM, BK)) return cudaErrorInvalidValue;
+    if (!make_tmap_2d(&maps.b[i], b.p, b.rows, (size_t)K, b.ld, box_n, BK)) return cudaErrorInvalidValue;
+  }
+  GemmShape shp{M, N, K, hi_round, ksplit, n_a > 1 ? 1 : 0};
+  const int groups = Epi::kDual ? 1 : std::max(n_a, n_b);
+  dim3 grid((N + box_n - 1) / box_n, (M + kGemmBM - 1) / kGemmBM, groups * ksplit);
   kern<<<grid, kGemmThreads, SM::kTotal, st>>>(maps, shp, epi);
   return cudaGetLastError();
 }

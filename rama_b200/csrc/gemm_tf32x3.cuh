@@ -161,14 +161,16 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32() {
 }
 
 // ---- kernel parameters ------------------------------------------------------------------------------
-struct GemmMaps {  // TMA descriptors: A and up to three B operands (grouped / dual launches)
-  CUtensorMap a;
+struct GemmMaps {  // TMA descriptors; grouped launches pick a[group] or b[group], dual tiles stack b[0] on b[1]
+  CUtensorMap a[3];
   CUtensorMap b[3];
 };
 
 struct GemmShape {
-  int M, N, K;   // logical problem (per group); rows ≥ M / cols ≥ N of a tile are masked
-  int hi_round;  // 1: also rewrite the B tile's hi half rounded to nearest (default 0: raw tile = hi by truncation)
+  int M, N, K;     // logical problem (per group); rows ≥ M / cols ≥ N of a tile are masked
+  int hi_round;    // 1: also rewrite the B tile's hi half rounded to nearest (default 0: raw tile = hi by truncation)
+  int ksplit;      // split-K: blockIdx.z = group·ksplit + split; split s reduces k-blocks [s·nkb/ksplit, (s+1)·nkb/ksplit)
+  int group_on_a;  // grouped launch: 1 = groups differ in the A operand (weights as A: batched decode), 0 = in B
 };
 
 constexpr int kGemmBK = 32;  // floats per k-block = one 128-byte swizzle row
@@ -198,9 +200,10 @@ struct GemmSmem {
 // Epilogue functor interface (device):
 //   static constexpr bool kDual        — the B tile stacks BN/2 rows of b[0] on BN/2 rows of b[1]; the epilogue
 //                                        receives both accumulator chunks of a column (SwiGLU)
-//   void operator()(int m, int n, const float (&v)[32], int group)               (!kDual)
-//   void operator()(int m, int n, const float (&v0)[32], const float (&v1)[32])  (kDual)
-// where m is the global row, n the first global column of the 32-column chunk.
+//   void operator()(int m, int n, const float (&v)[32], int group, int split, bool valid)    (!kDual)
+//   void operator()(int m, int n, const float (&v0)[32], const float (&v1)[32], bool valid)  (kDual)
+// where m is the global row, n the first global column of the 32-column chunk; the whole warp calls it
+// (valid = m < M) so an epilogue may shuffle between rows.
 
 template <int BN, int STAGES, int CH, class Epi>
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -221,16 +224,19 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, c
   uint8_t* gen_base = gemm_smem_raw + (base - smem_u32(gemm_smem_raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int group = blockIdx.z;
+  const int group = blockIdx.z / shp.ksplit, split = blockIdx.z - group * shp.ksplit;
   const int m0 = blockIdx.y * kGemmBM;
   const int tile_n = blockIdx.x;
-  const int num_kb = (shp.K + BK - 1) / BK;
+  const int total_kb = (shp.K + BK - 1) / BK;
+  const int kb_begin = (int)((long long)split * total_kb / shp.ksplit);
+  const int num_kb = (int)((long long)(split + 1) * total_kb / shp.ksplit) - kb_begin;  // may be 0: the tile is all zeros
   const int num_ch = (num_kb + CH - 1) / CH;
   constexpr int kBoxN = Epi::kDual ? BN / 2 : BN;  // rows per B box
-  const CUtensorMap* mapB0 = &maps.b[Epi::kDual ? 0 : group];
+  const CUtensorMap* mapA = &maps.a[shp.group_on_a ? group : 0];
+  const CUtensorMap* mapB0 = &maps.b[(Epi::kDual || shp.group_on_a) ? 0 : group];
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&maps.a);
+    tma_prefetch_desc(mapA);
     tma_prefetch_desc(mapB0);
     if (Epi::kDual) tma_prefetch_desc(&maps.b[1]);
     for (int s = 0; s < STAGES; ++s) {
@@ -260,12 +266,13 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, c
         mbar_wait(bar_empty + 8 * s, ph ^ 1);
         const uint32_t st = base + s * SM::kStageBytes;
         mbar_arrive_expect_tx(bar_full + 8 * s, SM::kTxBytes);
-        tma_load_2d(st, &maps.a, bar_full + 8 * s, kb * BK, m0);
+        const int kc = (kb_begin + kb) * BK;
+        tma_load_2d(st, mapA, bar_full + 8 * s, kc, m0);
         if (Epi::kDual) {
-          tma_load_2d(st + SM::kABytes, &maps.b[0], bar_full + 8 * s, kb * BK, tile_n * kBoxN);
-          tma_load_2d(st + SM::kABytes + kBoxN * BK * 4, &maps.b[1], bar_full + 8 * s, kb * BK, tile_n * kBoxN);
+          tma_load_2d(st + SM::kABytes, &maps.b[0], bar_full + 8 * s, kc, tile_n * kBoxN);
+          tma_load_2d(st + SM::kABytes + kBoxN * BK * 4, &maps.b[1], bar_full + 8 * s, kc, tile_n * kBoxN);
         } else {
-          tma_load_2d(st + SM::kABytes, mapB0, bar_full + 8 * s, kb * BK, tile_n * BN);
+          tma_load_2d(st + SM::kABytes, mapB0, bar_full + 8 * s, kc, tile_n * BN);
         }
       }
     }
@@ -395,13 +402,12 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, c
 
     Epi epi = epi_in;
     const int m = m0 + quarter * 32 + lane;
-    if (m < shp.M) {
-      if constexpr (Epi::kDual) {
-        epi(m, tile_n * (BN / 2) + 32 * half, acc[0], acc[1]);
-      } else {
+    const bool valid = m < shp.M;
+    if constexpr (Epi::kDual) {
+      epi(m, tile_n * (BN / 2) + 32 * half, acc[0], acc[1], valid);
+    } else {
 #pragma unroll
-        for (int j = 0; j < NSEG; ++j) epi(m, tile_n * BN + seg_col(j), acc[j], group);
-      }
+      for (int j = 0; j < NSEG; ++j) epi(m, tile_n * BN + seg_col(j), acc[j], group, split, valid);
     }
   }
   __syncthreads();
@@ -419,7 +425,8 @@ struct EpiStoreNT {
   float* c;
   int ldc, N;
   size_t group_stride;
-  __device__ __forceinline__ void operator()(int m, int n, const float (&v)[32], int group) const {
+  __device__ __forceinline__ void operator()(int m, int n, const float (&v)[32], int group, int, bool valid) const {
+    if (!valid) return;
     float* row = c + group * group_stride + (size_t)m * ldc + n;
     if (n + 32 <= N && ((reinterpret_cast<uintptr_t>(row) & 15) == 0)) {
 #pragma unroll
@@ -433,16 +440,20 @@ struct EpiStoreNT {
   }
 };
 
-// Cᵀ store: out[n][m] (batched decode: the tile rows are weight rows r = m, columns are sequences b = n;
-// consecutive lanes hold consecutive r ⇒ coalesced rows of out[b][·])
+// Cᵀ store of split-K partials: out[group][split][n][ldc] at column m (batched decode: the tile rows are
+// weight rows r = m, the columns are sequences b = n; consecutive lanes hold consecutive r ⇒ coalesced)
 struct EpiStoreT {
   static constexpr bool kDual = false;
-  float* c;      // out[b][ldc]
-  int ldc, N;    // N = number of sequences
-  __device__ __forceinline__ void operator()(int m, int n, const float (&v)[32], int) const {
+  float* c;
+  int ldc, N;          // N = number of sequences
+  int ksplit;
+  size_t slab;         // floats per (group, split) partial = N_max · ldc
+  __device__ __forceinline__ void operator()(int m, int n, const float (&v)[32], int group, int split, bool valid) const {
+    if (!valid) return;
+    float* base = c + (size_t)(group * ksplit + split) * slab + m;
 #pragma unroll
     for (int j = 0; j < 32; ++j)
-      if (n + j < N) c[(size_t)(n + j) * ldc + m] = v[j];
+      if (n + j < N) base[(size_t)(n + j) * ldc] = v[j];
   }
 };
 

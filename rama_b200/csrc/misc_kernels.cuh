@@ -111,12 +111,11 @@ __device__ void bitonic_sort_cta(unsigned long long* a, int n_pow2, unsigned lon
   }
 }
 
-__global__ void __launch_bounds__(kSampleThreads) sample_kernel(const SampleParams p, int use_pdl) {
+__device__ __forceinline__ void sample_body(const SampleParams& p) {
   __shared__ float red[2 * kWarp];
   __shared__ int s_next, s_count, s_done;
   __shared__ float s_cum;
   __shared__ unsigned long long s_sort[kSortSmem];  // 32 KB: sort tile / walk staging
-  if (use_pdl) { pdl_launch_dependents(); pdl_wait(); }
   StepCtrl* ctrl = p.ctrl;
   const float temperature = p.use_ctrl_params ? ctrl->temperature : p.temperature;
   const float topp = p.use_ctrl_params ? ctrl->topp : p.topp;
@@ -264,6 +263,17 @@ __global__ void __launch_bounds__(kSampleThreads) sample_kernel(const SamplePara
     }
     ctrl->next = next;
   }
+}
+
+__global__ void __launch_bounds__(kSampleThreads) sample_kernel(const SampleParams p, int use_pdl) {
+  if (use_pdl) { pdl_launch_dependents(); pdl_wait(); }
+  sample_body(p);
+}
+
+// one CTA per sequence of a batch (server path: concurrent requests, lib.rs:127-160)
+__global__ void __launch_bounds__(kSampleThreads) sample_batch_kernel(const SampleParams* __restrict__ ps) {
+  const SampleParams p = ps[blockIdx.x];
+  sample_body(p);
 }
 
 // ---- element-wise Device ops (trait parity; the fused step does not launch these) -----------------

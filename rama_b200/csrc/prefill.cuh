@@ -69,7 +69,8 @@ struct EpiQKVPrefill {
   const float* freq_real;   // [T][hs/2]
   const float* freq_imag;
   int pos0, Dq, hs2;
-  __device__ __forceinline__ void operator()(int m, int n, const float (&v)[32], int group) const {
+  __device__ __forceinline__ void operator()(int m, int n, const float (&v)[32], int group, int, bool valid) const {
+    if (!valid) return;
     const int pos = pos0 + m;
     float* dst = (group == 0 ? q + (size_t)m * Dq : (group == 1 ? key_cache : value_cache) + (size_t)pos * Dq) + n;
     float o[32];
@@ -104,7 +105,8 @@ struct EpiSwiGLUPrefill {
   static constexpr bool kDual = true;
   float* hb;   // [M][F]
   int F;
-  __device__ __forceinline__ void operator()(int m, int n, const float (&h1)[32], const float (&h3)[32]) const {
+  __device__ __forceinline__ void operator()(int m, int n, const float (&h1)[32], const float (&h3)[32], bool valid) const {
+    if (!valid) return;
     float* dst = hb + (size_t)m * F + n;
     float o[32];
 #pragma unroll

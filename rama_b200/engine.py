@@ -29,7 +29,7 @@ from . import _lib
 from ._lib import CConfig, CTp, RamaError, check, fp, ip
 from .checkpoint import Config, SynthSpec, TENSORS, T, rope_tables
 
-__all__ = ["GPU", "Session", "DeviceBuffer", "View", "forward", "forward_per_op", "generate",
+__all__ = ["GPU", "Session", "Batch", "DeviceBuffer", "View", "forward", "forward_per_op", "generate",
            "RamaError", "DeviceWeights", "DeviceRunState"]
 
 
@@ -383,6 +383,56 @@ class Session:
         ln = (C.c_int32 * _lib.K_COUNT)()
         check(_lib.lib().rama_profile_step(self.h, token, pos, ms, ln))
         return {k: (ms[i], ln[i]) for i, k in enumerate(_lib.KERNEL_KINDS)}
+
+
+class Batch:
+    """Batched multi-sequence decode: one step for several Sessions at once (the server path — the
+    reference runs one forward()/sample() loop per request, lib.rs:127-160)."""
+
+    def __init__(self, gpu: GPU, max_seqs: int = 64):
+        self.gpu = gpu
+        self.h = C.c_void_p()
+        check(_lib.lib().rama_batch_create(gpu.h, max_seqs, C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            _lib.lib().rama_batch_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def _handles(sessions):
+        arr = (C.c_void_p * len(sessions))()
+        for i, s in enumerate(sessions):
+            arr[i] = s.h
+        return arr
+
+    def forward(self, sessions: Sequence["Session"], tokens: Sequence[int], pos: Sequence[int]):
+        """≙ forward(cfg, wv, rsv_i, token_i, pos_i, device) for every session i, in one pass."""
+        n = len(sessions)
+        t = np.asarray(list(tokens), dtype=np.int32)
+        p = np.asarray(list(pos), dtype=np.int32)
+        assert t.size == n and p.size == n
+        check(_lib.lib().rama_forward_batch(self.h, self._handles(sessions), t.ctypes.data_as(ip), p.ctypes.data_as(ip), n))
+
+    def sample(self, sessions: Sequence["Session"], temperature: float, topp: float) -> List[int]:
+        n = len(sessions)
+        out = np.zeros(n, dtype=np.int32)
+        check(_lib.lib().rama_sample_batch(self.h, self._handles(sessions), n, temperature, topp, out.ctypes.data_as(ip)))
+        return [int(x) for x in out]
+
+    def sync(self):
+        check(_lib.lib().rama_batch_sync(self.h))
+
+    def launches_per_step(self) -> int:
+        n = C.c_int32()
+        check(_lib.lib().rama_batch_launches_per_step(self.h, C.byref(n)))
+        return n.value
 
 
 def forward(session: Session, token: int, pos: int):

@@ -1,0 +1,114 @@
+"""Batched multi-sequence decode (tensor-core GEMMs, split-K, per-sequence KV caches) vs the per-token
+path and the CPU oracle.  The reference runs one forward()/sample() loop per request (lib.rs:127-160), so
+the contract is: after rama_forward_batch every session is in the state its own forward(token, pos) call
+would have left (logits within the 1e-3 north-star tolerance, cache rows tighter)."""
+import numpy as np
+import pytest
+
+from oracle import ref
+from rama_b200 import checkpoint as ck
+from rama_b200.engine import GPU, Batch, RamaError, Session
+from util import LOGIT_TOL, model_tensors, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(name, **kw):
+    cfg, spec, tensors = model_tensors(name, **kw)
+    gpu = GPU(0)
+    gpu.load_host(cfg, tensors)
+    return cfg, tensors, gpu, ref.Model(cfg, tensors)
+
+
+@pytest.mark.parametrize("name", ["tiny", "tiny-sep"])
+@pytest.mark.parametrize("B", [1, 5, 64])
+def test_batched_steps_equal_per_session_forward(name, B):
+    cfg, tensors, gpu, om = _pair(name)
+    rng = np.random.default_rng(B)
+    steps = 12
+    start = [int(x) for x in rng.integers(0, 6, B)]  # sequences join the batch at different positions
+    streams = [[1] + [int(t) for t in rng.integers(0, cfg.vocab_size, start[i] + steps)] for i in range(B)]
+    solo = [Session(gpu) for _ in range(B)]
+    bat = [Session(gpu) for _ in range(B)]
+    states = [ref.State(om) for _ in range(min(B, 3))]
+    for i in range(B):  # warm the caches up to each sequence's own start position through the batch-1 path
+        for pos in range(start[i]):
+            solo[i].forward(streams[i][pos], pos)
+            bat[i].forward(streams[i][pos], pos)
+            if i < len(states):
+                ref.forward(om, states[i], streams[i][pos], pos)
+        bat[i].sync(); solo[i].sync()
+    batch = Batch(gpu, 64)
+    for k in range(steps):
+        toks = [streams[i][start[i] + k] for i in range(B)]
+        pos = [start[i] + k for i in range(B)]
+        batch.forward(bat, toks, pos)
+        for i in range(B):
+            solo[i].forward(toks[i], pos[i])
+            if i < len(states):
+                ref.forward(om, states[i], toks[i], pos[i])
+        batch.sync()
+        if k in (0, 5, steps - 1):
+            for i in sorted({0, B // 2, B - 1}):
+                assert rel_err(bat[i].logits(), solo[i].logits()) < LOGIT_TOL, (k, i)
+            for i in range(len(states)):
+                assert rel_err(bat[i].logits(), states[i].logits) < LOGIT_TOL, (k, i)
+    nxt = batch.sample(bat, 0.0, 0.9)
+    assert nxt == [s.sample(0.0, 0.9) for s in solo]
+    nxt_t = batch.sample(bat, 0.8, 0.9)
+    assert nxt_t == [s.sample(0.8, 0.9) for s in solo]
+    for i in sorted({0, B - 1}):
+        n = start[i] + steps
+        ka = solo[i].state("key_cache").reshape(cfg.n_layers, cfg.seq_len, -1)[:, :n]
+        kb = bat[i].state("key_cache").reshape(cfg.n_layers, cfg.seq_len, -1)[:, :n]
+        va = solo[i].state("value_cache").reshape(cfg.n_layers, cfg.seq_len, -1)[:, :n]
+        vb = bat[i].state("value_cache").reshape(cfg.n_layers, cfg.seq_len, -1)[:, :n]
+        assert rel_err(kb, ka) < 1e-4 and rel_err(vb, va) < 1e-4
+    batch.close()
+    for s in solo + bat:
+        s.close()
+    gpu.close()
+
+
+def test_batch_errors():
+    cfg, tensors, gpu, om = _pair("tiny")
+    a, b = Session(gpu), Session(gpu)
+    batch = Batch(gpu, 2)
+    with pytest.raises(RamaError):
+        batch.forward([a, a], [1, 1], [0, 0])                 # the same session twice
+    with pytest.raises(RamaError):
+        batch.forward([a, b], [1, 1], [0, cfg.seq_len])       # pos ≥ seq_len: the reference panics (infer.rs:32)
+    with pytest.raises(RamaError):
+        batch.forward([a, b], [1, cfg.vocab_size], [0, 0])    # token outside the vocabulary
+    with pytest.raises(RamaError):
+        Batch(gpu, 65)
+    batch.close(); a.close(); b.close(); gpu.close()
+
+
+def test_batch_64_at_7b_layer_shapes():
+    """BASELINE config 5 geometry (dim 4096, ffn 11008, 32 heads, 64 concurrent sequences) on 2 layers."""
+    cfg = ck.CONFIGS["l7-2layer"]
+    gpu = GPU(0)
+    gpu.load_synthetic(cfg, ck.SynthSpec())
+    B, steps = 64, 6
+    rng = np.random.default_rng(1)
+    streams = [[1] + [int(t) for t in rng.integers(0, cfg.vocab_size, steps)] for _ in range(B)]
+    bat = [Session(gpu) for _ in range(B)]
+    check = [0, 17, 63]
+    solo = {i: Session(gpu) for i in check}
+    batch = Batch(gpu, 64)
+    for k in range(steps):
+        batch.forward(bat, [streams[i][k] for i in range(B)], [k] * B)
+        for i in check:
+            solo[i].forward(streams[i][k], k)
+    batch.sync()
+    for i in check:
+        assert rel_err(bat[i].logits(), solo[i].logits()) < LOGIT_TOL, i
+    nxt = batch.sample(bat, 0.0, 0.9)
+    for i in check:
+        assert nxt[i] == solo[i].sample(0.0, 0.9)
+    print("launches per batched step", batch.launches_per_step())
+    batch.close()
+    for s in bat + list(solo.values()):
+        s.close()
+    gpu.close()
