@@ -154,6 +154,7 @@ def main():
     ap.add_argument("--cpu-tokens", type=int, default=0, help="tokens of the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-prefill", action="store_true", help="skip the prompt-prefill (tensor core) measurement")
+    ap.add_argument("--no-batched", action="store_true", help="skip the 64-sequence batched-decode measurement")
     ap.add_argument("--seed", type=int, default=1234)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -286,6 +287,45 @@ def main():
                       "fused RoPE/KV-write and SwiGLU epilogues, causal f32 attention; ms_by_kind from CUDA events "
                       "around every launch"}
 
+    # ---- batched decode (BASELINE config 5): 64 concurrent sequences, one tensor-core pass per step ----
+    bd = None
+    if not args.no_batched and world == 1:
+        from rama_b200.engine import Batch
+        kv_bytes = 2 * cfg.n_layers * cfg.seq_len * cfg.dim * 4 + 4 * (cfg.n_heads * cfg.seq_len + 2 * cfg.vocab_size) + (8 << 20)
+        free, _ = gpu.mem_info()
+        nb = int(max(0, min(64, (free - (10 << 30)) // kv_bytes)))
+        if nb >= 2:
+            bsess = [Session(gpu) for _ in range(nb)]
+            batch = Batch(gpu, 64)
+            cur = [1] * nb
+            b_steps, b_warm = 48, 8
+            def bstep(pos):
+                batch.forward(bsess, cur, [pos] * nb)
+                nxt = batch.sample(bsess, 0.0, 0.9)
+                return [PROMPT[pos]] * nb if pos < len(PROMPT) else nxt
+            for pos in range(b_warm):
+                cur = bstep(pos)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for pos in range(b_warm, b_warm + b_steps):
+                cur = bstep(pos)
+            torch.cuda.synchronize()
+            b_s = time.perf_counter() - t0
+            step_ms = b_s / b_steps * 1e3
+            avg_pos = b_warm + (b_steps - 1) / 2
+            wbytes = cfg.weight_bytes_per_token()
+            kvb = nb * (2 * cfg.n_layers * (avg_pos + 1) * cfg.dim * 4 + 2 * cfg.n_layers * cfg.dim * 4)
+            bd = {"sequences": nb, "steps": b_steps, "ms_per_step": round(step_ms, 3),
+                  "tok_per_s": round(nb / (step_ms * 1e-3), 1), "speedup_vs_batch1": None,
+                  "launches_per_step": batch.launches_per_step(),
+                  "hbm_gbs_algorithmic": round((wbytes + kvb) / (step_ms * 1e-3) / 1e9, 1),
+                  "tensor_tf32_tflops_issued": round(3 * nb * 2.0 * (wbytes / 4) / (step_ms * 1e-3) / 1e12, 1),
+                  "what": "rama_forward_batch + rama_sample_batch per step, host-driven (token ids cross PCIe both ways "
+                          "every step), wall clock around the loop; weights stream once per step for all sequences"}
+            batch.close()
+            for s_ in bsess:
+                s_.close()
+
     # ---- per-kernel event timing (un-graphed) at a few positions: dominant-kernel roofline ----
     prof = {}
     for pos in sorted({0, tokens // 4, tokens // 2, 3 * tokens // 4, tokens - 1}):
@@ -362,6 +402,10 @@ def main():
                                  "peak_source": "half of the measured cuBLAS bf16 burst (tf32 runs at half the bf16 rate; "
                                                 "MEASURED_PEAKS.json has no tf32 figure)"}
         line["prefill"] = pf
+    if bd is not None:
+        bd["speedup_vs_batch1"] = round(bd["tok_per_s"] / value, 1)
+        bd["hbm_frac_of_measured_peak"] = round(bd["hbm_gbs_algorithmic"] / peak, 4)
+        line["batched_decode"] = bd
     print(json.dumps(line), flush=True)
     teardown()
 

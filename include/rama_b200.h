@@ -97,6 +97,9 @@ int rama_ctx_config(const rama_ctx* ctx, rama_config* out);
 /* Copies this rank's shard of a weight tensor back (tests). n = capacity in floats; *n_out = shard size. */
 int rama_ctx_weight_to_host(rama_ctx* ctx, int tensor, float* dst, size_t n, size_t* n_out);
 int rama_ctx_weight_bytes(const rama_ctx* ctx, size_t* bytes);
+/* free / total HBM of the context's device (sizing the number of concurrent sessions: one session of
+ * llama2-7B holds a 2 GiB KV cache, ram.rs:20-21) */
+int rama_ctx_mem_info(rama_ctx* ctx, size_t* free_bytes, size_t* total_bytes);
 
 /* ---- session: RunState on the device --------------------------------------------------- */
 

@@ -54,6 +54,7 @@ _SIGS = {
     "rama_ctx_config": ([vp, C.POINTER(CConfig)], C.c_int),
     "rama_ctx_weight_to_host": ([vp, C.c_int, fp, sz, C.POINTER(sz)], C.c_int),
     "rama_ctx_weight_bytes": ([vp, C.POINTER(sz)], C.c_int),
+    "rama_ctx_mem_info": ([vp, C.POINTER(sz), C.POINTER(sz)], C.c_int),
     "rama_session_create": ([vp, C.POINTER(vp)], C.c_int),
     "rama_session_reset": ([vp], C.c_int),
     "rama_session_destroy": ([vp], C.c_int),

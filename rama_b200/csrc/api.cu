@@ -494,6 +494,13 @@ extern "C" int rama_ctx_weight_to_host(rama_ctx* c, int tensor, float* dst, size
   return RAMA_OK;
 }
 
+extern "C" int rama_ctx_mem_info(rama_ctx* c, size_t* free_bytes, size_t* total_bytes) {
+  if (!c || !free_bytes || !total_bytes) return fail(RAMA_E_INVALID, "NULL argument");
+  CK(cudaSetDevice(c->device));
+  CK(cudaMemGetInfo(free_bytes, total_bytes));
+  return RAMA_OK;
+}
+
 extern "C" int rama_ctx_weight_bytes(const rama_ctx* c, size_t* bytes) {
   if (!c || !bytes) return fail(RAMA_E_INVALID, "NULL argument");
   size_t t = 0;

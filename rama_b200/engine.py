@@ -185,6 +185,12 @@ class GPU:
     def sync(self):
         check(_lib.lib().rama_ctx_sync(self.h))
 
+    def mem_info(self) -> Tuple[int, int]:
+        """(free, total) bytes of HBM on this device."""
+        f, t = C.c_size_t(), C.c_size_t()
+        check(_lib.lib().rama_ctx_mem_info(self.h, C.byref(f), C.byref(t)))
+        return f.value, t.value
+
     # ---- trait Device<T> (device.rs:3-24) ---------------------------------------------------
     def array_add(self, target: View, source: View, n: int):
         check(_lib.lib().rama_op_array_add(self.h, target.ptr(), source.ptr(), n))
