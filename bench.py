@@ -289,11 +289,15 @@ def main():
 
     # ---- batched decode (BASELINE config 5): 64 concurrent sequences, one tensor-core pass per step ----
     bd = None
-    if not args.no_batched and world == 1:
+    if not args.no_batched:
         from rama_b200.engine import Batch
-        kv_bytes = 2 * cfg.n_layers * cfg.seq_len * cfg.dim * 4 + 4 * (cfg.n_heads * cfg.seq_len + 2 * cfg.vocab_size) + (8 << 20)
+        kv_bytes = 2 * cfg.n_layers * cfg.seq_len * cfg.dim * 4 // world + 4 * (cfg.n_heads * cfg.seq_len + 2 * cfg.vocab_size) + (8 << 20)
         free, _ = gpu.mem_info()
         nb = int(max(0, min(64, (free - (10 << 30)) // kv_bytes)))
+        if world > 1:  # every rank must run the same batch
+            nbt = torch.tensor([nb], dtype=torch.int64, device="cuda")
+            dist.all_reduce(nbt, op=dist.ReduceOp.MIN)
+            nb = int(nbt.item())
         if nb >= 2:
             bsess = [Session(gpu) for _ in range(nb)]
             batch = Batch(gpu, 64)
@@ -305,21 +309,25 @@ def main():
                 return [PROMPT[pos]] * nb if pos < len(PROMPT) else nxt
             for pos in range(b_warm):
                 cur = bstep(pos)
-            torch.cuda.synchronize()
+            barrier()
             t0 = time.perf_counter()
             for pos in range(b_warm, b_warm + b_steps):
                 cur = bstep(pos)
-            torch.cuda.synchronize()
+            barrier()
             b_s = time.perf_counter() - t0
+            bt = torch.tensor([b_s], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(bt, op=dist.ReduceOp.MAX)
+            b_s = float(bt.item())
             step_ms = b_s / b_steps * 1e3
             avg_pos = b_warm + (b_steps - 1) / 2
-            wbytes = cfg.weight_bytes_per_token()
-            kvb = nb * (2 * cfg.n_layers * (avg_pos + 1) * cfg.dim * 4 + 2 * cfg.n_layers * cfg.dim * 4)
+            wbytes = cfg.weight_bytes_per_token() / world   # per GPU
+            kvb = nb * (2 * cfg.n_layers * (avg_pos + 1) * cfg.dim * 4 + 2 * cfg.n_layers * cfg.dim * 4) / world
             bd = {"sequences": nb, "steps": b_steps, "ms_per_step": round(step_ms, 3),
                   "tok_per_s": round(nb / (step_ms * 1e-3), 1), "speedup_vs_batch1": None,
                   "launches_per_step": batch.launches_per_step(),
-                  "hbm_gbs_algorithmic": round((wbytes + kvb) / (step_ms * 1e-3) / 1e9, 1),
-                  "tensor_tf32_tflops_issued": round(3 * nb * 2.0 * (wbytes / 4) / (step_ms * 1e-3) / 1e12, 1),
+                  "hbm_gbs_algorithmic_per_gpu": round((wbytes + kvb) / (step_ms * 1e-3) / 1e9, 1),
+                  "tensor_tf32_tflops_issued_per_gpu": round(3 * nb * 2.0 * (wbytes / 4) / (step_ms * 1e-3) / 1e12, 1),
                   "what": "rama_forward_batch + rama_sample_batch per step, host-driven (token ids cross PCIe both ways "
                           "every step), wall clock around the loop; weights stream once per step for all sequences"}
             batch.close()
@@ -404,7 +412,7 @@ def main():
         line["prefill"] = pf
     if bd is not None:
         bd["speedup_vs_batch1"] = round(bd["tok_per_s"] / value, 1)
-        bd["hbm_frac_of_measured_peak"] = round(bd["hbm_gbs_algorithmic"] / peak, 4)
+        bd["hbm_frac_of_measured_peak"] = round(bd["hbm_gbs_algorithmic_per_gpu"] / peak, 4)
         line["batched_decode"] = bd
     print(json.dumps(line), flush=True)
     teardown()

@@ -179,6 +179,10 @@ enum rama_kernel_kind {
 int rama_profile_step(rama_session* s, int32_t token, int32_t pos, float ms[RAMA_K_COUNT],
                       int32_t launches[RAMA_K_COUNT]);
 
+/* Phase timeline of one persistent step (tools/step_trace.py): SM-clock stamps of CTA 0 at kernel entry and
+ * before/after each of the 5L+1 grid barriers. */
+int rama_step_trace(rama_session* s, int32_t token, int32_t pos, long long* stamps, int32_t cap, int32_t* n_out);
+
 /* ---- op level: 1:1 with `trait Device<T>` (engine/src/device/device.rs:3-24) -------------
  * Pointers are device pointers already offset by the view's range.start (a View is
  * (storage, absolute range), mod.rs:16-51).  Asynchronous on the ctx's op stream;

@@ -74,6 +74,7 @@ _SIGS = {
     "rama_logits_to_host": ([vp, fp, sz], C.c_int),
     "rama_session_set_debug": ([vp, C.c_int], C.c_int),
     "rama_session_launches_per_step": ([vp, C.POINTER(C.c_int)], C.c_int),
+    "rama_step_trace": ([vp, C.c_int32, C.c_int32, C.POINTER(C.c_longlong), C.c_int32, ip], C.c_int),
     "rama_profile_step": ([vp, C.c_int32, C.c_int32, fp, ip], C.c_int),
     "rama_dev_alloc": ([vp, sz, C.POINTER(fp)], C.c_int),
     "rama_dev_free": ([vp, fp], C.c_int),

@@ -26,6 +26,7 @@
 #include "gemv.cuh"
 #include "misc_kernels.cuh"
 #include "prefill.cuh"
+#include "step_kernel.cuh"
 #include "batch.cuh"
 
 using namespace rama;
@@ -127,6 +128,8 @@ struct rama_ctx {
   int use_pdl = 0;
   int variant_override = -1;
   int p2p = 0;  // TP exchange: 1 = fused peer-memory all-reduce (default), 0 = NCCL collectives
+  int persistent = 0;  // RAMA_STEP=persistent: the decode step as one persistent cooperative kernel (step_kernel.cuh);
+                       // default: one fused kernel per op group in a CUDA graph (measured faster)
   std::mutex mu;
 };
 
@@ -141,6 +144,8 @@ struct rama_session {
   unsigned int* tickets = nullptr;
   ArgPart* part = nullptr;      // [world * sm_count] greedy partials (single GPU / NCCL mode)
   unsigned* seq = nullptr;      // device step counter (epoch source of the fused TP exchange)
+  unsigned long long* bar = nullptr;  // persistent step kernel: [0] grid-barrier arrivals, [1] steps completed
+  bool persistent = false;
   int cls_grid = 0;             // CTAs of the classifier launch (slots that get written)
   // fused TP exchange: one IPC-exported block per session {flags[3][P] | parts[P][SMs] | inbox[2][P][D]}
   char* peer_mem = nullptr;
@@ -153,7 +158,10 @@ struct rama_session {
   StepCtrl* h_ring = nullptr;   // pinned ring for host-driven (token,pos)
   int ring_i = 0;
   int32_t* h_ret = nullptr;     // pinned {next, error}
-  cudaGraphExec_t g_fwd = nullptr, g_step[2] = {nullptr, nullptr};  // [0] greedy, [1] sampled
+  // step graphs per attention grid bucket (chunks-per-head CTAs for the position range): [mode][bucket],
+  // mode 0 = forward, 1 = chained greedy, 2 = chained sampled
+  cudaGraphExec_t g[3][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+  int attn_gy = 1;              // gridDim.y of the attention launch being enqueued
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int keep_att = 0;
   int n_split = 1;
@@ -272,6 +280,10 @@ extern "C" int rama_ctx_create(int device, const rama_tp* tp, rama_ctx** out) {
   c->sm_count = prop.multiProcessorCount;
   c->use_pdl = env_int("RAMA_PDL", 1);
   c->variant_override = env_int("RAMA_GEMV_VARIANT", -1);
+  {
+    const char* m = getenv("RAMA_STEP");
+    c->persistent = m && strcmp(m, "persistent") == 0;
+  }
   {
     const char* m = getenv("RAMA_TP_COMM");
     c->p2p = !(m && strcmp(m, "nccl") == 0);
@@ -523,8 +535,7 @@ static void session_free(rama_session* s) {
   if (!s) return;
   cudaSetDevice(s->ctx->device);
   if (s->stream) cudaStreamSynchronize(s->stream);
-  if (s->g_fwd) cudaGraphExecDestroy(s->g_fwd);
-  for (auto& g : s->g_step) if (g) cudaGraphExecDestroy(g);
+  for (auto& gm : s->g) for (auto& g : gm) if (g) cudaGraphExecDestroy(g);
   if (s->p2p) {
     rama_ctx* c = s->ctx;
     for (int r = 0; r < c->world; ++r)
@@ -538,7 +549,7 @@ static void session_free(rama_session* s) {
   }
   void* bufs[] = {s->x0, s->x1, s->xfinal, s->xb, s->xb2, s->w2out, s->hb, s->hb2, s->q, s->k, s->v, s->att,
                   s->logits, s->key_cache, s->value_cache, s->attn_ws, s->tickets, s->part, s->sort_keys,
-                  s->ctrl, s->d_prompt, s->d_out, s->seq, s->pf_x, s->pf_xn, s->pf_q, s->pf_att, s->pf_y, s->pf_h,
+                  s->ctrl, s->d_prompt, s->d_out, s->seq, s->bar, s->pf_x, s->pf_xn, s->pf_q, s->pf_att, s->pf_y, s->pf_h,
                   s->pf_tokens};
   for (void* b : bufs) if (b) cudaFree(b);
   if (s->h_ring) cudaFreeHost(s->h_ring);
@@ -657,8 +668,11 @@ extern "C" int rama_session_create(rama_ctx* c, rama_session** out) {
   A(dalloc(&s->attn_ws, (size_t)c->Hl * s->n_split * (c->hs + 2)));
   A(dalloc(&s->tickets, (size_t)c->Hl));
   s->p2p = c->world > 1 && c->p2p;
+  s->persistent = c->persistent && (c->world == 1 || s->p2p);
+  if (s->persistent) s->cls_grid = c->sm_count;  // every CTA of the persistent kernel writes a classifier partial
   A(dalloc(&s->part, (size_t)c->world * c->sm_count));
   A(dalloc(&s->seq, 1));
+  A(dalloc(&s->bar, 2));
   A(dalloc(&s->sort_keys, vp2));
   A(dalloc(&s->ctrl, 1));
   A(dalloc(&s->d_prompt, T)); A(dalloc(&s->d_out, T));
@@ -714,8 +728,7 @@ extern "C" int rama_session_set_debug(rama_session* s, int keep_att) {
   CK(cudaSetDevice(s->ctx->device));
   CK(cudaStreamSynchronize(s->stream));
   if (s->keep_att != keep_att) {  // the captured graphs bake the att pointer in
-    if (s->g_fwd) { cudaGraphExecDestroy(s->g_fwd); s->g_fwd = nullptr; }
-    for (auto& g : s->g_step) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+    for (auto& gm : s->g) for (auto& g : gm) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
   }
   s->keep_att = keep_att;
   return RAMA_OK;
@@ -766,9 +779,71 @@ static void launch_plain(StepEnq& q, int kind, F&& f) {
   q.post(cudaSuccess);
 }
 
+static int wk_for(int K4) { return K4 >= 1024 ? 8 : (K4 >= 512 ? 4 : (K4 >= 128 ? 2 : 1)); }
+
+// The step as ONE persistent cooperative launch (step_kernel.cuh); mode as enqueue_step.
+static int enqueue_step_persistent(rama_session* s, cudaStream_t st, int mode, int* n_launch, long long* trace = nullptr) {
+  rama_ctx* c = s->ctx;
+  StepParams p{};
+  p.trace = trace;
+  p.D = c->D; p.Dq = c->Dq; p.Fl = c->Fl; p.L = c->L; p.V = c->V; p.Vl = c->Vl; p.v0 = c->v0; p.T = c->T; p.hs = c->hs; p.Hl = c->Hl;
+  p.emb = c->w[RAMA_T_TOKEN_EMBEDDING]; p.rms_att = c->w[RAMA_T_RMS_ATT]; p.wq = c->w[RAMA_T_WQ]; p.wk = c->w[RAMA_T_WK];
+  p.wv = c->w[RAMA_T_WV]; p.wo = c->w[RAMA_T_WO]; p.rms_ffn = c->w[RAMA_T_RMS_FFN]; p.w1 = c->w[RAMA_T_W1]; p.w2 = c->w[RAMA_T_W2];
+  p.w3 = c->w[RAMA_T_W3]; p.rms_final = c->w[RAMA_T_RMS_FINAL]; p.freq_real = c->w[RAMA_T_FREQ_REAL];
+  p.freq_imag = c->w[RAMA_T_FREQ_IMAG]; p.wcls = c->wcls;
+  p.x0 = s->x0; p.x1 = s->x1; p.xfinal = s->xfinal; p.xb = s->xb; p.xb2 = s->xb2; p.w2out = s->w2out; p.hb = s->hb; p.hb2 = s->hb2;
+  p.q = s->q; p.k = s->k; p.v = s->v; p.att = s->keep_att ? s->att : nullptr; p.logits = s->logits;
+  p.key_cache = s->key_cache; p.value_cache = s->value_cache; p.attn_ws = s->attn_ws; p.tickets = s->tickets; p.part = s->part;
+  p.seq = s->seq; p.ctrl = s->ctrl; p.bar = s->bar; p.prompt = s->d_prompt; p.out_tokens = s->d_out; p.n_split = s->n_split;
+  p.wk_d = wk_for(c->D / 4); p.wk_wo = wk_for(c->Dq / 4); p.wk_w2 = wk_for(c->Fl / 4);
+  p.mode = mode == 1 ? 1 : 0;
+  p.rank = c->rank; p.world = s->p2p ? c->world : 1;
+  for (int r = 0; r < kMaxPeers; ++r) p.peer_base[r] = r < c->world ? s->peer_base[r] : nullptr;
+  p.off_inbox = s->off_inbox; p.off_parts = s->off_parts;
+  const int grid = c->sm_count;
+  size_t smem = 0;
+  auto need = [&](int K4, int n_pairs, int wk) { smem = std::max(smem, gemv_smem_bytes(K4, n_pairs, grid, wk)); };
+  need(c->D / 4, 3 * c->Dq / 2, p.wk_d); need(c->Dq / 4, c->D / 2, p.wk_wo); need(c->D / 4, c->Fl, p.wk_d);
+  need(c->Fl / 4, c->D / 2, p.wk_w2); need(c->D / 4, (c->Vl + 1) / 2, p.wk_d);
+  if (smem > kMaxDynSmem) return fail(RAMA_E_INVALID, "persistent step: %zu bytes of shared memory needed", smem);
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [&] {
+    attr_err = cudaFuncSetAttribute(decode_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
+  });
+  if (attr_err != cudaSuccess) return fail(RAMA_E_CUDA, "persistent step attribute: %s", cudaGetErrorString(attr_err));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kGemvThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative;  // all CTAs co-resident: the grid barriers cannot deadlock
+  at[0].val.cooperative = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, decode_step_kernel, p);
+  if (e != cudaSuccess) return fail(RAMA_E_CUDA, "persistent step launch: %s", cudaGetErrorString(e));
+  int launches = 1;
+  if (mode == 2) {
+    if (c->world > 1) {
+      NK(g_nccl.AllGather(s->logits + c->v0, s->logits, (size_t)c->Vl, kNcclFloat32, c->comm, st));
+      ++launches;
+    }
+    SampleParams sp{s->logits, s->part, (c->world > 1 ? c->world : 1) * c->sm_count, c->sm_count, c->V, s->ctrl, s->d_prompt,
+                    s->d_out, s->sort_keys, 0.f, 0.f, 1, peer_in_parts(s)};
+    sample_kernel<<<1, kSampleThreads, 0, st>>>(sp, 0);
+    CK(cudaGetLastError());
+    ++launches;
+  }
+  if (n_launch) *n_launch = launches;
+  return RAMA_OK;
+}
+
 // mode: 0 = forward only (logits + greedy partials), 1 = + chained greedy sampler, 2 = + chained top-p
 static int enqueue_step(rama_session* s, cudaStream_t st, int mode, StepTrace* tr, int* n_launch) {
   rama_ctx* c = s->ctx;
+  if (s->persistent && !tr) return enqueue_step_persistent(s, st, mode, n_launch);
   StepEnq q{s, st, tr};
   // PDL edges are only used inside captured graphs / plain streams without event timing
   q.pdl = tr ? 0 : c->use_pdl;
@@ -811,7 +886,7 @@ static int enqueue_step(rama_session* s, cudaStream_t st, int mode, StepTrace* t
                     // HBM idles during attention: pull this layer's wo (≤ 64 MB, fits L2) in meanwhile
                     W[RAMA_T_WO] + (size_t)l * D * Dq, std::min((size_t)D * Dq * sizeof(float), (size_t)96 << 20)};
       cudaLaunchConfig_t cfg{};
-      cfg.gridDim = dim3(c->Hl, s->n_split);
+      cfg.gridDim = dim3(c->Hl, s->attn_gy);
       cfg.blockDim = dim3(kAttnThreads);
       cfg.stream = st;
       cudaLaunchAttribute at[1];
@@ -926,6 +1001,14 @@ static int init_parts(rama_session* s) {
   return RAMA_OK;
 }
 
+// attention grid bucket for a position: one CTA per 32-timestep chunk up to 8 / 32 / all chunks of the window
+static int attn_bucket(const rama_session* s, int pos, int* gy) {
+  const int need = pos / kAttnChunk + 1;
+  const int b = need <= 8 ? 0 : (need <= 32 ? 1 : 2);
+  *gy = std::min(s->n_split, b == 0 ? 8 : (b == 1 ? 32 : s->n_split));
+  return b;
+}
+
 static int capture(rama_session* s, int mode, cudaGraphExec_t* out) {
   RK(init_parts(s));
   cudaGraph_t g = nullptr;
@@ -945,6 +1028,7 @@ static int capture(rama_session* s, int mode, cudaGraphExec_t* out) {
 extern "C" int rama_session_launches_per_step(const rama_session* s, int* n) {
   if (!s || !n) return fail(RAMA_E_INVALID, "NULL argument");
   const rama_ctx* c = s->ctx;
+  if (s->persistent) { *n = 1; return RAMA_OK; }  // the whole greedy step is one persistent cooperative launch
   // embed + L·(qkv, attn, wo, w13, w2) + cls + sample (+ collectives under TP)
   *n = 1 + 5 * c->L + 1 + 1 + (c->world > 1 && !s->p2p ? 2 * c->L + 1 : 0);
   return RAMA_OK;
@@ -957,7 +1041,8 @@ extern "C" int rama_forward(rama_session* s, int32_t token, int32_t pos) {
     return fail(RAMA_E_STATE, "pos %d outside [0, seq_len=%d)", pos, c->T);
   if (token < 0 || token >= c->V) return fail(RAMA_E_INVALID, "token %d outside the vocabulary", token);
   CK(cudaSetDevice(c->device));
-  if (!s->g_fwd) RK(capture(s, 0, &s->g_fwd));
+  const int bk = attn_bucket(s, pos, &s->attn_gy);
+  if (!s->g[0][bk]) RK(capture(s, 0, &s->g[0][bk]));
   StepCtrl* h = &s->h_ring[s->ring_i];
   if (++s->ring_i == kRing) {  // never overwrite a slot a pending copy may still read
     s->ring_i = 0;
@@ -968,7 +1053,7 @@ extern "C" int rama_forward(rama_session* s, int32_t token, int32_t pos) {
   h->token = token;
   h->chained = 0;
   CK(cudaMemcpyAsync(s->ctrl, h, sizeof(StepCtrl), cudaMemcpyHostToDevice, s->stream));
-  CK(cudaGraphLaunch(s->g_fwd, s->stream));
+  CK(cudaGraphLaunch(s->g[0][bk], s->stream));
   s->logits_gathered = false;
   s->parts_valid = true;
   return RAMA_OK;
@@ -989,6 +1074,7 @@ static int read_ret(rama_session* s, int32_t* next) {
   if (s->h_ret[1] == 1) return fail(RAMA_E_STATE, "token id outside the vocabulary reached the device step");
   if (s->h_ret[1] == 2) return fail(RAMA_E_STATE, "top-p candidate list is empty (the reference panics here, infer.rs:66)");
   if (s->h_ret[1] == 3) return fail(RAMA_E_NCCL, "timed out waiting for a tensor-parallel peer's partial results");
+  if (s->h_ret[1] == 4) return fail(RAMA_E_CUDA, "grid barrier of the persistent step kernel timed out");
   if (next) *next = s->h_ret[0];
   return RAMA_OK;
 }
@@ -1024,7 +1110,10 @@ extern "C" int rama_generate(rama_session* s, const int32_t* prompt, int32_t n_p
     if (prompt[i] < 0 || prompt[i] >= c->V) return fail(RAMA_E_INVALID, "prompt token %d outside the vocabulary", prompt[i]);
   CK(cudaSetDevice(c->device));
   const int gi = temperature == 0.0f ? 0 : 1;
-  if (!s->g_step[gi]) RK(capture(s, gi + 1, &s->g_step[gi]));
+  for (int i = 0; i < steps; i += kAttnChunk) {  // make sure every bucket this run touches is captured before timing
+    const int bk = attn_bucket(s, i, &s->attn_gy);
+    if (!s->g[gi + 1][bk]) RK(capture(s, gi + 1, &s->g[gi + 1][bk]));
+  }
   const int np = std::min<int>(n_prompt, c->T);
   if (np) CK(cudaMemcpyAsync(s->d_prompt, prompt, np * sizeof(int32_t), cudaMemcpyHostToDevice, s->stream));
   StepCtrl* h = &s->h_ring[s->ring_i];
@@ -1060,7 +1149,10 @@ extern "C" int rama_generate(rama_session* s, const int32_t* prompt, int32_t n_p
     CK(cudaMemcpyAsync(s->ctrl, h, sizeof(StepCtrl), cudaMemcpyHostToDevice, s->stream));
     CK(cudaEventRecord(s->ev0, s->stream));
   }
-  for (int i = first_step; i < steps; ++i) CK(cudaGraphLaunch(s->g_step[gi], s->stream));
+  for (int i = first_step; i < steps; ++i) {
+    int gy;
+    CK(cudaGraphLaunch(s->g[gi + 1][attn_bucket(s, i, &gy)], s->stream));
+  }
   CK(cudaEventRecord(s->ev1, s->stream));
   if (steps) CK(cudaMemcpyAsync(out_tokens, s->d_out, steps * sizeof(int32_t), cudaMemcpyDeviceToHost, s->stream));
   s->logits_gathered = gi == 1;
@@ -1077,6 +1169,7 @@ extern "C" int rama_profile_step(rama_session* s, int32_t token, int32_t pos, fl
   if (token < 0 || token >= c->V) return fail(RAMA_E_INVALID, "token outside the vocabulary");
   CK(cudaSetDevice(c->device));
   RK(init_parts(s));
+  attn_bucket(s, pos, &s->attn_gy);
   StepCtrl* h = &s->h_ring[s->ring_i];
   if (++s->ring_i == kRing) { s->ring_i = 0; CK(cudaStreamSynchronize(s->stream)); }
   memset(h, 0, sizeof(*h));
@@ -1098,6 +1191,35 @@ extern "C" int rama_profile_step(rama_session* s, int32_t token, int32_t pos, fl
   if (rc != RAMA_OK) return rc;
   if (e != cudaSuccess) return fail(RAMA_E_CUDA, "profile step: %s", cudaGetErrorString(e));
   return RAMA_OK;
+}
+
+// Phase timeline of one persistent step: clock64() of CTA 0 at kernel entry and before/after each grid barrier
+// (2·(5L+1)+1 stamps).  Tool for tools/step_trace.py.
+extern "C" int rama_step_trace(rama_session* s, int32_t token, int32_t pos, long long* stamps, int32_t cap, int32_t* n_out) {
+  if (!s || !stamps || !n_out) return fail(RAMA_E_INVALID, "NULL argument");
+  rama_ctx* c = s->ctx;
+  if (!s->persistent) return fail(RAMA_E_STATE, "session does not use the persistent step kernel");
+  if (pos < 0 || pos >= c->T || token < 0 || token >= c->V) return fail(RAMA_E_INVALID, "token/pos out of range");
+  const int n = 2 * (5 * c->L + 1) + 1;
+  if (cap < n) return fail(RAMA_E_INVALID, "need room for %d stamps", n);
+  CK(cudaSetDevice(c->device));
+  long long* d = nullptr;
+  CK(cudaMalloc((void**)&d, n * sizeof(long long)));
+  StepCtrl* h = &s->h_ring[s->ring_i];
+  if (++s->ring_i == kRing) { s->ring_i = 0; CK(cudaStreamSynchronize(s->stream)); }
+  memset(h, 0, sizeof(*h));
+  h->pos = pos; h->token = token;
+  CK(cudaMemcpyAsync(s->ctrl, h, sizeof(StepCtrl), cudaMemcpyHostToDevice, s->stream));
+  int rc = enqueue_step_persistent(s, s->stream, 0, nullptr, d);
+  if (rc == RAMA_OK) {
+    CK(cudaMemcpyAsync(stamps, d, n * sizeof(long long), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+  }
+  cudaFree(d);
+  *n_out = n;
+  s->logits_gathered = false;
+  s->parts_valid = true;
+  return rc;
 }
 
 extern "C" int rama_logits_to_host(rama_session* s, float* dst, size_t n) {
@@ -1347,12 +1469,17 @@ extern "C" int rama_session_set_prefill(rama_session* s, int32_t min_rows) {
 extern "C" int rama_batch_destroy(rama_batch* b);
 constexpr int kBatchMax = 64;    // one 64-column MMA tile of sequences
 constexpr int kBatchRing = 8;
+// batched-decode GEMM tile: 128 weight rows × 64 sequences, 2 stages, chunks of 2 k-blocks; two CTAs fit an SM
+// (64 KB of shared memory and 256 TMEM columns each) and interleave their pipelines
+#define BATCH_GEMM launch_gemm_tf32x3<64, 2, 2>
+constexpr int kBatchCtasPerSm = GemmSmem<64, 2>::kCtasPerSm;
 
 struct rama_batch {
   rama_ctx* ctx = nullptr;
   int cap = 0, n_split = 1;
   cudaStream_t stream = nullptr;
   float *x = nullptr, *xn = nullptr, *q = nullptr, *att = nullptr, *h = nullptr, *part = nullptr, *attn_ws = nullptr;
+  float *red = nullptr, *lstage = nullptr;  // tensor parallelism: all-reduce buffer [B][D], logits all-gather staging [P][B][Vl]
   unsigned int* tickets = nullptr;
   size_t part_floats = 0;
   BatchSeq* d_seqs = nullptr;
@@ -1374,8 +1501,9 @@ static int pick_ksplit(const rama_ctx* c, int tiles, int K) {
   double best_eff = 0.0;
   for (int S = 1; S <= 16; ++S) {
     if (S > 1 && total_kb / S < 8) break;
-    const int units = tiles * S, waves = (units + c->sm_count - 1) / c->sm_count;
-    const double eff = (double)units / ((double)waves * c->sm_count);
+    const int slots = c->sm_count * kBatchCtasPerSm;  // CTAs resident at once
+    const int units = tiles * S, waves = (units + slots - 1) / slots;
+    const double eff = (double)units / ((double)waves * slots);
     if (eff > best_eff + 0.02) { best_eff = eff; best = S; }
   }
   return best;
@@ -1385,7 +1513,6 @@ extern "C" int rama_batch_create(rama_ctx* c, int32_t max_seqs, rama_batch** out
   if (!c || !out) return fail(RAMA_E_INVALID, "NULL argument");
   if (!c->loaded) return fail(RAMA_E_STATE, "no weights loaded");
   if (max_seqs < 1 || max_seqs > kBatchMax) return fail(RAMA_E_INVALID, "max_seqs must be in [1, %d]", kBatchMax);
-  if (c->world > 1) return fail(RAMA_E_INVALID, "batched decode is single-GPU in this version (tensor parallelism: batch-1 and prefill)");
   CK(cudaSetDevice(c->device));
   rama_batch* b = new rama_batch();
   b->ctx = c;
@@ -1405,6 +1532,7 @@ extern "C" int rama_batch_create(rama_ctx* c, int32_t max_seqs, rama_batch** out
 #define A(call) if (e == cudaSuccess) e = (call)
   A(dalloc(&b->x, B * D)); A(dalloc(&b->xn, B * D)); A(dalloc(&b->q, B * Dq)); A(dalloc(&b->att, B * Dq));
   A(dalloc(&b->h, B * Fl)); A(dalloc(&b->part, pf));
+  if (c->world > 1) { A(dalloc(&b->red, B * D)); A(dalloc(&b->lstage, (size_t)c->world * B * c->Vl)); }
   A(dalloc(&b->attn_ws, B * c->Hl * b->n_split * (c->hs + 2)));
   A(dalloc(&b->tickets, B * c->Hl));
   A(dalloc(&b->d_seqs, B)); A(dalloc(&b->d_sp, B)); A(dalloc(&b->d_next, 2 * B));
@@ -1428,7 +1556,7 @@ extern "C" int rama_batch_destroy(rama_batch* b) {
   cudaSetDevice(b->ctx->device);
   if (b->stream) cudaStreamSynchronize(b->stream);
   for (auto g : b->graphs) if (g) cudaGraphExecDestroy(g);
-  void* bufs[] = {b->x, b->xn, b->q, b->att, b->h, b->part, b->attn_ws, b->tickets, b->d_seqs, b->d_sp, b->d_next};
+  void* bufs[] = {b->x, b->xn, b->q, b->att, b->h, b->part, b->attn_ws, b->tickets, b->d_seqs, b->d_sp, b->d_next, b->red, b->lstage};
   for (void* p : bufs) if (p) cudaFree(p);
   if (b->h_seqs) cudaFreeHost(b->h_seqs);
   if (b->h_sp) cudaFreeHost(b->h_sp);
@@ -1460,10 +1588,23 @@ static int enqueue_batch_step(rama_batch* b, int n, int* n_launch) {
   LK(cudaSuccess);
   GemmOperand X{b->xn, (size_t)n, (size_t)D};
   int S_prev = 0;  // split factor of the pending residual partials in b->part (0: none)
+  const float* pending = b->part;
+  // tensor parallelism: row-parallel wo / w2 leave a partial [n][D] on every rank — sum the split-K partials, all-reduce
+  // over NVLink (NCCL, 1 MB at 64 sequences), and hand the reduced buffer to the next addnorm as a single "split"
+  auto reduce_ranks = [&](int& S) -> int {
+    if (c->world <= 1) return RAMA_OK;
+    sum_partials_kernel<<<c->sm_count * 2, 256, 0, st>>>(b->red, b->part, (size_t)n * D, S);
+    ++launches;
+    NK(g_nccl.AllReduce(b->red, b->red, (size_t)n * D, kNcclFloat32, kNcclSum, c->comm, st));
+    ++launches;
+    S = 1;
+    pending = b->red;
+    return RAMA_OK;
+  };
   for (int l = 0; l < L; ++l) {
     const size_t layer_off = (size_t)l * T * Dq;
     // x += pending w2 output; xn = rmsnorm(x)   (infer.rs:19, :47 of the previous layer)
-    batch_addnorm_kernel<<<n, 256, 0, st>>>(b->x, S_prev ? b->part : nullptr, S_prev, (size_t)n * D,
+    batch_addnorm_kernel<<<n, 256, 0, st>>>(b->x, S_prev ? pending : nullptr, S_prev, (size_t)n * D,
                                             W[RAMA_T_RMS_ATT] + (size_t)l * D, b->xn, D);
     LK(cudaSuccess);
     {  // [wq;wk;wv] (weights = the 128-row operand, the batch = the 64-column operand)   (infer.rs:20-23)
@@ -1472,14 +1613,14 @@ static int enqueue_batch_step(rama_batch* b, int n, int* n_launch) {
                           {W[RAMA_T_WV] + (size_t)l * Dq * D, (size_t)Dq, (size_t)D}};
       const int S = pick_ksplit(c, 3 * tiles(Dq), D);
       EpiStoreT epi{b->part, Dq, n, S, (size_t)n * Dq};
-      LK((launch_gemm_tf32x3<64, 4, 2>(st, A, 3, &X, 1, Dq, n, D, 0, S, epi)));
+      LK((BATCH_GEMM(st, A, 3, &X, 1, Dq, n, D, 0, S, epi)));
       batch_qkv_finish_kernel<<<dim3(n, (Dq / 2 + 255) / 256), 256, 0, st>>>(
           b->part, S, (size_t)n * Dq, b->d_seqs, layer_off, b->q, W[RAMA_T_FREQ_REAL], W[RAMA_T_FREQ_IMAG], Dq, hs / 2);
       LK(cudaSuccess);
     }
     {  // attention per sequence   (infer.rs:34)
       AttnBatchParams ap{b->d_seqs, b->q, b->att, b->attn_ws, b->tickets, layer_off, T, Dq, hs, b->n_split, c->Hl};
-      attn_decode_batch_kernel<<<dim3(c->Hl, b->n_split, n), kAttnThreads, 0, st>>>(ap);
+      attn_decode_batch_kernel<<<dim3(c->Hl, std::min(b->n_split, 8), n), kAttnThreads, 0, st>>>(ap);  // CTAs stride over the chunks
       LK(cudaSuccess);
     }
     int S_wo;
@@ -1488,17 +1629,18 @@ static int enqueue_batch_step(rama_batch* b, int n, int* n_launch) {
       GemmOperand Bm{b->att, (size_t)n, (size_t)Dq};
       S_wo = pick_ksplit(c, tiles(D), Dq);
       EpiStoreT epi{b->part, D, n, S_wo, (size_t)n * D};
-      LK((launch_gemm_tf32x3<64, 4, 2>(st, &A, 1, &Bm, 1, D, n, Dq, 0, S_wo, epi)));
+      LK((BATCH_GEMM(st, &A, 1, &Bm, 1, D, n, Dq, 0, S_wo, epi)));
+      RK(reduce_ranks(S_wo));
     }
     // x += wo output; xn = rmsnorm(x)   (infer.rs:37-38)
-    batch_addnorm_kernel<<<n, 256, 0, st>>>(b->x, b->part, S_wo, (size_t)n * D, W[RAMA_T_RMS_FFN] + (size_t)l * D, b->xn, D);
+    batch_addnorm_kernel<<<n, 256, 0, st>>>(b->x, pending, S_wo, (size_t)n * D, W[RAMA_T_RMS_FFN] + (size_t)l * D, b->xn, D);
     LK(cudaSuccess);
     {  // [w1;w3] → SwiGLU   (infer.rs:39-45)
       GemmOperand A[2] = {{W[RAMA_T_W1] + (size_t)l * Fl * D, (size_t)Fl, (size_t)D},
                           {W[RAMA_T_W3] + (size_t)l * Fl * D, (size_t)Fl, (size_t)D}};
       const int S = pick_ksplit(c, 2 * tiles(Fl), D);
       EpiStoreT epi{b->part, Fl, n, S, (size_t)n * Fl};
-      LK((launch_gemm_tf32x3<64, 4, 2>(st, A, 2, &X, 1, Fl, n, D, 0, S, epi)));
+      LK((BATCH_GEMM(st, A, 2, &X, 1, Fl, n, D, 0, S, epi)));
       batch_swiglu_finish_kernel<<<std::min(c->sm_count * 4, (n * Fl + 255) / 256), 256, 0, st>>>(b->part, S, (size_t)n * Fl, b->h, Fl, n);
       LK(cudaSuccess);
     }
@@ -1507,19 +1649,30 @@ static int enqueue_batch_step(rama_batch* b, int n, int* n_launch) {
       GemmOperand Bm{b->h, (size_t)n, (size_t)Fl};
       S_prev = pick_ksplit(c, tiles(D), Fl);
       EpiStoreT epi{b->part, D, n, S_prev, (size_t)n * D};
-      LK((launch_gemm_tf32x3<64, 4, 2>(st, &A, 1, &Bm, 1, D, n, Fl, 0, S_prev, epi)));
+      LK((BATCH_GEMM(st, &A, 1, &Bm, 1, D, n, Fl, 0, S_prev, epi)));
+      RK(reduce_ranks(S_prev));
     }
   }
   // x += w2 output; final rmsnorm; classifier → each session's logits   (infer.rs:49-51)
-  batch_addnorm_kernel<<<n, 256, 0, st>>>(b->x, b->part, S_prev, (size_t)n * D, W[RAMA_T_RMS_FINAL], b->xn, D);
+  batch_addnorm_kernel<<<n, 256, 0, st>>>(b->x, pending, S_prev, (size_t)n * D, W[RAMA_T_RMS_FINAL], b->xn, D);
   LK(cudaSuccess);
   {
     GemmOperand A{c->wcls, (size_t)Vl, (size_t)D};
     const int S = pick_ksplit(c, tiles(Vl), D);
     EpiStoreT epi{b->part, Vl, n, S, (size_t)n * Vl};
-    LK((launch_gemm_tf32x3<64, 4, 2>(st, &A, 1, &X, 1, Vl, n, D, 0, S, epi)));
-    batch_cls_finish_kernel<<<dim3(std::min(64, (Vl + 255) / 256), n), 256, 0, st>>>(b->part, S, (size_t)n * Vl, b->d_seqs, Vl, c->v0);
-    LK(cudaSuccess);
+    LK((BATCH_GEMM(st, &A, 1, &X, 1, Vl, n, D, 0, S, epi)));
+    if (c->world > 1) {  // vocabulary rows are split: gather every rank's block, then scatter into the sessions' logits
+      float* mine = b->lstage + (size_t)c->rank * n * Vl;
+      batch_cls_stage_kernel<<<dim3(std::min(64, (Vl + 255) / 256), n), 256, 0, st>>>(b->part, S, (size_t)n * Vl, mine, Vl);
+      LK(cudaSuccess);
+      NK(g_nccl.AllGather(mine, b->lstage, (size_t)n * Vl, kNcclFloat32, c->comm, st));
+      ++launches;
+      batch_logits_scatter_kernel<<<dim3(std::min(64, (c->V + 255) / 256), n), 256, 0, st>>>(b->lstage, b->d_seqs, Vl, c->world, n);
+      LK(cudaSuccess);
+    } else {
+      batch_cls_finish_kernel<<<dim3(std::min(64, (Vl + 255) / 256), n), 256, 0, st>>>(b->part, S, (size_t)n * Vl, b->d_seqs, Vl, c->v0);
+      LK(cudaSuccess);
+    }
   }
 #undef LK
   if (n_launch) *n_launch = launches;
@@ -1551,7 +1704,7 @@ extern "C" int rama_forward_batch(rama_batch* b, rama_session* const* sessions, 
   for (int i = 0; i < n; ++i) {
     rama_session* s = sessions[i];
     hs[i] = BatchSeq{s->key_cache, s->value_cache, s->logits, s->ctrl, pos[i], tokens[i]};
-    s->logits_gathered = false;
+    s->logits_gathered = true;   // under TP the batched step leaves the full vocabulary in every session
     s->parts_valid = false;
   }
   CK(cudaMemcpyAsync(b->d_seqs, hs, (size_t)n * sizeof(BatchSeq), cudaMemcpyHostToDevice, b->stream));
@@ -1844,7 +1997,7 @@ extern "C" int rama_op_matmul_nt(rama_ctx* c, float* out, const float* a, const 
       case 0: e = launch_gemm_tf32x3<64, 6, 2>(c->op_stream, &A, 1, &B, 1, m, n, k, hi_round, ksplit, epi); break;
       case 1: e = launch_gemm_tf32x3<64, 6, 4>(c->op_stream, &A, 1, &B, 1, m, n, k, hi_round, ksplit, epi); break;
       case 2: e = launch_gemm_tf32x3<64, 4, 2>(c->op_stream, &A, 1, &B, 1, m, n, k, hi_round, ksplit, epi); break;
-      case 3: e = launch_gemm_tf32x3<64, 4, 4>(c->op_stream, &A, 1, &B, 1, m, n, k, hi_round, ksplit, epi); break;
+      case 3: e = launch_gemm_tf32x3<64, 2, 2>(c->op_stream, &A, 1, &B, 1, m, n, k, hi_round, ksplit, epi); break;  // 2 CTAs/SM
       default: return fail(RAMA_E_INVALID, "matmul_nt: unknown transposed variant %d", variant);
     }
     if (ksplit > 1) {
@@ -1860,7 +2013,7 @@ extern "C" int rama_op_matmul_nt(rama_ctx* c, float* out, const float* a, const 
     switch (variant) {
       case 0: e = launch_gemm_tf32x3<128, 4, 2>(c->op_stream, &A, 1, &B, 1, m, n, k, hi_round, 1, epi); break;
       case 1: e = launch_gemm_tf32x3<128, 4, 4>(c->op_stream, &A, 1, &B, 1, m, n, k, hi_round, 1, epi); break;
-      case 2: e = launch_gemm_tf32x3<128, 3, 2>(c->op_stream, &A, 1, &B, 1, m, n, k, hi_round, 1, epi); break;
+      case 2: e = launch_gemm_tf32x3<128, 4, 8>(c->op_stream, &A, 1, &B, 1, m, n, k, hi_round, 1, epi); break;
       case 3: e = launch_gemm_tf32x3<64, 6, 2>(c->op_stream, &A, 1, &B, 1, m, n, k, hi_round, 1, epi); break;
       default: return fail(RAMA_E_INVALID, "matmul_nt: unknown variant %d", variant);
     }

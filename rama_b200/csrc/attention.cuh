@@ -41,14 +41,18 @@ struct AttnParams {
   size_t prefetch_bytes;
 };
 
-// one (head = blockIdx.x, split = blockIdx.y) CTA of the flash-decode pass for the sequence described by p
-__device__ __forceinline__ void attn_decode_body(const AttnParams& p, int pos) {
-  __shared__ float s_m[kAttnWarps], s_l[kAttnWarps];
-  __shared__ __align__(16) float s_acc[kAttnWarps][kAttnMaxHs];
+// One (head h, chunk) work item of the flash-decode pass for the sequence described by p, executed by a
+// CTA of NW warps (NW·4 timesteps per item).  q is read with ld.global.cg: inside the persistent step kernel
+// it was written by other CTAs earlier in the same launch.
+template <int NW>
+__device__ __forceinline__ void attn_item(const AttnParams& p, int pos, int h, int chunk) {
+  constexpr int kChunk = NW * kAttnPerWarp;
+  constexpr int kThreads = NW * kWarp;
+  __shared__ float s_m[NW], s_l[NW];
+  __shared__ __align__(16) float s_acc[NW][kAttnMaxHs];
   __shared__ unsigned int s_ticket;
   const int n = pos + 1;
-  const int n_chunks = (n + kAttnChunk - 1) / kAttnChunk;
-  const int h = blockIdx.x, chunk = blockIdx.y;
+  const int n_chunks = (n + kChunk - 1) / kChunk;
   if (chunk >= n_chunks) return;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -59,7 +63,7 @@ __device__ __forceinline__ void attn_decode_body(const AttnParams& p, int pos) {
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
   // this warp's timesteps: t0 + j, j < kAttnPerWarp
-  const int t0 = chunk * kAttnChunk + warp * kAttnPerWarp;
+  const int t0 = chunk * kChunk + warp * kAttnPerWarp;
   float4 kk[kAttnPerWarp], vv[kAttnPerWarp];
 #pragma unroll
   for (int j = 0; j < kAttnPerWarp; ++j) {
@@ -71,7 +75,7 @@ __device__ __forceinline__ void attn_decode_body(const AttnParams& p, int pos) {
     const bool ok = active && (t0 + j) < n;
     vv[j] = ok ? reinterpret_cast<const float4*>(p.value_cache + (size_t)(t0 + j) * p.Dq + col)[lane] : zero4;
   }
-  const float4 q4 = active ? reinterpret_cast<const float4*>(p.q + col)[lane] : zero4;
+  const float4 q4 = active ? __ldcg(reinterpret_cast<const float4*>(p.q + col) + lane) : zero4;
 
   float sc[kAttnPerWarp];
 #pragma unroll
@@ -105,19 +109,19 @@ __device__ __forceinline__ void attn_decode_body(const AttnParams& p, int pos) {
   {
     float M = -INFINITY;
 #pragma unroll
-    for (int w = 0; w < kAttnWarps; ++w) M = fmaxf(M, s_m[w]);
+    for (int w = 0; w < NW; ++w) M = fmaxf(M, s_m[w]);
     // a warp that saw no timestep has m = -inf, l = 0, acc = 0: exp(-inf - M) = 0 contributes nothing
     // (warp 0 always has one, so M is finite)
-    for (int i = threadIdx.x; i < hs; i += kAttnThreads) {
+    for (int i = threadIdx.x; i < hs; i += kThreads) {
       float a = 0.f;
 #pragma unroll
-      for (int w = 0; w < kAttnWarps; ++w) a += s_acc[w][i] * expf(s_m[w] - M);
+      for (int w = 0; w < NW; ++w) a += s_acc[w][i] * expf(s_m[w] - M);
       wsp[2 + i] = a;
     }
     if (threadIdx.x == 0) {
       float L = 0.f;
 #pragma unroll
-      for (int w = 0; w < kAttnWarps; ++w) L += s_l[w] * expf(s_m[w] - M);
+      for (int w = 0; w < NW; ++w) L += s_l[w] * expf(s_m[w] - M);
       wsp[0] = M;
       wsp[1] = L;
     }
@@ -137,7 +141,7 @@ __device__ __forceinline__ void attn_decode_body(const AttnParams& p, int pos) {
   float L = 0.f;
   for (int c = 0; c < n_chunks; ++c)
     L += __ldcg(wh + (size_t)c * (hs + 2) + 1) * expf(__ldcg(wh + (size_t)c * (hs + 2)) - M);
-  for (int i = threadIdx.x; i < hs; i += kAttnThreads) {
+  for (int i = threadIdx.x; i < hs; i += kThreads) {
     float a = 0.f;
 #pragma unroll 4
     for (int c = 0; c < n_chunks; ++c)
@@ -145,12 +149,23 @@ __device__ __forceinline__ void attn_decode_body(const AttnParams& p, int pos) {
     p.out[(size_t)h * hs + i] = a / L;
   }
   if (p.att) {
-    for (int t = threadIdx.x; t < n; t += kAttnThreads) {
+    for (int t = threadIdx.x; t < n; t += kThreads) {
       const float s = __ldcg(p.att + (size_t)h * p.T + t);
       p.att[(size_t)h * p.T + t] = expf(s - M) / L;
     }
   }
   if (threadIdx.x == 0) p.tickets[h] = 0u;  // ready for the next launch
+}
+
+// CTA (head = blockIdx.x, y = blockIdx.y) of a flash-decode launch: chunks y, y + gridDim.y, … of the head.
+// The launch does not need one CTA per possible chunk of the whole context window (2048 CTAs at 7B, nearly all of
+// which would exit at once): the host picks gridDim.y for the current position range.
+__device__ __forceinline__ void attn_decode_body(const AttnParams& p, int pos) {
+  const int n_chunks = (pos + kAttnChunk) / kAttnChunk;
+  for (int chunk = blockIdx.y; chunk < n_chunks; chunk += gridDim.y) {
+    attn_item<kAttnWarps>(p, pos, blockIdx.x, chunk);
+    __syncthreads();
+  }
 }
 
 __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnParams p, int use_pdl) {

@@ -148,6 +148,28 @@ __global__ void __launch_bounds__(256) batch_swiglu_finish_kernel(const float* _
   }
 }
 
+// tensor parallelism: staging [P][B][Vl] (all-gathered) → every session's full logits [V]
+__global__ void __launch_bounds__(256) batch_logits_scatter_kernel(const float* __restrict__ staging,
+                                                                   const BatchSeq* __restrict__ seqs, int Vl, int P, int B) {
+  const int b = blockIdx.y;
+  float* dst = seqs[b].logits;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < P * Vl; i += gridDim.x * 256) {
+    const int r = i / Vl, j = i - r * Vl;
+    dst[i] = staging[((size_t)r * B + b) * Vl + j];
+  }
+}
+
+// classifier partials [S][B][Vl] → staging[b][Vl] (tensor parallelism: this rank's block of the all-gather buffer)
+__global__ void __launch_bounds__(256) batch_cls_stage_kernel(const float* __restrict__ part, int S, size_t slab,
+                                                              float* __restrict__ out, int Vl) {
+  const int b = blockIdx.y;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < Vl; i += gridDim.x * 256) {
+    float a = 0.f;
+    for (int s = 0; s < S; ++s) a += part[(size_t)s * slab + (size_t)b * Vl + i];
+    out[(size_t)b * Vl + i] = a;
+  }
+}
+
 // classifier partials [S][B][Vl] → the session's logits[v0 .. v0+Vl)
 __global__ void __launch_bounds__(256) batch_cls_finish_kernel(const float* __restrict__ part, int S, size_t slab,
                                                                const BatchSeq* __restrict__ seqs, int Vl, int v0) {

@@ -185,8 +185,11 @@ struct GemmSmem {
   static constexpr int kNumBars = 3 * STAGES + 4;               // full/ready/empty per stage, accfull[2], accfree[2]
   static constexpr int kTotal = kBarOff + kNumBars * 8 + 16 + 1024 /* alignment slack */;
   // TMEM: [0,BN) acc 0 | [BN,2BN) acc 1 | then per stage 32 columns A hi + 32 columns A lo
-  static constexpr int kTmemCols = 512;
-  static_assert(2 * BN + 64 * STAGES <= 512, "accumulators + A stages exceed tensor memory");
+  static constexpr int kTmemNeed = 2 * BN + 64 * STAGES;
+  static_assert(kTmemNeed <= 512, "accumulators + A stages exceed tensor memory");
+  static constexpr int kTmemCols = kTmemNeed <= 128 ? 128 : (kTmemNeed <= 256 ? 256 : 512);  // power of two
+  // two CTAs per SM when both shared memory and tensor memory allow it: their pipelines interleave
+  static constexpr int kCtasPerSm = (kTmemCols <= 256 && 2 * kTotal <= 226 * 1024) ? 2 : 1;
 };
 
 // Accumulation.  The tensor core adds into its f32 TMEM accumulator with truncation, which drifts
@@ -206,11 +209,14 @@ struct GemmSmem {
 // (valid = m < M) so an epilogue may shuffle between rows.
 
 template <int BN, int STAGES, int CH, class Epi>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(kGemmThreads, (GemmSmem<BN, STAGES>::kCtasPerSm))
 gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, const Epi epi_in) {
   using SM = GemmSmem<BN, STAGES>;
   constexpr int BK = kGemmBK;
   static_assert(BN == 64 || BN == 128, "BN");
+  // the two worker groups take alternate k-blocks: with an even stage count a stage always belongs to the same group,
+  // so no waiter ever skips a phase of a stage's mbarriers (parity waits alias after two phases)
+  static_assert(STAGES % 2 == 0, "STAGES must be even");
   static_assert(!Epi::kDual || BN == 128, "dual epilogue needs BN = 128");
   constexpr int NSEG = BN / 64;  // 32-column segments per epilogue warp
   extern __shared__ uint8_t gemm_smem_raw[];
@@ -241,7 +247,7 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, c
     if (Epi::kDual) tma_prefetch_desc(&maps.b[1]);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_ready + 8 * s, kGemmWorkerWarps);
+      mbar_init(bar_ready + 8 * s, kGemmWorkerWarps / 2);  // the four warps of the group that owns the k-block
       mbar_init(bar_empty + 8 * s, 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -278,13 +284,17 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, c
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
+    // One thread feeds the tensor core, so its instruction stream is on the critical path: descriptors are
+    // (constant high word, base low word + a small offset) — one 32-bit add per operand.
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_tf32<BN>();
+      const uint64_t d0 = umma_smem_desc<BK>(base + SM::kABytes);  // B hi of stage 0, k-step 0
+      const uint32_t d_hi32 = (uint32_t)(d0 >> 32), d_lo32 = (uint32_t)d0;
+      auto desc = [&](uint32_t lo) { return ((uint64_t)d_hi32 << 32) | lo; };
+      int s = 0, ch = 0, in_ch = 0;
+      uint32_t ph = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        const int ch = kb / CH;
-        const bool first = kb % CH == 0, last = (kb % CH == CH - 1) || kb == num_kb - 1;
+        const bool first = in_ch == 0, last = (in_ch == CH - 1) || kb == num_kb - 1;
         const uint32_t acc = tmem + (ch & 1) * BN;
         if (first && ch >= 2) {  // acc[ch&1] still holds chunk ch-2 until the workers have drained it
           mbar_wait(bar_accfree + 8 * (ch & 1), ((ch >> 1) - 1) & 1);
@@ -292,22 +302,22 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, c
         }
         mbar_wait(bar_ready + 8 * s, ph);
         tc_fence_after();
-        const uint32_t b_hi = base + s * SM::kStageBytes + SM::kABytes, b_lo = b_hi + SM::kBBytes;
+        const uint32_t bh = d_lo32 + s * (SM::kStageBytes >> 4), bl = bh + (SM::kBBytes >> 4);
         const uint32_t a_hi = tmem_a + 64 * s, a_lo = a_hi + 32;
 #pragma unroll
-        for (int ks = 0; ks < BK / 8; ++ks) {
-          const uint64_t dbh = umma_smem_desc<BK>(b_hi + ks * 32), dbl = umma_smem_desc<BK>(b_lo + ks * 32);
-          umma_tf32_ts(acc, a_lo + 8 * ks, dbh, idesc, !(first && ks == 0));  // small terms first
-          umma_tf32_ts(acc, a_hi + 8 * ks, dbl, idesc, 1);
-          umma_tf32_ts(acc, a_hi + 8 * ks, dbh, idesc, 1);
+        for (int ks = 0; ks < BK / 8; ++ks) {  // 8 tf32 = 32 bytes = 2 descriptor units inside the swizzle row
+          umma_tf32_ts(acc, a_lo + 8 * ks, desc(bh + 2 * ks), idesc, !(first && ks == 0));  // small terms first
+          umma_tf32_ts(acc, a_hi + 8 * ks, desc(bl + 2 * ks), idesc, 1);
+          umma_tf32_ts(acc, a_hi + 8 * ks, desc(bh + 2 * ks), idesc, 1);
         }
         umma_commit(bar_empty + 8 * s);  // smem stage + TMEM A stage reusable once these MMAs have read them
         if (last) umma_commit(bar_accfull + 8 * (ch & 1));
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+        if (++in_ch == CH) { in_ch = 0; ++ch; }
       }
     }
   } else {
     // ===== workers: operand split, second-level accumulation, epilogue =====
-    const int wt = threadIdx.x - 2 * kWarp;  // 0 .. 255
     const int quarter = warp & 3;            // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;        // which half of the k-block (split) / of the tile's columns (drain)
     const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16);
@@ -336,22 +346,27 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, c
       if (lane == 0) mbar_arrive(bar_accfree + 8 * b);
     };
 
-    // A: this thread owns row (quarter·32 + lane) of the tile and 16-byte chunks [4·half, 4·half+4) of its
-    // 128-byte row; SWIZZLE_128B puts chunk c of row r at r·128 + ((c ^ (r & 7)) · 16)
+    // The two groups of four worker warps (half = 0 / 1) take alternate k-blocks, so the latency chain of one
+    // k-block (LDS → split → STTM/STS → proxy fence → tcgen05.wait::st → arrive) overlaps the other group's.
+    // A: this thread owns row (quarter·32 + lane) of the tile; SWIZZLE_128B puts 16-byte chunk c of row r at
+    // r·128 + ((c ^ (r & 7)) · 16).  B: the group's 128 threads split the raw tile element-wise.
     const int arow = quarter * 32 + lane;
     const uint32_t arow_off = arow * 128;
+    const int gt = quarter * 32 + lane;  // thread index inside the group
     constexpr int kBVec = SM::kBBytes / 16;
+    constexpr int kGroupThreads = kGemmWorkerWarps / 2 * kWarp;
     constexpr int kLag = 1;  // k-blocks split beyond a chunk's end before draining it
-    for (int kb = 0; kb < num_kb; ++kb) {
+    for (int kb = half; kb < num_kb; kb += 2) {
       const int s = kb % STAGES;
       const uint32_t ph = (kb / STAGES) & 1;
       mbar_wait(bar_full + 8 * s, ph);
       const uint8_t* st = gen_base + s * SM::kStageBytes;
-      {
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {  // the row in two halves of 16 floats
         uint32_t hi[16], lo[16];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          const int chunk = 4 * half + c;
+          const int chunk = 4 * hh + c;
           const float4 a = *reinterpret_cast<const float4*>(st + arow_off + ((chunk ^ (arow & 7)) << 4));
           const float av[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
@@ -362,7 +377,7 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, c
             lo[4 * c + e] = __float_as_uint(av[e] - __uint_as_float(h));
           }
         }
-        const uint32_t ta = trow + 2 * BN + 64 * s + 16 * half;
+        const uint32_t ta = trow + 2 * BN + 64 * s + 16 * hh;
         tmem_st_32x16(ta, hi);
         tmem_st_32x16(ta + 32, lo);
       }
@@ -371,7 +386,7 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, c
         float4* bhi = reinterpret_cast<float4*>(const_cast<uint8_t*>(st) + SM::kABytes);
         float4* blo = reinterpret_cast<float4*>(const_cast<uint8_t*>(st) + SM::kABytes + SM::kBBytes);
 #pragma unroll
-        for (int i = wt; i < kBVec; i += kGemmWorkerWarps * kWarp) {
+        for (int i = gt; i < kBVec; i += kGroupThreads) {
           const float4 a = braw[i];
           float4 h, l;
           if (shp.hi_round) {
@@ -395,7 +410,7 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, c
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_ready + 8 * s);
-      // chunk c ends with k-block min((c+1)·CH, num_kb) − 1; drain it once kLag further blocks are split
+      // chunk c ends with k-block min((c+1)·CH, num_kb) − 1; drain it once this group is kLag blocks past it
       while (drained < num_ch && min((drained + 1) * CH, num_kb) - 1 + kLag <= kb) drain(drained++);
     }
     while (drained < num_ch) drain(drained++);

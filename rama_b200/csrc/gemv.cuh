@@ -44,7 +44,8 @@ struct PeerOut {
   const unsigned* seq;       // step counter (device)
   int P;                     // 0 ⇒ no exchange (single GPU / NCCL mode)
   int L, layer;
-  __device__ __forceinline__ unsigned epoch() const { return *seq * (unsigned)L + (unsigned)layer + 1u; }
+  unsigned seq_add;          // 1 inside the persistent step kernel (the counter is bumped at its end), else 0
+  __device__ __forceinline__ unsigned epoch() const { return (*seq + seq_add) * (unsigned)L + (unsigned)layer + 1u; }
   // select with static indices (a runtime index would spill the table to local memory)
   __device__ __forceinline__ uint2* inbox_of(int r) const {
     uint2* f = inbox[0];
@@ -59,7 +60,8 @@ struct PeerIn {
   int32_t* error;            // StepCtrl.error
   int P, n;                  // n = elements per partial (row stride of inbox)
   int L, layer;
-  __device__ __forceinline__ unsigned epoch() const { return *seq * (unsigned)L + (unsigned)layer + 1u; }
+  unsigned seq_add;
+  __device__ __forceinline__ unsigned epoch() const { return (*seq + seq_add) * (unsigned)L + (unsigned)layer + 1u; }
 };
 
 // ---- prologues: fill xs[0..K4) (float4) ---------------------------------------------------
@@ -69,7 +71,7 @@ struct ProPlain {
   const float* x;
   __device__ __forceinline__ void operator()(float4* xs, int K4, float* red) const {
     const float4* x4 = reinterpret_cast<const float4*>(x);
-    for (int i = threadIdx.x; i < K4; i += kGemvThreads) xs[i] = x4[i];
+    for (int i = threadIdx.x; i < K4; i += kGemvThreads) xs[i] = __ldcg(x4 + i);  // may be another CTA's output of this launch
     (void)red;
   }
 };
@@ -91,7 +93,7 @@ struct ProNorm {
     const unsigned ep = peers ? pin.epoch() : 0u;
     float ss = 0.f;
     for (int i = threadIdx.x; i < K4; i += kGemvThreads) {
-      float4 v = x4[i];
+      float4 v = __ldcg(x4 + i);
       if (peers) {
         // issue every rank's two 16-byte LL loads first (independent), then validate the epochs;
         // only an element that has not arrived yet falls into the spinning reload
@@ -118,7 +120,7 @@ struct ProNorm {
         v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
         if (blockIdx.x == 0) reinterpret_cast<float4*>(const_cast<float*>(add))[i] = a;  // RunState.xb2 / xb
       } else if (add) {
-        const float4 a = a4[i];
+        const float4 a = __ldcg(a4 + i);
         v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
       }
       xs[i] = v;
@@ -423,6 +425,113 @@ gemv_fused_kernel(const Pro pro, const Rows rows, const Epi epi_in, int K4, int 
     epi(p0 + i, v0, v1);
   }
   epi.finish(red);
+}
+
+// ---- the same streaming core with a run-time k-split (persistent step kernel: one instantiation per
+// phase type instead of one per variant); RP = 2, U = 4 as in every default variant ------------------------
+template <class Rows>
+__device__ __forceinline__ void gemv_pairs_rt(const Rows& rows, int K4, int p0, int np, const float4* __restrict__ xs,
+                                              float* __restrict__ part, int WK) {
+  constexpr int RP = 2, U = 4, R = 2 * RP;
+  const int WR = kGemvWarps / WK;
+  const int stride = kWarp * WK;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wr = warp / WK, wk = warp - wr * WK;
+
+  for (int base = wr * RP; base < np; base += WR * RP) {
+    const float4* rp[R];
+#pragma unroll
+    for (int j = 0; j < RP; ++j) {
+      const int p = min(base + j, np - 1);  // clamp: a duplicate is computed but never stored
+      rows(p0 + p, rp[2 * j], rp[2 * j + 1]);
+    }
+    float acc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r] = 0.f;
+
+    int c = wk * kWarp + lane;
+    for (; c + (U - 1) * stride < K4; c += U * stride) {
+      float4 w[U][R];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int r = 0; r < R; ++r) w[u][r] = ldg_stream(rp[r] + c + u * stride);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const float4 xv = xs[c + u * stride];
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = dot4(w[u][r], xv, acc[r]);
+      }
+    }
+    for (; c < K4; c += stride) {
+      float4 w[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) w[r] = ldg_stream(rp[r] + c);
+      const float4 xv = xs[c];
+#pragma unroll
+      for (int r = 0; r < R; ++r) acc[r] = dot4(w[r], xv, acc[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r] = warp_sum(acc[r]);
+    if (lane == 0) {
+#pragma unroll
+      for (int j = 0; j < RP; ++j) {
+        if (base + j < np) {
+          part[((base + j) * 2 + 0) * WK + wk] = acc[2 * j];
+          part[((base + j) * 2 + 1) * WK + wk] = acc[2 * j + 1];
+        }
+      }
+    }
+  }
+}
+
+// this CTA's balanced contiguous range of pairs
+__device__ __forceinline__ void gemv_cta_range(int n_pairs, int& p0, int& np) {
+  const int per = n_pairs / gridDim.x, rem = n_pairs % gridDim.x;
+  p0 = blockIdx.x * per + min((int)blockIdx.x, rem);
+  np = per + ((int)blockIdx.x < rem ? 1 : 0);
+}
+
+// L2 prefetch of the head of this CTA's slab of a coming phase (weights never depend on activations)
+template <class Rows>
+__device__ __forceinline__ void gemv_prefetch_slab(const Rows& rows, int n_pairs, size_t cap_bytes) {
+  if (threadIdx.x < Rows::kStreams) {
+    int p0, np;
+    gemv_cta_range(n_pairs, p0, np);
+    if (np > 0) {
+      const float* ptr;
+      size_t bytes;
+      rows.slab(p0, np, threadIdx.x, ptr, bytes);
+      bytes = min(bytes, cap_bytes / Rows::kStreams) & ~(size_t)15;
+      const char* c = reinterpret_cast<const char*>(ptr);
+      for (size_t off = 0; off < bytes; off += 65536)  // a bulk prefetch carries a 32-bit size; keep requests modest
+        l2_prefetch_bulk(c + off, (uint32_t)min((size_t)65536, bytes - off));
+    }
+  }
+}
+
+// one GEMV phase of the persistent step kernel: prologue → stream → fused epilogue (all CTAs of the grid)
+template <class Pro, class Rows, class Epi>
+__device__ __forceinline__ void gemv_phase(const Pro& pro, const Rows& rows, const Epi& epi_in, int K4, int n_pairs,
+                                           int WK, float4* xs, float* red) {
+  float* part = reinterpret_cast<float*>(xs + K4);
+  int p0, np;
+  gemv_cta_range(n_pairs, p0, np);
+  pro(xs, K4, red);
+  __syncthreads();
+  gemv_pairs_rt(rows, K4, p0, np, xs, part, WK);
+  __syncthreads();
+  Epi epi = epi_in;
+  for (int i = threadIdx.x; i < np; i += kGemvThreads) {
+    float v0 = 0.f, v1 = 0.f;
+    for (int k = 0; k < WK; ++k) {
+      v0 += part[(i * 2 + 0) * WK + k];
+      v1 += part[(i * 2 + 1) * WK + k];
+    }
+    epi(p0 + i, v0, v1);
+  }
+  epi.finish(red);
+  __syncthreads();  // xs / part / red are reused by the next phase
 }
 
 }  // namespace rama

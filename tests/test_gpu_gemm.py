@@ -35,7 +35,7 @@ def run(gpu, M, N, K, variant, flags, seed=0):
 
 
 SHAPES = [(128, 256, 64), (128, 256, 4096), (512, 4096, 4096), (512, 1024, 11008), (100, 300, 288),
-          (1, 32, 16), (130, 520, 1000), (512, 768, 768)]
+          (1, 32, 16), (130, 520, 1000), (512, 768, 768), (512, 11008, 1024)]  # the last one: more tiles than SMs
 
 
 @pytest.mark.parametrize("variant", [0, 1, 2, 3])
@@ -47,7 +47,7 @@ def test_matmul_nt_f32_accuracy(gpu, shape, variant):
     assert err < max(8 * ref_err, 6e-6), (err, ref_err)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
 @pytest.mark.parametrize("shape", [(4096, 64, 4096), (11008, 64, 4096), (4096, 64, 11008), (288, 3, 288), (1000, 17, 64)])
 def test_matmul_nt_transposed_store(gpu, shape, variant):
     M, N, K = shape

@@ -13,14 +13,14 @@ from rama_b200.engine import GPU, DeviceBuffer
 gpu = GPU(0)
 L = _lib.lib()
 PREFILL = [(512, 4096, 4096), (512, 11008, 4096), (512, 4096, 11008), (512, 32000, 4096), (2048, 4096, 4096)]
-DECODE = [(4096, 64, 4096), (11008, 64, 4096), (4096, 64, 11008), (32000, 64, 4096)]
-for shapes, variants, flags in ((PREFILL, [0, 1, 2, 3], 0), (DECODE, [0, 1, 2], 2)):
+DECODE = [(4096, 64, 4096), (11008, 64, 4096), (4096, 64, 11008), (32000, 64, 4096), (12288, 64, 4096), (22016, 64, 4096)]
+for shapes, variants, flags in ((PREFILL, [0, 1, 2, 3], 0), (DECODE, [0, 1, 2, 3], 2)):
     for (M, N, K) in shapes:
         a = DeviceBuffer(gpu, M * K); b = DeviceBuffer(gpu, N * K); o = DeviceBuffer(gpu, M * N)
         check(L.rama_synth_fill(gpu.h, a.ptr(), M * K, 1, 1, 0, 1.0, 0.0))
         check(L.rama_synth_fill(gpu.h, b.ptr(), N * K, 1, 2, 0, 0.02, 0.0))
         for v in variants:
-            for fl in (flags, flags | 1):
+            for fl in ((flags,) if flags else (flags, flags | 1)) + ((flags | (3 << 8), flags | (6 << 8)) if flags else ()):
                 ms = C.c_float()
                 check(L.rama_bench_matmul_nt(gpu.h, o.ptr(), a.ptr(), b.ptr(), M, N, K, v, fl, 20, C.byref(ms)))
                 tf = 2.0 * M * N * K / (ms.value * 1e-3) / 1e12
