@@ -1,7 +1,7 @@
 /* rama_b200.h — C ABI of the B200-native (sm_100a) llama2 f32 decode path.
  *
  * This is the drop-in boundary for ONE hot path of oliverhu/rama: the per-token decode loop
- * (engine/src/transformer/infer.rs:8-53 `forward`, engine/src/device/*.rs `Device`,
+ * (engine/src/transformer/infer.rs:8-53 `forward`, engine/src/device/{device,cpu,gpu}.rs `Device`,
  * engine/src/transformer/mod.rs:169-248 `generate`).  Every entry point below names the
  * reference interface it replaces (paths relative to the reference repo root).  The Rust
  * binding a maintainer adds (gpu.rs / hbm.rs / build.rs) is shown in INTEGRATION.md.
@@ -182,6 +182,19 @@ int rama_profile_step(rama_session* s, int32_t token, int32_t pos, float ms[RAMA
 /* Phase timeline of one persistent step (tools/step_trace.py): SM-clock stamps of CTA 0 at kernel entry and
  * before/after each of the 5L+1 grid barriers. */
 int rama_step_trace(rama_session* s, int32_t token, int32_t pos, long long* stamps, int32_t cap, int32_t* n_out);
+
+/* ---- tokenizer: the text boundary of generate() (engine/src/tokenizer/bpe.rs) ------------------------
+ * Host code (the reference tokenizes on the CPU as well).  tokenizer.bin keeps the llama2.c layout byte for
+ * byte: u32 max_token_length, then per token f32 score, i32 length, bytes (bpe.rs:27-43). */
+typedef struct rama_tokenizer rama_tokenizer;
+int rama_tokenizer_load(const char* path, int32_t vocab_size, rama_tokenizer** out);   /* Tokenizer::new, bpe.rs:19-45 */
+int rama_tokenizer_free(rama_tokenizer* t);
+int rama_tokenizer_info(const rama_tokenizer* t, int32_t* vocab_size, int32_t* max_token_length);
+/* Tokenizer::encode (bpe.rs:50-97): trim, drop '\n', per-char lookup, greedy best-score merges.  out may be NULL
+ * to query *n_out.  Inputs the reference panics on (unknown char, nothing left to encode) are RAMA_E_INVALID. */
+int rama_tokenizer_encode(const rama_tokenizer* t, const char* text, int32_t* out, int32_t cap, int32_t* n_out);
+/* decode(vocab[token]) (bpe.rs:102-116): "<s>" → "", "<0xAB>" → char::from(0xAB) as UTF-8, else the piece. */
+int rama_tokenizer_decode(const rama_tokenizer* t, int32_t token, char* out, int32_t cap, int32_t* n_out);
 
 /* ---- op level: 1:1 with `trait Device<T>` (engine/src/device/device.rs:3-24) -------------
  * Pointers are device pointers already offset by the view's range.start (a View is

@@ -502,11 +502,32 @@ static size_t utf8_len(unsigned char c) {
 // bpe.rs:55) and -2 for the whitespace-only underflow (bpe.rs:66).
 int ref_tok_encode(const RefTok* t, const char* s, int32_t* out, int cap) {
   std::string str(s);
-  // str::trim(): strip leading/trailing Unicode whitespace (ASCII subset handled here)
+  // str::trim(): strip leading/trailing chars with the Unicode White_Space property (char::is_whitespace)
   size_t b = 0, e = str.size();
-  auto ws = [](unsigned char c) { return c == ' ' || (c >= 9 && c <= 13); };
-  while (b < e && ws(str[b])) ++b;
-  while (e > b && ws(str[e - 1])) --e;
+  auto cp_at = [&](size_t i, size_t n) -> unsigned {
+    const unsigned char* q = (const unsigned char*)str.data() + i;
+    if (n == 1) return q[0];
+    if (n == 2) return ((q[0] & 0x1Fu) << 6) | (q[1] & 0x3Fu);
+    if (n == 3) return ((q[0] & 0x0Fu) << 12) | ((q[1] & 0x3Fu) << 6) | (q[2] & 0x3Fu);
+    return ((q[0] & 0x07u) << 18) | ((q[1] & 0x3Fu) << 12) | ((q[2] & 0x3Fu) << 6) | (q[3] & 0x3Fu);
+  };
+  auto ws = [](unsigned c) {
+    return (c >= 9 && c <= 13) || c == 0x20 || c == 0x85 || c == 0xA0 || c == 0x1680 || (c >= 0x2000 && c <= 0x200A) ||
+           c == 0x2028 || c == 0x2029 || c == 0x202F || c == 0x205F || c == 0x3000;
+  };
+  for (;;) {  // leading
+    if (b >= e) break;
+    size_t n = utf8_len((unsigned char)str[b]);
+    if (b + n > e || !ws(cp_at(b, n))) break;
+    b += n;
+  }
+  for (;;) {  // trailing: step back to the start byte of the last char
+    if (e <= b) break;
+    size_t i = e - 1;
+    while (i > b && ((unsigned char)str[i] & 0xC0) == 0x80) --i;
+    if (!ws(cp_at(i, e - i))) break;
+    e = i;
+  }
   std::vector<int> tokens;
   for (size_t i = b; i < e;) {
     size_t n = utf8_len((unsigned char)str[i]);
@@ -547,7 +568,8 @@ int ref_tok_decode(const RefTok* t, int id, char* out, int cap) {
   std::string r;
   if (s.find("<s>") != std::string::npos) {
     r = "";
-  } else if (!s.empty() && s.front() == '<' && s.back() == '>' && s.size() >= 5) {
+  } else if (!s.empty() && s.front() == '<' && s.back() == '>') {
+    if (s.size() < 5) return -2;  // &str[3..5] is out of bounds: the reference panics (e.g. "</s>")
     char* endp = nullptr;
     const std::string hex = s.substr(3, 2);
     unsigned c = (unsigned)strtoul(hex.c_str(), &endp, 16);

@@ -76,6 +76,11 @@ _SIGS = {
     "rama_session_launches_per_step": ([vp, C.POINTER(C.c_int)], C.c_int),
     "rama_step_trace": ([vp, C.c_int32, C.c_int32, C.POINTER(C.c_longlong), C.c_int32, ip], C.c_int),
     "rama_profile_step": ([vp, C.c_int32, C.c_int32, fp, ip], C.c_int),
+    "rama_tokenizer_load": ([C.c_char_p, C.c_int32, C.POINTER(vp)], C.c_int),
+    "rama_tokenizer_free": ([vp], C.c_int),
+    "rama_tokenizer_info": ([vp, ip, ip], C.c_int),
+    "rama_tokenizer_encode": ([vp, C.c_char_p, ip, C.c_int32, ip], C.c_int),
+    "rama_tokenizer_decode": ([vp, C.c_int32, C.c_char_p, C.c_int32, ip], C.c_int),
     "rama_dev_alloc": ([vp, sz, C.POINTER(fp)], C.c_int),
     "rama_dev_free": ([vp, fp], C.c_int),
     "rama_dev_h2d": ([vp, fp, fp, sz], C.c_int),

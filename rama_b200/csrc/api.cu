@@ -43,6 +43,9 @@ static int fail(int code, const char* fmt, ...) {
   va_end(ap);
   return code;
 }
+// used by the other translation units of the library (tokenizer.cpp)
+extern "C" int rama_set_error(int code, const char* msg) { return fail(code, "%s", msg); }
+
 #define CK(call)                                                                              \
   do {                                                                                        \
     cudaError_t e_ = (call);                                                                  \

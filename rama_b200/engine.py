@@ -29,7 +29,7 @@ from . import _lib
 from ._lib import CConfig, CTp, RamaError, check, fp, ip
 from .checkpoint import Config, SynthSpec, TENSORS, T, rope_tables
 
-__all__ = ["GPU", "Session", "Batch", "DeviceBuffer", "View", "forward", "forward_per_op", "generate",
+__all__ = ["GPU", "Session", "Batch", "Tokenizer", "generate_text", "DeviceBuffer", "View", "forward", "forward_per_op", "generate",
            "RamaError", "DeviceWeights", "DeviceRunState"]
 
 
@@ -389,6 +389,51 @@ class Session:
         ln = (C.c_int32 * _lib.K_COUNT)()
         check(_lib.lib().rama_profile_step(self.h, token, pos, ms, ln))
         return {k: (ms[i], ln[i]) for i, k in enumerate(_lib.KERNEL_KINDS)}
+
+
+class Tokenizer:
+    """≙ tokenizer::bpe::Tokenizer (bpe.rs:9-97) + decode() (bpe.rs:102-116) over the C ABI (host code)."""
+
+    def __init__(self, path: str, vocab_size: int):
+        self.h = C.c_void_p()
+        check(_lib.lib().rama_tokenizer_load(path.encode(), vocab_size, C.byref(self.h)))
+        v, m = C.c_int32(), C.c_int32()
+        check(_lib.lib().rama_tokenizer_info(self.h, C.byref(v), C.byref(m)))
+        self.vocab_size, self.max_token_length = v.value, m.value
+
+    def close(self):
+        if self.h:
+            _lib.lib().rama_tokenizer_free(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def encode(self, text: str) -> List[int]:
+        n = C.c_int32()
+        b = text.encode("utf-8")
+        check(_lib.lib().rama_tokenizer_encode(self.h, b, None, 0, C.byref(n)))
+        out = (C.c_int32 * max(n.value, 1))()
+        check(_lib.lib().rama_tokenizer_encode(self.h, b, out, n.value, C.byref(n)))
+        return list(out[: n.value])
+
+    def decode(self, token: int) -> bytes:
+        n = C.c_int32()
+        buf = C.create_string_buffer(256)
+        check(_lib.lib().rama_tokenizer_decode(self.h, token, buf, 256, C.byref(n)))
+        return buf.raw[: n.value]
+
+
+def generate_text(session: "Session", tokenizer: Tokenizer, prompt: str, temperature: float, steps: int,
+                  topp: float) -> str:
+    """≙ generate(cfg, tokenizer, prompt, temperature, steps, topp, wv, rsv, device) -> String (mod.rs:169-206):
+    encode the prompt (empty prompt → no tokens), run the loop, decode every `next` and concatenate."""
+    prompt_tokens = tokenizer.encode(prompt) if len(prompt) > 0 else []
+    toks = generate(session, prompt_tokens, steps, temperature, topp)
+    return b"".join(tokenizer.decode(t) for t in toks).decode("utf-8", errors="replace")
 
 
 class Batch:

@@ -66,3 +66,72 @@ def test_reference_tokenizer_bin():
         theirs = sp.encode("x " + text)
         assert ours[1:] == theirs[1:], text
     ref.lib().ref_tok_free(t)
+
+
+# ---- the product's tokenizer (rama_b200/csrc/tokenizer.cpp through the C ABI) vs the oracle's restatement -----
+
+def _write_tok(path, vocab, max_len=3):
+    with open(path, "wb") as f:
+        f.write(struct.pack("<I", max_len))
+        for s, sc in vocab:
+            b = s if isinstance(s, bytes) else s.encode()
+            f.write(struct.pack("<fi", sc, len(b)) + b)
+
+
+def test_product_tokenizer_synthetic(tmp_path):
+    from rama_b200.engine import RamaError, Tokenizer
+    vocab = [("<unk>", 0.0), ("<s>", 0.0), ("</s>", 0.0), ("<0x41>", 0.0), ("a", -1.0), ("b", -2.0),
+             ("ab", -0.5), ("abb", -0.2), ("ba", -0.4), (" ", -3.0), ("bab", -0.4), ("é", -1.5), ("<0xE9>", 0.0),
+             ("aé", -0.1), ("a", -9.0)]  # duplicate "a": HashMap::insert keeps the later index (bpe.rs:42)
+    p = tmp_path / "tok.bin"
+    _write_tok(p, vocab)
+    t = Tokenizer(str(p), len(vocab))
+    o = ref.lib().ref_tok_load(str(p).encode(), len(vocab))
+    assert t.max_token_length == 3 and t.vocab_size == len(vocab)
+    for text in ["ab", "abb", "  bab \n", "aab", "a\nb", "ba ab", "aé", "éa b", " ab ", "b" * 40 + "a" * 3]:
+        want = _encode(o, text)
+        assert t.encode(text) == want, text
+    for bad in ["abc", "   ", "\n", ""]:
+        assert _encode(o, bad) < 0 if bad else True
+        with pytest.raises(RamaError):
+            t.encode(bad)
+    for i in range(len(vocab)):
+        want = _decode(o, i)
+        if isinstance(want, int):
+            with pytest.raises(RamaError):
+                t.decode(i)
+        else:
+            assert t.decode(i) == want, i
+    assert t.decode(12) == "é".encode()  # <0xE9> → char::from(0xE9) → UTF-8 (bpe.rs:110-111)
+    ref.lib().ref_tok_free(o)
+    t.close()
+
+
+@pytest.mark.skipif(not os.path.exists(REF_TOK), reason="reference tokenizer.bin only exists in the build container")
+def test_product_tokenizer_on_reference_bin():
+    import random
+    from rama_b200.engine import RamaError, Tokenizer
+    t = Tokenizer(REF_TOK, 32000)
+    o = ref.lib().ref_tok_load(REF_TOK.encode(), 32000)
+    assert t.max_token_length == 27
+    assert t.encode("once upon a time") == PROMPT_IDS
+    rnd = random.Random(5)
+    words = ["once", "upon", "a", "time", "there", "was", "little", "girl", "Lily", "dragon", "the", "and", "she",
+             "happy", "castle", "Tom", "said", "\"Hello!\"", "it's", "1234", "naïve", "ünïcödé", "…"]
+    for _ in range(200):
+        text = " ".join(rnd.choice(words) for _ in range(rnd.randint(1, 12)))
+        want = _encode(o, text)
+        if isinstance(want, int):
+            with pytest.raises(RamaError):
+                t.encode(text)
+        else:
+            assert t.encode(text) == want, text
+    for i in range(32000):
+        want = _decode(o, i)
+        if isinstance(want, int):
+            with pytest.raises(RamaError):
+                t.decode(i)
+        else:
+            assert t.decode(i) == want, i
+    ref.lib().ref_tok_free(o)
+    t.close()
