@@ -44,7 +44,21 @@ extern "C" {
     pub fn rama_op_softmax(ctx: *mut rama_ctx, x: *mut c_float, n: usize) -> c_int;
     pub fn rama_op_sample(ctx: *mut rama_ctx, logits: *mut c_float, vocab: usize, temperature: c_float,
         topp: c_float, next: *mut i32) -> c_int;
+    // no counterpart in the reference: prompt prefill and multi-request batching on tensor cores
+    pub fn rama_prefill(s: *mut rama_session, tokens: *const i32, n: i32, pos0: i32, elapsed_ms: *mut c_float,
+        ms_kind: *mut c_float, n_launch: *mut i32) -> c_int;
+    pub fn rama_session_set_prefill(s: *mut rama_session, min_rows: i32) -> c_int;
+    pub fn rama_batch_create(ctx: *mut rama_ctx, max_seqs: i32, out: *mut *mut rama_batch) -> c_int;
+    pub fn rama_batch_destroy(b: *mut rama_batch) -> c_int;
+    pub fn rama_forward_batch(b: *mut rama_batch, sessions: *const *mut rama_session, tokens: *const i32,
+        pos: *const i32, n: i32) -> c_int;
+    pub fn rama_sample_batch(b: *mut rama_batch, sessions: *const *mut rama_session, n: i32, temperature: c_float,
+        topp: c_float, next: *mut i32) -> c_int;
+    pub fn rama_batch_sync(b: *mut rama_batch) -> c_int;
 }
+
+#[repr(C)]
+pub struct rama_batch { _private: [u8; 0] }
 
 /// Reference behaviour on any device error is a panic (`.unwrap()` on every cudarc call, gpu.rs:73-209).
 pub fn ck(rc: c_int) {
