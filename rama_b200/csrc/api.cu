@@ -1497,16 +1497,18 @@ struct rama_batch {
   int launches = 0;
 };
 
-// split-K factor: fill the SMs (tiles·S close to a multiple of the SM count), keep ≥ 8 k-blocks per split
+// split-K factor: the smallest one that fills ≥ 92 % of the CTA slots of its last wave (every extra split writes and
+// re-reads another [n][rows] partial), else the best-filling one; ≥ 8 k-blocks per split
 static int pick_ksplit(const rama_ctx* c, int tiles, int K) {
   const int total_kb = (K + kGemmBK - 1) / kGemmBK;
+  const int slots = c->sm_count * kBatchCtasPerSm;  // CTAs resident at once
   int best = 1;
   double best_eff = 0.0;
   for (int S = 1; S <= 16; ++S) {
     if (S > 1 && total_kb / S < 8) break;
-    const int slots = c->sm_count * kBatchCtasPerSm;  // CTAs resident at once
     const int units = tiles * S, waves = (units + slots - 1) / slots;
     const double eff = (double)units / ((double)waves * slots);
+    if (eff >= 0.92) return S;
     if (eff > best_eff + 0.02) { best_eff = eff; best = S; }
   }
   return best;
@@ -1607,7 +1609,7 @@ static int enqueue_batch_step(rama_batch* b, int n, int* n_launch) {
   for (int l = 0; l < L; ++l) {
     const size_t layer_off = (size_t)l * T * Dq;
     // x += pending w2 output; xn = rmsnorm(x)   (infer.rs:19, :47 of the previous layer)
-    batch_addnorm_kernel<<<n, 256, 0, st>>>(b->x, S_prev ? pending : nullptr, S_prev, (size_t)n * D,
+    batch_addnorm_kernel<<<n, kBatchNormThreads, 0, st>>>(b->x, S_prev ? pending : nullptr, S_prev, (size_t)n * D,
                                             W[RAMA_T_RMS_ATT] + (size_t)l * D, b->xn, D);
     LK(cudaSuccess);
     {  // [wq;wk;wv] (weights = the 128-row operand, the batch = the 64-column operand)   (infer.rs:20-23)
@@ -1623,7 +1625,7 @@ static int enqueue_batch_step(rama_batch* b, int n, int* n_launch) {
     }
     {  // attention per sequence   (infer.rs:34)
       AttnBatchParams ap{b->d_seqs, b->q, b->att, b->attn_ws, b->tickets, layer_off, T, Dq, hs, b->n_split, c->Hl};
-      attn_decode_batch_kernel<<<dim3(c->Hl, std::min(b->n_split, 8), n), kAttnThreads, 0, st>>>(ap);  // CTAs stride over the chunks
+      attn_decode_batch_kernel<<<dim3(c->Hl, std::min(b->n_split, 2), n), kAttnThreads, 0, st>>>(ap);  // CTAs stride over the chunks
       LK(cudaSuccess);
     }
     int S_wo;
@@ -1636,7 +1638,7 @@ static int enqueue_batch_step(rama_batch* b, int n, int* n_launch) {
       RK(reduce_ranks(S_wo));
     }
     // x += wo output; xn = rmsnorm(x)   (infer.rs:37-38)
-    batch_addnorm_kernel<<<n, 256, 0, st>>>(b->x, pending, S_wo, (size_t)n * D, W[RAMA_T_RMS_FFN] + (size_t)l * D, b->xn, D);
+    batch_addnorm_kernel<<<n, kBatchNormThreads, 0, st>>>(b->x, pending, S_wo, (size_t)n * D, W[RAMA_T_RMS_FFN] + (size_t)l * D, b->xn, D);
     LK(cudaSuccess);
     {  // [w1;w3] → SwiGLU   (infer.rs:39-45)
       GemmOperand A[2] = {{W[RAMA_T_W1] + (size_t)l * Fl * D, (size_t)Fl, (size_t)D},
@@ -1657,7 +1659,7 @@ static int enqueue_batch_step(rama_batch* b, int n, int* n_launch) {
     }
   }
   // x += w2 output; final rmsnorm; classifier → each session's logits   (infer.rs:49-51)
-  batch_addnorm_kernel<<<n, 256, 0, st>>>(b->x, pending, S_prev, (size_t)n * D, W[RAMA_T_RMS_FINAL], b->xn, D);
+  batch_addnorm_kernel<<<n, kBatchNormThreads, 0, st>>>(b->x, pending, S_prev, (size_t)n * D, W[RAMA_T_RMS_FINAL], b->xn, D);
   LK(cudaSuccess);
   {
     GemmOperand A{c->wcls, (size_t)Vl, (size_t)D};

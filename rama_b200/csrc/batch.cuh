@@ -45,20 +45,33 @@ __global__ void __launch_bounds__(256) batch_embed_kernel(const BatchSeq* __rest
 }
 
 // x[b] += Σ_s y[s][b] (pending residual as split-K partials, may be null); xn[b] = w·(scale·x[b])
-// ≙ array_add (cpu.rs:16-21) + rmsnorm (cpu.rs:99-117); one CTA per sequence
-__global__ void __launch_bounds__(256) batch_addnorm_kernel(float* __restrict__ x, const float* __restrict__ y, int S,
-                                                            size_t slab, const float* __restrict__ w,
-                                                            float* __restrict__ xn, int D) {
+// ≙ array_add (cpu.rs:16-21) + rmsnorm (cpu.rs:99-117); one 1024-thread CTA per sequence, the S partial loads of an
+// element issued back to back (the kernel is pure latency: 64 CTAs, a few KB each)
+constexpr int kBatchNormThreads = 1024;
+__global__ void __launch_bounds__(kBatchNormThreads) batch_addnorm_kernel(float* __restrict__ x, const float* __restrict__ y,
+                                                                          int S, size_t slab, const float* __restrict__ w,
+                                                                          float* __restrict__ xn, int D) {
   __shared__ float red[2 * kWarp];
   const int b = blockIdx.x;
   float4* xr = reinterpret_cast<float4*>(x + (size_t)b * D);
   float ss = 0.f;
-  for (int i = threadIdx.x; i < (D >> 2); i += 256) {
+  for (int i = threadIdx.x; i < (D >> 2); i += kBatchNormThreads) {
     float4 v = xr[i];
     if (y) {
+      const float4* yp = reinterpret_cast<const float4*>(y + (size_t)b * D) + i;
+      const size_t slab4 = slab >> 2;
       float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int s = 0; s < S; ++s) {
-        const float4 t = reinterpret_cast<const float4*>(y + (size_t)s * slab + (size_t)b * D)[i];
+      int s = 0;
+      for (; s + 4 <= S; s += 4) {  // four independent loads in flight, summed in split order
+        const float4 t0 = yp[(size_t)s * slab4], t1 = yp[(size_t)(s + 1) * slab4], t2 = yp[(size_t)(s + 2) * slab4],
+                     t3 = yp[(size_t)(s + 3) * slab4];
+        a.x += t0.x; a.y += t0.y; a.z += t0.z; a.w += t0.w;
+        a.x += t1.x; a.y += t1.y; a.z += t1.z; a.w += t1.w;
+        a.x += t2.x; a.y += t2.y; a.z += t2.z; a.w += t2.w;
+        a.x += t3.x; a.y += t3.y; a.z += t3.z; a.w += t3.w;
+      }
+      for (; s < S; ++s) {
+        const float4 t = yp[(size_t)s * slab4];
         a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
       }
       v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
@@ -66,11 +79,11 @@ __global__ void __launch_bounds__(256) batch_addnorm_kernel(float* __restrict__ 
     }
     ss = dot4(v, v, ss);
   }
-  ss = block_sum<256>(ss, red);
+  ss = block_sum<kBatchNormThreads>(ss, red);
   const float scale = 1.0f / sqrtf(ss / (float)D + 1e-5f);
   const float4* w4 = reinterpret_cast<const float4*>(w);
   float4* o = reinterpret_cast<float4*>(xn + (size_t)b * D);
-  for (int i = threadIdx.x; i < (D >> 2); i += 256) {
+  for (int i = threadIdx.x; i < (D >> 2); i += kBatchNormThreads) {
     const float4 v = xr[i], g = w4[i];
     o[i] = make_float4(g.x * (scale * v.x), g.y * (scale * v.y), g.z * (scale * v.z), g.w * (scale * v.w));
   }
