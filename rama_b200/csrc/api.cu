@@ -1352,7 +1352,8 @@ static int prefill_chunk(rama_session* s, const int32_t* tokens, int M, int pos0
     {
       PrefillAttnParams ap{s->pf_q, kc, vc, s->pf_att, M, pos0, Dq, hs};
       tr.pre(RAMA_PK_ATTN);
-      prefill_attn_kernel<<<dim3((M + kPfBQ - 1) / kPfBQ, c->Hl), kPfThreads, prefill_attn_smem_bytes(hs), st>>>(ap);
+      const int nq = (M + kPfBQ - 1) / kPfBQ;
+      prefill_attn_kernel<<<dim3((nq + 1) / 2, c->Hl), kPfThreads, prefill_attn_smem_bytes(hs), st>>>(ap);
       tr.post(); ++launches;
     }
     // wo   (infer.rs:35); the residual add is the next addnorm

@@ -75,7 +75,8 @@ cudaError_t launch_gemm_tf32x3(cudaStream_t st, const GemmOperand* A, int n_a, c
   }
   GemmShape shp{M, N, K, hi_round, ksplit, n_a > 1 ? 1 : 0};
   const int groups = Epi::kDual ? 1 : std::max(n_a, n_b);
-  dim3 grid((N + box_n - 1) / box_n, (M + kGemmBM - 1) / kGemmBM, groups * ksplit);
+  dim3 grid((M + kGemmBM - 1) / kGemmBM, (N + box_n - 1) / box_n, groups * ksplit);
+  if (grid.y > 65535) return cudaErrorInvalidValue;
   kern<<<grid, kGemmThreads, SM::kTotal, st>>>(maps, shp, epi);
   return cudaGetLastError();
 }

@@ -231,8 +231,10 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, c
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int group = blockIdx.z / shp.ksplit, split = blockIdx.z - group * shp.ksplit;
-  const int m0 = blockIdx.y * kGemmBM;
-  const int tile_n = blockIdx.x;
+  // M-tiles vary fastest in launch order: the CTAs that share a B (weight) tile run together, so with M = 512
+  // prompt rows the four readers of a weight tile hit L2 and the matrix leaves HBM once (ncu before: 4×)
+  const int m0 = blockIdx.x * kGemmBM;
+  const int tile_n = blockIdx.y;
   const int total_kb = (shp.K + BK - 1) / BK;
   const int kb_begin = (int)((long long)split * total_kb / shp.ksplit);
   const int num_kb = (int)((long long)(split + 1) * total_kb / shp.ksplit) - kb_begin;  // may be 0: the tile is all zeros

@@ -126,7 +126,7 @@ struct EpiSwiGLUPrefill {
 // ---- causal attention over the KV cache for a block of query positions -----------------------------------
 // Query row m (position pos0+m) attends to cache rows 0..pos0+m of its head: exactly what
 // multi_head_attention computes for that position (cpu.rs:23-52), with an online softmax.
-// Grid (ceil(M/64), heads); 256 threads as 16×16: thread (ty,tx) owns score rows 4ty..4ty+3 × key columns
+// Grid (ceil(ceil(M/64)/2), heads), each CTA two query blocks (see below); 256 threads as 16×16: thread (ty,tx) owns score rows 4ty..4ty+3 × key columns
 // tx+16j, and output rows 4ty..4ty+3 × head columns 4tx+64j.  f32 CUDA-core math: attention is ~1 % of the
 // prefill flops, the GEMMs own the tensor cores.
 constexpr int kPfBQ = 64, kPfBK = 64, kPfThreads = 256, kPfMaxHs = 128;
@@ -152,11 +152,19 @@ __global__ void __launch_bounds__(kPfThreads) prefill_attn_kernel(const PrefillA
   float* Ps = Vs + kPfBK * hs;         // [64][68]
   constexpr int ldp = kPfBK + 4;
 
-  const int q0 = blockIdx.x * kPfBQ, h = blockIdx.y;
+  const int h = blockIdx.y;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const size_t col = (size_t)h * hs;
   const int hs4 = hs >> 2;
   const float div = sqrtf((float)hs);
+  // Causal work grows with the query block index, so a CTA takes blocks x and nq−1−x: every CTA does the same
+  // number of key-block iterations (nq+1) and the whole grid is one balanced wave.
+  const int nq = (p.M + kPfBQ - 1) / kPfBQ;
+  for (int pass = 0; pass < 2; ++pass) {
+  const int qb = pass == 0 ? (int)blockIdx.x : nq - 1 - (int)blockIdx.x;
+  if (pass == 1 && qb <= (int)blockIdx.x) break;
+  const int q0 = qb * kPfBQ;
+  __syncthreads();  // the previous pass is done with Qs
 
   for (int i = tid; i < kPfBQ * hs4; i += kPfThreads) {
     const int r = i / hs4, c = i - r * hs4;
@@ -271,6 +279,7 @@ __global__ void __launch_bounds__(kPfThreads) prefill_attn_kernel(const PrefillA
                         acc[i][4 * jj + 3] / lrow[i]);
     }
   }
+  }  // pass
 }
 
 // last prompt row → the decode path's residual buffer: x0 = x[M-1] + y[M-1]
