@@ -131,6 +131,7 @@ struct rama_ctx {
   int use_pdl = 0;
   int variant_override = -1;
   int p2p = 0;  // TP exchange: 1 = fused peer-memory all-reduce (default), 0 = NCCL collectives
+  int staged = 1;      // RAMA_GEMV_STAGED=0 disables the shared-memory-staged GEMV for small slabs
   int persistent = 0;  // RAMA_STEP=persistent: the decode step as one persistent cooperative kernel (step_kernel.cuh);
                        // default: one fused kernel per op group in a CUDA graph (measured faster)
   std::mutex mu;
@@ -183,6 +184,7 @@ struct rama_session {
 // GEMV dispatch
 // ------------------------------------------------------------------------------------------------
 constexpr int kNumVariants = 8;
+constexpr int kVariantStaged = 100;  // gemv_smem_kernel
 struct Variant { int WK, RP, U; };
 static const Variant kVariants[kNumVariants] = {{16, 2, 2}, {8, 2, 4}, {4, 2, 4}, {1, 2, 4},
                                                 {16, 4, 2}, {8, 4, 2}, {2, 2, 4}, {16, 1, 4}};
@@ -215,9 +217,42 @@ static cudaError_t launch_gemv_t(int grid, cudaStream_t st, int pdl, const Pro& 
   return cudaLaunchKernelEx(&cfg, kern, pro, rows, epi, K4, n_pairs, pdl);
 }
 
+// bytes of shared memory the staged variant needs for this launch (x + the largest CTA slab)
+static size_t gemv_stage_bytes(int K4, int n_pairs, int grid, int rows_per_pair) {
+  const int maxp = (n_pairs + grid - 1) / grid;
+  return (size_t)K4 * 16 + (size_t)maxp * rows_per_pair * K4 * 16;
+}
+
+template <class Pro, class Rows, class Epi>
+static cudaError_t launch_gemv_staged(int grid, cudaStream_t st, int pdl, const Pro& pro, const Rows& rows, const Epi& epi,
+                                      int K4, int n_pairs) {
+  auto kern = gemv_smem_kernel<Pro, Rows, Epi>;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [&] {
+    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemvSmemStageMax);
+  });
+  if (attr_err != cudaSuccess) return attr_err;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kGemvThreads);
+  cfg.dynamicSmemBytes = gemv_stage_bytes(K4, n_pairs, grid, 2);
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  if (pdl) {
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+  }
+  return cudaLaunchKernelEx(&cfg, kern, pro, rows, epi, K4, n_pairs, pdl);
+}
+
 template <class Pro, class Rows, class Epi>
 static cudaError_t launch_gemv(int variant, int grid, cudaStream_t st, int pdl, const Pro& pro,
                                const Rows& rows, const Epi& epi, int K4, int n_pairs) {
+  // small slabs (the small models): whole slab staged in shared memory ahead of the dependency (gemv_smem_kernel)
+  if (variant == kVariantStaged) return launch_gemv_staged(grid, st, pdl, pro, rows, epi, K4, n_pairs);
   switch (variant) {
     case 0: return launch_gemv_t<16, 2, 2>(grid, st, pdl, pro, rows, epi, K4, n_pairs);
     case 1: return launch_gemv_t<8, 2, 4>(grid, st, pdl, pro, rows, epi, K4, n_pairs);
@@ -231,14 +266,18 @@ static cudaError_t launch_gemv(int variant, int grid, cudaStream_t st, int pdl, 
   }
 }
 
-static int pick_variant(const rama_ctx* c, int K4) {
+static int pick_variant(const rama_ctx* c, int K4, int n_pairs = 0) {
   if (c->variant_override >= 0 && c->variant_override < kNumVariants) return c->variant_override;
+  if (c->staged && n_pairs > 0 && gemv_stage_bytes(K4, n_pairs, c->sm_count, 2) <= kGemvSmemStageMax &&
+      n_pairs >= c->sm_count)
+    return kVariantStaged;
   if (K4 >= 1024) return 1;
   if (K4 >= 512) return 2;
   if (K4 >= 128) return 6;
   return 3;
 }
 static int pick_grid(const rama_ctx* c, int variant, int n_pairs) {
+  if (variant == kVariantStaged) return c->sm_count;
   const int rp = kVariants[variant].RP;
   return std::max(1, std::min(c->sm_count, (n_pairs + rp - 1) / rp));
 }
@@ -283,6 +322,7 @@ extern "C" int rama_ctx_create(int device, const rama_tp* tp, rama_ctx** out) {
   c->sm_count = prop.multiProcessorCount;
   c->use_pdl = env_int("RAMA_PDL", 1);
   c->variant_override = env_int("RAMA_GEMV_VARIANT", -1);
+  c->staged = env_int("RAMA_GEMV_STAGED", 1);
   {
     const char* m = getenv("RAMA_STEP");
     c->persistent = m && strcmp(m, "persistent") == 0;
@@ -878,7 +918,7 @@ static int enqueue_step(rama_session* s, cudaStream_t st, int mode, StepTrace* t
                    W[RAMA_T_WV] + (size_t)l * Dq * D, D, Dq / 2};
       EpiQKV epi{s->q, s->k, s->v, s->key_cache + (size_t)l * T * Dq, s->value_cache + (size_t)l * T * Dq,
                  W[RAMA_T_FREQ_REAL], W[RAMA_T_FREQ_IMAG], s->ctrl, Dq / 2, hs / 2, Dq};
-      const int np = 3 * Dq / 2, var = pick_variant(c, D / 4);
+      const int np = 3 * Dq / 2, var = pick_variant(c, D / 4, np);
       q.pre(RAMA_K_QKV);
       q.post(launch_gemv(var, pick_grid(c, var, np), st, q.pdl, pro, rows, epi, D / 4, np));
     }
@@ -906,7 +946,7 @@ static int enqueue_step(rama_session* s, cudaStream_t st, int mode, StepTrace* t
       ProPlain pro{s->xb};
       RowsPlain rows{W[RAMA_T_WO] + (size_t)l * D * Dq, Dq, D};
       EpiStore epi{s->xb2, D, peer_out(s, 0, l)};
-      const int np = D / 2, var = pick_variant(c, Dq / 4);
+      const int np = D / 2, var = pick_variant(c, Dq / 4, np);
       q.pre(RAMA_K_WO);
       q.post(launch_gemv(var, pick_grid(c, var, np), st, q.pdl, pro, rows, epi, Dq / 4, np));
     }
@@ -921,7 +961,7 @@ static int enqueue_step(rama_session* s, cudaStream_t st, int mode, StepTrace* t
       ProNorm pro{s->x1, s->xb2, s->x0, W[RAMA_T_RMS_FFN] + (size_t)l * D, nullptr, peer_in(s, 0, l)};
       RowsW13 rows{W[RAMA_T_W1] + (size_t)l * Fl * D, W[RAMA_T_W3] + (size_t)l * Fl * D, D};
       EpiSwiGLU epi{s->hb, s->hb2};
-      const int np = Fl, var = pick_variant(c, D / 4);
+      const int np = Fl, var = pick_variant(c, D / 4, np);
       q.pre(RAMA_K_W13);
       q.post(launch_gemv(var, pick_grid(c, var, np), st, q.pdl, pro, rows, epi, D / 4, np));
     }
@@ -930,7 +970,7 @@ static int enqueue_step(rama_session* s, cudaStream_t st, int mode, StepTrace* t
       ProPlain pro{s->hb};
       RowsPlain rows{W[RAMA_T_W2] + (size_t)l * D * Fl, Fl, D};
       EpiStore epi{s->w2out, D, peer_out(s, 1, l)};
-      const int np = D / 2, var = pick_variant(c, Fl / 4);
+      const int np = D / 2, var = pick_variant(c, Fl / 4, np);
       q.pre(RAMA_K_W2);
       q.post(launch_gemv(var, pick_grid(c, var, np), st, q.pdl, pro, rows, epi, Fl / 4, np));
     }

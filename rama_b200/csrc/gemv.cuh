@@ -157,6 +157,17 @@ struct RowsPlain {  // rows 2p, 2p+1 of one matrix
     r0 = reinterpret_cast<const float4*>(w + a);
     r1 = (2 * p + 1 < n_rows) ? reinterpret_cast<const float4*>(w + a + K) : r0;
   }
+  // shared-memory staging (gemv_smem_kernel): contiguous global ranges of pairs [p0, p0+np) and where they land
+  static constexpr int kMaxRanges = 1;
+  __device__ __forceinline__ int ranges(int p0, int np, const float* (&src)[3], uint32_t (&dst_off)[3], uint32_t (&bytes)[3]) const {
+    src[0] = w + (size_t)(2 * p0) * K; dst_off[0] = 0;
+    bytes[0] = (uint32_t)min(2 * np, n_rows - 2 * p0) * K * 4;
+    return 1;
+  }
+  __device__ __forceinline__ void staged(int i, int np, const float* base, const float4*& r0, const float4*& r1, int p0) const {
+    r0 = reinterpret_cast<const float4*>(base + (size_t)(2 * i) * K);
+    r1 = (2 * (p0 + i) + 1 < n_rows) ? r0 + (K >> 2) : r0;
+  }
 };
 
 struct RowsQKV {  // virtual matrix [wq; wk; wv] of this layer, each `rows_per` rows (even)
@@ -177,6 +188,25 @@ struct RowsQKV {  // virtual matrix [wq; wk; wv] of this layer, each `rows_per` 
     r0 = reinterpret_cast<const float4*>(b + (size_t)(2 * i) * K);
     r1 = r0 + (K >> 2);
   }
+  static constexpr int kMaxRanges = 3;
+  __device__ __forceinline__ int ranges(int p0, int np, const float* (&src)[3], uint32_t (&dst_off)[3], uint32_t (&bytes)[3]) const {
+    int n = 0;
+    for (int sec = 0; sec < 3; ++sec) {  // intersect [p0, p0+np) with the section's pairs
+      const int a = max(p0, sec * pairs_per), b = min(p0 + np, (sec + 1) * pairs_per);
+      if (a < b) {
+        const float* base = sec == 0 ? wq : (sec == 1 ? wk : wv);
+        src[n] = base + (size_t)(2 * (a - sec * pairs_per)) * K;
+        dst_off[n] = (uint32_t)(2 * (a - p0)) * K * 4;
+        bytes[n] = (uint32_t)(2 * (b - a)) * K * 4;
+        ++n;
+      }
+    }
+    return n;
+  }
+  __device__ __forceinline__ void staged(int i, int, const float* base, const float4*& r0, const float4*& r1, int) const {
+    r0 = reinterpret_cast<const float4*>(base + (size_t)(2 * i) * K);
+    r1 = r0 + (K >> 2);
+  }
 };
 
 struct RowsW13 {  // pair p = (w1 row p, w3 row p)
@@ -191,6 +221,16 @@ struct RowsW13 {  // pair p = (w1 row p, w3 row p)
   __device__ __forceinline__ void operator()(int p, const float4*& r0, const float4*& r1) const {
     r0 = reinterpret_cast<const float4*>(w1 + (size_t)p * K);
     r1 = reinterpret_cast<const float4*>(w3 + (size_t)p * K);
+  }
+  static constexpr int kMaxRanges = 2;
+  __device__ __forceinline__ int ranges(int p0, int np, const float* (&src)[3], uint32_t (&dst_off)[3], uint32_t (&bytes)[3]) const {
+    src[0] = w1 + (size_t)p0 * K; dst_off[0] = 0; bytes[0] = (uint32_t)np * K * 4;
+    src[1] = w3 + (size_t)p0 * K; dst_off[1] = bytes[0]; bytes[1] = bytes[0];
+    return 2;
+  }
+  __device__ __forceinline__ void staged(int i, int np, const float* base, const float4*& r0, const float4*& r1, int) const {
+    r0 = reinterpret_cast<const float4*>(base + (size_t)i * K);
+    r1 = reinterpret_cast<const float4*>(base + (size_t)(np + i) * K);
   }
 };
 
@@ -427,6 +467,81 @@ gemv_fused_kernel(const Pro pro, const Rows rows, const Epi epi_in, int K4, int 
   epi.finish(red);
 }
 
+// this CTA's balanced contiguous range of pairs
+__device__ __forceinline__ void gemv_cta_range(int n_pairs, int& p0, int& np) {
+  const int per = n_pairs / gridDim.x, rem = n_pairs % gridDim.x;
+  p0 = blockIdx.x * per + min((int)blockIdx.x, rem);
+  np = per + ((int)blockIdx.x < rem ? 1 : 0);
+}
+
+// ---- small slabs: stage the CTA's whole weight slab in shared memory BEFORE waiting for the previous kernel ---
+// For the small models a CTA's share of a matrix is 16-90 KB and a launch is pure latency (dependency → x →
+// norm → first weight byte → reduce → store).  Weights never depend on the previous kernel, so this variant
+// issues cp.async.bulk copies of its whole slab into shared memory at entry, only then executes
+// griddepcontrol.wait, and computes out of shared memory.  It is sized (≤ 64 registers, ≤ 110 KB of shared
+// memory) so that TWO such CTAs fit an SM: with programmatic dependent launch the next kernel of the graph is
+// resident and has its weights on chip while the current one is still finishing.
+constexpr size_t kGemvSmemStageMax = 110 * 1024;
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+template <class Pro, class Rows, class Epi>
+__global__ void __launch_bounds__(kGemvThreads, 2)
+gemv_smem_kernel(const Pro pro, const Rows rows, const Epi epi_in, int K4, int n_pairs, int use_pdl) {
+  extern __shared__ float4 gemv_smem[];
+  __shared__ float red[2 * kWarp];
+  __shared__ __align__(8) unsigned long long bar_storage;
+  float4* xs = gemv_smem;
+  float* slab = reinterpret_cast<float*>(xs + K4);
+  const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&bar_storage);
+
+  int p0, np;
+  gemv_cta_range(n_pairs, p0, np);
+  if (use_pdl) pdl_launch_dependents();
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const float* src[3];
+    uint32_t off[3], bytes[3], total = 0;
+    const int nr = np > 0 ? rows.ranges(p0, np, src, off, bytes) : 0;
+    for (int i = 0; i < nr; ++i) total += bytes[i];
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(total) : "memory");
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(slab);
+    for (int i = 0; i < nr; ++i) bulk_g2s(sbase + off[i], src[i], bytes[i], bar);
+  }
+  if (use_pdl) pdl_wait();
+
+  pro(xs, K4, red);
+  __syncthreads();  // xs complete; also makes the mbarrier init visible to every waiter
+  {
+    uint32_t done = 0;
+    while (!done)
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                   : "=r"(done) : "r"(bar) : "memory");
+  }
+  Epi epi = epi_in;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = warp; i < np; i += kGemvWarps) {
+    const float4 *r0, *r1;
+    rows.staged(i, np, slab, r0, r1, p0);
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll 2
+    for (int c = lane; c < K4; c += kWarp) {
+      const float4 xv = xs[c];
+      a0 = dot4(r0[c], xv, a0);
+      a1 = dot4(r1[c], xv, a1);
+    }
+    a0 = warp_sum(a0);
+    a1 = warp_sum(a1);
+    if (lane == 0) epi(p0 + i, a0, a1);
+  }
+  epi.finish(red);
+}
+
 // ---- the same streaming core with a run-time k-split (persistent step kernel: one instantiation per
 // phase type instead of one per variant); RP = 2, U = 4 as in every default variant ------------------------
 template <class Rows>
@@ -483,13 +598,6 @@ __device__ __forceinline__ void gemv_pairs_rt(const Rows& rows, int K4, int p0, 
       }
     }
   }
-}
-
-// this CTA's balanced contiguous range of pairs
-__device__ __forceinline__ void gemv_cta_range(int n_pairs, int& p0, int& np) {
-  const int per = n_pairs / gridDim.x, rem = n_pairs % gridDim.x;
-  p0 = blockIdx.x * per + min((int)blockIdx.x, rem);
-  np = per + ((int)blockIdx.x < rem ? 1 : 0);
 }
 
 // L2 prefetch of the head of this CTA's slab of a coming phase (weights never depend on activations)
