@@ -1328,8 +1328,11 @@ static int ensure_prefill_ws(rama_session* s) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] {
-    attr_err = cudaFuncSetAttribute(prefill_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)prefill_attn_smem_bytes(kPfMaxHs));
+    attr_err = cudaFuncSetAttribute(prefill_attn_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)prefill_attn_smem_bytes(kPfMaxHs, 4));
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(prefill_attn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)prefill_attn_smem_bytes(kPfMaxHs, 1));
   });
   if (attr_err != cudaSuccess) return fail(RAMA_E_CUDA, "prefill attention smem: %s", cudaGetErrorString(attr_err));
   s->pf_cap = (int)cap;
@@ -1392,8 +1395,12 @@ static int prefill_chunk(rama_session* s, const int32_t* tokens, int M, int pos0
     {
       PrefillAttnParams ap{s->pf_q, kc, vc, s->pf_att, M, pos0, Dq, hs};
       tr.pre(RAMA_PK_ATTN);
-      const int nq = (M + kPfBQ - 1) / kPfBQ;
-      prefill_attn_kernel<<<dim3((nq + 1) / 2, c->Hl), kPfThreads, prefill_attn_smem_bytes(hs), st>>>(ap);
+      // 64-query blocks when that still fills the machine, else 16-query blocks (few heads per rank, short prompts)
+      const int nq64 = (M + 63) / 64, nq16 = (M + 15) / 16;
+      if (((nq64 + 1) / 2) * c->Hl >= 96)
+        prefill_attn_kernel<4><<<dim3((nq64 + 1) / 2, c->Hl), kPfThreads, prefill_attn_smem_bytes(hs, 4), st>>>(ap);
+      else
+        prefill_attn_kernel<1><<<dim3((nq16 + 1) / 2, c->Hl), kPfThreads, prefill_attn_smem_bytes(hs, 1), st>>>(ap);
       tr.post(); ++launches;
     }
     // wo   (infer.rs:35); the residual add is the next addnorm

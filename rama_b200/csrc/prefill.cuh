@@ -129,7 +129,10 @@ struct EpiSwiGLUPrefill {
 // Grid (ceil(ceil(M/64)/2), heads), each CTA two query blocks (see below); 256 threads as 16×16: thread (ty,tx) owns score rows 4ty..4ty+3 × key columns
 // tx+16j, and output rows 4ty..4ty+3 × head columns 4tx+64j.  f32 CUDA-core math: attention is ~1 % of the
 // prefill flops, the GEMMs own the tensor cores.
-constexpr int kPfBQ = 64, kPfBK = 64, kPfThreads = 256, kPfMaxHs = 128;
+constexpr int kPfBK = 64, kPfThreads = 256, kPfMaxHs = 128;
+// query rows per thread RQ ∈ {4, 1} → 64 or 16 queries per block: the small block keeps the SMs busy when a rank
+// holds few heads (tensor parallelism) or the prompt is short
+__host__ __device__ constexpr int pf_bq(int rq) { return 16 * rq; }
 
 struct PrefillAttnParams {
   const float* q;          // [M][Dq]
@@ -139,11 +142,13 @@ struct PrefillAttnParams {
   int M, pos0, Dq, hs;
 };
 
-__host__ __device__ inline size_t prefill_attn_smem_bytes(int hs) {
-  return (size_t)(2 * kPfBQ * (hs + 4) + kPfBK * hs + kPfBQ * (kPfBK + 4)) * sizeof(float);
+__host__ __device__ inline size_t prefill_attn_smem_bytes(int hs, int rq) {
+  return (size_t)(pf_bq(rq) * (hs + 4) + kPfBK * (hs + 4) + kPfBK * hs + pf_bq(rq) * (kPfBK + 4)) * sizeof(float);
 }
 
+template <int RQ>
 __global__ void __launch_bounds__(kPfThreads) prefill_attn_kernel(const PrefillAttnParams p) {
+  constexpr int kPfBQ = pf_bq(RQ);
   extern __shared__ __align__(16) float pf_smem[];
   const int hs = p.hs, ldq = hs + 4;
   float* Qs = pf_smem;                 // [64][hs+4]
@@ -173,9 +178,9 @@ __global__ void __launch_bounds__(kPfThreads) prefill_attn_kernel(const PrefillA
     reinterpret_cast<float4*>(Qs + r * ldq)[c] = v;
   }
 
-  float mrow[4], lrow[4], acc[4][8];
+  float mrow[RQ], lrow[RQ], acc[RQ][8];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < RQ; ++i) {
     mrow[i] = -INFINITY; lrow[i] = 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
@@ -198,26 +203,26 @@ __global__ void __launch_bounds__(kPfThreads) prefill_attn_kernel(const PrefillA
     __syncthreads();
 
     // scores: 4 rows × 4 key columns per thread
-    float s[4][4];
+    float s[RQ][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < RQ; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
     for (int d = 0; d < hs4; ++d) {
-      float4 qv[4], kv[4];
+      float4 qv[RQ], kv[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) qv[i] = reinterpret_cast<const float4*>(Qs + (4 * ty + i) * ldq)[d];
+      for (int i = 0; i < RQ; ++i) qv[i] = reinterpret_cast<const float4*>(Qs + (RQ * ty + i) * ldq)[d];
 #pragma unroll
       for (int j = 0; j < 4; ++j) kv[j] = reinterpret_cast<const float4*>(Ks + (tx + 16 * j) * ldq)[d];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < RQ; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) s[i][j] = dot4(qv[i], kv[j], s[i][j]);
     }
     // scale, causal mask, online softmax (row statistics shared by the 16 tx lanes of a row group)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int qpos = p.pos0 + q0 + 4 * ty + i;
+    for (int i = 0; i < RQ; ++i) {
+      const int qpos = p.pos0 + q0 + RQ * ty + i;
       float mx = -INFINITY;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -233,7 +238,7 @@ __global__ void __launch_bounds__(kPfThreads) prefill_attn_kernel(const PrefillA
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float e = expf(s[i][j] - mn);           // exp(-inf) = 0 for masked keys
-        Ps[(4 * ty + i) * ldp + tx + 16 * j] = e;
+        Ps[(RQ * ty + i) * ldp + tx + 16 * j] = e;
         ps += e;
       }
 #pragma unroll
@@ -247,16 +252,16 @@ __global__ void __launch_bounds__(kPfThreads) prefill_attn_kernel(const PrefillA
     // O += P · V : rows 4ty+i, head columns 4tx + 64·jj + (0..3)
     const int kmax = min(kPfBK, n_keys - k0);
     for (int t = 0; t < kmax; ++t) {
-      float pv[4];
+      float pv[RQ];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) pv[i] = Ps[(4 * ty + i) * ldp + t];
+      for (int i = 0; i < RQ; ++i) pv[i] = Ps[(RQ * ty + i) * ldp + t];
 #pragma unroll
       for (int jj = 0; jj < 2; ++jj) {
         const int c = 4 * tx + 64 * jj;
         if (c < hs) {
           const float4 vv = *reinterpret_cast<const float4*>(Vs + t * hs + c);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
+          for (int i = 0; i < RQ; ++i) {
             acc[i][4 * jj + 0] = fmaf(pv[i], vv.x, acc[i][4 * jj + 0]);
             acc[i][4 * jj + 1] = fmaf(pv[i], vv.y, acc[i][4 * jj + 1]);
             acc[i][4 * jj + 2] = fmaf(pv[i], vv.z, acc[i][4 * jj + 2]);
@@ -267,8 +272,8 @@ __global__ void __launch_bounds__(kPfThreads) prefill_attn_kernel(const PrefillA
     }
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = q0 + 4 * ty + i;
+  for (int i = 0; i < RQ; ++i) {
+    const int m = q0 + RQ * ty + i;
     if (m >= p.M) continue;
 #pragma unroll
     for (int jj = 0; jj < 2; ++jj) {
