@@ -107,3 +107,29 @@ def test_prefill_512_at_7b_layer_shapes():
     assert rel_err(b.logits(), a.logits()) < LOGIT_TOL
     assert b.sample(0.0, 0.9) == a.sample(0.0, 0.9)
     a.close(); b.close(); gpu.close()
+
+
+def test_prefill_longer_than_one_chunk_stories110m_shapes():
+    """700 prompt rows = two chunks (512 + 188) at stories110M geometry (seq_len 1024): the second chunk attends
+    to the first chunk's cache rows (pos0 = 512)."""
+    cfg = ck.CONFIGS["stories110M"]
+    gpu = GPU(0)
+    gpu.load_synthetic(cfg, ck.SynthSpec())
+    rng = np.random.default_rng(13)
+    n = 700
+    toks = [1] + [int(t) for t in rng.integers(0, cfg.vocab_size, n - 1)]
+    a, b = Session(gpu), Session(gpu)
+    for pos, t in enumerate(toks):
+        a.forward(t, pos)
+    b.prefill(toks, 0)
+    ka, va = _kv(a, cfg, n)
+    kb, vb = _kv(b, cfg, n)
+    assert rel_err(kb, ka) < 1e-4 and rel_err(vb, va) < 1e-4
+    assert rel_err(b.logits(), a.logits()) < LOGIT_TOL
+    # generate() with a long prompt takes the prefill path and continues identically
+    prompt = toks[1:601]
+    a.set_prefill(0); b.set_prefill(16)
+    ta = generate(a, prompt, 640, 0.0, 0.9)
+    tb = generate(b, prompt, 640, 0.0, 0.9)
+    assert ta == tb and ta[:600] == prompt
+    a.close(); b.close(); gpu.close()
