@@ -83,6 +83,8 @@ int rama_tp_unique_id(uint8_t out[128]);
  * (mod.rs:140-166, ram.rs:27-51, hbm.rs:55-90): mmap the v0 .bin, stream it through pinned
  * staging into HBM once, keeping only this rank's shard under TP. */
 int rama_ctx_load_file(rama_ctx* ctx, const char* path);
+/* throughput of this rank's window through the last rama_ctx_load_file (tools/load_bench.py) */
+int rama_last_load_gbps(double* out);
 /* ≙ TransformerWeights::from_weight(&mut TransformerWeights<Vec<f32>>, &GPU) (hbm.rs:55-90).
  * tensors[] in rama_tensor order, full (unsharded) host arrays; tensors[WCLS] may be NULL when
  * cfg->shared_weight (state.rs:111-117: wcls then aliases the embedding). */

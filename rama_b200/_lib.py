@@ -49,6 +49,7 @@ _SIGS = {
     "rama_ctx_destroy": ([vp], C.c_int),
     "rama_tp_unique_id": ([C.POINTER(C.c_uint8)], C.c_int),
     "rama_ctx_load_file": ([vp, C.c_char_p], C.c_int),
+    "rama_last_load_gbps": ([C.POINTER(C.c_double)], C.c_int),
     "rama_ctx_load_host": ([vp, C.POINTER(CConfig), C.POINTER(fp)], C.c_int),
     "rama_ctx_load_synthetic": ([vp, C.POINTER(CConfig), C.c_uint64, fp, fp, fp, fp], C.c_int),
     "rama_ctx_config": ([vp, C.POINTER(CConfig)], C.c_int),

@@ -11,6 +11,10 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <thread>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -460,18 +464,121 @@ extern "C" int rama_ctx_load_host(rama_ctx* c, const rama_config* cfg, const flo
   return RAMA_OK;
 }
 
+// ---- file → HBM pipeline --------------------------------------------------------------------------------------
+// The reference reads the checkpoint one f32 at a time (read.rs:25-33: minutes at 7B) into Vecs and then uploads
+// them.  Here reader threads pread() row blocks of this rank's window straight into a ring of pinned buffers while the
+// calling thread issues the DMA of the blocks that are ready (1-D, or 2-D for the column windows of row-parallel
+// wo / w2): disk/page-cache reads, and PCIe transfers overlap, nothing is staged in pageable memory, and under TP
+// a rank only reads the rows it keeps.
+struct LoadPiece {
+  size_t file_off;     // first byte of the block in the file (full rows)
+  size_t rows, row_bytes;         // rows in the block, bytes of a full file row
+  size_t col_off, col_bytes;      // window inside a row
+  char* dst;                      // device destination (pitch col_bytes)
+};
+
+static int load_file_pipelined(rama_ctx* c, int fd, const std::vector<LoadPiece>& pieces, double* gbps) {
+  constexpr int kBuf = 8, kReaders = 4;
+  constexpr size_t kBufBytes = (size_t)32 << 20;
+  char* ring[kBuf] = {nullptr};
+  cudaEvent_t done[kBuf];
+  for (int i = 0; i < kBuf; ++i) {
+    if (cudaHostAlloc((void**)&ring[i], kBufBytes, cudaHostAllocDefault) != cudaSuccess ||
+        cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming) != cudaSuccess) {
+      for (int j = 0; j <= i; ++j) if (ring[j]) cudaFreeHost(ring[j]);
+      return fail(RAMA_E_CUDA, "pinned staging ring: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+  }
+  // slot state: 0 free, 1 being filled, 2 ready (filled), 3 in flight (DMA issued, `done` recorded)
+  std::mutex mu;
+  std::condition_variable cv;
+  std::vector<int> state(kBuf, 0);
+  std::atomic<size_t> next{0};
+  std::atomic<int> io_error{0};
+  const size_t n = pieces.size();
+  auto reader = [&](int) {
+    cudaSetDevice(c->device);
+    for (;;) {
+      const size_t i = next.fetch_add(1);
+      if (i >= n || io_error.load()) return;
+      const int slot = (int)(i % kBuf);
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        // piece i may use its slot once piece i-kBuf has been issued and its DMA has finished
+        cv.wait(lk, [&] { return state[slot] == 0 || state[slot] == 3 || io_error.load(); });
+        if (io_error.load()) return;
+        const bool wait_dma = state[slot] == 3;
+        state[slot] = 1;
+        lk.unlock();
+        if (wait_dma) cudaEventSynchronize(done[slot]);
+      }
+      const LoadPiece& p = pieces[i];
+      size_t got = 0;
+      const size_t want = p.rows * p.row_bytes;
+      while (got < want) {
+        const ssize_t r = pread(fd, ring[slot] + got, want - got, (off_t)(p.file_off + got));
+        if (r <= 0) { io_error.store(1); break; }
+        got += (size_t)r;
+      }
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        state[slot] = 2;
+      }
+      cv.notify_all();
+    }
+  };
+  // pieces are claimed in order by fetch_add, so slot (i % kBuf) is always filled by piece i after piece i-kBuf
+  std::vector<std::thread> th;
+  for (int t = 0; t < kReaders; ++t) th.emplace_back(reader, t);
+  const auto t0 = std::chrono::steady_clock::now();
+  size_t bytes = 0;
+  int rc = RAMA_OK;
+  for (size_t i = 0; i < n && rc == RAMA_OK; ++i) {
+    const int slot = (int)(i % kBuf);
+    {
+      std::unique_lock<std::mutex> lk(mu);
+      cv.wait(lk, [&] { return state[slot] == 2 || io_error.load(); });
+    }
+    if (io_error.load()) { rc = fail(RAMA_E_IO, "short read from the checkpoint file"); break; }
+    const LoadPiece& p = pieces[i];
+    cudaError_t e;
+    if (p.col_bytes == p.row_bytes)
+      e = cudaMemcpyAsync(p.dst, ring[slot], p.rows * p.row_bytes, cudaMemcpyHostToDevice, c->op_stream);
+    else
+      e = cudaMemcpy2DAsync(p.dst, p.col_bytes, ring[slot] + p.col_off, p.row_bytes, p.col_bytes, p.rows,
+                            cudaMemcpyHostToDevice, c->op_stream);
+    if (e == cudaSuccess) e = cudaEventRecord(done[slot], c->op_stream);
+    if (e != cudaSuccess) { rc = fail(RAMA_E_CUDA, "upload: %s", cudaGetErrorString(e)); io_error.store(1); }
+    bytes += p.rows * p.col_bytes;
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      state[slot] = 3;
+    }
+    cv.notify_all();
+  }
+  if (rc != RAMA_OK) { io_error.store(1); cv.notify_all(); }
+  for (auto& t : th) t.join();
+  if (rc == RAMA_OK && cudaStreamSynchronize(c->op_stream) != cudaSuccess) rc = fail(RAMA_E_CUDA, "sync after upload");
+  const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  if (gbps) *gbps = sec > 0 ? bytes / sec / 1e9 : 0.0;
+  for (int i = 0; i < kBuf; ++i) { cudaFreeHost(ring[i]); cudaEventDestroy(done[i]); }
+  return rc;
+}
+
+static double g_last_load_gbps = 0.0;
+
 extern "C" int rama_ctx_load_file(rama_ctx* c, const char* path) {
   if (!c || !path) return fail(RAMA_E_INVALID, "NULL argument");
   int fd = open(path, O_RDONLY);
   if (fd < 0) return fail(RAMA_E_IO, "cannot open %s", path);
   struct stat st;
-  if (fstat(fd, &st) != 0 || st.st_size < 28) { close(fd); return fail(RAMA_E_IO, "%s: too short for a v0 header", path); }
-  void* map = mmap(nullptr, st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
-  close(fd);
-  if (map == MAP_FAILED) return fail(RAMA_E_IO, "mmap of %s failed", path);
-  madvise(map, st.st_size, MADV_SEQUENTIAL);
+  int32_t h[7];
+  if (fstat(fd, &st) != 0 || st.st_size < 28 || pread(fd, h, 28, 0) != 28) {
+    close(fd);
+    return fail(RAMA_E_IO, "%s: too short for a v0 header", path);
+  }
+  posix_fadvise(fd, 0, 0, POSIX_FADV_SEQUENTIAL);
   // header: 7 LE i32; vocab > 0 ⇒ shared classifier (mod.rs:140-166)
-  const int32_t* h = (const int32_t*)map;
   rama_config cfg{h[0], h[1], h[2], h[3], h[4], h[5] > 0 ? h[5] : -h[5], h[6], h[5] > 0 ? 1 : 0};
   int rc;
   {
@@ -485,17 +592,36 @@ extern "C" int rama_ctx_load_file(rama_ctx* c, const char* path) {
     }
     if (rc == RAMA_OK) rc = alloc_weights(c);
     if (rc == RAMA_OK) {
-      const float* f = (const float*)((const char*)map + 28);
-      for (int i = 0; i < RAMA_T_COUNT && rc == RAMA_OK; ++i) {
-        rc = upload_tensor(c, i, f, c->op_stream);
-        f += c->plan[i].global_elems();
+      // row blocks of ≤ 32 MB (the staging buffer) of every (tensor, layer) window of this rank
+      std::vector<LoadPiece> pieces;
+      size_t base = 28;
+      for (int i = 0; i < RAMA_T_COUNT; ++i) {
+        const TensorPlan& p = c->plan[i];
+        if (p.local_elems()) {
+          const size_t row_bytes = p.C * 4, max_rows = std::max<size_t>(1, ((size_t)32 << 20) / row_bytes);
+          for (size_t l = 0; l < p.Lc; ++l) {
+            for (size_t r = 0; r < p.Rl; r += max_rows) {
+              const size_t nr = std::min(max_rows, p.Rl - r);
+              pieces.push_back(LoadPiece{base + ((l * p.R + p.r0 + r) * p.C) * 4, nr, row_bytes, p.c0 * 4, p.Cl * 4,
+                                         (char*)(c->w[i] + (l * p.Rl + r) * p.Cl)});
+            }
+          }
+        }
+        base += p.global_elems() * 4;
       }
-      if (rc == RAMA_OK && cudaStreamSynchronize(c->op_stream) != cudaSuccess) rc = fail(RAMA_E_CUDA, "sync after upload");
+      rc = load_file_pipelined(c, fd, pieces, &g_last_load_gbps);
       if (rc != RAMA_OK) free_weights(c); else c->loaded = true;
     }
   }
-  munmap(map, st.st_size);
+  close(fd);
   return rc;
+}
+
+// GB/s of this rank's window through the last rama_ctx_load_file (file → pinned ring → HBM), for tools/load_bench.py
+extern "C" int rama_last_load_gbps(double* out) {
+  if (!out) return fail(RAMA_E_INVALID, "NULL argument");
+  *out = g_last_load_gbps;
+  return RAMA_OK;
 }
 
 extern "C" int rama_ctx_load_synthetic(rama_ctx* c, const rama_config* cfg, uint64_t seed,
