@@ -83,6 +83,10 @@ constexpr int kMaxPeers = 8;
 __device__ __forceinline__ void st_ll(void* p, unsigned payload, unsigned epoch) {
   asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(payload), "r"(epoch) : "memory");
 }
+// two adjacent LL elements in ONE 16-byte store (each half still carries its own epoch, so a split delivery is harmless)
+__device__ __forceinline__ void st_ll2(void* p, unsigned payload0, unsigned payload1, unsigned epoch) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %2};" ::"l"(p), "r"(payload0), "r"(epoch), "r"(payload1) : "memory");
+}
 __device__ __forceinline__ uint4 ld_ll2(const void* p) {  // two adjacent {payload, epoch} elements
   uint4 v;
   asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"

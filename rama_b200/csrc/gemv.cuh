@@ -245,9 +245,9 @@ struct EpiStore {  // o[2p], o[2p+1]    (wo → xb2, w2 → residual contributio
       const unsigned ep = po.epoch();
 #pragma unroll
       for (int r = 0; r < kMaxPeers; ++r) {  // static indexing keeps the pointer table in param space
-        if (r < po.P) {
-          st_ll(po.inbox[r] + 2 * p, __float_as_uint(v0), ep);
-          if (2 * p + 1 < n_rows) st_ll(po.inbox[r] + 2 * p + 1, __float_as_uint(v1), ep);
+        if (r < po.P) {  // the pair's two elements are adjacent and 16-byte aligned: one remote store instead of two
+          if (2 * p + 1 < n_rows) st_ll2(po.inbox[r] + 2 * p, __float_as_uint(v0), __float_as_uint(v1), ep);
+          else st_ll(po.inbox[r] + 2 * p, __float_as_uint(v0), ep);
         }
       }
       return;

@@ -89,8 +89,7 @@ struct StepEpiStore {  // wo (stage 0 → xb2) / w2 (stage 1 → w2out); under T
       for (int r = 0; r < kMaxPeers; ++r) {
         if (r < p.world) {
           uint2* inbox = reinterpret_cast<uint2*>(p.peer_base[r] + p.off_inbox) + ((size_t)stage * p.world + p.rank) * p.D;
-          st_ll(inbox + 2 * pr, __float_as_uint(v0), ep);
-          st_ll(inbox + 2 * pr + 1, __float_as_uint(v1), ep);
+          st_ll2(inbox + 2 * pr, __float_as_uint(v0), __float_as_uint(v1), ep);
         }
       }
       return;
