@@ -170,6 +170,8 @@ struct rama_session {
   // mode 0 = forward, 1 = chained greedy, 2 = chained sampled
   cudaGraphExec_t g[3][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
   int attn_gy = 1;              // gridDim.y of the attention launch being enqueued
+  int attn_bk = 0;              // its bucket (0: positions < 256)
+  float* wo_part = nullptr;     // [H][D] per-head wo partials of the fused attention+wo kernel (small models), or null
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int keep_att = 0;
   int n_split = 1;
@@ -718,7 +720,7 @@ static void session_free(rama_session* s) {
   }
   void* bufs[] = {s->x0, s->x1, s->xfinal, s->xb, s->xb2, s->w2out, s->hb, s->hb2, s->q, s->k, s->v, s->att,
                   s->logits, s->key_cache, s->value_cache, s->attn_ws, s->tickets, s->part, s->sort_keys,
-                  s->ctrl, s->d_prompt, s->d_out, s->seq, s->bar, s->pf_x, s->pf_xn, s->pf_q, s->pf_att, s->pf_y, s->pf_h,
+                  s->ctrl, s->d_prompt, s->d_out, s->seq, s->bar, s->wo_part, s->pf_x, s->pf_xn, s->pf_q, s->pf_att, s->pf_y, s->pf_h,
                   s->pf_tokens};
   for (void* b : bufs) if (b) cudaFree(b);
   if (s->h_ring) cudaFreeHost(s->h_ring);
@@ -842,6 +844,13 @@ extern "C" int rama_session_create(rama_ctx* c, rama_session** out) {
   A(dalloc(&s->part, (size_t)c->world * c->sm_count));
   A(dalloc(&s->seq, 1));
   A(dalloc(&s->bar, 2));
+  // small models: attention + wo as one kernel with per-head partial outputs (attention.cuh attn_wo_kernel)
+  // (measured: a win up to stories15M's size — 8425 → 9340 tok/s; at stories110M the redundant per-CTA attention and the
+  // 12-way partial sum cost more than the saved launch — 3757 → 3536 — so dim ≤ 512 only)
+  if (c->world == 1 && c->D <= 512 && (size_t)c->H * c->D * sizeof(float) <= (size_t)64 * 1024 && c->H <= c->sm_count &&
+      (c->D + c->sm_count / c->H - 1) / (c->sm_count / c->H) <= 8 * kAttnWoWarps &&  // wo rows per CTA held in registers
+      env_int("RAMA_ATTN_WO", 1))
+    A(dalloc(&s->wo_part, (size_t)c->H * c->D));
   A(dalloc(&s->sort_keys, vp2));
   A(dalloc(&s->ctrl, 1));
   A(dalloc(&s->d_prompt, T)); A(dalloc(&s->d_out, T));
@@ -1048,6 +1057,25 @@ static int enqueue_step(rama_session* s, cudaStream_t st, int mode, StepTrace* t
       q.pre(RAMA_K_QKV);
       q.post(launch_gemv(var, pick_grid(c, var, np), st, q.pdl, pro, rows, epi, D / 4, np));
     }
+    const bool fuse_attn_wo = s->wo_part && s->attn_bk == 0 && !s->keep_att;
+    if (fuse_attn_wo) {
+      // ---- attention + wo in one launch, per-head partial outputs (infer.rs:34-35) ----
+      const int J = c->sm_count / c->H;
+      AttnWoParams ap{s->q, s->key_cache + (size_t)l * T * Dq, s->value_cache + (size_t)l * T * Dq,
+                      W[RAMA_T_WO] + (size_t)l * D * Dq, s->xb, s->wo_part, s->ctrl, Dq, hs, D, J};
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(c->H * J);
+      cfg.blockDim = dim3(kAttnWoThreads);
+      cfg.stream = st;
+      cudaLaunchAttribute at[1];
+      if (q.pdl) {
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+      }
+      q.pre(RAMA_K_ATTN);
+      q.post(cudaLaunchKernelEx(&cfg, attn_wo_kernel, ap, q.pdl));
+    } else {
     // ---- attention (infer.rs:34) ----
     {
       AttnParams ap{s->q, s->key_cache + (size_t)l * T * Dq, s->value_cache + (size_t)l * T * Dq, s->xb,
@@ -1082,9 +1110,11 @@ static int enqueue_step(rama_session* s, cudaStream_t st, int mode, StepTrace* t
       if (e && !q.nccl_err) q.nccl_err = e;
       q.post(cudaSuccess);
     }
+    }  // !fuse_attn_wo
     // ---- x += xb2; rmsnorm → [w1|w3] → SwiGLU (infer.rs:37-45) ----
     {
       ProNorm pro{s->x1, s->xb2, s->x0, W[RAMA_T_RMS_FFN] + (size_t)l * D, nullptr, peer_in(s, 0, l)};
+      if (fuse_attn_wo) { pro.add = s->wo_part; pro.n_add = c->H; pro.add_out = s->xb2; }
       RowsW13 rows{W[RAMA_T_W1] + (size_t)l * Fl * D, W[RAMA_T_W3] + (size_t)l * Fl * D, D};
       EpiSwiGLU epi{s->hb, s->hb2};
       const int np = Fl, var = pick_variant(c, D / 4, np);
@@ -1177,6 +1207,10 @@ static int attn_bucket(const rama_session* s, int pos, int* gy) {
   *gy = std::min(s->n_split, b == 0 ? 8 : (b == 1 ? 32 : s->n_split));
   return b;
 }
+static int set_attn_bucket(rama_session* s, int pos) {
+  s->attn_bk = attn_bucket(s, pos, &s->attn_gy);
+  return s->attn_bk;
+}
 
 static int capture(rama_session* s, int mode, cudaGraphExec_t* out) {
   RK(init_parts(s));
@@ -1198,8 +1232,9 @@ extern "C" int rama_session_launches_per_step(const rama_session* s, int* n) {
   if (!s || !n) return fail(RAMA_E_INVALID, "NULL argument");
   const rama_ctx* c = s->ctx;
   if (s->persistent) { *n = 1; return RAMA_OK; }  // the whole greedy step is one persistent cooperative launch
-  // embed + L·(qkv, attn, wo, w13, w2) + cls + sample (+ collectives under TP)
-  *n = 1 + 5 * c->L + 1 + 1 + (c->world > 1 && !s->p2p ? 2 * c->L + 1 : 0);
+  // embed + L·(qkv, attn, wo, w13, w2) + cls + sample (+ collectives under TP); attention + wo are one launch
+  // for the small models at positions < 256
+  *n = 1 + (s->wo_part ? 4 : 5) * c->L + 1 + 1 + (c->world > 1 && !s->p2p ? 2 * c->L + 1 : 0);
   return RAMA_OK;
 }
 
@@ -1210,7 +1245,7 @@ extern "C" int rama_forward(rama_session* s, int32_t token, int32_t pos) {
     return fail(RAMA_E_STATE, "pos %d outside [0, seq_len=%d)", pos, c->T);
   if (token < 0 || token >= c->V) return fail(RAMA_E_INVALID, "token %d outside the vocabulary", token);
   CK(cudaSetDevice(c->device));
-  const int bk = attn_bucket(s, pos, &s->attn_gy);
+  const int bk = set_attn_bucket(s, pos);
   if (!s->g[0][bk]) RK(capture(s, 0, &s->g[0][bk]));
   StepCtrl* h = &s->h_ring[s->ring_i];
   if (++s->ring_i == kRing) {  // never overwrite a slot a pending copy may still read
@@ -1280,7 +1315,7 @@ extern "C" int rama_generate(rama_session* s, const int32_t* prompt, int32_t n_p
   CK(cudaSetDevice(c->device));
   const int gi = temperature == 0.0f ? 0 : 1;
   for (int i = 0; i < steps; i += kAttnChunk) {  // make sure every bucket this run touches is captured before timing
-    const int bk = attn_bucket(s, i, &s->attn_gy);
+    const int bk = set_attn_bucket(s, i);
     if (!s->g[gi + 1][bk]) RK(capture(s, gi + 1, &s->g[gi + 1][bk]));
   }
   const int np = std::min<int>(n_prompt, c->T);
@@ -1338,7 +1373,7 @@ extern "C" int rama_profile_step(rama_session* s, int32_t token, int32_t pos, fl
   if (token < 0 || token >= c->V) return fail(RAMA_E_INVALID, "token outside the vocabulary");
   CK(cudaSetDevice(c->device));
   RK(init_parts(s));
-  attn_bucket(s, pos, &s->attn_gy);
+  set_attn_bucket(s, pos);
   StepCtrl* h = &s->h_ring[s->ring_i];
   if (++s->ring_i == kRing) { s->ring_i = 0; CK(cudaStreamSynchronize(s->stream)); }
   memset(h, 0, sizeof(*h));

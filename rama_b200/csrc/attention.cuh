@@ -183,4 +183,113 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnPar
   attn_decode_body(p, p.pos_override >= 0 ? p.pos_override : p.ctrl->pos);
 }
 
+// ---- attention + wo in one launch (small models, short contexts) ---------------------------------------------
+// The small models are bound by the length of the kernel chain, not by bytes.  Here CTA (h, j) computes the whole
+// attention of head h over the cache (cpu.rs:23-52; redundantly for its J row-splits — a few KB of K/V at these
+// sizes) and then its rows of the head's slice of wo:  part[h][r] = Σ_i wo[r][h·hs+i] · xb_h[i]  (infer.rs:35 split by
+// head).  The next kernel's prologue sums the H partials in head order (deterministic) into the residual.  One launch
+// fewer per layer, no tickets, no workspace.  Grid = H·J CTAs of kAttnWoThreads.
+constexpr int kAttnWoThreads = 512;
+constexpr int kAttnWoWarps = kAttnWoThreads / kWarp;
+
+struct AttnWoParams {
+  const float* q;            // [H*hs]
+  const float* key_cache;    // this layer: [T][Dq]
+  const float* value_cache;
+  const float* wo;           // this layer: [D][Dq]
+  float* xb;                 // [Dq] attention output (RunState.xb), written by the j = 0 CTAs
+  float* part;               // [H][D] per-head partial outputs of wo
+  const StepCtrl* ctrl;
+  int Dq, hs, D, J;
+};
+
+__global__ void __launch_bounds__(kAttnWoThreads) attn_wo_kernel(const AttnWoParams p, int use_pdl) {
+  __shared__ float s_m[kAttnWoWarps], s_l[kAttnWoWarps];
+  __shared__ __align__(16) float s_acc[kAttnWoWarps][kAttnMaxHs];
+  __shared__ __align__(16) float s_xb[kAttnMaxHs];
+  constexpr int kB = 8;        // timesteps per warp and batch
+  constexpr int kRowsMax = 8;  // wo rows per warp held in registers (host guarantees nr ≤ kRowsMax · warps)
+  if (use_pdl) { pdl_launch_dependents(); pdl_wait(); }
+  const int h = blockIdx.x / p.J, j = blockIdx.x - h * p.J;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int hs = p.hs, hs4 = hs >> 2;
+  const bool active = lane < hs4;
+  const float div = sqrtf((float)hs);
+  const size_t col = (size_t)h * hs;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  // this warp's rows of wo[:, h·hs .. +hs): issued first, needed last — their latency hides behind the attention
+  const int per = p.D / p.J, rem = p.D % p.J;
+  const int r0 = j * per + min(j, rem), nr = per + (j < rem ? 1 : 0);
+  float4 wrow[kRowsMax];
+#pragma unroll
+  for (int i = 0; i < kRowsMax; ++i) {
+    const int r = warp + i * kAttnWoWarps;
+    wrow[i] = (active && r < nr) ? ldg_stream(reinterpret_cast<const float4*>(p.wo + (size_t)(r0 + r) * p.Dq + col) + lane) : zero4;
+  }
+  const int n = p.ctrl->pos + 1;
+  const float4 q4 = active ? __ldcg(reinterpret_cast<const float4*>(p.q + col) + lane) : zero4;
+  float m = -INFINITY, l = 0.f;
+  float4 acc = zero4;
+  for (int tb = warp; tb < n; tb += kB * kAttnWoWarps) {
+    float4 kk[kB], vv[kB];
+#pragma unroll
+    for (int i = 0; i < kB; ++i) {
+      const int t = tb + i * kAttnWoWarps;
+      kk[i] = (active && t < n) ? reinterpret_cast<const float4*>(p.key_cache + (size_t)t * p.Dq + col)[lane] : zero4;
+    }
+#pragma unroll
+    for (int i = 0; i < kB; ++i) {
+      const int t = tb + i * kAttnWoWarps;
+      vv[i] = (active && t < n) ? reinterpret_cast<const float4*>(p.value_cache + (size_t)t * p.Dq + col)[lane] : zero4;
+    }
+    float sc[kB];
+#pragma unroll
+    for (int i = 0; i < kB; ++i) sc[i] = dot4(q4, kk[i], 0.f);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int i = 0; i < kB; ++i) sc[i] += __shfl_xor_sync(0xffffffffu, sc[i], o);
+#pragma unroll
+    for (int i = 0; i < kB; ++i) {
+      if (tb + i * kAttnWoWarps < n) {                 // warp-uniform
+        const float s = sc[i] / div;                   // divide, as cpu.rs:41
+        const float mn = fmaxf(m, s);
+        const float f = expf(m - mn), pe = expf(s - mn);
+        l = l * f + pe;
+        acc.x = acc.x * f + pe * vv[i].x; acc.y = acc.y * f + pe * vv[i].y;
+        acc.z = acc.z * f + pe * vv[i].z; acc.w = acc.w * f + pe * vv[i].w;
+        m = mn;
+      }
+    }
+  }
+  if (lane == 0) { s_m[warp] = m; s_l[warp] = l; }
+  if (active) reinterpret_cast<float4*>(s_acc[warp])[lane] = acc;
+  __syncthreads();
+  {  // merge the warps in fixed order (a warp without timesteps has m = -inf, l = 0: contributes nothing)
+    float M = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < kAttnWoWarps; ++w) M = fmaxf(M, s_m[w]);
+    float L = 0.f;
+#pragma unroll
+    for (int w = 0; w < kAttnWoWarps; ++w) L += s_l[w] * expf(s_m[w] - M);
+    for (int i = threadIdx.x; i < hs; i += kAttnWoThreads) {
+      float a = 0.f;
+#pragma unroll
+      for (int w = 0; w < kAttnWoWarps; ++w) a += s_acc[w][i] * expf(s_m[w] - M);
+      const float o = a / L;
+      s_xb[i] = o;
+      if (j == 0) p.xb[col + i] = o;
+    }
+  }
+  __syncthreads();
+  const float4 x4 = active ? reinterpret_cast<const float4*>(s_xb)[lane] : zero4;
+#pragma unroll
+  for (int i = 0; i < kRowsMax; ++i) {
+    const int r = warp + i * kAttnWoWarps;
+    const float v = warp_sum(dot4(wrow[i], x4, 0.f));
+    if (lane == 0 && r < nr) p.part[(size_t)h * p.D + r0 + r] = v;
+  }
+}
+
 }  // namespace rama

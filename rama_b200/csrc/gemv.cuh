@@ -86,6 +86,8 @@ struct ProNorm {
   const float* w;      // norm weight (D)
   float* xnorm;        // optional: normalised vector out (final rmsnorm → RunState.x) or nullptr
   PeerIn pin;          // pin.P > 0: the pending contribution is the sum of P peer partials instead of `add`
+  int n_add = 1;       // > 1: `add` holds n_add partial vectors (per-head wo partials of attn_wo_kernel), stride K floats,
+  float* add_out = nullptr;  //      summed in index order; CTA 0 stores the sum here (RunState.xb2)
   __device__ __forceinline__ void operator()(float4* xs, int K4, float* red) const {
     const float4* x4 = reinterpret_cast<const float4*>(xin);
     const float4* a4 = reinterpret_cast<const float4*>(add);
@@ -120,8 +122,13 @@ struct ProNorm {
         v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
         if (blockIdx.x == 0) reinterpret_cast<float4*>(const_cast<float*>(add))[i] = a;  // RunState.xb2 / xb
       } else if (add) {
-        const float4 a = __ldcg(a4 + i);
+        float4 a = __ldcg(a4 + i);
+        for (int h = 1; h < n_add; ++h) {
+          const float4 t = __ldcg(a4 + (size_t)h * K4 + i);
+          a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+        }
         v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+        if (add_out && blockIdx.x == 0) reinterpret_cast<float4*>(add_out)[i] = a;
       }
       xs[i] = v;
       ss = dot4(v, v, ss);
