@@ -1550,7 +1550,7 @@ static int prefill_chunk(rama_session* s, const int32_t* tokens, int M, int pos0
                           {W[RAMA_T_WK] + (size_t)l * Dq * D, (size_t)Dq, (size_t)D},
                           {W[RAMA_T_WV] + (size_t)l * Dq * D, (size_t)Dq, (size_t)D}};
       EpiQKVPrefill epi{s->pf_q, kc, vc, W[RAMA_T_FREQ_REAL], W[RAMA_T_FREQ_IMAG], pos0, Dq, hs / 2};
-      GK(RAMA_PK_GEMM, (launch_gemm_tf32x3<128, 4, 4>(st, &A, 1, B, 3, M, Dq, D, 0, 1, epi)));
+      GK(RAMA_PK_GEMM, (launch_gemm_tf32x3<128, 4, 4, 0>(st, &A, 1, B, 3, M, Dq, D, 0, 1, epi)));
     }
     // causal attention of every prompt row over the cache   (infer.rs:34)
     {
@@ -1569,7 +1569,7 @@ static int prefill_chunk(rama_session* s, const int32_t* tokens, int M, int pos0
       GemmOperand A{s->pf_att, (size_t)M, (size_t)Dq};
       GemmOperand B{W[RAMA_T_WO] + (size_t)l * D * Dq, (size_t)D, (size_t)Dq};
       EpiStoreNT epi{s->pf_y, D, D, 0};
-      GK(RAMA_PK_GEMM, (launch_gemm_tf32x3<128, 4, 4>(st, &A, 1, &B, 1, M, D, Dq, 0, 1, epi)));
+      GK(RAMA_PK_GEMM, (launch_gemm_tf32x3<128, 4, 4, 0>(st, &A, 1, &B, 1, M, D, Dq, 0, 1, epi)));
     }
     if (c->world > 1) {
       tr.pre(RAMA_PK_COMM);
@@ -1585,14 +1585,14 @@ static int prefill_chunk(rama_session* s, const int32_t* tokens, int M, int pos0
       GemmOperand B[2] = {{W[RAMA_T_W1] + (size_t)l * Fl * D, (size_t)Fl, (size_t)D},
                           {W[RAMA_T_W3] + (size_t)l * Fl * D, (size_t)Fl, (size_t)D}};
       EpiSwiGLUPrefill epi{s->pf_h, Fl};
-      GK(RAMA_PK_GEMM, (launch_gemm_tf32x3<128, 4, 4>(st, &A, 1, B, 2, M, Fl, D, 0, 1, epi)));
+      GK(RAMA_PK_GEMM, (launch_gemm_tf32x3<128, 4, 4, 0>(st, &A, 1, B, 2, M, Fl, D, 0, 1, epi)));
     }
     // w2   (infer.rs:46)
     {
       GemmOperand A{s->pf_h, (size_t)M, (size_t)Fl};
       GemmOperand B{W[RAMA_T_W2] + (size_t)l * D * Fl, (size_t)D, (size_t)Fl};
       EpiStoreNT epi{s->pf_y, D, D, 0};
-      GK(RAMA_PK_GEMM, (launch_gemm_tf32x3<128, 4, 4>(st, &A, 1, &B, 1, M, D, Fl, 0, 1, epi)));
+      GK(RAMA_PK_GEMM, (launch_gemm_tf32x3<128, 4, 4, 0>(st, &A, 1, &B, 1, M, D, Fl, 0, 1, epi)));
     }
     if (c->world > 1) {
       tr.pre(RAMA_PK_COMM);
@@ -1683,8 +1683,8 @@ constexpr int kBatchMax = 64;    // one 64-column MMA tile of sequences
 constexpr int kBatchRing = 8;
 // batched-decode GEMM tile: 128 weight rows × 64 sequences, 2 stages, chunks of 2 k-blocks; two CTAs fit an SM
 // (64 KB of shared memory and 256 TMEM columns each) and interleave their pipelines
-#define BATCH_GEMM launch_gemm_tf32x3<64, 2, 2>
-constexpr int kBatchCtasPerSm = GemmSmem<64, 2>::kCtasPerSm;
+#define BATCH_GEMM launch_gemm_tf32x3<64, 2, 2, 0>
+constexpr int kBatchCtasPerSm = GemmSmem<64, 2, 0>::kCtasPerSm;
 
 struct rama_batch {
   rama_ctx* ctx = nullptr;
@@ -2208,10 +2208,10 @@ extern "C" int rama_op_matmul_nt(rama_ctx* c, float* out, const float* a, const 
     if (ksplit > 1) CK(cudaMallocAsync((void**)&dst, (size_t)ksplit * N * M * sizeof(float), c->op_stream));
     EpiStoreT epi{dst, m, n, ksplit, (size_t)N * M};
     switch (variant) {
-      case 0: e = launch_gemm_tf32x3<64, 6, 2>(c->op_stream, &A, 1, &B, 1, m, n, k, hi_round, ksplit, epi); break;
-      case 1: e = launch_gemm_tf32x3<64, 6, 4>(c->op_stream, &A, 1, &B, 1, m, n, k, hi_round, ksplit, epi); break;
-      case 2: e = launch_gemm_tf32x3<64, 4, 2>(c->op_stream, &A, 1, &B, 1, m, n, k, hi_round, ksplit, epi); break;
-      case 3: e = launch_gemm_tf32x3<64, 2, 2>(c->op_stream, &A, 1, &B, 1, m, n, k, hi_round, ksplit, epi); break;  // 2 CTAs/SM
+      case 0: e = launch_gemm_tf32x3<64, 4, 2, 2>(c->op_stream, &A, 1, &B, 1, m, n, k, hi_round, ksplit, epi); break;
+      case 1: e = launch_gemm_tf32x3<64, 4, 4, 2>(c->op_stream, &A, 1, &B, 1, m, n, k, hi_round, ksplit, epi); break;
+      case 2: e = launch_gemm_tf32x3<64, 4, 2, 0>(c->op_stream, &A, 1, &B, 1, m, n, k, hi_round, ksplit, epi); break;
+      case 3: e = launch_gemm_tf32x3<64, 2, 2, 0>(c->op_stream, &A, 1, &B, 1, m, n, k, hi_round, ksplit, epi); break;  // 2 CTAs/SM
       default: return fail(RAMA_E_INVALID, "matmul_nt: unknown transposed variant %d", variant);
     }
     if (ksplit > 1) {
@@ -2225,10 +2225,10 @@ extern "C" int rama_op_matmul_nt(rama_ctx* c, float* out, const float* a, const 
     if (ksplit > 1) return fail(RAMA_E_INVALID, "matmul_nt: split-K only in the transposed (batched decode) orientation");
     EpiStoreNT epi{out, n, n, 0};
     switch (variant) {
-      case 0: e = launch_gemm_tf32x3<128, 4, 2>(c->op_stream, &A, 1, &B, 1, m, n, k, hi_round, 1, epi); break;
-      case 1: e = launch_gemm_tf32x3<128, 4, 4>(c->op_stream, &A, 1, &B, 1, m, n, k, hi_round, 1, epi); break;
-      case 2: e = launch_gemm_tf32x3<128, 4, 8>(c->op_stream, &A, 1, &B, 1, m, n, k, hi_round, 1, epi); break;
-      case 3: e = launch_gemm_tf32x3<64, 6, 2>(c->op_stream, &A, 1, &B, 1, m, n, k, hi_round, 1, epi); break;
+      case 0: e = launch_gemm_tf32x3<128, 2, 4, 1>(c->op_stream, &A, 1, &B, 1, m, n, k, hi_round, 1, epi); break;
+      case 1: e = launch_gemm_tf32x3<128, 4, 4, 0>(c->op_stream, &A, 1, &B, 1, m, n, k, hi_round, 1, epi); break;
+      case 2: e = launch_gemm_tf32x3<128, 2, 2, 1>(c->op_stream, &A, 1, &B, 1, m, n, k, hi_round, 1, epi); break;
+      case 3: e = launch_gemm_tf32x3<64, 4, 2, 2>(c->op_stream, &A, 1, &B, 1, m, n, k, hi_round, 1, epi); break;
       default: return fail(RAMA_E_INVALID, "matmul_nt: unknown variant %d", variant);
     }
   }

@@ -175,7 +175,7 @@ struct GemmShape {
 
 constexpr int kGemmBK = 32;  // floats per k-block = one 128-byte swizzle row
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int NX = 0>
 struct GemmSmem {
   static constexpr int kABytes = kGemmBM * kGemmBK * 4;         // raw A k-block (only the workers read it)
   static constexpr int kBBytes = BN * kGemmBK * 4;              // raw B k-block = hi operand
@@ -184,8 +184,9 @@ struct GemmSmem {
   static constexpr int kBarOff = STAGES * kStageBytes;
   static constexpr int kNumBars = 3 * STAGES + 4;               // full/ready/empty per stage, accfull[2], accfree[2]
   static constexpr int kTotal = kBarOff + kNumBars * 8 + 16 + 1024 /* alignment slack */;
-  // TMEM: [0,BN) acc 0 | [BN,2BN) acc 1 | then per stage 32 columns A hi + 32 columns A lo
-  static constexpr int kTmemNeed = 2 * BN + 64 * STAGES;
+  // TMEM: [0,BN) acc 0 | [BN,2BN) acc 1 | NX cross-term accumulators | then per stage 32 columns A hi + 32 columns A lo
+  static constexpr int kAccCols = (2 + NX) * BN;
+  static constexpr int kTmemNeed = kAccCols + 64 * STAGES;
   static_assert(kTmemNeed <= 512, "accumulators + A stages exceed tensor memory");
   static constexpr int kTmemCols = kTmemNeed <= 128 ? 128 : (kTmemNeed <= 256 ? 256 : 512);  // power of two
   // two CTAs per SM when both shared memory and tensor memory allow it: their pipelines interleave
@@ -199,6 +200,12 @@ struct GemmSmem {
 // tcgen05.ld it and add it into per-thread f32 registers while the tensor core already fills the other.
 // Chunk partials have random signs, so the truncation bias (≈ 3·CH·4·½ ulp of a partial) no longer adds up
 // coherently: CH = 2 (64 k) keeps the result within ~1.5e-6 relative, the class of an f32 FMA GEMM.
+//
+// Independent accumulators (NX > 0, an experiment kept for the record): NX cross-term accumulators next to the ping-pong
+// pair let the issue order rotate over accumulators (NX = 2: a_lo·b_hi → X0, a_hi·b_lo → X1, a_hi·b_hi → main), so
+// consecutive MMAs never accumulate into the tile the previous one wrote.  Measured: no change at BN = 64 (0.082 ms
+// per 128×64×4096 tile either way) — back-to-back dependent accumulation is NOT what bounds the k-block — and at
+// BN = 128 the two stages that fit next to three accumulators are slower than four.  Production uses NX = 0.
 
 // Epilogue functor interface (device):
 //   static constexpr bool kDual        — the B tile stacks BN/2 rows of b[0] on BN/2 rows of b[1]; the epilogue
@@ -208,10 +215,10 @@ struct GemmSmem {
 // where m is the global row, n the first global column of the 32-column chunk; the whole warp calls it
 // (valid = m < M) so an epilogue may shuffle between rows.
 
-template <int BN, int STAGES, int CH, class Epi>
-__global__ void __launch_bounds__(kGemmThreads, (GemmSmem<BN, STAGES>::kCtasPerSm))
+template <int BN, int STAGES, int CH, int NX, class Epi>
+__global__ void __launch_bounds__(kGemmThreads, (GemmSmem<BN, STAGES, NX>::kCtasPerSm))
 gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, const Epi epi_in) {
-  using SM = GemmSmem<BN, STAGES>;
+  using SM = GemmSmem<BN, STAGES, NX>;
   constexpr int BK = kGemmBK;
   static_assert(BN == 64 || BN == 128, "BN");
   // the two worker groups take alternate k-blocks: with an even stage count a stage always belongs to the same group,
@@ -263,25 +270,27 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen_base + SM::kBarOff + SM::kNumBars * 8);
-  const uint32_t tmem_a = tmem + 2 * BN;  // A stages: stage s at +64·s (hi), +64·s+32 (lo)
+  const uint32_t tmem_a = tmem + SM::kAccCols;  // A stages: stage s at +64·s (hi), +64·s+32 (lo)
 
   if (warp == 0) {
     // ===== TMA producer =====
+    // (the role loops are single threads on the critical path of a k-block: running counters, no divisions)
     if (lane == 0) {
+      const int nb0 = tile_n * kBoxN;
+      int s = 0, kc = kb_begin * BK;
+      uint32_t ph = 1, st = base, bf = bar_full, be = bar_empty;
       for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(bar_empty + 8 * s, ph ^ 1);
-        const uint32_t st = base + s * SM::kStageBytes;
-        mbar_arrive_expect_tx(bar_full + 8 * s, SM::kTxBytes);
-        const int kc = (kb_begin + kb) * BK;
-        tma_load_2d(st, mapA, bar_full + 8 * s, kc, m0);
+        mbar_wait(be, ph);
+        mbar_arrive_expect_tx(bf, SM::kTxBytes);
+        tma_load_2d(st, mapA, bf, kc, m0);
         if (Epi::kDual) {
-          tma_load_2d(st + SM::kABytes, &maps.b[0], bar_full + 8 * s, kc, tile_n * kBoxN);
-          tma_load_2d(st + SM::kABytes + kBoxN * BK * 4, &maps.b[1], bar_full + 8 * s, kc, tile_n * kBoxN);
+          tma_load_2d(st + SM::kABytes, &maps.b[0], bf, kc, nb0);
+          tma_load_2d(st + SM::kABytes + kBoxN * BK * 4, &maps.b[1], bf, kc, nb0);
         } else {
-          tma_load_2d(st + SM::kABytes, mapB0, bar_full + 8 * s, kc, tile_n * BN);
+          tma_load_2d(st + SM::kABytes, mapB0, bf, kc, nb0);
         }
+        kc += BK; st += SM::kStageBytes; bf += 8; be += 8;
+        if (++s == STAGES) { s = 0; ph ^= 1; st = base; bf = bar_full; be = bar_empty; }
       }
     }
   } else if (warp == 1) {
@@ -306,11 +315,30 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, c
         tc_fence_after();
         const uint32_t bh = d_lo32 + s * (SM::kStageBytes >> 4), bl = bh + (SM::kBBytes >> 4);
         const uint32_t a_hi = tmem_a + 64 * s, a_lo = a_hi + 32;
+        // 8 tf32 = 32 bytes = 2 descriptor units inside the swizzle row; TMEM A: 8 columns per k-step
+        if constexpr (NX == 0) {
 #pragma unroll
-        for (int ks = 0; ks < BK / 8; ++ks) {  // 8 tf32 = 32 bytes = 2 descriptor units inside the swizzle row
-          umma_tf32_ts(acc, a_lo + 8 * ks, desc(bh + 2 * ks), idesc, !(first && ks == 0));  // small terms first
-          umma_tf32_ts(acc, a_hi + 8 * ks, desc(bl + 2 * ks), idesc, 1);
-          umma_tf32_ts(acc, a_hi + 8 * ks, desc(bh + 2 * ks), idesc, 1);
+          for (int ks = 0; ks < BK / 8; ++ks) {
+            umma_tf32_ts(acc, a_lo + 8 * ks, desc(bh + 2 * ks), idesc, !(first && ks == 0));  // small terms first
+            umma_tf32_ts(acc, a_hi + 8 * ks, desc(bl + 2 * ks), idesc, 1);
+            umma_tf32_ts(acc, a_hi + 8 * ks, desc(bh + 2 * ks), idesc, 1);
+          }
+        } else if constexpr (NX == 2) {  // rotate X0, X1, main: every accumulator is reused at distance 3
+          const uint32_t x0 = tmem + 2 * BN, x1 = x0 + BN;
+#pragma unroll
+          for (int ks = 0; ks < BK / 8; ++ks) {
+            umma_tf32_ts(x0, a_lo + 8 * ks, desc(bh + 2 * ks), idesc, (kb | ks) != 0);
+            umma_tf32_ts(x1, a_hi + 8 * ks, desc(bl + 2 * ks), idesc, (kb | ks) != 0);
+            umma_tf32_ts(acc, a_hi + 8 * ks, desc(bh + 2 * ks), idesc, !(first && ks == 0));
+          }
+        } else {  // NX == 1: X M X M X M X M X X X X — main and the cross accumulator alternate while main lasts
+          static_assert(BK / 8 == 4, "issue order written out for 4 k-steps");
+          const uint32_t x0 = tmem + 2 * BN;
+          auto XA = [&](int ks, uint32_t accum) { umma_tf32_ts(x0, a_lo + 8 * ks, desc(bh + 2 * ks), idesc, accum); };
+          auto XB = [&](int ks) { umma_tf32_ts(x0, a_hi + 8 * ks, desc(bl + 2 * ks), idesc, 1); };
+          auto MM = [&](int ks, uint32_t accum) { umma_tf32_ts(acc, a_hi + 8 * ks, desc(bh + 2 * ks), idesc, accum); };
+          XA(0, kb != 0); MM(0, !first); XB(0); MM(1, 1); XA(1, 1); MM(2, 1); XB(1); MM(3, 1);
+          XA(2, 1); XB(2); XA(3, 1); XB(3);
         }
         umma_commit(bar_empty + 8 * s);  // smem stage + TMEM A stage reusable once these MMAs have read them
         if (last) umma_commit(bar_accfull + 8 * (ch & 1));
@@ -358,9 +386,10 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, c
     constexpr int kBVec = SM::kBBytes / 16;
     constexpr int kGroupThreads = kGemmWorkerWarps / 2 * kWarp;
     constexpr int kLag = 1;  // k-blocks split beyond a chunk's end before draining it
+    int s = half;      // this group's stage walks half, half+2, … (STAGES is even)
+    uint32_t ph = 0;
+    int next_end = min(CH, num_kb) - 1 + kLag;  // k-block after which chunk `drained` may be drained
     for (int kb = half; kb < num_kb; kb += 2) {
-      const int s = kb % STAGES;
-      const uint32_t ph = (kb / STAGES) & 1;
       mbar_wait(bar_full + 8 * s, ph);
       const uint8_t* st = gen_base + s * SM::kStageBytes;
 #pragma unroll
@@ -379,7 +408,7 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, c
             lo[4 * c + e] = __float_as_uint(av[e] - __uint_as_float(h));
           }
         }
-        const uint32_t ta = trow + 2 * BN + 64 * s + 16 * hh;
+        const uint32_t ta = trow + SM::kAccCols + 64 * s + 16 * hh;
         tmem_st_32x16(ta, hi);
         tmem_st_32x16(ta + 32, lo);
       }
@@ -412,10 +441,30 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, c
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_ready + 8 * s);
+      s += 2;
+      if (s >= STAGES) { s -= STAGES; ph ^= 1; }
       // chunk c ends with k-block min((c+1)·CH, num_kb) − 1; drain it once this group is kLag blocks past it
-      while (drained < num_ch && min((drained + 1) * CH, num_kb) - 1 + kLag <= kb) drain(drained++);
+      while (drained < num_ch && next_end <= kb) {
+        drain(drained++);
+        next_end = min((drained + 1) * CH, num_kb) - 1 + kLag;
+      }
     }
     while (drained < num_ch) drain(drained++);
+    if constexpr (NX > 0) {
+      // cross terms: complete once the last chunk's commit has fired (tcgen05.commit covers all prior MMAs)
+      if (num_kb > 0) {
+#pragma unroll
+        for (int x = 0; x < NX; ++x)
+#pragma unroll
+          for (int j = 0; j < NSEG; ++j) {
+            float v[32];
+            tmem_ld_32x32(trow + (2 + x) * BN + seg_col(j), v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc[j][i] += v[i];
+          }
+        tc_fence_before();
+      }
+    }
 
     Epi epi = epi_in;
     const int m = m0 + quarter * 32 + lane;
