@@ -136,6 +136,7 @@ struct rama_ctx {
   int variant_override = -1;
   int p2p = 0;  // TP exchange: 1 = fused peer-memory all-reduce (default), 0 = NCCL collectives
   int staged = 1;      // RAMA_GEMV_STAGED=0 disables the shared-memory-staged GEMV for small slabs
+  int attn_cluster = 1;  // RAMA_ATTN=split selects the global-memory split merge (attn_decode_kernel) at every context length
   int persistent = 0;  // RAMA_STEP=persistent: the decode step as one persistent cooperative kernel (step_kernel.cuh);
                        // default: one fused kernel per op group in a CUDA graph (measured faster)
   std::mutex mu;
@@ -329,6 +330,10 @@ extern "C" int rama_ctx_create(int device, const rama_tp* tp, rama_ctx** out) {
   c->use_pdl = env_int("RAMA_PDL", 1);
   c->variant_override = env_int("RAMA_GEMV_VARIANT", -1);
   c->staged = env_int("RAMA_GEMV_STAGED", 1);
+  {
+    const char* m = getenv("RAMA_ATTN");
+    c->attn_cluster = !(m && strcmp(m, "split") == 0);
+  }
   {
     const char* m = getenv("RAMA_STEP");
     c->persistent = m && strcmp(m, "persistent") == 0;
@@ -1028,6 +1033,9 @@ static int enqueue_step(rama_session* s, cudaStream_t st, int mode, StepTrace* t
   const int D = c->D, Dq = c->Dq, Fl = c->Fl, T = c->T, hs = c->hs, L = c->L;
   const float* W[RAMA_T_COUNT];
   for (int i = 0; i < RAMA_T_COUNT; ++i) W[i] = c->w[i];
+  const bool fuse_attn_wo = s->wo_part && s->attn_bk == 0 && !s->keep_att;
+  // contexts below 1024 positions: the splits of a head merge inside a thread-block cluster (attention.cuh)
+  const bool attn_cluster = c->attn_cluster && !fuse_attn_wo && !s->keep_att && s->attn_bk < 2;
 
   // x0 ← embedding row of ctrl->token (infer.rs:13)
   q.pre(RAMA_K_EMBED);
@@ -1055,9 +1063,10 @@ static int enqueue_step(rama_session* s, cudaStream_t st, int mode, StepTrace* t
                  W[RAMA_T_FREQ_REAL], W[RAMA_T_FREQ_IMAG], s->ctrl, Dq / 2, hs / 2, Dq};
       const int np = 3 * Dq / 2, var = pick_variant(c, D / 4, np);
       q.pre(RAMA_K_QKV);
-      q.post(launch_gemv(var, pick_grid(c, var, np), st, q.pdl, pro, rows, epi, D / 4, np));
+      // the cluster attention kernel reads older K/V rows ahead of its wait: release it after this kernel's own wait
+      const int pdl_flags = q.pdl ? (attn_cluster ? 3 : 1) : 0;
+      q.post(launch_gemv(var, pick_grid(c, var, np), st, pdl_flags, pro, rows, epi, D / 4, np));
     }
-    const bool fuse_attn_wo = s->wo_part && s->attn_bk == 0 && !s->keep_att;
     if (fuse_attn_wo) {
       // ---- attention + wo in one launch, per-head partial outputs (infer.rs:34-35) ----
       const int J = c->sm_count / c->H;
@@ -1083,17 +1092,27 @@ static int enqueue_step(rama_session* s, cudaStream_t st, int mode, StepTrace* t
                     // HBM idles during attention: pull this layer's wo (≤ 64 MB, fits L2) in meanwhile
                     W[RAMA_T_WO] + (size_t)l * D * Dq, std::min((size_t)D * Dq * sizeof(float), (size_t)96 << 20)};
       cudaLaunchConfig_t cfg{};
-      cfg.gridDim = dim3(c->Hl, s->attn_gy);
+      cfg.gridDim = attn_cluster ? dim3(c->Hl * kAttnClusterMax) : dim3(c->Hl, s->attn_gy);
       cfg.blockDim = dim3(kAttnThreads);
       cfg.stream = st;
-      cudaLaunchAttribute at[1];
+      cudaLaunchAttribute at[2];
+      int na = 0;
       if (q.pdl) {
-        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        at[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
+        at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
       }
+      if (attn_cluster) {
+        at[na].id = cudaLaunchAttributeClusterDimension;
+        at[na].val.clusterDim.x = kAttnClusterMax;
+        at[na].val.clusterDim.y = 1;
+        at[na].val.clusterDim.z = 1;
+        ++na;
+      }
+      cfg.attrs = at; cfg.numAttrs = na;
       q.pre(RAMA_K_ATTN);
-      q.post(cudaLaunchKernelEx(&cfg, attn_decode_kernel, ap, q.pdl));
+      if (attn_cluster) q.post(cudaLaunchKernelEx(&cfg, attn_cluster_kernel, ap, q.pdl));
+      else q.post(cudaLaunchKernelEx(&cfg, attn_decode_kernel, ap, q.pdl));
     }
     // ---- wo (infer.rs:35); the residual add (:37) is folded into the next prologue ----
     {

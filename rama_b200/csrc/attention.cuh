@@ -16,6 +16,8 @@
 // While it runs, HBM is otherwise idle: every CTA (also the ones beyond `pos` that exit at once)
 // prefetches its slice of the NEXT kernel's weights (wo of this layer) into L2.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace rama {
@@ -181,6 +183,176 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnPar
   }
   if (use_pdl) pdl_wait();
   attn_decode_body(p, p.pos_override >= 0 ? p.pos_override : p.ctrl->pos);
+}
+
+// ---- flash-decode with the splits of a head in ONE thread-block cluster ---------------------------------------
+// attn_decode_kernel merges the splits of a head through global memory: partial → __threadfence → atomic ticket →
+// the last CTA re-reads the partials in three dependent L2 round trips.  At decode contexts of a few hundred
+// positions the launch is pure latency (8 µs for ~4 MB of K/V at 7B), and that chain is half of it.  Here the
+// CS CTAs that share a head form a cluster: each folds its chunks (rank, rank+CS, …) into a running (M, L, acc[hs]),
+// publishes it in its own shared memory, and after ONE cluster barrier every CTA merges hs/CS output elements
+// straight out of its siblings' shared memory (DSMEM) in split order — no workspace, no fence, no atomics.
+//
+// Second change: the K/V rows of EARLIER positions do not depend on the previous kernel (the fused QKV GEMV, which
+// only appends row `pos`).  That kernel releases this launch after its own griddepcontrol.wait (gemv.cuh use_pdl
+// bit 1), so when a CTA of this kernel starts, every kernel older than the QKV GEMV has completed: the position
+// and the rows t < pos are read BEFORE griddepcontrol.wait and their latency overlaps the QKV kernel's tail.  After the
+// wait only q and row `pos` remain to be fetched.
+constexpr int kAttnClusterMax = 8;  // portable cluster size
+
+__global__ void __launch_bounds__(kAttnThreads, 2) attn_cluster_kernel(const AttnParams p, int use_pdl) {
+  namespace cg = cooperative_groups;
+  constexpr int NW = kAttnWarps;
+  __shared__ float s_m[NW], s_l[NW];
+  __shared__ __align__(16) float s_acc[NW][kAttnMaxHs];
+  __shared__ __align__(16) float s_part[kAttnMaxHs + 4];  // this CTA's acc[hs] | M | L, read by the whole cluster
+  cg::cluster_group cluster = cg::this_cluster();
+  const int CS = (int)cluster.num_blocks();
+  const int rank = (int)cluster.block_rank();
+  const int h = blockIdx.x / CS;
+
+  if ((use_pdl & 3) == 1) pdl_launch_dependents();
+  if (p.prefetch && threadIdx.x == 0) {  // HBM idles during attention: pull the next kernel's weights (wo) into L2
+    const size_t n_cta = gridDim.x, me = blockIdx.x;
+    const size_t per = ((p.prefetch_bytes + n_cta - 1) / n_cta + 15) & ~(size_t)15;
+    const size_t off = me * per;
+    if (off < p.prefetch_bytes) {
+      const size_t nb = min(per, p.prefetch_bytes - off) & ~(size_t)15;
+      if (nb) l2_prefetch_bulk(reinterpret_cast<const char*>(p.prefetch) + off, (uint32_t)nb);
+    }
+  }
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int hs = p.hs, hs4 = hs >> 2;
+  const bool active = lane < hs4;
+  const float div = sqrtf((float)hs);
+  const size_t col = (size_t)h * hs;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4* kbase = reinterpret_cast<const float4*>(p.key_cache + col) + lane;
+  const float4* vbase = reinterpret_cast<const float4*>(p.value_cache + col) + lane;
+  const size_t row4 = (size_t)p.Dq >> 2;
+
+  // (older than the previous kernel ⇒ complete: see the header comment)
+  const int pos = p.pos_override >= 0 ? p.pos_override : *reinterpret_cast<const volatile int32_t*>(&p.ctrl->pos);
+  const int n = pos + 1;
+  const int n_chunks = pos / kAttnChunk + 1;
+
+  int c = rank;
+  int t0 = c * kAttnChunk + warp * kAttnPerWarp;
+  float4 kk[kAttnPerWarp], vv[kAttnPerWarp];
+#pragma unroll
+  for (int j = 0; j < kAttnPerWarp; ++j) kk[j] = (active && t0 + j < pos) ? __ldcg(kbase + (size_t)(t0 + j) * row4) : zero4;
+#pragma unroll
+  for (int j = 0; j < kAttnPerWarp; ++j) vv[j] = (active && t0 + j < pos) ? __ldcg(vbase + (size_t)(t0 + j) * row4) : zero4;
+
+  if (use_pdl & 1) pdl_wait();
+  if ((use_pdl & 3) == 3) pdl_launch_dependents();
+
+  const float4 q4 = active ? __ldcg(reinterpret_cast<const float4*>(p.q + col) + lane) : zero4;
+#pragma unroll
+  for (int j = 0; j < kAttnPerWarp; ++j) {  // this step's row, appended by the previous kernel
+    if (active && t0 + j == pos) {
+      kk[j] = __ldcg(kbase + (size_t)pos * row4);
+      vv[j] = __ldcg(vbase + (size_t)pos * row4);
+    }
+  }
+
+  float m = -INFINITY, l = 0.f;
+  float4 acc = zero4;
+  while (c < n_chunks) {
+    // next pass of this CTA (contexts beyond CS·32 positions): loads in flight while this pass is folded
+    const int c2 = c + CS, t2 = t0 + CS * kAttnChunk;
+    float4 kn[kAttnPerWarp], vn[kAttnPerWarp];
+    if (c2 < n_chunks) {
+#pragma unroll
+      for (int j = 0; j < kAttnPerWarp; ++j) kn[j] = (active && t2 + j < n) ? __ldcg(kbase + (size_t)(t2 + j) * row4) : zero4;
+#pragma unroll
+      for (int j = 0; j < kAttnPerWarp; ++j) vn[j] = (active && t2 + j < n) ? __ldcg(vbase + (size_t)(t2 + j) * row4) : zero4;
+    }
+    float sc[kAttnPerWarp];
+#pragma unroll
+    for (int j = 0; j < kAttnPerWarp; ++j) sc[j] = dot4(q4, kk[j], 0.f);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int j = 0; j < kAttnPerWarp; ++j) sc[j] += __shfl_xor_sync(0xffffffffu, sc[j], o);
+#pragma unroll
+    for (int j = 0; j < kAttnPerWarp; ++j) {
+      if (t0 + j < n) {                                  // warp-uniform
+        const float s = sc[j] / div;                     // divide, as cpu.rs:41
+        const float mn = fmaxf(m, s);
+        const float f = expf(m - mn), pe = expf(s - mn);
+        l = l * f + pe;
+        acc.x = acc.x * f + pe * vv[j].x; acc.y = acc.y * f + pe * vv[j].y;
+        acc.z = acc.z * f + pe * vv[j].z; acc.w = acc.w * f + pe * vv[j].w;
+        m = mn;
+      }
+    }
+    if (c2 < n_chunks) {
+#pragma unroll
+      for (int j = 0; j < kAttnPerWarp; ++j) { kk[j] = kn[j]; vv[j] = vn[j]; }
+    }
+    c = c2; t0 = t2;
+  }
+
+  // merge the warps of this CTA (fixed order) into s_part
+  if (lane == 0) { s_m[warp] = m; s_l[warp] = l; }
+  if (active) reinterpret_cast<float4*>(s_acc[warp])[lane] = acc;
+  __syncthreads();
+  {
+    float M = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) M = fmaxf(M, s_m[w]);
+    const bool live = M > -INFINITY;  // a CTA (or warp) without timesteps contributes (−inf, 0, 0)
+    for (int i = threadIdx.x; i < hs; i += kAttnThreads) {
+      float a = 0.f;
+      if (live) {
+#pragma unroll
+        for (int w = 0; w < NW; ++w) a += s_acc[w][i] * expf(s_m[w] - M);
+      }
+      s_part[i] = a;
+    }
+    if (threadIdx.x == 0) {
+      float L = 0.f;
+      if (live) {
+#pragma unroll
+        for (int w = 0; w < NW; ++w) L += s_l[w] * expf(s_m[w] - M);
+      }
+      s_part[hs] = M;
+      s_part[hs + 1] = L;
+    }
+  }
+  cluster.sync();  // every CTA's partial is published (release/acquire at cluster scope)
+
+  // CTA `rank` produces output elements [rank·per, rank·per + per) of the head from all CS partials, in split order
+  {
+    const int per = (hs + CS - 1) / CS;
+    const int i = rank * per + (int)threadIdx.x;
+    if ((int)threadIdx.x < per && i < hs) {
+      float Mc[kAttnClusterMax], Lc[kAttnClusterMax], ac[kAttnClusterMax];
+#pragma unroll
+      for (int r = 0; r < kAttnClusterMax; ++r) {
+        if (r < CS) {
+          const float* rp = cluster.map_shared_rank(s_part, r);
+          Mc[r] = rp[hs]; Lc[r] = rp[hs + 1]; ac[r] = rp[i];
+        } else {
+          Mc[r] = -INFINITY; Lc[r] = 0.f; ac[r] = 0.f;
+        }
+      }
+      float M = -INFINITY;
+#pragma unroll
+      for (int r = 0; r < kAttnClusterMax; ++r) M = fmaxf(M, Mc[r]);  // chunk 0 always holds a timestep: M is finite
+      float L = 0.f, a = 0.f;
+#pragma unroll
+      for (int r = 0; r < kAttnClusterMax; ++r) {
+        const float e = expf(Mc[r] - M);
+        L += Lc[r] * e;
+        a += ac[r] * e;
+      }
+      p.out[col + i] = a / L;
+    }
+  }
+  cluster.sync();  // no CTA may exit while a sibling still reads its shared memory
 }
 
 // ---- attention + wo in one launch (small models, short contexts) ---------------------------------------------

@@ -69,7 +69,12 @@ struct PeerIn {
 // xs = x                                      (wo: attention output; w2: SwiGLU output)
 struct ProPlain {
   const float* x;
-  __device__ __forceinline__ void operator()(float4* xs, int K4, float* red) const {
+  template <int N>
+  struct Pre {};
+  template <int N>
+  __device__ __forceinline__ Pre<N> preload(int) const { return Pre<N>{}; }
+  template <int N>
+  __device__ __forceinline__ void operator()(float4* xs, int K4, float* red, const Pre<N>&) const {
     const float4* x4 = reinterpret_cast<const float4*>(x);
     for (int i = threadIdx.x; i < K4; i += kGemvThreads) xs[i] = __ldcg(x4 + i);  // may be another CTA's output of this launch
     (void)red;
@@ -88,7 +93,23 @@ struct ProNorm {
   PeerIn pin;          // pin.P > 0: the pending contribution is the sum of P peer partials instead of `add`
   int n_add = 1;       // > 1: `add` holds n_add partial vectors (per-head wo partials of attn_wo_kernel), stride K floats,
   float* add_out = nullptr;  //      summed in index order; CTA 0 stores the sum here (RunState.xb2)
-  __device__ __forceinline__ void operator()(float4* xs, int K4, float* red) const {
+  // The norm weights never depend on the previous kernel: the first N float4 per thread are loaded BEFORE
+  // griddepcontrol.wait (one L2 round trip off the critical path of every norm-prologue kernel).
+  template <int N>
+  struct Pre { float4 g[N]; };
+  template <int N>
+  __device__ __forceinline__ Pre<N> preload(int K4) const {
+    Pre<N> r;
+    const float4* w4 = reinterpret_cast<const float4*>(w);
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      const int i = threadIdx.x + j * kGemvThreads;
+      r.g[j] = i < K4 ? __ldg(w4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    return r;
+  }
+  template <int N>
+  __device__ __forceinline__ void operator()(float4* xs, int K4, float* red, const Pre<N>& pre) const {
     const float4* x4 = reinterpret_cast<const float4*>(xin);
     const float4* a4 = reinterpret_cast<const float4*>(add);
     const bool peers = pin.P > 0 && add != nullptr;
@@ -137,14 +158,19 @@ struct ProNorm {
     ss = block_sum<kGemvThreads>(ss, red);
     const float scale = 1.0f / sqrtf(ss / (float)(K4 * 4) + 1e-5f);
     const float4* w4 = reinterpret_cast<const float4*>(w);
-    for (int i = threadIdx.x; i < K4; i += kGemvThreads) {  // same i as above: no sync needed
+    auto apply = [&](int i, const float4 g) {  // same i as above: no sync needed
       float4 v = xs[i];
-      const float4 g = w4[i];
       v.x = g.x * (scale * v.x); v.y = g.y * (scale * v.y);
       v.z = g.z * (scale * v.z); v.w = g.w * (scale * v.w);
       xs[i] = v;
       if (xnorm && blockIdx.x == 0) reinterpret_cast<float4*>(xnorm)[i] = v;
+    };
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      const int i = threadIdx.x + j * kGemvThreads;
+      if (i < K4) apply(i, pre.g[j]);
     }
+    for (int i = threadIdx.x + N * kGemvThreads; i < K4; i += kGemvThreads) apply(i, w4[i]);
   }
 };
 
@@ -247,6 +273,7 @@ struct EpiStore {  // o[2p], o[2p+1]    (wo → xb2, w2 → residual contributio
   float* o;
   int n_rows;
   PeerOut po;      // po.P > 0: the outputs are a TP partial → stored into every rank's inbox instead
+  __device__ __forceinline__ void prepare() {}
   __device__ __forceinline__ void operator()(int p, float v0, float v1) {
     if (po.P > 0) {
       const unsigned ep = po.epoch();
@@ -278,12 +305,28 @@ struct EpiQKV {
   const float* freq_imag;
   const StepCtrl* ctrl;
   int pairs_per, hs2, Dq;  // pairs per section, head_size/2, row stride of the cache
+  int pos;                 // set by prepare()
+  const float* s_cs;       // shared memory: cos row [hs2] | sin row [hs2] of this position
+  // Called by every thread right after griddepcontrol.wait (before the prologue, whose barriers publish the
+  // table): the position and its RoPE row are fetched while x is still in flight, so the epilogue — the tail of
+  // the kernel — touches no global memory before its stores.
+  __device__ __forceinline__ void prepare() {
+    __shared__ float s_rope[2 * 64];
+    pos = ctrl->pos;
+    if (hs2 <= 64) {
+      for (int j = threadIdx.x; j < 2 * hs2; j += kGemvThreads)
+        s_rope[j] = j < hs2 ? freq_real[(size_t)pos * hs2 + j] : freq_imag[(size_t)pos * hs2 + j - hs2];
+      s_cs = s_rope;
+    } else {
+      s_cs = nullptr;
+    }
+  }
   __device__ __forceinline__ void operator()(int p, float v0, float v1) {
-    const int pos = ctrl->pos;
     const int sec = p / pairs_per, i = p - sec * pairs_per;
     if (sec < 2) {
-      const int f = pos * hs2 + (i % hs2);
-      const float c = freq_real[f], s = freq_imag[f];
+      const int j = i % hs2;
+      const float c = s_cs ? s_cs[j] : freq_real[(size_t)pos * hs2 + j];
+      const float s = s_cs ? s_cs[hs2 + j] : freq_imag[(size_t)pos * hs2 + j];
       const float o0 = __fsub_rn(__fmul_rn(v0, c), __fmul_rn(v1, s));
       const float o1 = __fadd_rn(__fmul_rn(v0, s), __fmul_rn(v1, c));
       if (sec == 0) {
@@ -304,6 +347,7 @@ struct EpiQKV {
 struct EpiSwiGLU {
   float* hb;
   float* hb2;
+  __device__ __forceinline__ void prepare() {}
   __device__ __forceinline__ void operator()(int p, float h1, float h3) {
     const float a = h1 * (1.0f / (1.0f + expf(-h1)));
     hb[p] = a * h3;
@@ -320,6 +364,7 @@ struct EpiCls {
   float bv;
   int bi;
   PeerOut po;          // po.P > 0: the partial goes to every rank's part array (po.inbox[r] = its slot base)
+  __device__ __forceinline__ void prepare() {}
   __device__ __forceinline__ void operator()(int p, float v0, float v1) {
     logits[2 * p] = v0;
     argmax_merge(bv, bi, v0, row_offset + 2 * p);
@@ -444,7 +489,11 @@ gemv_fused_kernel(const Pro pro, const Rows rows, const Epi epi_in, int K4, int 
   // Weights never depend on the previous kernel: pull the head of this CTA's slab into L2 while
   // the previous kernel drains (PDL) and while the prologue below computes the norm, then wait
   // for the previous kernel's activations.
-  if (use_pdl) pdl_launch_dependents();
+  // use_pdl: bit 0 = launched with programmatic stream serialization; bit 1 = release the dependent launch only
+  // AFTER this kernel's own wait (then everything older than this kernel is complete when the dependent starts,
+  // which lets the dependent read older results — the KV cache, the step control block — ahead of ITS wait).
+  if ((use_pdl & 3) == 1) pdl_launch_dependents();
+  const auto pre = pro.template preload<2>(K4);
   {
     if (np > 0 && threadIdx.x < Rows::kStreams) {
       const float* ptr;
@@ -454,14 +503,16 @@ gemv_fused_kernel(const Pro pro, const Rows rows, const Epi epi_in, int K4, int 
       if (bytes >= 16) l2_prefetch_bulk(ptr, (uint32_t)(bytes & ~(size_t)15));
     }
   }
-  if (use_pdl) pdl_wait();
+  if (use_pdl & 1) pdl_wait();
+  if ((use_pdl & 3) == 3) pdl_launch_dependents();
 
-  pro(xs, K4, red);
+  Epi epi = epi_in;
+  epi.prepare();
+  pro(xs, K4, red, pre);
   __syncthreads();
   gemv_pairs<WK, RP, U>(rows, K4, p0, np, xs, part);
   __syncthreads();
 
-  Epi epi = epi_in;
   for (int i = threadIdx.x; i < np; i += kGemvThreads) {
     float v0 = 0.f, v1 = 0.f;
 #pragma unroll
@@ -508,7 +559,7 @@ gemv_smem_kernel(const Pro pro, const Rows rows, const Epi epi_in, int K4, int n
 
   int p0, np;
   gemv_cta_range(n_pairs, p0, np);
-  if (use_pdl) pdl_launch_dependents();
+  if ((use_pdl & 3) == 1) pdl_launch_dependents();
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -520,9 +571,13 @@ gemv_smem_kernel(const Pro pro, const Rows rows, const Epi epi_in, int K4, int n
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(slab);
     for (int i = 0; i < nr; ++i) bulk_g2s(sbase + off[i], src[i], bytes[i], bar);
   }
-  if (use_pdl) pdl_wait();
+  const auto pre = pro.template preload<1>(K4);
+  if (use_pdl & 1) pdl_wait();
+  if ((use_pdl & 3) == 3) pdl_launch_dependents();
 
-  pro(xs, K4, red);
+  Epi epi = epi_in;
+  epi.prepare();
+  pro(xs, K4, red, pre);
   __syncthreads();  // xs complete; also makes the mbarrier init visible to every waiter
   {
     uint32_t done = 0;
@@ -530,7 +585,6 @@ gemv_smem_kernel(const Pro pro, const Rows rows, const Epi epi_in, int K4, int n
       asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
                    : "=r"(done) : "r"(bar) : "memory");
   }
-  Epi epi = epi_in;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = warp; i < np; i += kGemvWarps) {
     const float4 *r0, *r1;
@@ -632,11 +686,12 @@ __device__ __forceinline__ void gemv_phase(const Pro& pro, const Rows& rows, con
   float* part = reinterpret_cast<float*>(xs + K4);
   int p0, np;
   gemv_cta_range(n_pairs, p0, np);
-  pro(xs, K4, red);
+  Epi epi = epi_in;
+  epi.prepare();
+  pro(xs, K4, red, pro.template preload<1>(K4));
   __syncthreads();
   gemv_pairs_rt(rows, K4, p0, np, xs, part, WK);
   __syncthreads();
-  Epi epi = epi_in;
   for (int i = threadIdx.x; i < np; i += kGemvThreads) {
     float v0 = 0.f, v1 = 0.f;
     for (int k = 0; k < WK; ++k) {

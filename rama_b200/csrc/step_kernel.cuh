@@ -98,6 +98,7 @@ struct StepEpiStore {  // wo (stage 0 → xb2) / w2 (stage 1 → w2out); under T
     *reinterpret_cast<float2*>(o + 2 * pr) = make_float2(v0, v1);  // D is even
   }
   __device__ __forceinline__ void finish(float*) const {}
+  __device__ __forceinline__ void prepare() const {}
 };
 
 struct StepEpiQKV {  // RoPE (cpu.rs:74-97) on q,k + KV-cache row write (infer.rs:31-33)
@@ -123,6 +124,7 @@ struct StepEpiQKV {  // RoPE (cpu.rs:74-97) on q,k + KV-cache row write (infer.r
     }
   }
   __device__ __forceinline__ void finish(float*) const {}
+  __device__ __forceinline__ void prepare() const {}
 };
 
 struct StepEpiSwiGLU {  // cpu.rs:54-64
@@ -132,6 +134,7 @@ struct StepEpiSwiGLU {  // cpu.rs:54-64
     p.hb2[pr] = h3;
   }
   __device__ __forceinline__ void finish(float*) const {}
+  __device__ __forceinline__ void prepare() const {}
 };
 
 struct StepEpiCls {  // logits + per-CTA greedy partial (ties → higher index, cpu.rs:165-167)
@@ -147,6 +150,7 @@ struct StepEpiCls {  // logits + per-CTA greedy partial (ties → higher index, 
       argmax_merge(bv, bi, v1, p.v0 + 2 * pr + 1);
     }
   }
+  __device__ __forceinline__ void prepare() const {}
   __device__ __forceinline__ void finish(float* red) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
