@@ -241,6 +241,12 @@ int rama_op_matmul_nt(rama_ctx* ctx, float* out, const float* a, const float* b,
 int rama_bench_matmul_nt(rama_ctx* ctx, float* out, const float* a, const float* b, size_t M, size_t N, size_t K,
                          int variant, int flags, int iters, float* avg_ms);
 
+/* Debug hook used by tools/gemm_trace.py: one rama_op_matmul_nt launch whose CTA (0,0,0) stamps clock64() per k-block and
+ * role into host_trace[128][8] (0 TMA issue, 1 tile landed, 2 split done, 3 MMA sees ready, 4 MMAs issued,
+ * 5/6 drain wait begin/end per (chunk, worker group), 7 MMA got its accumulator back). */
+int rama_debug_gemm_trace(rama_ctx* ctx, float* out, const float* a, const float* b, size_t M, size_t N, size_t K,
+                          int variant, int flags, long long* host_trace);
+
 /* Synthetic fill of a device buffer (bench/test data): elements [start, start+n) of tensor_id. */
 int rama_synth_fill(rama_ctx* ctx, float* dst, size_t n, uint64_t seed, uint64_t tensor_id,
                     uint64_t start, float scale, float offset);

@@ -97,6 +97,7 @@ _SIGS = {
     "rama_op_matmul": ([vp, fp, fp, fp, sz, sz, sz], C.c_int),
     "rama_op_matmul_nt": ([vp, fp, fp, fp, sz, sz, sz, C.c_int, C.c_int], C.c_int),
     "rama_bench_matmul_nt": ([vp, fp, fp, fp, sz, sz, sz, C.c_int, C.c_int, C.c_int, fp], C.c_int),
+    "rama_debug_gemm_trace": ([vp, fp, fp, fp, sz, sz, sz, C.c_int, C.c_int, C.POINTER(C.c_longlong)], C.c_int),
     "rama_op_softmax": ([vp, fp, sz], C.c_int),
     "rama_op_sample": ([vp, fp, sz, C.c_float, C.c_float, ip], C.c_int),
     "rama_synth_fill": ([vp, fp, sz, C.c_uint64, C.c_uint64, C.c_uint64, C.c_float, C.c_float], C.c_int),

@@ -94,6 +94,8 @@ CONFIGS: Dict[str, Config] = {
     # test-sized models (same code paths: shared / separate classifier, odd shapes)
     "tiny": Config(64, 176, 2, 4, 4, 512, 64, True),
     "tiny-sep": Config(96, 256, 3, 2, 2, 300, 48, False),
+    # long context at test size (head_size 32): every pass count of the cluster attention kernel and the split-merge kernel
+    "tiny-long": Config(64, 176, 2, 2, 2, 512, 2048, True),
     # 7B layer shapes with 2 layers: exercises the 7B kernel configuration cheaply
     "l7-2layer": Config(4096, 11008, 2, 32, 32, 32000, 2048, False),
 }

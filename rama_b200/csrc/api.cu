@@ -140,6 +140,10 @@ struct rama_ctx {
   int persistent = 0;  // RAMA_STEP=persistent: the decode step as one persistent cooperative kernel (step_kernel.cuh);
                        // default: one fused kernel per op group in a CUDA graph (measured faster)
   std::mutex mu;
+  // A stream capture is invalidated by a device-wide synchronisation (cudaDeviceSynchronize, default-stream work,
+  // cudaFree) issued by ANOTHER host thread of the same context — the server creates and drops sessions while other
+  // request threads capture their step graphs.  Captures and those device-wide operations take this lock.
+  std::mutex cap_mu;
 };
 
 struct rama_session {
@@ -173,6 +177,7 @@ struct rama_session {
   int attn_gy = 1;              // gridDim.y of the attention launch being enqueued
   int attn_bk = 0;              // its bucket (0: positions < 256)
   float* wo_part = nullptr;     // [H][D] per-head wo partials of the fused attention+wo kernel (small models), or null
+  int attn_wo_mode = 0;         // 1: attn_wo_cluster_kernel, 2: attn_wo_kernel, 0: separate launches
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int keep_att = 0;
   int n_split = 1;
@@ -822,6 +827,7 @@ extern "C" int rama_session_create(rama_ctx* c, rama_session** out) {
   if (!c || !out) return fail(RAMA_E_INVALID, "NULL argument");
   if (!c->loaded) return fail(RAMA_E_STATE, "no weights loaded");
   CK(cudaSetDevice(c->device));
+  std::lock_guard<std::mutex> cap_lk(c->cap_mu);
   rama_session* s = new rama_session();
   s->ctx = c;
   s->n_split = (c->T + kAttnChunk - 1) / kAttnChunk;
@@ -852,10 +858,25 @@ extern "C" int rama_session_create(rama_ctx* c, rama_session** out) {
   // small models: attention + wo as one kernel with per-head partial outputs (attention.cuh attn_wo_kernel)
   // (measured: a win up to stories15M's size — 8425 → 9340 tok/s; at stories110M the redundant per-CTA attention and the
   // 12-way partial sum cost more than the saved launch — 3757 → 3536 — so dim ≤ 512 only)
-  if (c->world == 1 && c->D <= 512 && (size_t)c->H * c->D * sizeof(float) <= (size_t)64 * 1024 && c->H <= c->sm_count &&
-      (c->D + c->sm_count / c->H - 1) / (c->sm_count / c->H) <= 8 * kAttnWoWarps &&  // wo rows per CTA held in registers
-      env_int("RAMA_ATTN_WO", 1))
-    A(dalloc(&s->wo_part, (size_t)c->H * c->D));
+  // Attention + wo as ONE launch (per-head partial outputs of wo, summed by the next prologue) — opt-in since the cluster
+  // attention kernel: RAMA_ATTN_WO = 0 (default) separate launches, 1 = attn_wo_cluster_kernel, 2 = attn_wo_kernel (per-CTA
+  // redundant attention); RAMA_ATTN_WO_MAXDIM moves the size limit of mode 1.  Measured on B200 (tok/s):
+  //   stories15M   separate split-merge attention 8425 | per-CTA fused 9487 | cluster fused 10286 | cluster attention + wo 10342
+  //   stories110M  3745 | 3536 | 4212 | 4577
+  // — with the K/V fetch ahead of the dependency and the DSMEM merge the separate attention launch costs less than the
+  // H-way partial sum in the next prologue, so the fused variants are kept only as measured alternatives.
+  s->attn_wo_mode = env_int("RAMA_ATTN_WO", 0);
+  if (s->attn_wo_mode == 1) {
+    const int rpl = c->hs <= 64 ? 2 : 1;  // wo rows per 128-bit warp load
+    if (!(c->world == 1 && c->D <= std::min(1024, env_int("RAMA_ATTN_WO_MAXDIM", 512)) && (size_t)c->H * c->D * sizeof(float) <= (size_t)64 * 1024 &&
+          (c->D + kAttnClusterMax - 1) / kAttnClusterMax <= kAwcRowLoads * kAttnWarps * rpl))
+      s->attn_wo_mode = 0;
+  } else if (s->attn_wo_mode == 2) {
+    if (!(c->world == 1 && c->D <= 512 && (size_t)c->H * c->D * sizeof(float) <= (size_t)64 * 1024 && c->H <= c->sm_count &&
+          (c->D + c->sm_count / c->H - 1) / (c->sm_count / c->H) <= 8 * kAttnWoWarps))  // wo rows per CTA held in registers
+      s->attn_wo_mode = 0;
+  }
+  if (s->attn_wo_mode) A(dalloc(&s->wo_part, (size_t)c->H * c->D));
   A(dalloc(&s->sort_keys, vp2));
   A(dalloc(&s->ctrl, 1));
   A(dalloc(&s->d_prompt, T)); A(dalloc(&s->d_out, T));
@@ -881,6 +902,8 @@ extern "C" int rama_session_create(rama_ctx* c, rama_session** out) {
 }
 
 extern "C" int rama_session_destroy(rama_session* s) {
+  if (!s) return RAMA_OK;
+  std::lock_guard<std::mutex> cap_lk(s->ctx->cap_mu);
   session_free(s);
   return RAMA_OK;
 }
@@ -1033,7 +1056,8 @@ static int enqueue_step(rama_session* s, cudaStream_t st, int mode, StepTrace* t
   const int D = c->D, Dq = c->Dq, Fl = c->Fl, T = c->T, hs = c->hs, L = c->L;
   const float* W[RAMA_T_COUNT];
   for (int i = 0; i < RAMA_T_COUNT; ++i) W[i] = c->w[i];
-  const bool fuse_attn_wo = s->wo_part && s->attn_bk == 0 && !s->keep_att;
+  const bool fuse_attn_wo = s->wo_part && !s->keep_att && (s->attn_wo_mode == 1 ? s->attn_bk < 2 : s->attn_bk == 0);
+  const bool fuse_cluster = fuse_attn_wo && s->attn_wo_mode == 1;
   // contexts below 1024 positions: the splits of a head merge inside a thread-block cluster (attention.cuh)
   const bool attn_cluster = c->attn_cluster && !fuse_attn_wo && !s->keep_att && s->attn_bk < 2;
 
@@ -1064,7 +1088,7 @@ static int enqueue_step(rama_session* s, cudaStream_t st, int mode, StepTrace* t
       const int np = 3 * Dq / 2, var = pick_variant(c, D / 4, np);
       q.pre(RAMA_K_QKV);
       // the cluster attention kernel reads older K/V rows ahead of its wait: release it after this kernel's own wait
-      const int pdl_flags = q.pdl ? (attn_cluster ? 3 : 1) : 0;
+      const int pdl_flags = q.pdl ? ((attn_cluster || fuse_cluster) ? 3 : 1) : 0;
       q.post(launch_gemv(var, pick_grid(c, var, np), st, pdl_flags, pro, rows, epi, D / 4, np));
     }
     if (fuse_attn_wo) {
@@ -1073,17 +1097,27 @@ static int enqueue_step(rama_session* s, cudaStream_t st, int mode, StepTrace* t
       AttnWoParams ap{s->q, s->key_cache + (size_t)l * T * Dq, s->value_cache + (size_t)l * T * Dq,
                       W[RAMA_T_WO] + (size_t)l * D * Dq, s->xb, s->wo_part, s->ctrl, Dq, hs, D, J};
       cudaLaunchConfig_t cfg{};
-      cfg.gridDim = dim3(c->H * J);
-      cfg.blockDim = dim3(kAttnWoThreads);
+      cfg.gridDim = fuse_cluster ? dim3(c->H * kAttnClusterMax) : dim3(c->H * J);
+      cfg.blockDim = fuse_cluster ? dim3(kAttnThreads) : dim3(kAttnWoThreads);
       cfg.stream = st;
-      cudaLaunchAttribute at[1];
+      cudaLaunchAttribute at[2];
+      int na = 0;
       if (q.pdl) {
-        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        at[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
+        at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
       }
+      if (fuse_cluster) {
+        at[na].id = cudaLaunchAttributeClusterDimension;
+        at[na].val.clusterDim.x = kAttnClusterMax;
+        at[na].val.clusterDim.y = 1;
+        at[na].val.clusterDim.z = 1;
+        ++na;
+      }
+      cfg.attrs = at; cfg.numAttrs = na;
       q.pre(RAMA_K_ATTN);
-      q.post(cudaLaunchKernelEx(&cfg, attn_wo_kernel, ap, q.pdl));
+      if (fuse_cluster) q.post(cudaLaunchKernelEx(&cfg, attn_wo_cluster_kernel, ap, q.pdl));
+      else q.post(cudaLaunchKernelEx(&cfg, attn_wo_kernel, ap, q.pdl));
     } else {
     // ---- attention (infer.rs:34) ----
     {
@@ -1232,6 +1266,7 @@ static int set_attn_bucket(rama_session* s, int pos) {
 }
 
 static int capture(rama_session* s, int mode, cudaGraphExec_t* out) {
+  std::lock_guard<std::mutex> cap_lk(s->ctx->cap_mu);
   RK(init_parts(s));
   cudaGraph_t g = nullptr;
   CK(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeRelaxed));
@@ -1747,6 +1782,7 @@ extern "C" int rama_batch_create(rama_ctx* c, int32_t max_seqs, rama_batch** out
   if (!c->loaded) return fail(RAMA_E_STATE, "no weights loaded");
   if (max_seqs < 1 || max_seqs > kBatchMax) return fail(RAMA_E_INVALID, "max_seqs must be in [1, %d]", kBatchMax);
   CK(cudaSetDevice(c->device));
+  std::lock_guard<std::mutex> cap_lk(c->cap_mu);
   rama_batch* b = new rama_batch();
   b->ctx = c;
   b->cap = max_seqs;
@@ -1788,6 +1824,7 @@ extern "C" int rama_batch_destroy(rama_batch* b) {
   if (!b) return RAMA_OK;
   cudaSetDevice(b->ctx->device);
   if (b->stream) cudaStreamSynchronize(b->stream);
+  std::lock_guard<std::mutex> cap_lk(b->ctx->cap_mu);
   for (auto g : b->graphs) if (g) cudaGraphExecDestroy(g);
   void* bufs[] = {b->x, b->xn, b->q, b->att, b->h, b->part, b->attn_ws, b->tickets, b->d_seqs, b->d_sp, b->d_next, b->red, b->lstage};
   for (void* p : bufs) if (p) cudaFree(p);
@@ -1803,12 +1840,31 @@ extern "C" int rama_batch_destroy(rama_batch* b) {
 
 // enqueue one batched step for n sequences (everything per-sequence is read from b->d_seqs on the device,
 // so the captured graph of a batch size serves every step)
+// kernel launch with the programmatic-stream-serialization attribute (PDL): the next kernel's CTAs start while this one
+// drains; every kernel of the batched step executes griddepcontrol.wait before it touches memory (batch.cuh)
+template <class... P, class... A>
+static cudaError_t launch_k(bool pdl, void (*kern)(P...), dim3 grid, dim3 block, cudaStream_t st, A&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  if (pdl) {
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+  }
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<A>(args)...);
+}
+
 static int enqueue_batch_step(rama_batch* b, int n, int* n_launch) {
   rama_ctx* c = b->ctx;
   cudaStream_t st = b->stream;
   const int D = c->D, Dq = c->Dq, Fl = c->Fl, T = c->T, hs = c->hs, L = c->L, Vl = c->Vl;
   const float* const* W = c->w;
   int launches = 0;
+  const bool pdl = c->use_pdl && env_int("RAMA_BATCH_PDL", 1);
   auto tiles = [](int rows) { return (rows + kGemmBM - 1) / kGemmBM; };
 #define LK(call)                                                                                              \
   do {                                                                                                        \
@@ -1817,8 +1873,7 @@ static int enqueue_batch_step(rama_batch* b, int n, int* n_launch) {
     ++launches;                                                                                               \
     if (e_ != cudaSuccess) return fail(RAMA_E_CUDA, "batched step launch %s: %s", #call, cudaGetErrorString(e_)); \
   } while (0)
-  batch_embed_kernel<<<n, 256, 0, st>>>(b->d_seqs, W[RAMA_T_TOKEN_EMBEDDING], b->x, D, c->V);
-  LK(cudaSuccess);
+  LK(launch_k(pdl, batch_embed_kernel, dim3(n), dim3(256), st, b->d_seqs, W[RAMA_T_TOKEN_EMBEDDING], b->x, D, c->V));
   GemmOperand X{b->xn, (size_t)n, (size_t)D};
   int S_prev = 0;  // split factor of the pending residual partials in b->part (0: none)
   const float* pending = b->part;
@@ -1826,8 +1881,7 @@ static int enqueue_batch_step(rama_batch* b, int n, int* n_launch) {
   // over NVLink (NCCL, 1 MB at 64 sequences), and hand the reduced buffer to the next addnorm as a single "split"
   auto reduce_ranks = [&](int& S) -> int {
     if (c->world <= 1) return RAMA_OK;
-    sum_partials_kernel<<<c->sm_count * 2, 256, 0, st>>>(b->red, b->part, (size_t)n * D, S);
-    ++launches;
+    LK(launch_k(pdl, sum_partials_kernel, dim3(c->sm_count * 2), dim3(256), st, b->red, (const float*)b->part, (size_t)n * D, S));
     NK(g_nccl.AllReduce(b->red, b->red, (size_t)n * D, kNcclFloat32, kNcclSum, c->comm, st));
     ++launches;
     S = 1;
@@ -1837,24 +1891,20 @@ static int enqueue_batch_step(rama_batch* b, int n, int* n_launch) {
   for (int l = 0; l < L; ++l) {
     const size_t layer_off = (size_t)l * T * Dq;
     // x += pending w2 output; xn = rmsnorm(x)   (infer.rs:19, :47 of the previous layer)
-    batch_addnorm_kernel<<<n, kBatchNormThreads, 0, st>>>(b->x, S_prev ? pending : nullptr, S_prev, (size_t)n * D,
-                                            W[RAMA_T_RMS_ATT] + (size_t)l * D, b->xn, D);
-    LK(cudaSuccess);
+    LK(launch_k(pdl, batch_addnorm_kernel, dim3(n), dim3(kBatchNormThreads), st, b->x, S_prev ? pending : nullptr, S_prev,
+                (size_t)n * D, W[RAMA_T_RMS_ATT] + (size_t)l * D, b->xn, D));
     {  // [wq;wk;wv] (weights = the 128-row operand, the batch = the 64-column operand)   (infer.rs:20-23)
       GemmOperand A[3] = {{W[RAMA_T_WQ] + (size_t)l * Dq * D, (size_t)Dq, (size_t)D},
                           {W[RAMA_T_WK] + (size_t)l * Dq * D, (size_t)Dq, (size_t)D},
                           {W[RAMA_T_WV] + (size_t)l * Dq * D, (size_t)Dq, (size_t)D}};
       const int S = pick_ksplit(c, 3 * tiles(Dq), D);
       EpiStoreT epi{b->part, Dq, n, S, (size_t)n * Dq};
-      LK((BATCH_GEMM(st, A, 3, &X, 1, Dq, n, D, 0, S, epi)));
-      batch_qkv_finish_kernel<<<dim3(n, (Dq / 2 + 255) / 256), 256, 0, st>>>(
-          b->part, S, (size_t)n * Dq, b->d_seqs, layer_off, b->q, W[RAMA_T_FREQ_REAL], W[RAMA_T_FREQ_IMAG], Dq, hs / 2);
-      LK(cudaSuccess);
+      LK((BATCH_GEMM(st, A, 3, &X, 1, Dq, n, D, 0, S, epi, pdl)));
+      LK(launch_k(pdl, batch_qkv_finish_kernel, dim3(n, (Dq / 2 + 255) / 256), dim3(256), st, b->part, S, (size_t)n * Dq, b->d_seqs, layer_off, b->q, W[RAMA_T_FREQ_REAL], W[RAMA_T_FREQ_IMAG], Dq, hs / 2));
     }
     {  // attention per sequence   (infer.rs:34)
       AttnBatchParams ap{b->d_seqs, b->q, b->att, b->attn_ws, b->tickets, layer_off, T, Dq, hs, b->n_split, c->Hl};
-      attn_decode_batch_kernel<<<dim3(c->Hl, std::min(b->n_split, 2), n), kAttnThreads, 0, st>>>(ap);  // CTAs stride over the chunks
-      LK(cudaSuccess);
+      LK(launch_k(pdl, attn_decode_batch_kernel, dim3(c->Hl, std::min(b->n_split, 2), n), dim3(kAttnThreads), st, ap));  // CTAs stride over the chunks
     }
     int S_wo;
     {  // wo   (infer.rs:35)
@@ -1862,49 +1912,43 @@ static int enqueue_batch_step(rama_batch* b, int n, int* n_launch) {
       GemmOperand Bm{b->att, (size_t)n, (size_t)Dq};
       S_wo = pick_ksplit(c, tiles(D), Dq);
       EpiStoreT epi{b->part, D, n, S_wo, (size_t)n * D};
-      LK((BATCH_GEMM(st, &A, 1, &Bm, 1, D, n, Dq, 0, S_wo, epi)));
+      LK((BATCH_GEMM(st, &A, 1, &Bm, 1, D, n, Dq, 0, S_wo, epi, pdl)));
       RK(reduce_ranks(S_wo));
     }
     // x += wo output; xn = rmsnorm(x)   (infer.rs:37-38)
-    batch_addnorm_kernel<<<n, kBatchNormThreads, 0, st>>>(b->x, pending, S_wo, (size_t)n * D, W[RAMA_T_RMS_FFN] + (size_t)l * D, b->xn, D);
-    LK(cudaSuccess);
+    LK(launch_k(pdl, batch_addnorm_kernel, dim3(n), dim3(kBatchNormThreads), st, b->x, pending, S_wo, (size_t)n * D, W[RAMA_T_RMS_FFN] + (size_t)l * D, b->xn, D));
     {  // [w1;w3] → SwiGLU   (infer.rs:39-45)
       GemmOperand A[2] = {{W[RAMA_T_W1] + (size_t)l * Fl * D, (size_t)Fl, (size_t)D},
                           {W[RAMA_T_W3] + (size_t)l * Fl * D, (size_t)Fl, (size_t)D}};
       const int S = pick_ksplit(c, 2 * tiles(Fl), D);
       EpiStoreT epi{b->part, Fl, n, S, (size_t)n * Fl};
-      LK((BATCH_GEMM(st, A, 2, &X, 1, Fl, n, D, 0, S, epi)));
-      batch_swiglu_finish_kernel<<<std::min(c->sm_count * 4, (n * Fl + 255) / 256), 256, 0, st>>>(b->part, S, (size_t)n * Fl, b->h, Fl, n);
-      LK(cudaSuccess);
+      LK((BATCH_GEMM(st, A, 2, &X, 1, Fl, n, D, 0, S, epi, pdl)));
+      LK(launch_k(pdl, batch_swiglu_finish_kernel, dim3(std::min(c->sm_count * 4, (n * Fl + 255) / 256)), dim3(256), st, b->part, S, (size_t)n * Fl, b->h, Fl, n));
     }
     {  // w2   (infer.rs:46)
       GemmOperand A{W[RAMA_T_W2] + (size_t)l * D * Fl, (size_t)D, (size_t)Fl};
       GemmOperand Bm{b->h, (size_t)n, (size_t)Fl};
       S_prev = pick_ksplit(c, tiles(D), Fl);
       EpiStoreT epi{b->part, D, n, S_prev, (size_t)n * D};
-      LK((BATCH_GEMM(st, &A, 1, &Bm, 1, D, n, Fl, 0, S_prev, epi)));
+      LK((BATCH_GEMM(st, &A, 1, &Bm, 1, D, n, Fl, 0, S_prev, epi, pdl)));
       RK(reduce_ranks(S_prev));
     }
   }
   // x += w2 output; final rmsnorm; classifier → each session's logits   (infer.rs:49-51)
-  batch_addnorm_kernel<<<n, kBatchNormThreads, 0, st>>>(b->x, pending, S_prev, (size_t)n * D, W[RAMA_T_RMS_FINAL], b->xn, D);
-  LK(cudaSuccess);
+  LK(launch_k(pdl, batch_addnorm_kernel, dim3(n), dim3(kBatchNormThreads), st, b->x, pending, S_prev, (size_t)n * D, W[RAMA_T_RMS_FINAL], b->xn, D));
   {
     GemmOperand A{c->wcls, (size_t)Vl, (size_t)D};
     const int S = pick_ksplit(c, tiles(Vl), D);
     EpiStoreT epi{b->part, Vl, n, S, (size_t)n * Vl};
-    LK((BATCH_GEMM(st, &A, 1, &X, 1, Vl, n, D, 0, S, epi)));
+    LK((BATCH_GEMM(st, &A, 1, &X, 1, Vl, n, D, 0, S, epi, pdl)));
     if (c->world > 1) {  // vocabulary rows are split: gather every rank's block, then scatter into the sessions' logits
       float* mine = b->lstage + (size_t)c->rank * n * Vl;
-      batch_cls_stage_kernel<<<dim3(std::min(64, (Vl + 255) / 256), n), 256, 0, st>>>(b->part, S, (size_t)n * Vl, mine, Vl);
-      LK(cudaSuccess);
+      LK(launch_k(pdl, batch_cls_stage_kernel, dim3(std::min(64, (Vl + 255) / 256), n), dim3(256), st, b->part, S, (size_t)n * Vl, mine, Vl));
       NK(g_nccl.AllGather(mine, b->lstage, (size_t)n * Vl, kNcclFloat32, c->comm, st));
       ++launches;
-      batch_logits_scatter_kernel<<<dim3(std::min(64, (c->V + 255) / 256), n), 256, 0, st>>>(b->lstage, b->d_seqs, Vl, c->world, n);
-      LK(cudaSuccess);
+      LK(launch_k(pdl, batch_logits_scatter_kernel, dim3(std::min(64, (c->V + 255) / 256), n), dim3(256), st, b->lstage, b->d_seqs, Vl, c->world, n));
     } else {
-      batch_cls_finish_kernel<<<dim3(std::min(64, (Vl + 255) / 256), n), 256, 0, st>>>(b->part, S, (size_t)n * Vl, b->d_seqs, Vl, c->v0);
-      LK(cudaSuccess);
+      LK(launch_k(pdl, batch_cls_finish_kernel, dim3(std::min(64, (Vl + 255) / 256), n), dim3(256), st, b->part, S, (size_t)n * Vl, b->d_seqs, Vl, c->v0));
     }
   }
 #undef LK
@@ -1942,6 +1986,7 @@ extern "C" int rama_forward_batch(rama_batch* b, rama_session* const* sessions, 
   }
   CK(cudaMemcpyAsync(b->d_seqs, hs, (size_t)n * sizeof(BatchSeq), cudaMemcpyHostToDevice, b->stream));
   if (!b->graphs[n]) {
+    std::lock_guard<std::mutex> cap_lk(c->cap_mu);
     cudaGraph_t g = nullptr;
     CK(cudaStreamBeginCapture(b->stream, cudaStreamCaptureModeRelaxed));
     int nl = 0;
@@ -2231,6 +2276,7 @@ extern "C" int rama_op_matmul_nt(rama_ctx* c, float* out, const float* a, const 
       case 1: e = launch_gemm_tf32x3<64, 4, 4, 2>(c->op_stream, &A, 1, &B, 1, m, n, k, hi_round, ksplit, epi); break;
       case 2: e = launch_gemm_tf32x3<64, 4, 2, 0>(c->op_stream, &A, 1, &B, 1, m, n, k, hi_round, ksplit, epi); break;
       case 3: e = launch_gemm_tf32x3<64, 2, 2, 0>(c->op_stream, &A, 1, &B, 1, m, n, k, hi_round, ksplit, epi); break;  // 2 CTAs/SM
+      case 4: e = launch_gemm_tf32x3<64, 2, 4, 0>(c->op_stream, &A, 1, &B, 1, m, n, k, hi_round, ksplit, epi); break;  // + 128-k chunks
       default: return fail(RAMA_E_INVALID, "matmul_nt: unknown transposed variant %d", variant);
     }
     if (ksplit > 1) {
@@ -2253,6 +2299,25 @@ extern "C" int rama_op_matmul_nt(rama_ctx* c, float* out, const float* a, const 
   }
   if (e != cudaSuccess) return fail(RAMA_E_CUDA, "gemm_tf32x3 launch: %s", cudaGetErrorString(e));
   return RAMA_OK;
+}
+
+// Debug hook (tools/gemm_trace.py): per-role clock64() timeline of CTA (0,0,0) of one GEMM launch, [128 k-blocks][8 events].
+extern "C" int rama_debug_gemm_trace(rama_ctx* c, float* out, const float* a, const float* b, size_t M, size_t N, size_t K,
+                                     int variant, int flags, long long* host_trace) {
+  OP_PRE(c);
+  if (!host_trace) return fail(RAMA_E_INVALID, "NULL trace");
+  long long* d = nullptr;
+  CK(cudaMalloc((void**)&d, 128 * 8 * sizeof(long long)));
+  CK(cudaMemset(d, 0, 128 * 8 * sizeof(long long)));
+  CK(cudaDeviceSynchronize());
+  for (int i = 0; i < 3; ++i) RK(rama_op_matmul_nt(c, out, a, b, M, N, K, variant, flags));  // warm
+  g_gemm_trace = d;
+  int rc = rama_op_matmul_nt(c, out, a, b, M, N, K, variant, flags);
+  g_gemm_trace = nullptr;
+  cudaStreamSynchronize(c->op_stream);
+  if (rc == RAMA_OK) cudaMemcpy(host_trace, d, 128 * 8 * sizeof(long long), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  return rc;
 }
 
 // Micro-benchmark hook (tools/gemm_sweep.py): average milliseconds of rama_op_matmul_nt over `iters` launches.

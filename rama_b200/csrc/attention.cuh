@@ -464,4 +464,179 @@ __global__ void __launch_bounds__(kAttnWoThreads) attn_wo_kernel(const AttnWoPar
   }
 }
 
+// ---- attention + wo in one CLUSTER launch (small models) -----------------------------------------------------
+// Same idea as attn_wo_kernel below (one launch fewer per layer; per-head partial outputs of wo summed by the next
+// prologue), but the head's attention is computed ONCE, split over the CS CTAs of a cluster exactly like
+// attn_cluster_kernel, instead of redundantly by every CTA that owns rows of wo.  After the cluster barrier each CTA
+// rebuilds the head's output vector from its siblings' shared memory and multiplies it into its D/CS rows of the head's
+// column block of wo — which it loaded into registers BEFORE griddepcontrol.wait (weights depend on nothing).
+// Rows of hs ≤ 64 floats take half a warp: two rows per 128-bit warp load.
+constexpr int kAwcRowLoads = 8;  // 128-bit wo loads per lane held in registers across the attention
+
+__global__ void __launch_bounds__(kAttnThreads, 2) attn_wo_cluster_kernel(const AttnWoParams p, int use_pdl) {
+  namespace cg = cooperative_groups;
+  constexpr int NW = kAttnWarps;
+  __shared__ float s_m[NW], s_l[NW];
+  __shared__ __align__(16) float s_acc[NW][kAttnMaxHs];
+  __shared__ __align__(16) float s_part[kAttnMaxHs + 4];  // this CTA's acc[hs] | M | L, read by the whole cluster
+  __shared__ __align__(16) float s_xb[kAttnMaxHs];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int CS = (int)cluster.num_blocks();
+  const int rank = (int)cluster.block_rank();
+  const int h = blockIdx.x / CS;
+  if ((use_pdl & 3) == 1) pdl_launch_dependents();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int hs = p.hs, hs4 = hs >> 2;
+  const bool active = lane < hs4;
+  const float div = sqrtf((float)hs);
+  const size_t col = (size_t)h * hs;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  // this CTA's rows [r0, r0+nr) of wo[:, h·hs .. +hs): row (k·NW + warp)·RPL + sub sits in lanes [sub·seg, sub·seg + hs4)
+  const int seg = hs4 > 16 ? 32 : 16, RPL = 32 / seg;
+  const int sub = lane / seg, sl = lane - sub * seg;
+  const bool wactive = sl < hs4;
+  const int per = p.D / CS, rem = p.D % CS;
+  const int r0 = rank * per + min(rank, rem), nr = per + (rank < rem ? 1 : 0);
+  float4 wrow[kAwcRowLoads];
+#pragma unroll
+  for (int k = 0; k < kAwcRowLoads; ++k) {
+    const int r = (k * NW + warp) * RPL + sub;
+    wrow[k] = (wactive && r < nr) ? ldg_stream(reinterpret_cast<const float4*>(p.wo + (size_t)(r0 + r) * p.Dq + col) + sl) : zero4;
+  }
+
+  const float4* kbase = reinterpret_cast<const float4*>(p.key_cache + col) + lane;
+  const float4* vbase = reinterpret_cast<const float4*>(p.value_cache + col) + lane;
+  const size_t row4 = (size_t)p.Dq >> 2;
+  // older than the previous kernel (which released this launch after its own wait) ⇒ complete: see attn_cluster_kernel
+  const int pos = *reinterpret_cast<const volatile int32_t*>(&p.ctrl->pos);
+  const int n = pos + 1;
+  const int n_chunks = pos / kAttnChunk + 1;
+  int c = rank;
+  int t0 = c * kAttnChunk + warp * kAttnPerWarp;
+  float4 kk[kAttnPerWarp], vv[kAttnPerWarp];
+#pragma unroll
+  for (int j = 0; j < kAttnPerWarp; ++j) kk[j] = (active && t0 + j < pos) ? __ldcg(kbase + (size_t)(t0 + j) * row4) : zero4;
+#pragma unroll
+  for (int j = 0; j < kAttnPerWarp; ++j) vv[j] = (active && t0 + j < pos) ? __ldcg(vbase + (size_t)(t0 + j) * row4) : zero4;
+
+  if (use_pdl & 1) pdl_wait();
+  if ((use_pdl & 3) == 3) pdl_launch_dependents();
+
+  const float4 q4 = active ? __ldcg(reinterpret_cast<const float4*>(p.q + col) + lane) : zero4;
+#pragma unroll
+  for (int j = 0; j < kAttnPerWarp; ++j) {  // this step's row, appended by the previous kernel
+    if (active && t0 + j == pos) {
+      kk[j] = __ldcg(kbase + (size_t)pos * row4);
+      vv[j] = __ldcg(vbase + (size_t)pos * row4);
+    }
+  }
+  float m = -INFINITY, l = 0.f;
+  float4 acc = zero4;
+  while (c < n_chunks) {
+    const int c2 = c + CS, t2 = t0 + CS * kAttnChunk;
+    float4 kn[kAttnPerWarp], vn[kAttnPerWarp];
+    if (c2 < n_chunks) {
+#pragma unroll
+      for (int j = 0; j < kAttnPerWarp; ++j) kn[j] = (active && t2 + j < n) ? __ldcg(kbase + (size_t)(t2 + j) * row4) : zero4;
+#pragma unroll
+      for (int j = 0; j < kAttnPerWarp; ++j) vn[j] = (active && t2 + j < n) ? __ldcg(vbase + (size_t)(t2 + j) * row4) : zero4;
+    }
+    float sc[kAttnPerWarp];
+#pragma unroll
+    for (int j = 0; j < kAttnPerWarp; ++j) sc[j] = dot4(q4, kk[j], 0.f);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int j = 0; j < kAttnPerWarp; ++j) sc[j] += __shfl_xor_sync(0xffffffffu, sc[j], o);
+#pragma unroll
+    for (int j = 0; j < kAttnPerWarp; ++j) {
+      if (t0 + j < n) {                                  // warp-uniform
+        const float s = sc[j] / div;                     // divide, as cpu.rs:41
+        const float mn = fmaxf(m, s);
+        const float f = expf(m - mn), pe = expf(s - mn);
+        l = l * f + pe;
+        acc.x = acc.x * f + pe * vv[j].x; acc.y = acc.y * f + pe * vv[j].y;
+        acc.z = acc.z * f + pe * vv[j].z; acc.w = acc.w * f + pe * vv[j].w;
+        m = mn;
+      }
+    }
+    if (c2 < n_chunks) {
+#pragma unroll
+      for (int j = 0; j < kAttnPerWarp; ++j) { kk[j] = kn[j]; vv[j] = vn[j]; }
+    }
+    c = c2; t0 = t2;
+  }
+  if (lane == 0) { s_m[warp] = m; s_l[warp] = l; }
+  if (active) reinterpret_cast<float4*>(s_acc[warp])[lane] = acc;
+  __syncthreads();
+  {
+    float M = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) M = fmaxf(M, s_m[w]);
+    const bool live = M > -INFINITY;
+    for (int i = threadIdx.x; i < hs; i += kAttnThreads) {
+      float a = 0.f;
+      if (live) {
+#pragma unroll
+        for (int w = 0; w < NW; ++w) a += s_acc[w][i] * expf(s_m[w] - M);
+      }
+      s_part[i] = a;
+    }
+    if (threadIdx.x == 0) {
+      float L = 0.f;
+      if (live) {
+#pragma unroll
+        for (int w = 0; w < NW; ++w) L += s_l[w] * expf(s_m[w] - M);
+      }
+      s_part[hs] = M;
+      s_part[hs + 1] = L;
+    }
+  }
+  cluster.sync();
+  // every CTA rebuilds the whole head output (it multiplies all of it into its rows of wo)
+  if ((int)threadIdx.x < hs) {
+    const int i = threadIdx.x;
+    float Mc[kAttnClusterMax], Lc[kAttnClusterMax], ac[kAttnClusterMax];
+#pragma unroll
+    for (int r = 0; r < kAttnClusterMax; ++r) {
+      if (r < CS) {
+        const float* rp = cluster.map_shared_rank(s_part, r);
+        Mc[r] = rp[hs]; Lc[r] = rp[hs + 1]; ac[r] = rp[i];
+      } else {
+        Mc[r] = -INFINITY; Lc[r] = 0.f; ac[r] = 0.f;
+      }
+    }
+    float M = -INFINITY;
+#pragma unroll
+    for (int r = 0; r < kAttnClusterMax; ++r) M = fmaxf(M, Mc[r]);
+    float L = 0.f, a = 0.f;
+#pragma unroll
+    for (int r = 0; r < kAttnClusterMax; ++r) {
+      const float e = expf(Mc[r] - M);
+      L += Lc[r] * e;
+      a += ac[r] * e;
+    }
+    const float o = a / L;
+    s_xb[i] = o;
+    if (rank == 0) p.xb[col + i] = o;
+  }
+  cluster.barrier_arrive();  // done reading the siblings' shared memory
+  __syncthreads();
+  const float4 x4 = wactive ? reinterpret_cast<const float4*>(s_xb)[sl] : zero4;
+#pragma unroll
+  for (int k = 0; k < kAwcRowLoads; ++k) {
+    const int r = (k * NW + warp) * RPL + sub;
+    float v = dot4(wrow[k], x4, 0.f);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    if (seg == 32) v += __shfl_xor_sync(0xffffffffu, v, 16);
+    if (sl == 0 && r < nr) p.part[(size_t)h * p.D + r0 + r] = v;
+  }
+  cluster.barrier_wait();  // no CTA may exit while a sibling still reads its shared memory
+}
+
 }  // namespace rama

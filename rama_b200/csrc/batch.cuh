@@ -22,6 +22,7 @@ struct BatchSeq {  // one sequence of a batched step (device array, rewritten by
 
 // out[i] = Σ_s part[s][i], s ascending
 __global__ void sum_partials_kernel(float* __restrict__ out, const float* __restrict__ part, size_t n, int S) {
+  pdl_launch_dependents(); pdl_wait();  // (no-ops unless launched with programmatic stream serialization)
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     float a = 0.f;
     for (int s = 0; s < S; ++s) a += part[(size_t)s * n + i];
@@ -32,6 +33,7 @@ __global__ void sum_partials_kernel(float* __restrict__ out, const float* __rest
 // x[b] = token_embedding_table[token_b] (infer.rs:13); mirrors (token,pos) into the session's control block
 __global__ void __launch_bounds__(256) batch_embed_kernel(const BatchSeq* __restrict__ seqs, const float* __restrict__ emb,
                                                           float* __restrict__ x, int D, int vocab) {
+  pdl_launch_dependents(); pdl_wait();  // (no-ops unless launched with programmatic stream serialization)
   const BatchSeq sq = seqs[blockIdx.x];
   int token = sq.token;
   if (threadIdx.x == 0) {
@@ -51,6 +53,7 @@ constexpr int kBatchNormThreads = 1024;
 __global__ void __launch_bounds__(kBatchNormThreads) batch_addnorm_kernel(float* __restrict__ x, const float* __restrict__ y,
                                                                           int S, size_t slab, const float* __restrict__ w,
                                                                           float* __restrict__ xn, int D) {
+  pdl_launch_dependents(); pdl_wait();  // (no-ops unless launched with programmatic stream serialization)
   __shared__ float red[2 * kWarp];
   const int b = blockIdx.x;
   float4* xr = reinterpret_cast<float4*>(x + (size_t)b * D);
@@ -95,6 +98,7 @@ __global__ void __launch_bounds__(256) batch_qkv_finish_kernel(const float* __re
                                                                const BatchSeq* __restrict__ seqs, size_t layer_off,
                                                                float* __restrict__ q, const float* __restrict__ freq_real,
                                                                const float* __restrict__ freq_imag, int Dq, int hs2) {
+  pdl_launch_dependents(); pdl_wait();  // (no-ops unless launched with programmatic stream serialization)
   const int b = blockIdx.x;
   const int i = blockIdx.y * 256 + threadIdx.x;  // pair index
   if (2 * i >= Dq) return;
@@ -131,6 +135,7 @@ struct AttnBatchParams {
   int T, Dq, hs, n_split, H;
 };
 __global__ void __launch_bounds__(kAttnThreads) attn_decode_batch_kernel(const AttnBatchParams bp) {
+  pdl_launch_dependents(); pdl_wait();  // (no-ops unless launched with programmatic stream serialization)
   const int b = blockIdx.z;
   const BatchSeq sq = bp.seqs[b];
   AttnParams p;
@@ -150,6 +155,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_batch_kernel(const A
 // [w1;w3] partials [2][S][B][F] → hb[b][j] = (h1·(1/(1+exp(−h1))))·h3   (cpu.rs:54-64)
 __global__ void __launch_bounds__(256) batch_swiglu_finish_kernel(const float* __restrict__ part, int S, size_t slab,
                                                                   float* __restrict__ hb, int F, int B) {
+  pdl_launch_dependents(); pdl_wait();  // (no-ops unless launched with programmatic stream serialization)
   const size_t n = (size_t)B * F;
   for (size_t i = blockIdx.x * (size_t)256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
     float h1 = 0.f, h3 = 0.f;
@@ -164,6 +170,7 @@ __global__ void __launch_bounds__(256) batch_swiglu_finish_kernel(const float* _
 // tensor parallelism: staging [P][B][Vl] (all-gathered) → every session's full logits [V]
 __global__ void __launch_bounds__(256) batch_logits_scatter_kernel(const float* __restrict__ staging,
                                                                    const BatchSeq* __restrict__ seqs, int Vl, int P, int B) {
+  pdl_launch_dependents(); pdl_wait();  // (no-ops unless launched with programmatic stream serialization)
   const int b = blockIdx.y;
   float* dst = seqs[b].logits;
   for (int i = blockIdx.x * 256 + threadIdx.x; i < P * Vl; i += gridDim.x * 256) {
@@ -175,6 +182,7 @@ __global__ void __launch_bounds__(256) batch_logits_scatter_kernel(const float* 
 // classifier partials [S][B][Vl] → staging[b][Vl] (tensor parallelism: this rank's block of the all-gather buffer)
 __global__ void __launch_bounds__(256) batch_cls_stage_kernel(const float* __restrict__ part, int S, size_t slab,
                                                               float* __restrict__ out, int Vl) {
+  pdl_launch_dependents(); pdl_wait();  // (no-ops unless launched with programmatic stream serialization)
   const int b = blockIdx.y;
   for (int i = blockIdx.x * 256 + threadIdx.x; i < Vl; i += gridDim.x * 256) {
     float a = 0.f;
@@ -186,6 +194,7 @@ __global__ void __launch_bounds__(256) batch_cls_stage_kernel(const float* __res
 // classifier partials [S][B][Vl] → the session's logits[v0 .. v0+Vl)
 __global__ void __launch_bounds__(256) batch_cls_finish_kernel(const float* __restrict__ part, int S, size_t slab,
                                                                const BatchSeq* __restrict__ seqs, int Vl, int v0) {
+  pdl_launch_dependents(); pdl_wait();  // (no-ops unless launched with programmatic stream serialization)
   const int b = blockIdx.y;
   float* dst = seqs[b].logits + v0;
   for (int i = blockIdx.x * 256 + threadIdx.x; i < Vl; i += gridDim.x * 256) {

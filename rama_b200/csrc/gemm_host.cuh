@@ -44,6 +44,8 @@ inline bool make_tmap_2d(CUtensorMap* m, const float* base, size_t rows, size_t 
            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+inline long long* g_gemm_trace = nullptr;  // debug: set by rama_debug_gemm_trace (device buffer [128][8]) or null
+
 struct GemmOperand {  // a K-major f32 matrix [rows][K], row pitch ld
   const float* p;
   size_t rows, ld;
@@ -53,7 +55,7 @@ struct GemmOperand {  // a K-major f32 matrix [rows][K], row pitch ld
 // n_b > 1: groups differ in B (prefill QKV); a dual epilogue stacks B[0] on B[1] inside one tile.
 template <int BN, int STAGES, int CH, int NX, class Epi>
 cudaError_t launch_gemm_tf32x3(cudaStream_t st, const GemmOperand* A, int n_a, const GemmOperand* B, int n_b, int M,
-                               int N, int K, int hi_round, int ksplit, const Epi& epi) {
+                               int N, int K, int hi_round, int ksplit, const Epi& epi, bool pdl = false) {
   using SM = GemmSmem<BN, STAGES, NX>;
   constexpr int BK = kGemmBK;
   static_assert(SM::kTotal <= 227 * 1024, "tile does not fit shared memory");
@@ -73,10 +75,23 @@ cudaError_t launch_gemm_tf32x3(cudaStream_t st, const GemmOperand* A, int n_a, c
     if (!make_tmap_2d(&maps.a[i], a.p, a.rows, (size_t)K, a.ld, kGemmBM, BK)) return cudaErrorInvalidValue;
     if (!make_tmap_2d(&maps.b[i], b.p, b.rows, (size_t)K, b.ld, box_n, BK)) return cudaErrorInvalidValue;
   }
-  GemmShape shp{M, N, K, hi_round, ksplit, n_a > 1 ? 1 : 0};
+  GemmShape shp{M, N, K, hi_round, ksplit, n_a > 1 ? 1 : 0, g_gemm_trace};
   const int groups = Epi::kDual ? 1 : std::max(n_a, n_b);
   dim3 grid((M + kGemmBM - 1) / kGemmBM, (N + box_n - 1) / box_n, groups * ksplit);
   if (grid.y > 65535) return cudaErrorInvalidValue;
+  if (pdl) {  // programmatic dependent launch: barrier init / TMEM allocation overlap the previous kernel's tail
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = SM::kTotal;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, maps, shp, epi);
+  }
   kern<<<grid, kGemmThreads, SM::kTotal, st>>>(maps, shp, epi);
   return cudaGetLastError();
 }

@@ -171,6 +171,7 @@ struct GemmShape {
   int hi_round;    // 1: also rewrite the B tile's hi half rounded to nearest (default 0: raw tile = hi by truncation)
   int ksplit;      // split-K: blockIdx.z = group·ksplit + split; split s reduces k-blocks [s·nkb/ksplit, (s+1)·nkb/ksplit)
   int group_on_a;  // grouped launch: 1 = groups differ in the A operand (weights as A: batched decode), 0 = in B
+  long long* trace;  // debug (tools/gemm_trace.py): CTA (0,0,0) stamps clock64() per k-block and role, [128][8]; else nullptr
 };
 
 constexpr int kGemmBK = 32;  // floats per k-block = one 128-byte swizzle row
@@ -236,6 +237,7 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, c
   const uint32_t tmem_slot = bar_accfree + 16;
   uint8_t* gen_base = gemm_smem_raw + (base - smem_u32(gemm_smem_raw));
 
+  pdl_launch_dependents();  // (no-ops unless launched with programmatic stream serialization)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int group = blockIdx.z / shp.ksplit, split = blockIdx.z - group * shp.ksplit;
   // M-tiles vary fastest in launch order: the CTAs that share a B (weight) tile run together, so with M = 512
@@ -247,6 +249,8 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, c
   const int num_kb = (int)((long long)(split + 1) * total_kb / shp.ksplit) - kb_begin;  // may be 0: the tile is all zeros
   const int num_ch = (num_kb + CH - 1) / CH;
   constexpr int kBoxN = Epi::kDual ? BN / 2 : BN;  // rows per B box
+  const bool tr = shp.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+#define RAMA_GEMM_TR(kb_, e_) do { if (tr && (kb_) < 128) shp.trace[(kb_) * 8 + (e_)] = clock64(); } while (0)
   const CUtensorMap* mapA = &maps.a[shp.group_on_a ? group : 0];
   const CUtensorMap* mapB0 = &maps.b[(Epi::kDual || shp.group_on_a) ? 0 : group];
 
@@ -269,6 +273,7 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, c
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();  // the operands (and the buffers the epilogue overwrites) belong to the previous kernel until here
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen_base + SM::kBarOff + SM::kNumBars * 8);
   const uint32_t tmem_a = tmem + SM::kAccCols;  // A stages: stage s at +64·s (hi), +64·s+32 (lo)
 
@@ -281,6 +286,7 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, c
       uint32_t ph = 1, st = base, bf = bar_full, be = bar_empty;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(be, ph);
+        RAMA_GEMM_TR(kb, 0);
         mbar_arrive_expect_tx(bf, SM::kTxBytes);
         tma_load_2d(st, mapA, bf, kc, m0);
         if (Epi::kDual) {
@@ -308,11 +314,12 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, c
         const bool first = in_ch == 0, last = (in_ch == CH - 1) || kb == num_kb - 1;
         const uint32_t acc = tmem + (ch & 1) * BN;
         if (first && ch >= 2) {  // acc[ch&1] still holds chunk ch-2 until the workers have drained it
-          mbar_wait(bar_accfree + 8 * (ch & 1), ((ch >> 1) - 1) & 1);
-          tc_fence_after();
+          mbar_wait(bar_accfree + 8 * (ch & 1), ((ch >> 1) - 1) & 1);  // (the fence after the `ready` wait below covers this one too)
+          RAMA_GEMM_TR(kb, 7);
         }
         mbar_wait(bar_ready + 8 * s, ph);
         tc_fence_after();
+        RAMA_GEMM_TR(kb, 3);
         const uint32_t bh = d_lo32 + s * (SM::kStageBytes >> 4), bl = bh + (SM::kBBytes >> 4);
         const uint32_t a_hi = tmem_a + 64 * s, a_lo = a_hi + 32;
         // 8 tf32 = 32 bytes = 2 descriptor units inside the swizzle row; TMEM A: 8 columns per k-step
@@ -342,6 +349,7 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, c
         }
         umma_commit(bar_empty + 8 * s);  // smem stage + TMEM A stage reusable once these MMAs have read them
         if (last) umma_commit(bar_accfull + 8 * (ch & 1));
+        RAMA_GEMM_TR(kb, 4);
         if (++s == STAGES) { s = 0; ph ^= 1; }
         if (++in_ch == CH) { in_ch = 0; ++ch; }
       }
@@ -362,8 +370,10 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, c
     int drained = 0;
     auto drain = [&](int c) {  // acc += acc_tmem[c&1] (chunk c), then hand the buffer back
       const int b = c & 1;
+      if (quarter == 0 && lane == 0) RAMA_GEMM_TR(2 * c + half, 5);
       mbar_wait(bar_accfull + 8 * b, (c >> 1) & 1);
       tc_fence_after();
+      if (quarter == 0 && lane == 0) RAMA_GEMM_TR(2 * c + half, 6);
 #pragma unroll
       for (int j = 0; j < NSEG; ++j) {
         float v[32];
@@ -391,6 +401,7 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, c
     int next_end = min(CH, num_kb) - 1 + kLag;  // k-block after which chunk `drained` may be drained
     for (int kb = half; kb < num_kb; kb += 2) {
       mbar_wait(bar_full + 8 * s, ph);
+      if (quarter == 0 && lane == 0) RAMA_GEMM_TR(kb, 1);
       const uint8_t* st = gen_base + s * SM::kStageBytes;
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {  // the row in two halves of 16 floats
@@ -441,6 +452,7 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, c
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_ready + 8 * s);
+      if (quarter == 0 && lane == 0) RAMA_GEMM_TR(kb, 2);
       s += 2;
       if (s >= STAGES) { s -= STAGES; ph ^= 1; }
       // chunk c ends with k-block min((c+1)·CH, num_kb) − 1; drain it once this group is kLag blocks past it

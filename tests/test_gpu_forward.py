@@ -137,6 +137,27 @@ def test_llama7B_layer_shapes_greedy_and_long_positions():
     sess.close(); gpu.close()
 
 
+def test_long_context_attention_with_live_cache():
+    """Teacher-forced decode far into the context window with a LIVE KV cache: the cluster attention kernel folds
+    1, 2, 3, 4 passes per CTA (positions < 256, < 512, < 768, < 1024) and positions >= 1024 go back to the split-merge
+    kernel; logits vs the oracle at the boundaries of every regime."""
+    cfg, tensors, gpu, om = _pair("tiny-long")
+    os_, sess = ref.State(om), Session(gpu)
+    rng = np.random.default_rng(11)
+    toks = [1] + [int(t) for t in rng.integers(0, cfg.vocab_size, 1100)]
+    check = {0, 1, 31, 32, 33, 254, 255, 256, 257, 300, 511, 512, 513, 700, 767, 768, 1000, 1023, 1024, 1025, 1099}
+    worst = 0.0
+    for pos, tok in enumerate(toks[:1100]):
+        ref.forward(om, os_, tok, pos)
+        sess.forward(tok, pos)
+        if pos in check:
+            e = rel_err(sess.logits(), os_.logits)
+            worst = max(worst, e)
+            assert e < LOGIT_TOL, (pos, e)
+    assert rel_err(sess.to_cpu()["key_cache"], os_.key_cache) < 1e-4
+    sess.close(); gpu.close()
+
+
 def test_generate_edge_cases_and_errors():
     cfg, tensors, gpu, om = _pair("tiny")
     sess = Session(gpu)
