@@ -155,6 +155,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-prefill", action="store_true", help="skip the prompt-prefill (tensor core) measurement")
     ap.add_argument("--no-batched", action="store_true", help="skip the 64-sequence batched-decode measurement")
+    ap.add_argument("--no-small", action="store_true", help="skip the stories110M line (second model of BASELINE.json's metric)")
     ap.add_argument("--seed", type=int, default=1234)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -168,7 +169,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     workload = (f"{args.model} (dim {cfg.dim}, {cfg.n_layers} layers, {cfg.n_heads} heads, ffn {cfg.hidden_dim}, "
                 f"vocab {cfg.vocab_size}) f32 batch-1 greedy decode, {tokens} tokens per step, prompt 'once upon a time'")
-    auto_cpu_tokens = args.cpu_tokens or (8 if cfg.file_bytes() > (4 << 30) else min(tokens, 64 if cfg.dim > 512 else 256))
+    auto_cpu_tokens = args.cpu_tokens or (32 if cfg.file_bytes() > (4 << 30) else min(tokens, 64 if cfg.dim > 512 else 256))
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
@@ -334,6 +335,39 @@ def main():
             for s_ in bsess:
                 s_.close()
 
+    # ---- stories110M (the second model BASELINE.json's metric names; 1 GPU): device loop and host-driven e2e ----
+    small = None
+    if world == 1 and args.model == "llama2-7B" and not args.no_small:
+        scfg = ck.CONFIGS["stories110M"]
+        sgpu = GPU(local_rank)
+        sgpu.load_synthetic(scfg, spec)
+        ss = Session(sgpu)
+        for _ in range(args.warmup):
+            ss.generate(PROMPT, tokens, 0.0, 0.9)
+        torch.cuda.synchronize()
+        s_ms = sum(ss.generate(PROMPT, tokens, 0.0, 0.9)[1] for _ in range(args.steps))
+        def s_host_loop():
+            token = 1
+            for pos in range(tokens):
+                ss.forward(token, pos)
+                token = PROMPT[pos] if pos < len(PROMPT) else ss.sample(0.0, 0.9)
+            ss.sync()
+        s_host_loop()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            s_host_loop()
+        s_e2e = time.perf_counter() - t0
+        s_val = args.steps * tokens / (s_ms * 1e-3)
+        s_bytes = scfg.avg_bytes_per_token(tokens)
+        hbm_peak, _ = measured_peaks()
+        small = {"model": "stories110M (dim 768, 12 layers, 12 heads, seq 1024)", "value": round(s_val, 1), "unit": "tok/s",
+                 "e2e": round(args.steps * tokens / s_e2e, 1), "us_per_token": round(1e6 / s_val, 1),
+                 "launches_per_token": ss.launches_per_step(),
+                 "step_frac_of_hbm_roofline": round(s_bytes * s_val / 1e9 / hbm_peak, 4),
+                 "note": "438 MB of weights per token: the step is bound by the length of the kernel chain "
+                         "(launches_per_token dependent kernels), not by bytes"}
+        ss.close(); sgpu.close()
+
     # ---- per-kernel event timing (un-graphed) at a few positions: dominant-kernel roofline ----
     prof = {}
     for pos in sorted({0, tokens // 4, tokens // 2, 3 * tokens // 4, tokens - 1}):
@@ -410,6 +444,8 @@ def main():
                                  "peak_source": "half of the measured cuBLAS bf16 burst (tf32 runs at half the bf16 rate; "
                                                 "MEASURED_PEAKS.json has no tf32 figure)"}
         line["prefill"] = pf
+    if small is not None:
+        line["stories110M"] = small
     if bd is not None:
         bd["speedup_vs_batch1"] = round(bd["tok_per_s"] / value, 1)
         bd["hbm_frac_of_measured_peak"] = round(bd["hbm_gbs_algorithmic_per_gpu"] / peak, 4)

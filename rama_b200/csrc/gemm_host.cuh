@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -44,6 +45,7 @@ inline bool make_tmap_2d(CUtensorMap* m, const float* base, size_t rows, size_t 
            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+inline int g_gemm_pf_ahead = -1;  // RAMA_GEMM_PF (read once): k-blocks of L2 prefetch ahead of the ring when the A operand streams from HBM
 inline long long* g_gemm_trace = nullptr;  // debug: set by rama_debug_gemm_trace (device buffer [128][8]) or null
 
 struct GemmOperand {  // a K-major f32 matrix [rows][K], row pitch ld
@@ -75,7 +77,12 @@ cudaError_t launch_gemm_tf32x3(cudaStream_t st, const GemmOperand* A, int n_a, c
     if (!make_tmap_2d(&maps.a[i], a.p, a.rows, (size_t)K, a.ld, kGemmBM, BK)) return cudaErrorInvalidValue;
     if (!make_tmap_2d(&maps.b[i], b.p, b.rows, (size_t)K, b.ld, box_n, BK)) return cudaErrorInvalidValue;
   }
-  GemmShape shp{M, N, K, hi_round, ksplit, n_a > 1 ? 1 : 0, g_gemm_trace};
+  if (g_gemm_pf_ahead < 0) {
+    const char* v = getenv("RAMA_GEMM_PF");
+    g_gemm_pf_ahead = v && *v ? atoi(v) : 2;  // measured on B200 (batched-decode GEMMs, µs): 0 → 70.4/126.5/63.1, 2 → 66.6/119.1/59.8, 8 → 75.9/133.0/68.6
+  }
+  // only where A is the streamed operand (weights as the 128-row operand: BN = 64, batched decode)
+  GemmShape shp{M, N, K, hi_round, ksplit, n_a > 1 ? 1 : 0, BN == 64 ? g_gemm_pf_ahead : 0, g_gemm_trace};
   const int groups = Epi::kDual ? 1 : std::max(n_a, n_b);
   dim3 grid((M + kGemmBM - 1) / kGemmBM, (N + box_n - 1) / box_n, groups * ksplit);
   if (grid.y > 65535) return cudaErrorInvalidValue;

@@ -74,6 +74,10 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// L2 prefetch of one box (no shared-memory destination, no barrier): HBM → L2 ahead of the TMA load that will need it
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -171,6 +175,7 @@ struct GemmShape {
   int hi_round;    // 1: also rewrite the B tile's hi half rounded to nearest (default 0: raw tile = hi by truncation)
   int ksplit;      // split-K: blockIdx.z = group·ksplit + split; split s reduces k-blocks [s·nkb/ksplit, (s+1)·nkb/ksplit)
   int group_on_a;  // grouped launch: 1 = groups differ in the A operand (weights as A: batched decode), 0 = in B
+  int pf_ahead;    // > 0: the producer L2-prefetches the A box (weights streaming from HBM) this many k-blocks ahead
   long long* trace;  // debug (tools/gemm_trace.py): CTA (0,0,0) stamps clock64() per k-block and role, [128][8]; else nullptr
 };
 
@@ -284,7 +289,11 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, c
       const int nb0 = tile_n * kBoxN;
       int s = 0, kc = kb_begin * BK;
       uint32_t ph = 1, st = base, bf = bar_full, be = bar_empty;
+      if (shp.pf_ahead > 0)  // the first boxes beyond the ring
+        for (int j = STAGES; j < STAGES + shp.pf_ahead && j < num_kb; ++j) tma_prefetch_l2_2d(mapA, kc + j * BK, m0);
       for (int kb = 0; kb < num_kb; ++kb) {
+        if (shp.pf_ahead > 0 && kb + STAGES + shp.pf_ahead < num_kb)
+          tma_prefetch_l2_2d(mapA, kc + (STAGES + shp.pf_ahead) * BK, m0);
         mbar_wait(be, ph);
         RAMA_GEMM_TR(kb, 0);
         mbar_arrive_expect_tx(bf, SM::kTxBytes);
