@@ -96,6 +96,8 @@ CONFIGS: Dict[str, Config] = {
     "tiny-sep": Config(96, 256, 3, 2, 2, 300, 48, False),
     # long context at test size (head_size 32): every pass count of the cluster attention kernel and the split-merge kernel
     "tiny-long": Config(64, 176, 2, 2, 2, 512, 2048, True),
+    # per-SM weight slabs of 60-190 KB per kernel (what a rank of llama2-7B holds under TP = 4 / 8), 1 GPU
+    "mid-4layer": Config(1536, 4096, 4, 12, 12, 32000, 1024, False),
     # 7B layer shapes with 2 layers: exercises the 7B kernel configuration cheaply
     "l7-2layer": Config(4096, 11008, 2, 32, 32, 32000, 2048, False),
 }

@@ -136,6 +136,7 @@ struct rama_ctx {
   int variant_override = -1;
   int p2p = 0;  // TP exchange: 1 = fused peer-memory all-reduce (default), 0 = NCCL collectives
   int staged = 1;      // RAMA_GEMV_STAGED=0 disables the shared-memory-staged GEMV for small slabs
+  int stage_max_kb = 110;  // RAMA_GEMV_STAGE_KB: largest x + slab the staged GEMV takes (≤ 110: two CTAs per SM; ≤ 208: one)
   int attn_cluster = 1;  // RAMA_ATTN=split selects the global-memory split merge (attn_decode_kernel) at every context length
   int persistent = 0;  // RAMA_STEP=persistent: the decode step as one persistent cooperative kernel (step_kernel.cuh);
                        // default: one fused kernel per op group in a CUDA graph (measured faster)
@@ -242,7 +243,7 @@ static cudaError_t launch_gemv_staged(int grid, cudaStream_t st, int pdl, const 
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] {
-    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemvSmemStageMax);
+    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemvSmemStageMaxSolo);
   });
   if (attr_err != cudaSuccess) return attr_err;
   cudaLaunchConfig_t cfg{};
@@ -280,7 +281,7 @@ static cudaError_t launch_gemv(int variant, int grid, cudaStream_t st, int pdl, 
 
 static int pick_variant(const rama_ctx* c, int K4, int n_pairs = 0) {
   if (c->variant_override >= 0 && c->variant_override < kNumVariants) return c->variant_override;
-  if (c->staged && n_pairs > 0 && gemv_stage_bytes(K4, n_pairs, c->sm_count, 2) <= kGemvSmemStageMax &&
+  if (c->staged && n_pairs > 0 && gemv_stage_bytes(K4, n_pairs, c->sm_count, 2) <= (size_t)c->stage_max_kb * 1024 &&
       n_pairs >= c->sm_count)
     return kVariantStaged;
   if (K4 >= 1024) return 1;
@@ -335,6 +336,7 @@ extern "C" int rama_ctx_create(int device, const rama_tp* tp, rama_ctx** out) {
   c->use_pdl = env_int("RAMA_PDL", 1);
   c->variant_override = env_int("RAMA_GEMV_VARIANT", -1);
   c->staged = env_int("RAMA_GEMV_STAGED", 1);
+  c->stage_max_kb = std::max(0, std::min((int)(kGemvSmemStageMaxSolo / 1024), env_int("RAMA_GEMV_STAGE_KB", 110)));
   {
     const char* m = getenv("RAMA_ATTN");
     c->attn_cluster = !(m && strcmp(m, "split") == 0);

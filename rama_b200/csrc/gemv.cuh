@@ -539,7 +539,8 @@ __device__ __forceinline__ void gemv_cta_range(int n_pairs, int& p0, int& np) {
 // griddepcontrol.wait, and computes out of shared memory.  It is sized (≤ 64 registers, ≤ 110 KB of shared
 // memory) so that TWO such CTAs fit an SM: with programmatic dependent launch the next kernel of the graph is
 // resident and has its weights on chip while the current one is still finishing.
-constexpr size_t kGemvSmemStageMax = 110 * 1024;
+constexpr size_t kGemvSmemStageMax = 110 * 1024;       // two CTAs per SM below this
+constexpr size_t kGemvSmemStageMaxSolo = 208 * 1024;   // one CTA per SM: the slab still lands ahead of the dependency
 
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
