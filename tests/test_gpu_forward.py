@@ -194,6 +194,27 @@ def test_long_context_attention_with_live_cache():
     sess.close(); gpu.close()
 
 
+@pytest.mark.parametrize("env", [{"RAMA_ATTN": "split"}, {"RAMA_ATTN_WO": "1"}, {"RAMA_ATTN_WO": "2"}, {"RAMA_PDL": "0"},
+                                 {"RAMA_GEMV_STAGED": "0"}, {"RAMA_GEMV_STAGE_KB": "208"}])
+def test_kernel_variants_kept_as_options_agree_with_the_oracle(env, monkeypatch):
+    """Every measured alternative that stays selectable at run time is held to the same parity
+    bar as the default path: teacher-forced logits and the greedy stream on the tiny models."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)   # read at rama_ctx_create / rama_session_create
+    for name in ("tiny", "tiny-sep"):
+        cfg, tensors, gpu, om = _pair(name)
+        os_, sess = ref.State(om), Session(gpu)
+        rng = np.random.default_rng(3)
+        toks = [1] + [int(t) for t in rng.integers(0, cfg.vocab_size, cfg.seq_len - 1)]
+        for pos, tok in enumerate(toks):
+            ref.forward(om, os_, tok, pos)
+            sess.forward(tok, pos)
+            assert rel_err(sess.logits(), os_.logits) < LOGIT_TOL, (env, name, pos)
+        want, _, _, _ = ref.generate(om, ref.State(om), [5, 6], cfg.seq_len, 0.0, 0.9)
+        assert generate(sess, [5, 6], cfg.seq_len, 0.0, 0.9) == list(want), (env, name)
+        sess.close(); gpu.close()
+
+
 def test_generate_edge_cases_and_errors():
     cfg, tensors, gpu, om = _pair("tiny")
     sess = Session(gpu)
