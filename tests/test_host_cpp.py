@@ -14,6 +14,7 @@ from conftest import GOLDEN, ROOT
 HOST = os.path.join(ROOT, "rama_b200", "host")
 ENGINE = os.path.join(HOST, "engine")
 MIRROR = os.path.join(ROOT, "tests", "cpp", "host_mirror_test")
+SERVICE = os.path.join(ROOT, "tests", "cpp", "service_test")
 
 
 def _build():
@@ -23,7 +24,7 @@ def _build():
 
 def test_host_programs_build_and_link():
     _build()
-    assert os.access(ENGINE, os.X_OK) and os.access(MIRROR, os.X_OK)
+    assert os.access(ENGINE, os.X_OK) and os.access(MIRROR, os.X_OK) and os.access(SERVICE, os.X_OK)
     r = subprocess.run([ENGINE, "--help"], capture_output=True, text=True)   # no CUDA call before the arguments are valid
     assert r.returncode == 2 and "Usage: engine -m <MODEL> -t <TOKENIZER>" in r.stderr
     r = subprocess.run([ENGINE, "-m", "/nonexistent.bin", "-t", "/nonexistent.bin"], capture_output=True, text=True)
@@ -90,3 +91,35 @@ def test_engine_cli_prints_the_oracles_greedy_text(tmp_path):
             assert got == [int(t) for t in want], (extra, gap)
         else:   # a special piece in the stream: compare the text itself
             assert text == "".join("" if int(t) == 1 else pieces[int(t)] for t in want)
+
+
+def _letter_tokenizer(path, vocab_size):
+    """llama2.c tokenizer.bin (bpe.rs:27-43) whose pieces are the specials, the lower-case letters, the space, a few merges and
+    fillers: enough for Tokenizer::encode of plain prompts and a printable piece for every id the model may emit."""
+    # (not "<unk>" / "</s>": decode() of such a piece panics in the reference, bpe.rs:105-110, and ends that request)
+    pieces = ["[unk]", "<s>", "[/s]"] + [chr(ord("a") + i) for i in range(26)] + [" ", "th", "the", "on", "ce", "once", " a"]
+    pieces += [f"[{i}]" for i in range(len(pieces), vocab_size)]
+    scores = [0.0] * 3 + [-10.0] * 27 + [-1.0, -0.5, -2.0, -2.5, -0.8, -3.0] + [-20.0] * (vocab_size - 36)
+    with open(path, "wb") as f:
+        f.write(struct.pack("<I", max(len(p) for p in pieces)))
+        for p, sc in zip(pieces[:vocab_size], scores):
+            b = p.encode()
+            f.write(struct.pack("<fi", sc, len(b)) + b)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["ref_shared", "ref_untied"])
+@pytest.mark.parametrize("temperature", ["0.0", "0.8"])
+def test_engine_service_streams_equal_single_request_generate(tmp_path, name, temperature):
+    """EngineService (lib.rs) + get_batch (batcher.rs) in C++ over rama_forward_batch: 9 concurrent clients through 4 slots;
+    every stream equals generate() for its prompt, and the steps really were shared."""
+    from rama_b200 import checkpoint as ck
+    _build()
+    model = os.path.join(GOLDEN, name + ".bin")
+    cfg, _ = ck.read_checkpoint(model)
+    tok = tmp_path / "tokenizer.bin"
+    _letter_tokenizer(tok, cfg.vocab_size)
+    r = subprocess.run([SERVICE, model, str(tok), "9", "4", str(cfg.seq_len), temperature], capture_output=True, text=True,
+                       timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "service ok: 9 requests" in r.stdout
