@@ -2279,6 +2279,7 @@ extern "C" int rama_op_matmul_nt(rama_ctx* c, float* out, const float* a, const 
       case 2: e = launch_gemm_tf32x3<64, 4, 2, 0>(c->op_stream, &A, 1, &B, 1, m, n, k, hi_round, ksplit, epi); break;
       case 3: e = launch_gemm_tf32x3<64, 2, 2, 0>(c->op_stream, &A, 1, &B, 1, m, n, k, hi_round, ksplit, epi); break;  // 2 CTAs/SM
       case 4: e = launch_gemm_tf32x3<64, 2, 4, 0>(c->op_stream, &A, 1, &B, 1, m, n, k, hi_round, ksplit, epi); break;  // + 128-k chunks
+      case 5: e = launch_gemm_tf32x3<64, 2, 2, 0, 4>(c->op_stream, &A, 1, &B, 1, m, n, k, hi_round, ksplit, epi); break;  // decoupled A ring
       default: return fail(RAMA_E_INVALID, "matmul_nt: unknown transposed variant %d", variant);
     }
     if (ksplit > 1) {

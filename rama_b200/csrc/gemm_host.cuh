@@ -55,13 +55,13 @@ struct GemmOperand {  // a K-major f32 matrix [rows][K], row pitch ld
 
 // C (per group g) = A[ga] · B[gb]ᵀ.  n_a > 1: groups differ in A (weights as the 128-row operand, batched decode);
 // n_b > 1: groups differ in B (prefill QKV); a dual epilogue stacks B[0] on B[1] inside one tile.
-template <int BN, int STAGES, int CH, int NX, class Epi>
+template <int BN, int STAGES, int CH, int NX, int AS = 0, class Epi>
 cudaError_t launch_gemm_tf32x3(cudaStream_t st, const GemmOperand* A, int n_a, const GemmOperand* B, int n_b, int M,
                                int N, int K, int hi_round, int ksplit, const Epi& epi, bool pdl = false) {
-  using SM = GemmSmem<BN, STAGES, NX>;
+  using SM = GemmSmem<BN, STAGES, NX, AS>;
   constexpr int BK = kGemmBK;
   static_assert(SM::kTotal <= 227 * 1024, "tile does not fit shared memory");
-  auto kern = gemm_tf32x3_kernel<BN, STAGES, CH, NX, Epi>;
+  auto kern = gemm_tf32x3_kernel<BN, STAGES, CH, NX, Epi, AS>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal); });

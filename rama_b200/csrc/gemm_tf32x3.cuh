@@ -63,6 +63,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "}" ::"r"(bar), "r"(parity)
       : "memory");
 }
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {  // one non-blocking probe
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -181,19 +194,26 @@ struct GemmShape {
 
 constexpr int kGemmBK = 32;  // floats per k-block = one 128-byte swizzle row
 
-template <int BN, int STAGES, int NX = 0>
+// AS > 0 ("decoupled A ring", batched decode where the A operand = weights streams from HBM): the raw A k-blocks live in their
+// own ring of AS slots that a slot leaves as soon as the workers have split it into TMEM, while the B tile (raw + lo) and the TMEM
+// A slot keep the STAGES-deep ring that the MMAs release.  The long-latency HBM loads then run AS k-blocks ahead inside the same
+// shared-memory budget (AS = 4, STAGES = 2 at BN = 64: 64 + 32 KB = the 96 KB of two coupled 48 KB... stages).
+template <int BN, int STAGES, int NX = 0, int AS = 0>
 struct GemmSmem {
   static constexpr int kABytes = kGemmBM * kGemmBK * 4;         // raw A k-block (only the workers read it)
   static constexpr int kBBytes = BN * kGemmBK * 4;              // raw B k-block = hi operand
   static constexpr int kTxBytes = kABytes + kBBytes;
-  static constexpr int kStageBytes = kABytes + 2 * kBBytes;     // + B lo
-  static constexpr int kBarOff = STAGES * kStageBytes;
-  static constexpr int kNumBars = 3 * STAGES + 4;               // full/ready/empty per stage, accfull[2], accfree[2]
+  static constexpr int kStageBytes = AS > 0 ? 2 * kBBytes : kABytes + 2 * kBBytes;  // (+ B lo); coupled: A in front of B
+  static constexpr int kARingBytes = AS * kABytes;              // decoupled A ring in front of the stages
+  static constexpr int kBOff = AS > 0 ? 0 : kABytes;            // B hi inside a stage
+  static constexpr int kBarOff = kARingBytes + STAGES * kStageBytes;
+  static constexpr int kNumBars = 3 * STAGES + 4 + 2 * AS;      // full/ready/empty per stage, accfull[2], accfree[2], a_full/a_empty[AS]
   static constexpr int kTotal = kBarOff + kNumBars * 8 + 16 + 1024 /* alignment slack */;
   // TMEM: [0,BN) acc 0 | [BN,2BN) acc 1 | NX cross-term accumulators | then per stage 32 columns A hi + 32 columns A lo
   static constexpr int kAccCols = (2 + NX) * BN;
   static constexpr int kTmemNeed = kAccCols + 64 * STAGES;
   static_assert(kTmemNeed <= 512, "accumulators + A stages exceed tensor memory");
+  static_assert(AS % 2 == 0, "the two worker groups alternate k-blocks: an A slot must always belong to the same group");
   static constexpr int kTmemCols = kTmemNeed <= 128 ? 128 : (kTmemNeed <= 256 ? 256 : 512);  // power of two
   // two CTAs per SM when both shared memory and tensor memory allow it: their pipelines interleave
   static constexpr int kCtasPerSm = (kTmemCols <= 256 && 2 * kTotal <= 226 * 1024) ? 2 : 1;
@@ -221,10 +241,10 @@ struct GemmSmem {
 // where m is the global row, n the first global column of the 32-column chunk; the whole warp calls it
 // (valid = m < M) so an epilogue may shuffle between rows.
 
-template <int BN, int STAGES, int CH, int NX, class Epi>
-__global__ void __launch_bounds__(kGemmThreads, (GemmSmem<BN, STAGES, NX>::kCtasPerSm))
+template <int BN, int STAGES, int CH, int NX, class Epi, int AS = 0>
+__global__ void __launch_bounds__(kGemmThreads, (GemmSmem<BN, STAGES, NX, AS>::kCtasPerSm))
 gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, const Epi epi_in) {
-  using SM = GemmSmem<BN, STAGES, NX>;
+  using SM = GemmSmem<BN, STAGES, NX, AS>;
   constexpr int BK = kGemmBK;
   static_assert(BN == 64 || BN == 128, "BN");
   // the two worker groups take alternate k-blocks: with an even stage count a stage always belongs to the same group,
@@ -239,7 +259,10 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, c
   const uint32_t bar_empty = bar_ready + 8 * STAGES;       // [STAGES] MMAs finished reading
   const uint32_t bar_accfull = bar_empty + 8 * STAGES;     // [2] chunk accumulated in acc[b]
   const uint32_t bar_accfree = bar_accfull + 16;           // [2] acc[b] drained into registers
-  const uint32_t tmem_slot = bar_accfree + 16;
+  const uint32_t bar_afull = bar_accfree + 16;             // [AS] raw A k-block landed            (decoupled A ring only)
+  const uint32_t bar_aempty = bar_afull + 8 * AS;          // [AS] the group's four warps have read it
+  const uint32_t tmem_slot = bar_aempty + 8 * AS;
+  const uint32_t stage0 = base + SM::kARingBytes;          // first (B) stage
   uint8_t* gen_base = gemm_smem_raw + (base - smem_u32(gemm_smem_raw));
 
   pdl_launch_dependents();  // (no-ops unless launched with programmatic stream serialization)
@@ -272,6 +295,10 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, c
       mbar_init(bar_accfull + 8 * b, 1);
       mbar_init(bar_accfree + 8 * b, kGemmWorkerWarps);
     }
+    for (int a = 0; a < AS; ++a) {
+      mbar_init(bar_afull + 8 * a, 1);
+      mbar_init(bar_aempty + 8 * a, kGemmWorkerWarps / 2);
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<SM::kTmemCols>(tmem_slot);
@@ -285,6 +312,38 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, c
   if (warp == 0) {
     // ===== TMA producer =====
     // (the role loops are single threads on the critical path of a k-block: running counters, no divisions)
+    if constexpr (AS > 0) {
+      // two independent rings fed by one polling thread: A (weights, HBM latency) runs up to AS k-blocks ahead and is gated by
+      // the workers; B (activations, L2) is gated by the MMAs like a coupled stage
+      if (lane == 0) {
+        static_assert(!Epi::kDual || AS == 0, "decoupled A ring: plain B boxes only");
+        const int nb0 = tile_n * kBoxN;
+        int ka = 0, kbb = 0;
+        if (shp.pf_ahead > 0)
+          for (int j = AS; j < AS + shp.pf_ahead && j < num_kb; ++j) tma_prefetch_l2_2d(mapA, (kb_begin + j) * BK, m0);
+        while (ka < num_kb || kbb < num_kb) {
+          if (ka < num_kb) {
+            const int sa = ka % AS;
+            if (mbar_try(bar_aempty + 8 * sa, ((ka / AS) & 1) ^ 1)) {
+              if (shp.pf_ahead > 0 && ka + AS + shp.pf_ahead < num_kb)
+                tma_prefetch_l2_2d(mapA, (kb_begin + ka + AS + shp.pf_ahead) * BK, m0);
+              RAMA_GEMM_TR(ka, 0);
+              mbar_arrive_expect_tx(bar_afull + 8 * sa, SM::kABytes);
+              tma_load_2d(base + sa * SM::kABytes, mapA, bar_afull + 8 * sa, (kb_begin + ka) * BK, m0);
+              ++ka;
+            }
+          }
+          if (kbb < num_kb) {
+            const int sb = kbb % STAGES;
+            if (mbar_try(bar_empty + 8 * sb, ((kbb / STAGES) & 1) ^ 1)) {
+              mbar_arrive_expect_tx(bar_full + 8 * sb, SM::kBBytes);
+              tma_load_2d(stage0 + sb * SM::kStageBytes, mapB0, bar_full + 8 * sb, (kb_begin + kbb) * BK, nb0);
+              ++kbb;
+            }
+          }
+        }
+      }
+    } else
     if (lane == 0) {
       const int nb0 = tile_n * kBoxN;
       int s = 0, kc = kb_begin * BK;
@@ -314,7 +373,7 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, c
     // (constant high word, base low word + a small offset) — one 32-bit add per operand.
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_tf32<BN>();
-      const uint64_t d0 = umma_smem_desc<BK>(base + SM::kABytes);  // B hi of stage 0, k-step 0
+      const uint64_t d0 = umma_smem_desc<BK>(stage0 + SM::kBOff);  // B hi of stage 0, k-step 0
       const uint32_t d_hi32 = (uint32_t)(d0 >> 32), d_lo32 = (uint32_t)d0;
       auto desc = [&](uint32_t lo) { return ((uint64_t)d_hi32 << 32) | lo; };
       int s = 0, ch = 0, in_ch = 0;
@@ -409,16 +468,22 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, c
     uint32_t ph = 0;
     int next_end = min(CH, num_kb) - 1 + kLag;  // k-block after which chunk `drained` may be drained
     for (int kb = half; kb < num_kb; kb += 2) {
-      mbar_wait(bar_full + 8 * s, ph);
+      mbar_wait(bar_full + 8 * s, ph);  // (decoupled: the B tile — and with it the TMEM A slot, freed by the same MMAs)
+      const uint8_t* st = gen_base + SM::kARingBytes + s * SM::kStageBytes;
+      const uint8_t* sta = st;          // raw A k-block
+      if constexpr (AS > 0) {
+        const int sa = kb % AS;
+        mbar_wait(bar_afull + 8 * sa, (kb / AS) & 1);
+        sta = gen_base + sa * SM::kABytes;
+      }
       if (quarter == 0 && lane == 0) RAMA_GEMM_TR(kb, 1);
-      const uint8_t* st = gen_base + s * SM::kStageBytes;
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {  // the row in two halves of 16 floats
         uint32_t hi[16], lo[16];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const int chunk = 4 * hh + c;
-          const float4 a = *reinterpret_cast<const float4*>(st + arow_off + ((chunk ^ (arow & 7)) << 4));
+          const float4 a = *reinterpret_cast<const float4*>(sta + arow_off + ((chunk ^ (arow & 7)) << 4));
           const float av[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
@@ -432,10 +497,14 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, c
         tmem_st_32x16(ta, hi);
         tmem_st_32x16(ta + 32, lo);
       }
+      if constexpr (AS > 0) {  // the raw A slot is in registers / on its way to TMEM: hand it back to the producer
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_aempty + 8 * (kb % AS));
+      }
       {
-        const float4* braw = reinterpret_cast<const float4*>(st + SM::kABytes);
-        float4* bhi = reinterpret_cast<float4*>(const_cast<uint8_t*>(st) + SM::kABytes);
-        float4* blo = reinterpret_cast<float4*>(const_cast<uint8_t*>(st) + SM::kABytes + SM::kBBytes);
+        const float4* braw = reinterpret_cast<const float4*>(st + SM::kBOff);
+        float4* bhi = reinterpret_cast<float4*>(const_cast<uint8_t*>(st) + SM::kBOff);
+        float4* blo = reinterpret_cast<float4*>(const_cast<uint8_t*>(st) + SM::kBOff + SM::kBBytes);
 #pragma unroll
         for (int i = gt; i < kBVec; i += kGroupThreads) {
           const float4 a = braw[i];

@@ -47,7 +47,7 @@ def test_matmul_nt_f32_accuracy(gpu, shape, variant):
     assert err < max(8 * ref_err, 6e-6), (err, ref_err)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
 @pytest.mark.parametrize("shape", [(4096, 64, 4096), (11008, 64, 4096), (4096, 64, 11008), (288, 3, 288), (1000, 17, 64)])
 def test_matmul_nt_transposed_store(gpu, shape, variant):
     M, N, K = shape
