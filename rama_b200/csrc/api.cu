@@ -1530,6 +1530,7 @@ constexpr int kPrefillChunk = 512;
 static int ensure_prefill_ws(rama_session* s) {
   if (s->pf_cap) return RAMA_OK;
   rama_ctx* c = s->ctx;
+  std::lock_guard<std::mutex> cap_lk(c->cap_mu);  // allocations vs another thread's stream capture (rama_ctx::cap_mu)
   const size_t cap = std::min(c->T, kPrefillChunk);
   cudaError_t e = cudaSuccess;
 #define A(call) if (e == cudaSuccess) e = (call)

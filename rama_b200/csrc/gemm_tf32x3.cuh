@@ -573,6 +573,8 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, c
   }
 }
 
+#undef RAMA_GEMM_TR
+
 // ---- epilogues ------------------------------------------------------------------------------------------
 
 // C[m][n] row-major with leading dimension ldc (per group: base + group·group_stride)
