@@ -136,6 +136,7 @@ struct rama_ctx {
   int variant_override = -1;
   int p2p = 0;  // TP exchange: 1 = fused peer-memory all-reduce (default), 0 = NCCL collectives
   int staged = 1;      // RAMA_GEMV_STAGED=0 disables the shared-memory-staged GEMV for small slabs
+  int embed_kernel = 1;  // RAMA_EMBED_KERNEL=0: fold the embedding gather into the layer-0 QKV prologue (ProNorm::emb)
   int stage_max_kb = 110;  // RAMA_GEMV_STAGE_KB: largest x + slab the staged GEMV takes (≤ 110: two CTAs per SM; ≤ 208: one)
   int attn_cluster = 1;  // RAMA_ATTN=split selects the global-memory split merge (attn_decode_kernel) at every context length
   int persistent = 0;  // RAMA_STEP=persistent: the decode step as one persistent cooperative kernel (step_kernel.cuh);
@@ -336,6 +337,7 @@ extern "C" int rama_ctx_create(int device, const rama_tp* tp, rama_ctx** out) {
   c->use_pdl = env_int("RAMA_PDL", 1);
   c->variant_override = env_int("RAMA_GEMV_VARIANT", -1);
   c->staged = env_int("RAMA_GEMV_STAGED", 1);
+  c->embed_kernel = env_int("RAMA_EMBED_KERNEL", 1);  // the fold measured +0.3 % (stories15M 10173 → 10201 tok/s): a tiny kernel in a PDL chain is almost free
   c->stage_max_kb = std::max(0, std::min((int)(kGemvSmemStageMaxSolo / 1024), env_int("RAMA_GEMV_STAGE_KB", 110)));
   {
     const char* m = getenv("RAMA_ATTN");
@@ -1063,9 +1065,11 @@ static int enqueue_step(rama_session* s, cudaStream_t st, int mode, StepTrace* t
   // contexts below 1024 positions: the splits of a head merge inside a thread-block cluster (attention.cuh)
   const bool attn_cluster = c->attn_cluster && !fuse_attn_wo && !s->keep_att && s->attn_bk < 2;
 
-  // x0 ← embedding row of ctrl->token (infer.rs:13)
-  q.pre(RAMA_K_EMBED);
-  {
+  // x ← embedding row of ctrl->token (infer.rs:13): a gather kernel of its own, or (RAMA_EMBED_KERNEL=0) folded into the
+  // layer-0 QKV prologue (ProNorm::emb)
+  const bool embed_kernel = c->embed_kernel != 0;
+  if (embed_kernel) {
+    q.pre(RAMA_K_EMBED);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(std::max(1, std::min(8, D / 4 / 256)));
     cfg.blockDim = dim3(256);
@@ -1083,6 +1087,7 @@ static int enqueue_step(rama_session* s, cudaStream_t st, int mode, StepTrace* t
     // ---- rmsnorm → [wq|wk|wv] → RoPE → KV write (infer.rs:19-33) ----
     {
       ProNorm pro{s->x0, l == 0 ? nullptr : s->w2out, s->x1, W[RAMA_T_RMS_ATT] + (size_t)l * D, nullptr, peer_in(s, 1, l - 1)};
+      if (l == 0 && !embed_kernel) { pro.emb = W[RAMA_T_TOKEN_EMBEDDING]; pro.ctrl = s->ctrl; pro.seq = s->seq; pro.vocab = c->V; }
       RowsQKV rows{W[RAMA_T_WQ] + (size_t)l * Dq * D, W[RAMA_T_WK] + (size_t)l * Dq * D,
                    W[RAMA_T_WV] + (size_t)l * Dq * D, D, Dq / 2};
       EpiQKV epi{s->q, s->k, s->v, s->key_cache + (size_t)l * T * Dq, s->value_cache + (size_t)l * T * Dq,
@@ -1290,7 +1295,7 @@ extern "C" int rama_session_launches_per_step(const rama_session* s, int* n) {
   if (s->persistent) { *n = 1; return RAMA_OK; }  // the whole greedy step is one persistent cooperative launch
   // embed + L·(qkv, attn, wo, w13, w2) + cls + sample (+ collectives under TP); attention + wo are one launch
   // for the small models at positions < 256
-  *n = 1 + (s->wo_part ? 4 : 5) * c->L + 1 + 1 + (c->world > 1 && !s->p2p ? 2 * c->L + 1 : 0);
+  *n = (c->embed_kernel ? 1 : 0) + (s->wo_part ? 4 : 5) * c->L + 1 + 1 + (c->world > 1 && !s->p2p ? 2 * c->L + 1 : 0);
   return RAMA_OK;
 }
 

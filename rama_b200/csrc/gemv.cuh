@@ -93,6 +93,12 @@ struct ProNorm {
   PeerIn pin;          // pin.P > 0: the pending contribution is the sum of P peer partials instead of `add`
   int n_add = 1;       // > 1: `add` holds n_add partial vectors (per-head wo partials of attn_wo_kernel), stride K floats,
   float* add_out = nullptr;  //      summed in index order; CTA 0 stores the sum here (RunState.xb2)
+  // First kernel of a step (layer 0): the residual stream starts as the embedding row of ctrl->token (infer.rs:13) — the gather
+  // is this prologue's load instead of a kernel of its own; CTA 0 also validates the token and bumps the step counter.
+  const float* emb = nullptr;  // token_embedding_table, or null
+  StepCtrl* ctrl = nullptr;
+  unsigned* seq = nullptr;     // step counter: epoch source of the TP exchange
+  int vocab = 0;
   // The norm weights never depend on the previous kernel: the first N float4 per thread are loaded BEFORE
   // griddepcontrol.wait (one L2 round trip off the critical path of every norm-prologue kernel).
   template <int N>
@@ -110,7 +116,17 @@ struct ProNorm {
   }
   template <int N>
   __device__ __forceinline__ void operator()(float4* xs, int K4, float* red, const Pre<N>& pre) const {
-    const float4* x4 = reinterpret_cast<const float4*>(xin);
+    const float* xsrc = xin;
+    if (emb) {
+      int token = ctrl->token;
+      if (token < 0 || token >= vocab) {  // the reference would panic on the slice (infer.rs:13)
+        if (threadIdx.x == 0 && blockIdx.x == 0) ctrl->error = 1;
+        token = 0;
+      }
+      if (threadIdx.x == 0 && blockIdx.x == 0) *seq += 1u;
+      xsrc = emb + (size_t)token * (size_t)(K4 * 4);
+    }
+    const float4* x4 = reinterpret_cast<const float4*>(xsrc);
     const float4* a4 = reinterpret_cast<const float4*>(add);
     const bool peers = pin.P > 0 && add != nullptr;
     const unsigned ep = peers ? pin.epoch() : 0u;

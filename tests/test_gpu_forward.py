@@ -195,7 +195,7 @@ def test_long_context_attention_with_live_cache():
 
 
 @pytest.mark.parametrize("env", [{"RAMA_ATTN": "split"}, {"RAMA_ATTN_WO": "1"}, {"RAMA_ATTN_WO": "2"}, {"RAMA_PDL": "0"},
-                                 {"RAMA_GEMV_STAGED": "0"}, {"RAMA_GEMV_STAGE_KB": "208"}])
+                                 {"RAMA_GEMV_STAGED": "0"}, {"RAMA_GEMV_STAGE_KB": "208"}, {"RAMA_EMBED_KERNEL": "0"}])
 def test_kernel_variants_kept_as_options_agree_with_the_oracle(env, monkeypatch):
     """Every measured alternative that stays selectable at run time is held to the same parity
     bar as the default path: teacher-forced logits and the greedy stream on the tiny models."""
