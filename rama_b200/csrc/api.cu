@@ -1530,6 +1530,24 @@ extern "C" int rama_state_to_host(rama_session* s, int buf, float* dst, size_t n
 // ------------------------------------------------------------------------------------------------
 // prompt prefill (tensor cores): ≙ the prompt part of generate()'s loop, mod.rs:187-192
 // ------------------------------------------------------------------------------------------------
+// kernel launch with the programmatic-stream-serialization attribute (PDL): the next kernel's CTAs start while this one
+// drains; every kernel of the batched step executes griddepcontrol.wait before it touches memory (batch.cuh)
+template <class... P, class... A>
+static cudaError_t launch_k(bool pdl, void (*kern)(P...), dim3 grid, dim3 block, cudaStream_t st, A&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  if (pdl) {
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+  }
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<A>(args)...);
+}
+
 constexpr int kPrefillChunk = 512;
 
 static int ensure_prefill_ws(rama_session* s) {
@@ -1595,7 +1613,10 @@ static int prefill_chunk(rama_session* s, const int32_t* tokens, int M, int pos0
   } while (0)
   CK(cudaMemcpyAsync(s->pf_tokens, tokens, (size_t)M * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   tr.pre(RAMA_PK_OTHER);
-  prefill_embed_kernel<<<M, 256, 0, st>>>(s->pf_tokens, W[RAMA_T_TOKEN_EMBEDDING], s->pf_x, D, c->V, &s->ctrl->error, s->seq);
+  // programmatic dependent launch along the whole chain (not while per-launch events are being recorded)
+  const bool pdl = c->use_pdl && !tr.on && env_int("RAMA_PREFILL_PDL", 1);
+  CK(launch_k(pdl, prefill_embed_kernel, dim3(M), dim3(256), st, (const int32_t*)s->pf_tokens, W[RAMA_T_TOKEN_EMBEDDING], s->pf_x, D, c->V,
+              &s->ctrl->error, s->seq));
   tr.post(); ++launches;
   CK(cudaGetLastError());
   for (int l = 0; l < L; ++l) {
@@ -1603,7 +1624,8 @@ static int prefill_chunk(rama_session* s, const int32_t* tokens, int M, int pos0
     float* vc = s->value_cache + (size_t)l * T * Dq;
     // x += pending w2 output; xn = rmsnorm(x)·w_att   (infer.rs:19)
     tr.pre(RAMA_PK_NORM);
-    prefill_addnorm_kernel<<<M, 256, 0, st>>>(s->pf_x, l == 0 ? nullptr : s->pf_y, W[RAMA_T_RMS_ATT] + (size_t)l * D, s->pf_xn, D);
+    CK(launch_k(pdl, prefill_addnorm_kernel, dim3(M), dim3(256), st, s->pf_x, (const float*)(l == 0 ? nullptr : s->pf_y),
+                W[RAMA_T_RMS_ATT] + (size_t)l * D, s->pf_xn, D));
     tr.post(); ++launches;
     // [wq;wk;wv] → RoPE → Q, KV-cache rows   (infer.rs:20-33)
     {
@@ -1612,7 +1634,7 @@ static int prefill_chunk(rama_session* s, const int32_t* tokens, int M, int pos0
                           {W[RAMA_T_WK] + (size_t)l * Dq * D, (size_t)Dq, (size_t)D},
                           {W[RAMA_T_WV] + (size_t)l * Dq * D, (size_t)Dq, (size_t)D}};
       EpiQKVPrefill epi{s->pf_q, kc, vc, W[RAMA_T_FREQ_REAL], W[RAMA_T_FREQ_IMAG], pos0, Dq, hs / 2};
-      GK(RAMA_PK_GEMM, (launch_gemm_tf32x3<128, 4, 4, 0>(st, &A, 1, B, 3, M, Dq, D, 0, 1, epi)));
+      GK(RAMA_PK_GEMM, (launch_gemm_tf32x3<128, 4, 4, 0>(st, &A, 1, B, 3, M, Dq, D, 0, 1, epi, pdl)));
     }
     // causal attention of every prompt row over the cache   (infer.rs:34)
     {
@@ -1620,10 +1642,24 @@ static int prefill_chunk(rama_session* s, const int32_t* tokens, int M, int pos0
       tr.pre(RAMA_PK_ATTN);
       // 64-query blocks when that still fills the machine, else 16-query blocks (few heads per rank, short prompts)
       const int nq64 = (M + 63) / 64, nq16 = (M + 15) / 16;
-      if (((nq64 + 1) / 2) * c->Hl >= 96)
-        prefill_attn_kernel<4><<<dim3((nq64 + 1) / 2, c->Hl), kPfThreads, prefill_attn_smem_bytes(hs, 4), st>>>(ap);
-      else
-        prefill_attn_kernel<1><<<dim3((nq16 + 1) / 2, c->Hl), kPfThreads, prefill_attn_smem_bytes(hs, 1), st>>>(ap);
+      cudaLaunchConfig_t cfg{};
+      cfg.blockDim = dim3(kPfThreads);
+      cfg.stream = st;
+      cudaLaunchAttribute at[1];
+      if (pdl) {
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+      }
+      if (((nq64 + 1) / 2) * c->Hl >= 96) {
+        cfg.gridDim = dim3((nq64 + 1) / 2, c->Hl);
+        cfg.dynamicSmemBytes = prefill_attn_smem_bytes(hs, 4);
+        CK(cudaLaunchKernelEx(&cfg, prefill_attn_kernel<4>, ap));
+      } else {
+        cfg.gridDim = dim3((nq16 + 1) / 2, c->Hl);
+        cfg.dynamicSmemBytes = prefill_attn_smem_bytes(hs, 1);
+        CK(cudaLaunchKernelEx(&cfg, prefill_attn_kernel<1>, ap));
+      }
       tr.post(); ++launches;
     }
     // wo   (infer.rs:35); the residual add is the next addnorm
@@ -1631,7 +1667,7 @@ static int prefill_chunk(rama_session* s, const int32_t* tokens, int M, int pos0
       GemmOperand A{s->pf_att, (size_t)M, (size_t)Dq};
       GemmOperand B{W[RAMA_T_WO] + (size_t)l * D * Dq, (size_t)D, (size_t)Dq};
       EpiStoreNT epi{s->pf_y, D, D, 0};
-      GK(RAMA_PK_GEMM, (launch_gemm_tf32x3<128, 4, 4, 0>(st, &A, 1, &B, 1, M, D, Dq, 0, 1, epi)));
+      GK(RAMA_PK_GEMM, (launch_gemm_tf32x3<128, 4, 4, 0>(st, &A, 1, &B, 1, M, D, Dq, 0, 1, epi, pdl)));
     }
     if (c->world > 1) {
       tr.pre(RAMA_PK_COMM);
@@ -1639,7 +1675,8 @@ static int prefill_chunk(rama_session* s, const int32_t* tokens, int M, int pos0
       tr.post(); ++launches;
     }
     tr.pre(RAMA_PK_NORM);
-    prefill_addnorm_kernel<<<M, 256, 0, st>>>(s->pf_x, s->pf_y, W[RAMA_T_RMS_FFN] + (size_t)l * D, s->pf_xn, D);
+    CK(launch_k(pdl, prefill_addnorm_kernel, dim3(M), dim3(256), st, s->pf_x, (const float*)s->pf_y, W[RAMA_T_RMS_FFN] + (size_t)l * D,
+                s->pf_xn, D));
     tr.post(); ++launches;
     // [w1|w3] → SwiGLU   (infer.rs:39-45)
     {
@@ -1647,14 +1684,14 @@ static int prefill_chunk(rama_session* s, const int32_t* tokens, int M, int pos0
       GemmOperand B[2] = {{W[RAMA_T_W1] + (size_t)l * Fl * D, (size_t)Fl, (size_t)D},
                           {W[RAMA_T_W3] + (size_t)l * Fl * D, (size_t)Fl, (size_t)D}};
       EpiSwiGLUPrefill epi{s->pf_h, Fl};
-      GK(RAMA_PK_GEMM, (launch_gemm_tf32x3<128, 4, 4, 0>(st, &A, 1, B, 2, M, Fl, D, 0, 1, epi)));
+      GK(RAMA_PK_GEMM, (launch_gemm_tf32x3<128, 4, 4, 0>(st, &A, 1, B, 2, M, Fl, D, 0, 1, epi, pdl)));
     }
     // w2   (infer.rs:46)
     {
       GemmOperand A{s->pf_h, (size_t)M, (size_t)Fl};
       GemmOperand B{W[RAMA_T_W2] + (size_t)l * D * Fl, (size_t)D, (size_t)Fl};
       EpiStoreNT epi{s->pf_y, D, D, 0};
-      GK(RAMA_PK_GEMM, (launch_gemm_tf32x3<128, 4, 4, 0>(st, &A, 1, &B, 1, M, D, Fl, 0, 1, epi)));
+      GK(RAMA_PK_GEMM, (launch_gemm_tf32x3<128, 4, 4, 0>(st, &A, 1, &B, 1, M, D, Fl, 0, 1, epi, pdl)));
     }
     if (c->world > 1) {
       tr.pre(RAMA_PK_COMM);
@@ -1667,7 +1704,8 @@ static int prefill_chunk(rama_session* s, const int32_t* tokens, int M, int pos0
     // only the last row's logits exist after the reference's prompt loop: x0 = x + y of that row, then the
     // decode path's fused final-rmsnorm → classifier GEMV (infer.rs:49-51)
     tr.pre(RAMA_PK_OTHER);
-    prefill_last_row_kernel<<<std::max(1, D / 256), 256, 0, st>>>(s->pf_x + (size_t)(M - 1) * D, s->pf_y + (size_t)(M - 1) * D, s->x0, D);
+    CK(launch_k(pdl, prefill_last_row_kernel, dim3(std::max(1, D / 256)), dim3(256), st, (const float*)(s->pf_x + (size_t)(M - 1) * D),
+                (const float*)(s->pf_y + (size_t)(M - 1) * D), s->x0, D));
     tr.post(); ++launches;
     RK(init_parts(s));
     ProNorm pro{s->x0, nullptr, s->x1, W[RAMA_T_RMS_FINAL], s->xfinal, PeerIn{}};
@@ -1848,24 +1886,6 @@ extern "C" int rama_batch_destroy(rama_batch* b) {
 
 // enqueue one batched step for n sequences (everything per-sequence is read from b->d_seqs on the device,
 // so the captured graph of a batch size serves every step)
-// kernel launch with the programmatic-stream-serialization attribute (PDL): the next kernel's CTAs start while this one
-// drains; every kernel of the batched step executes griddepcontrol.wait before it touches memory (batch.cuh)
-template <class... P, class... A>
-static cudaError_t launch_k(bool pdl, void (*kern)(P...), dim3 grid, dim3 block, cudaStream_t st, A&&... args) {
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = grid;
-  cfg.blockDim = block;
-  cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  if (pdl) {
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-  }
-  return cudaLaunchKernelEx(&cfg, kern, std::forward<A>(args)...);
-}
-
 static int enqueue_batch_step(rama_batch* b, int n, int* n_launch) {
   rama_ctx* c = b->ctx;
   cudaStream_t st = b->stream;

@@ -17,6 +17,7 @@ namespace rama {
 __global__ void __launch_bounds__(256) prefill_embed_kernel(const int32_t* __restrict__ tokens, const float* __restrict__ emb,
                                                             float* __restrict__ x, int D, int vocab, int32_t* error,
                                                             unsigned* seq) {
+  pdl_launch_dependents(); pdl_wait();  // (no-ops unless launched with programmatic stream serialization)
   const int m = blockIdx.x;
   if (m == 0 && threadIdx.x == 0 && seq) *seq += 1u;  // one "step" for the TP exchange epochs (see step_begin_kernel)
   int token = tokens[m];
@@ -33,6 +34,7 @@ __global__ void __launch_bounds__(256) prefill_embed_kernel(const int32_t* __res
 // one CTA per row; ≙ array_add (cpu.rs:16-21) folded in front of rmsnorm (cpu.rs:99-117)
 __global__ void __launch_bounds__(256) prefill_addnorm_kernel(float* __restrict__ x, const float* __restrict__ y,
                                                               const float* __restrict__ w, float* __restrict__ xn, int D) {
+  pdl_launch_dependents(); pdl_wait();  // (no-ops unless launched with programmatic stream serialization)
   __shared__ float red[2 * kWarp];
   const int m = blockIdx.x;
   float4* xr = reinterpret_cast<float4*>(x + (size_t)m * D);
@@ -148,6 +150,7 @@ __host__ __device__ inline size_t prefill_attn_smem_bytes(int hs, int rq) {
 
 template <int RQ>
 __global__ void __launch_bounds__(kPfThreads) prefill_attn_kernel(const PrefillAttnParams p) {
+  pdl_launch_dependents(); pdl_wait();  // (no-ops unless launched with programmatic stream serialization)
   constexpr int kPfBQ = pf_bq(RQ);
   extern __shared__ __align__(16) float pf_smem[];
   const int hs = p.hs, ldq = hs + 4;
@@ -290,6 +293,7 @@ __global__ void __launch_bounds__(kPfThreads) prefill_attn_kernel(const PrefillA
 // last prompt row → the decode path's residual buffer: x0 = x[M-1] + y[M-1]
 __global__ void prefill_last_row_kernel(const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ x0,
                                         int D) {
+  pdl_launch_dependents(); pdl_wait();  // (no-ops unless launched with programmatic stream serialization)
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < D; i += gridDim.x * blockDim.x) x0[i] = x[i] + y[i];
 }
 
