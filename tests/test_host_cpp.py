@@ -31,6 +31,14 @@ def test_host_programs_build_and_link():
     assert r.returncode == 101 and "panicked" in r.stderr                     # File::open(path).unwrap()
 
 
+def test_host_mirror_pure_host_logic():
+    """Config::from_file, absolute-range views, from_file sizes + wcls alias, bounded channel, get_batch — no CUDA call."""
+    _build()
+    r = subprocess.run([os.path.join(ROOT, "tests", "cpp", "host_units_test"), os.path.join(GOLDEN, "ref_shared.bin"),
+                        os.path.join(GOLDEN, "ref_untied.bin")], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and "host units ok" in r.stdout, r.stdout + r.stderr
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["ref_shared", "ref_untied"])
 @pytest.mark.parametrize("mode", ["fused", "per-op"])
