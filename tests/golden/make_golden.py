@@ -33,6 +33,10 @@ CASES = {
                         max_seq_len=24), True, 11, 24),
     "ref_untied": (dict(dim=48, n_layers=3, n_heads=4, vocab_size=64, hidden_dim=None, multiple_of=16,
                         max_seq_len=20), False, 12, 20),
+    # stories15M's head geometry (head_size 48: 12 of 32 lanes per K/V row) and a context that spans three 32-timestep
+    # attention chunks — pins RoPE at hs/2 = 24 and the chunked flash-decode kernels against the reference's torch attention
+    "ref_hs48": (dict(dim=96, n_layers=2, n_heads=2, vocab_size=128, hidden_dim=128, multiple_of=8,
+                      max_seq_len=72), True, 13, 72),
 }
 
 
@@ -60,5 +64,7 @@ def make(name, kw, shared, seed, n_tok):
 
 
 if __name__ == "__main__":
+    # python make_golden.py [case ...]   (no argument: every case; committed fixtures are only rewritten on purpose)
     for name, (kw, shared, seed, n) in CASES.items():
-        make(name, kw, shared, seed, n)
+        if len(sys.argv) == 1 or name in sys.argv[1:]:
+            make(name, kw, shared, seed, n)

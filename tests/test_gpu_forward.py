@@ -47,14 +47,14 @@ def test_teacher_forced_logits_and_state(name):
     sess.close(); gpu.close()
 
 
-@pytest.mark.parametrize("name", ["ref_shared", "ref_untied"])
+@pytest.mark.parametrize("name", ["ref_shared", "ref_untied", "ref_hs48"])
 def test_golden_checkpoints_through_file_loader(name):
     """rama_ctx_load_file (mmap → HBM) on the .bin the reference's exporter wrote, against the
     logits the reference's torch model produced (tests/golden/make_golden.py)."""
     g = np.load(os.path.join(GOLDEN, name + ".npz"))
     gpu = GPU(0)
     cfg = gpu.load_file(os.path.join(GOLDEN, name + ".bin"))
-    assert cfg.shared_weight == (name == "ref_shared")
+    assert cfg.shared_weight == (name != "ref_untied")
     sess = Session(gpu)
     for pos, tok in enumerate(g["tokens"]):
         sess.forward(int(tok), pos)

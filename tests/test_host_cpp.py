@@ -40,7 +40,7 @@ def test_host_mirror_pure_host_logic():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["ref_shared", "ref_untied"])
+@pytest.mark.parametrize("name", ["ref_shared", "ref_untied", "ref_hs48"])
 @pytest.mark.parametrize("mode", ["fused", "per-op"])
 def test_cpp_mirror_forward_matches_reference_goldens(tmp_path, name, mode):
     from oracle import ref
