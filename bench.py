@@ -121,26 +121,28 @@ def host_mem_available() -> int:
     return avail
 
 
-def run_cpu(cfg, spec, n_tokens: int, reps: int, warm: int):
+def run_cpu(cfg, spec, n_tokens: int, reps: int, warm: int, want_logits: bool = False):
     """Times the oracle (CPU restatement of engine/src/device/cpu.rs + infer.rs) on all host cores.
-    Returns (tok/s, cores, tokens of the last run, sample description, seconds per rep)."""
+    Returns (tok/s, cores, tokens of the last run, sample description, seconds per rep[, logits of the last run])."""
     from oracle import ref
     need = cfg.file_bytes() + (2 << 30)
     have = host_mem_available()
     if have and have < need:
-        return None, ref.lib().ref_get_threads(), None, f"skipped: {need >> 30} GiB host RAM needed, {have >> 30} GiB available", None
+        skipped = (None, ref.lib().ref_get_threads(), None, f"skipped: {need >> 30} GiB host RAM needed, {have >> 30} GiB available", None)
+        return skipped + (None,) if want_logits else skipped
     tensors = ref.synth_tensors(cfg, spec)
     om = ref.Model(cfg, tensors)
     cores = ref.lib().ref_get_threads()
-    el, toks = [], None
+    el, toks, lg = [], None, None
     for i in range(warm + reps):
         st = ref.State(om)
-        toks, _, _, e = ref.generate(om, st, PROMPT, n_tokens, 0.0, 0.9)
+        toks, lg, _, e = ref.generate(om, st, PROMPT, n_tokens, 0.0, 0.9, want_logits=want_logits and i == warm + reps - 1)
         if i >= warm:
             el.append(e)
         del st
     t = sum(el) / len(el)
-    return n_tokens / t, cores, [int(x) for x in toks], f"first {n_tokens} tokens of the {METRIC} workload, {reps} rep(s)", t
+    res = (n_tokens / t, cores, [int(x) for x in toks], f"first {n_tokens} tokens of the {METRIC} workload, {reps} rep(s)", t)
+    return res + (lg,) if want_logits else res
 
 
 def main():
@@ -401,21 +403,35 @@ def main():
     step_bytes = cfg.avg_bytes_per_token(tokens) / world
     roofline = {"bound": "hbm", "kernel": "gemv_fused<ProNorm,RowsW13,EpiSwiGLU> (rmsnorm -> [w1|w3] -> SwiGLU)",
                 "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                "frac_of_nominal_8TBs": round(achieved / 8000.0, 4),
                 "traffic": traffic, "peak_source": peak_src, "bytes_per_launch": w13_bytes,
                 "avg_launch_ms": round(w13_ms, 5),
                 "timing": "CUDA events around each launch on the session stream, un-graphed (includes launch latency)",
                 "kernel_share_of_step": round(prof["w13"][0] / tot_ms, 4),
                 "step_achieved": round(step_bytes * value / 1e9, 1),
                 "step_frac": round(step_bytes * value / 1e9 / peak, 4),
+                "step_frac_of_nominal_8TBs": round(step_bytes * value / 1e9 / 8000.0, 4),
                 "step_bytes_per_token_per_gpu": step_bytes}
     kernels = {k: {"ms_per_token": round(v[0] / 5, 4), "launches_per_token": v[1] // 5} for k, v in prof.items() if v[1]}
 
     cpu = {"value": None, "unit": "tok/s", "cores": None, "kind": "port", "sample": "skipped"}
     if world == 1 and not args.no_cpu:
-        v, cores, ctoks, sample, _ = run_cpu(cfg, spec, auto_cpu_tokens, 1, 0)
+        v, cores, ctoks, sample, _, clog = run_cpu(cfg, spec, auto_cpu_tokens, 1, 0, want_logits=True)
         cpu = {"value": v, "unit": "tok/s", "cores": cores, "kind": "port", "sample": sample}
         if ctoks is not None:
             cpu["tokens_match_gpu"] = ctoks == [int(x) for x in toks[: len(ctoks)]]
+            # parity at THIS size, in the same run: teacher-force the oracle's own token stream through forward() and compare
+            # the logits (north star: max-abs/rel 1e-3) — outside every timed region
+            import numpy as np
+            worst, token = 0.0, 1
+            for pos in range(len(ctoks)):
+                sess.forward(token, pos)
+                if pos in (0, len(ctoks) // 2, len(ctoks) - 1):
+                    got, want = sess.logits().astype(np.float64), clog[pos].astype(np.float64)
+                    worst = max(worst, float(np.max(np.abs(got - want)) / max(1.0, float(np.max(np.abs(want))))))
+                token = ctoks[pos]
+            cpu["logits_max_rel_err_vs_gpu"] = worst
+            cpu["logit_tol"] = 1e-3
 
     line = {"metric": METRIC, "value": round(value, 3), "unit": "tok/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(dev_ms / args.steps, 4), "higher_is_better": True,
