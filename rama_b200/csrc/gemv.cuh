@@ -290,6 +290,7 @@ struct EpiStore {  // o[2p], o[2p+1]    (wo → xb2, w2 → residual contributio
   int n_rows;
   PeerOut po;      // po.P > 0: the outputs are a TP partial → stored into every rank's inbox instead
   __device__ __forceinline__ void prepare() {}
+  __device__ __forceinline__ void prefetch(int) {}
   __device__ __forceinline__ void operator()(int p, float v0, float v1) {
     if (po.P > 0) {
       const unsigned ep = po.epoch();
@@ -322,27 +323,28 @@ struct EpiQKV {
   const StepCtrl* ctrl;
   int pairs_per, hs2, Dq;  // pairs per section, head_size/2, row stride of the cache
   int pos;                 // set by prepare()
-  const float* s_cs;       // shared memory: cos row [hs2] | sin row [hs2] of this position
-  // Called by every thread right after griddepcontrol.wait (before the prologue, whose barriers publish the
-  // table): the position and its RoPE row are fetched while x is still in flight, so the epilogue — the tail of
-  // the kernel — touches no global memory before its stores.
-  __device__ __forceinline__ void prepare() {
-    __shared__ float s_rope[2 * 64];
-    pos = ctrl->pos;
-    if (hs2 <= 64) {
-      for (int j = threadIdx.x; j < 2 * hs2; j += kGemvThreads)
-        s_rope[j] = j < hs2 ? freq_real[(size_t)pos * hs2 + j] : freq_imag[(size_t)pos * hs2 + j - hs2];
-      s_cs = s_rope;
-    } else {
-      s_cs = nullptr;
+  int pf_p = -1;           // pair whose RoPE factors this thread fetched ahead (prefetch())
+  float pf_c = 0.f, pf_s = 0.f;
+  // prepare(): every thread, right after griddepcontrol.wait — only ISSUES the load of the step's position (its first use is
+  // in prefetch(), after the prologue has issued the activation loads, so it delays nothing).
+  // prefetch(p): the thread that will run the epilogue of pair p fetches that pair's cos/sin before the dot products, so the
+  // epilogue — the tail of the kernel — touches no global memory before its stores.
+  __device__ __forceinline__ void prepare() { pos = ctrl->pos; }
+  __device__ __forceinline__ void prefetch(int p) {
+    const int sec = p / pairs_per;
+    if (sec < 2) {
+      const int j = (p - sec * pairs_per) % hs2;
+      pf_c = freq_real[(size_t)pos * hs2 + j];
+      pf_s = freq_imag[(size_t)pos * hs2 + j];
+      pf_p = p;
     }
   }
   __device__ __forceinline__ void operator()(int p, float v0, float v1) {
     const int sec = p / pairs_per, i = p - sec * pairs_per;
     if (sec < 2) {
       const int j = i % hs2;
-      const float c = s_cs ? s_cs[j] : freq_real[(size_t)pos * hs2 + j];
-      const float s = s_cs ? s_cs[hs2 + j] : freq_imag[(size_t)pos * hs2 + j];
+      const float c = p == pf_p ? pf_c : freq_real[(size_t)pos * hs2 + j];
+      const float s = p == pf_p ? pf_s : freq_imag[(size_t)pos * hs2 + j];
       const float o0 = __fsub_rn(__fmul_rn(v0, c), __fmul_rn(v1, s));
       const float o1 = __fadd_rn(__fmul_rn(v0, s), __fmul_rn(v1, c));
       if (sec == 0) {
@@ -364,6 +366,7 @@ struct EpiSwiGLU {
   float* hb;
   float* hb2;
   __device__ __forceinline__ void prepare() {}
+  __device__ __forceinline__ void prefetch(int) {}
   __device__ __forceinline__ void operator()(int p, float h1, float h3) {
     const float a = h1 * (1.0f / (1.0f + expf(-h1)));
     hb[p] = a * h3;
@@ -381,6 +384,7 @@ struct EpiCls {
   int bi;
   PeerOut po;          // po.P > 0: the partial goes to every rank's part array (po.inbox[r] = its slot base)
   __device__ __forceinline__ void prepare() {}
+  __device__ __forceinline__ void prefetch(int) {}
   __device__ __forceinline__ void operator()(int p, float v0, float v1) {
     logits[2 * p] = v0;
     argmax_merge(bv, bi, v0, row_offset + 2 * p);
@@ -525,6 +529,7 @@ gemv_fused_kernel(const Pro pro, const Rows rows, const Epi epi_in, int K4, int 
   Epi epi = epi_in;
   epi.prepare();
   pro(xs, K4, red, pre);
+  if ((int)threadIdx.x < np) epi.prefetch(p0 + threadIdx.x);  // this thread's (first) epilogue pair
   __syncthreads();
   gemv_pairs<WK, RP, U>(rows, K4, p0, np, xs, part);
   __syncthreads();
@@ -606,6 +611,7 @@ gemv_smem_kernel(const Pro pro, const Rows rows, const Epi epi_in, int K4, int n
   for (int i = warp; i < np; i += kGemvWarps) {
     const float4 *r0, *r1;
     rows.staged(i, np, slab, r0, r1, p0);
+    if (lane == 0) epi.prefetch(p0 + i);
     float a0 = 0.f, a1 = 0.f;
 #pragma unroll 2
     for (int c = lane; c < K4; c += kWarp) {
@@ -706,6 +712,7 @@ __device__ __forceinline__ void gemv_phase(const Pro& pro, const Rows& rows, con
   Epi epi = epi_in;
   epi.prepare();
   pro(xs, K4, red, pro.template preload<1>(K4));
+  if ((int)threadIdx.x < np) epi.prefetch(p0 + threadIdx.x);
   __syncthreads();
   gemv_pairs_rt(rows, K4, p0, np, xs, part, WK);
   __syncthreads();

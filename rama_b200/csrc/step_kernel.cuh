@@ -99,6 +99,7 @@ struct StepEpiStore {  // wo (stage 0 → xb2) / w2 (stage 1 → w2out); under T
   }
   __device__ __forceinline__ void finish(float*) const {}
   __device__ __forceinline__ void prepare() const {}
+  __device__ __forceinline__ void prefetch(int) const {}
 };
 
 struct StepEpiQKV {  // RoPE (cpu.rs:74-97) on q,k + KV-cache row write (infer.rs:31-33)
@@ -125,6 +126,7 @@ struct StepEpiQKV {  // RoPE (cpu.rs:74-97) on q,k + KV-cache row write (infer.r
   }
   __device__ __forceinline__ void finish(float*) const {}
   __device__ __forceinline__ void prepare() const {}
+  __device__ __forceinline__ void prefetch(int) const {}
 };
 
 struct StepEpiSwiGLU {  // cpu.rs:54-64
@@ -135,6 +137,7 @@ struct StepEpiSwiGLU {  // cpu.rs:54-64
   }
   __device__ __forceinline__ void finish(float*) const {}
   __device__ __forceinline__ void prepare() const {}
+  __device__ __forceinline__ void prefetch(int) const {}
 };
 
 struct StepEpiCls {  // logits + per-CTA greedy partial (ties → higher index, cpu.rs:165-167)
@@ -151,6 +154,7 @@ struct StepEpiCls {  // logits + per-CTA greedy partial (ties → higher index, 
     }
   }
   __device__ __forceinline__ void prepare() const {}
+  __device__ __forceinline__ void prefetch(int) const {}
   __device__ __forceinline__ void finish(float* red) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
