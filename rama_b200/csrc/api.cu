@@ -1783,7 +1783,7 @@ constexpr int kBatchMax = 64;    // one 64-column MMA tile of sequences
 constexpr int kBatchRing = 8;
 // batched-decode GEMM tile: 128 weight rows × 64 sequences, 2 stages, chunks of 2 k-blocks; two CTAs fit an SM
 // (64 KB of shared memory and 256 TMEM columns each) and interleave their pipelines
-#define BATCH_GEMM launch_gemm_tf32x3<64, 2, 2, 0>
+#define BATCH_GEMM launch_gemm_tf32x3<64, 2, 4, 0>  // 128-k chunks as in prefill (CH = 2: 9.18 ms per 64-sequence step)
 constexpr int kBatchCtasPerSm = GemmSmem<64, 2, 0>::kCtasPerSm;
 
 struct rama_batch {
