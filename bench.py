@@ -121,28 +121,50 @@ def host_mem_available() -> int:
     return avail
 
 
-def run_cpu(cfg, spec, n_tokens: int, reps: int, warm: int, want_logits: bool = False):
-    """Times the oracle (CPU restatement of engine/src/device/cpu.rs + infer.rs) on all host cores.
-    Returns (tok/s, cores, tokens of the last run, sample description, seconds per rep[, logits of the last run])."""
+def host_threads() -> int:
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def oracle_model(cfg, spec):
+    """The CPU oracle on ALL host cores: torchrun exports OMP_NUM_THREADS=1 when nproc > 1, which would leave the
+    oracle single-threaded (round 1: the reference arm timed out at N = 2/4/8) — set the thread count explicitly.
+    Returns (ref module, model or None, cores, reason-if-skipped)."""
     from oracle import ref
+    ref.lib().ref_set_threads(host_threads())
+    cores = ref.lib().ref_get_threads()
     need = cfg.file_bytes() + (2 << 30)
     have = host_mem_available()
     if have and have < need:
-        skipped = (None, ref.lib().ref_get_threads(), None, f"skipped: {need >> 30} GiB host RAM needed, {have >> 30} GiB available", None)
-        return skipped + (None,) if want_logits else skipped
-    tensors = ref.synth_tensors(cfg, spec)
-    om = ref.Model(cfg, tensors)
-    cores = ref.lib().ref_get_threads()
-    el, toks, lg = [], None, None
+        return ref, None, cores, f"skipped: {need >> 30} GiB host RAM needed, {have >> 30} GiB available"
+    return ref, ref.Model(cfg, ref.synth_tensors(cfg, spec)), cores, None
+
+
+def run_cpu(cfg, spec, n_tokens: int, reps: int, warm: int, want_logits: bool = False, budget_s: float = 0.0):
+    """Times the oracle (CPU restatement of engine/src/device/cpu.rs + infer.rs) on all host cores.
+    budget_s > 0: the sample (tokens per step) is sized from a 4-token calibration run so that warm + reps steps end
+    within about budget_s (never more than n_tokens, never fewer than 4 tokens per step).
+    Returns dict(value, cores, tokens, sample, sec_per_rep, logits, min_gap)."""
+    ref, om, cores, why = oracle_model(cfg, spec)
+    if om is None:
+        return {"value": None, "cores": cores, "tokens": None, "sample": why, "sec_per_rep": None, "logits": None, "min_gap": None}
+    if budget_s > 0:
+        _, _, _, e = ref.generate(om, ref.State(om), PROMPT, 4, 0.0, 0.9)   # also pages the weights in
+        _, _, _, e = ref.generate(om, ref.State(om), PROMPT, 4, 0.0, 0.9)
+        n_tokens = int(max(4, min(n_tokens, budget_s / max(1, warm + reps) / (e / 4))))
+    el, toks, lg, gap = [], None, None, None
     for i in range(warm + reps):
         st = ref.State(om)
-        toks, lg, _, e = ref.generate(om, st, PROMPT, n_tokens, 0.0, 0.9, want_logits=want_logits and i == warm + reps - 1)
+        toks, lg, gap, e = ref.generate(om, st, PROMPT, n_tokens, 0.0, 0.9, want_logits=want_logits and i == warm + reps - 1)
         if i >= warm:
             el.append(e)
         del st
     t = sum(el) / len(el)
-    res = (n_tokens / t, cores, [int(x) for x in toks], f"first {n_tokens} tokens of the {METRIC} workload, {reps} rep(s)", t)
-    return res + (lg,) if want_logits else res
+    return {"value": n_tokens / t, "cores": cores, "tokens": [int(x) for x in toks],
+            "sample": f"first {n_tokens} tokens of the {METRIC} workload per step, {reps} timed step(s)",
+            "sec_per_rep": t, "logits": lg, "min_gap": None if gap is None else float(gap)}
 
 
 def main():
@@ -171,22 +193,30 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     workload = (f"{args.model} (dim {cfg.dim}, {cfg.n_layers} layers, {cfg.n_heads} heads, ffn {cfg.hidden_dim}, "
                 f"vocab {cfg.vocab_size}) f32 batch-1 greedy decode, {tokens} tokens per step, prompt 'once upon a time'")
-    auto_cpu_tokens = args.cpu_tokens or (32 if cfg.file_bytes() > (4 << 30) else min(tokens, 64 if cfg.dim > 512 else 256))
+    big = cfg.file_bytes() > (4 << 30)
+    # both arms print the same `config` (the driver compares them); run-specific facts live under `run`
+    config = {"workload": workload, "parallelism": f"tp{world}", "seed": args.seed,
+              "l2": "weights streamed per token exceed L2 (no flush needed)" if cfg.weight_bytes_per_token() / world > 200e6
+                    else "working set near/below the 126 MB L2: numbers are L2-assisted, reported as is"}
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
         if rank != 0:
             return
-        v, cores, _, sample, t = run_cpu(cfg, spec, auto_cpu_tokens, max(args.steps, 1), args.warmup)
+        # every step = a bounded sample of the workload (its first n tokens), n sized so that the whole
+        # --steps K --warmup W run ends within ~2 min at N = 1 and ~1 min under torchrun (the other ranks' GPUs idle meanwhile)
+        r = run_cpu(cfg, spec, args.cpu_tokens or min(tokens, 32 if big else 256), max(args.steps, 1), args.warmup,
+                    budget_s=(110.0 if world == 1 else 50.0) if big else 30.0)
+        v, t = r["value"], r["sec_per_rep"]
         line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "tok/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": None if t is None else t * 1e3,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic",
-                "config": {"workload": workload, "step": f"bounded sample: {sample}",
-                           "what": "CPU oracle = C++ restatement of the reference's Rust CPU path "
-                                   "(engine/src/device/cpu.rs + transformer/infer.rs); the Rust crate cannot be "
-                                   "built in this image (no cargo/rustc)"},
-                "cpu_baseline": {"value": v, "unit": "tok/s", "cores": cores, "kind": "port", "sample": sample},
+                "data": "synthetic", "config": config,
+                "run": {"step": f"bounded sample: {r['sample']}",
+                        "what": "CPU oracle = C++ restatement of the reference's Rust CPU path "
+                                "(engine/src/device/cpu.rs + transformer/infer.rs) on all host cores; the Rust crate "
+                                "cannot be built in this image (no cargo/rustc)"},
+                "cpu_baseline": {"value": v, "unit": "tok/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
                 "e2e": {"value": v, "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         print(json.dumps(line))
@@ -337,38 +367,41 @@ def main():
             for s_ in bsess:
                 s_.close()
 
-    # ---- stories110M (the second model BASELINE.json's metric names; 1 GPU): device loop and host-driven e2e ----
-    small = None
+    # ---- the small models of BASELINE.json's metric (configs[0..1]; 1 GPU): device loop and host-driven e2e ----
+    small = {}
     if world == 1 and args.model == "llama2-7B" and not args.no_small:
-        scfg = ck.CONFIGS["stories110M"]
-        sgpu = GPU(local_rank)
-        sgpu.load_synthetic(scfg, spec)
-        ss = Session(sgpu)
-        for _ in range(args.warmup):
-            ss.generate(PROMPT, tokens, 0.0, 0.9)
-        torch.cuda.synchronize()
-        s_ms = sum(ss.generate(PROMPT, tokens, 0.0, 0.9)[1] for _ in range(args.steps))
-        def s_host_loop():
-            token = 1
-            for pos in range(tokens):
-                ss.forward(token, pos)
-                token = PROMPT[pos] if pos < len(PROMPT) else ss.sample(0.0, 0.9)
-            ss.sync()
-        s_host_loop()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            s_host_loop()
-        s_e2e = time.perf_counter() - t0
-        s_val = args.steps * tokens / (s_ms * 1e-3)
-        s_bytes = scfg.avg_bytes_per_token(tokens)
         hbm_peak, _ = measured_peaks()
-        small = {"model": "stories110M (dim 768, 12 layers, 12 heads, seq 1024)", "value": round(s_val, 1), "unit": "tok/s",
-                 "e2e": round(args.steps * tokens / s_e2e, 1), "us_per_token": round(1e6 / s_val, 1),
-                 "launches_per_token": ss.launches_per_step(),
-                 "step_frac_of_hbm_roofline": round(s_bytes * s_val / 1e9 / hbm_peak, 4),
-                 "note": "438 MB of weights per token: the step is bound by the length of the kernel chain "
-                         "(launches_per_token dependent kernels), not by bytes"}
-        ss.close(); sgpu.close()
+        for sname in ("stories110M", "stories15M"):
+            scfg = ck.CONFIGS[sname]
+            stoks = min(tokens, scfg.seq_len)
+            sgpu = GPU(local_rank)
+            sgpu.load_synthetic(scfg, spec)
+            ss = Session(sgpu)
+            for _ in range(args.warmup):
+                ss.generate(PROMPT, stoks, 0.0, 0.9)
+            torch.cuda.synchronize()
+            s_ms = sum(ss.generate(PROMPT, stoks, 0.0, 0.9)[1] for _ in range(args.steps))
+            def s_host_loop():
+                token = 1
+                for pos in range(stoks):
+                    ss.forward(token, pos)
+                    token = PROMPT[pos] if pos < len(PROMPT) else ss.sample(0.0, 0.9)
+                ss.sync()
+            s_host_loop()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                s_host_loop()
+            s_e2e = time.perf_counter() - t0
+            s_val = args.steps * stoks / (s_ms * 1e-3)
+            s_bytes = scfg.avg_bytes_per_token(stoks)
+            small[sname] = {"model": f"{sname} (dim {scfg.dim}, {scfg.n_layers} layers, {scfg.n_heads} heads, seq {scfg.seq_len})",
+                            "value": round(s_val, 1), "unit": "tok/s", "tokens_per_step": stoks,
+                            "e2e": round(args.steps * stoks / s_e2e, 1), "us_per_token": round(1e6 / s_val, 1),
+                            "launches_per_token": ss.launches_per_step(),
+                            "step_frac_of_hbm_roofline": round(s_bytes * s_val / 1e9 / hbm_peak, 4),
+                            "note": f"{scfg.weight_bytes_per_token() / 1e6:.0f} MB of weights per token (L2-resident or close): the step "
+                                    "is bound by the length of the dependent kernel chain, not by bytes"}
+            ss.close(); sgpu.close()
 
     # ---- per-kernel event timing (un-graphed) at a few positions: dominant-kernel roofline ----
     prof = {}
@@ -382,6 +415,53 @@ def main():
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
+
+    # ---- parity of THIS run at THIS size against the CPU oracle (outside every timed region) ----
+    # N = 1: the oracle decodes the full 256-token workload (≈50 s at 7B on the box's cores; also the cpu_baseline figure):
+    #        all tokens must equal the device loop's, logits compared every 16th position on the oracle's own stream.
+    # N > 1: rank 0 runs the oracle for 32 tokens, the stream is broadcast, every rank teacher-forces it through
+    #        forward() and the gathered logits are compared: the only way a scaling line can carry TP correctness.
+    import numpy as np
+    cpu = {"value": None, "unit": "tok/s", "cores": None, "kind": "port", "sample": "skipped"}
+    tp_parity = None
+    if not args.no_cpu:
+        n_par = args.cpu_tokens or ((tokens if world == 1 else min(tokens, 32)) if big else min(tokens, 256))
+        r = None
+        if rank == 0:
+            r = run_cpu(cfg, spec, n_par, 1, 0, want_logits=True)
+        ctoks = [r["tokens"] if r else None]
+        if world > 1:
+            dist.broadcast_object_list(ctoks, src=0)
+        ctoks = ctoks[0]
+        if ctoks is not None:
+            every = 16
+            worst, token, checked = 0.0, 1, 0
+            for pos in range(len(ctoks)):
+                sess.forward(token, pos)
+                if pos % every == 0 or pos == len(ctoks) - 1:
+                    got = sess.logits()   # under TP: all-gather of the vocabulary slices (every rank takes part)
+                    if rank == 0:
+                        want = r["logits"][pos].astype(np.float64)
+                        worst = max(worst, float(np.max(np.abs(got.astype(np.float64) - want)) / max(1.0, float(np.max(np.abs(want))))))
+                        checked += 1
+                token = ctoks[pos]
+            if rank == 0:
+                par = {"tokens": len(ctoks), "tokens_match_gpu": ctoks == [int(x) for x in toks[: len(ctoks)]],
+                       "logits_max_rel_err_vs_gpu": worst, "logit_positions_checked": checked, "logit_tol": 1e-3,
+                       "min_top2_gap": r["min_gap"], "oracle_cores": r["cores"],
+                       "what": "greedy tokens of the device-resident loop vs the CPU oracle's, and teacher-forced logits "
+                               "(the oracle's own stream through forward()) every 16th position, same weights and prompt"}
+                if world == 1:
+                    cpu = {"value": r["value"], "unit": "tok/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+                    cpu.update({k: par[k] for k in ("tokens_match_gpu", "logits_max_rel_err_vs_gpu", "logit_positions_checked",
+                                                    "logit_tol", "min_top2_gap")})
+                else:
+                    tp_parity = par
+                    cpu["sample"] = "N > 1: see tp_parity (the oracle ran 32 tokens on rank 0 for parity, not as a baseline)"
+                    cpu["cores"] = r["cores"]
+        elif rank == 0 and r is not None:
+            cpu["sample"] = r["sample"]
+            cpu["cores"] = r["cores"]
 
     if rank != 0:
         teardown()
@@ -414,37 +494,16 @@ def main():
                 "step_bytes_per_token_per_gpu": step_bytes}
     kernels = {k: {"ms_per_token": round(v[0] / 5, 4), "launches_per_token": v[1] // 5} for k, v in prof.items() if v[1]}
 
-    cpu = {"value": None, "unit": "tok/s", "cores": None, "kind": "port", "sample": "skipped"}
-    if world == 1 and not args.no_cpu:
-        v, cores, ctoks, sample, _, clog = run_cpu(cfg, spec, auto_cpu_tokens, 1, 0, want_logits=True)
-        cpu = {"value": v, "unit": "tok/s", "cores": cores, "kind": "port", "sample": sample}
-        if ctoks is not None:
-            cpu["tokens_match_gpu"] = ctoks == [int(x) for x in toks[: len(ctoks)]]
-            # parity at THIS size, in the same run: teacher-force the oracle's own token stream through forward() and compare
-            # the logits (north star: max-abs/rel 1e-3) — outside every timed region
-            import numpy as np
-            worst, token = 0.0, 1
-            for pos in range(len(ctoks)):
-                sess.forward(token, pos)
-                if pos in (0, len(ctoks) // 2, len(ctoks) - 1):
-                    got, want = sess.logits().astype(np.float64), clog[pos].astype(np.float64)
-                    worst = max(worst, float(np.max(np.abs(got - want)) / max(1.0, float(np.max(np.abs(want))))))
-                token = ctoks[pos]
-            cpu["logits_max_rel_err_vs_gpu"] = worst
-            cpu["logit_tol"] = 1e-3
-
     line = {"metric": METRIC, "value": round(value, 3), "unit": "tok/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(dev_ms / args.steps, 4), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload, "parallelism": f"tp{world}", "seed": args.seed,
-                       "tp_exchange": None if world == 1 else os.environ.get("RAMA_TP_COMM", "p2p") +
-                       (" (one-shot all-reduce over peer memory fused into the wo/w2 GEMV epilogue + next prologue)"
-                        if os.environ.get("RAMA_TP_COMM", "p2p") == "p2p" else " (ncclAllReduce in the graph)"),
-                       "l2": "weights streamed per token exceed L2 (no flush needed)" if cfg.weight_bytes_per_token() / world > 200e6
-                             else "working set near/below the 126 MB L2: numbers are L2-assisted, reported as is",
-                       "timing": "CUDA events around each 256-token graph-replay loop, summed over steps, max over ranks",
-                       "wall_ms_per_step": round(wall_ms / args.steps, 3),
-                       "e2e_matches_device_loop": [int(x) for x in toks] == e2e_toks},
+            "config": config,
+            "run": {"tp_exchange": None if world == 1 else os.environ.get("RAMA_TP_COMM", "p2p") +
+                    (" (one-shot all-reduce over peer memory fused into the wo/w2 GEMV epilogue + next prologue)"
+                     if os.environ.get("RAMA_TP_COMM", "p2p") == "p2p" else " (ncclAllReduce in the graph)"),
+                    "timing": "CUDA events around each 256-token graph-replay loop, summed over steps, max over ranks",
+                    "wall_ms_per_step": round(wall_ms / args.steps, 3),
+                    "e2e_matches_device_loop": [int(x) for x in toks] == e2e_toks},
             "clocks": clk,
             "e2e": {"value": round(e2e_value, 3), "unit": "tok/s", "h2d_bytes_per_step": 32 * tokens,
                     "d2h_bytes_per_step": 8 * (tokens - len(PROMPT)),
@@ -460,8 +519,10 @@ def main():
                                  "peak_source": "half of the measured cuBLAS bf16 burst (tf32 runs at half the bf16 rate; "
                                                 "MEASURED_PEAKS.json has no tf32 figure)"}
         line["prefill"] = pf
-    if small is not None:
-        line["stories110M"] = small
+    for sname, sv in small.items():
+        line[sname] = sv
+    if tp_parity is not None:
+        line["tp_parity"] = tp_parity
     if bd is not None:
         bd["speedup_vs_batch1"] = round(bd["tok_per_s"] / value, 1)
         bd["hbm_frac_of_measured_peak"] = round(bd["hbm_gbs_algorithmic_per_gpu"] / peak, 4)

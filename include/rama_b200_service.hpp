@@ -171,6 +171,13 @@ class BatchedEngine {
     return n;
   }
   void run_until_idle() { while (!idle()) step(); }
+  // A failed step (e.g. the empty top-p candidate list the reference panics on, infer.rs:66) ends the requests that were
+  // in it — in the reference only that request's task dies — and the engine keeps serving: their streams are closed, the
+  // sessions go back to the pool (the next batched step rewrites each session's error flag).
+  void abort_live() {
+    for (auto& r : live_) finish(std::move(r));
+    live_.clear();
+  }
 
  private:
   bool emit(Request& r, int32_t token) {
@@ -276,7 +283,14 @@ class EngineService {
         get_batch(*receiver_, fresh, room, eng.idle() ? idle_wait_ : std::chrono::duration<double>(0));
       for (auto& cr : fresh) admit(eng, std::move(cr));
       if (eng.idle()) continue;
-      const usize n = eng.step();
+      usize n = 0;
+      try {
+        n = eng.step();
+      } catch (const Panic& e) {  // must not escape the handler thread (std::terminate would take the server down)
+        std::fprintf(stderr, "batched step panicked: %s\n", e.what());
+        eng.abort_live();
+        continue;
+      }
       steps_run_ += 1;
       if (n > max_live_) max_live_ = n;
     }

@@ -20,6 +20,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -61,6 +62,11 @@ extern "C" int rama_set_error(int code, const char* msg) { return fail(code, "%s
     int r_ = (call);                 \
     if (r_ != RAMA_OK) return r_;    \
   } while (0)
+
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
 
 // ------------------------------------------------------------------------------------------------
 // NCCL, resolved at run time (only when tp->world > 1) so that the single-GPU path has no
@@ -146,6 +152,15 @@ struct rama_ctx {
   // cudaFree) issued by ANOTHER host thread of the same context — the server creates and drops sessions while other
   // request threads capture their step graphs.  Captures and those device-wide operations take this lock.
   std::mutex cap_mu;
+  std::atomic<int> n_objects{0};  // live sessions + batches: their captured graphs hold the weight pointers, so no reload
+};
+
+// A batched step runs on the batch's stream, the per-session entry points on the session's own stream.  The batch
+// re-records ONE event after every step it launches; each session of that step keeps a reference and makes its own
+// stream wait on it before its next operation (waiting on a later record of the same event is merely conservative).
+struct BatchFence {
+  cudaEvent_t ev = nullptr;
+  ~BatchFence() { if (ev) cudaEventDestroy(ev); }
 };
 
 struct rama_session {
@@ -192,7 +207,17 @@ struct rama_session {
   int pf_min = 16;               // rama_generate: prompts of at least this many rows (BOS included) are prefilled
   float *pf_x = nullptr, *pf_xn = nullptr, *pf_q = nullptr, *pf_att = nullptr, *pf_y = nullptr, *pf_h = nullptr;
   int32_t* pf_tokens = nullptr;
+  std::shared_ptr<BatchFence> fence;  // set by rama_forward_batch: work of another stream this session must wait for
+  bool async_pending = false;         // work enqueued on s->stream since it was last synchronised (a batch must wait for it)
 };
+
+// called first by every per-session entry point: order this session's stream after the batched step that touched it
+static cudaError_t session_enter(rama_session* s) {
+  if (!s->fence) return cudaSuccess;
+  cudaError_t e = cudaStreamWaitEvent(s->stream, s->fence->ev, 0);
+  s->fence.reset();
+  return e;
+}
 
 // ------------------------------------------------------------------------------------------------
 // GEMV dispatch
@@ -313,11 +338,6 @@ extern "C" int rama_tp_unique_id(uint8_t out[128]) {
   NK(g_nccl.GetUniqueId(&id));
   memcpy(out, &id, 128);
   return RAMA_OK;
-}
-
-static int env_int(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return v && *v ? atoi(v) : dflt;
 }
 
 extern "C" int rama_ctx_create(int device, const rama_tp* tp, rama_ctx** out) {
@@ -450,6 +470,14 @@ static int alloc_weights(rama_ctx* c) {
   return RAMA_OK;
 }
 
+// Sessions and batches hold captured graphs with the weight pointers baked in: loading again under them would leave
+// dangling pointers in every replay.
+static int reload_allowed(const rama_ctx* c) {
+  const int n = c->n_objects.load();
+  if (n > 0) return fail(RAMA_E_STATE, "%d session(s)/batch(es) of this context are alive: destroy them before loading weights again", n);
+  return RAMA_OK;
+}
+
 // One pass host → HBM of this rank's window of tensor i (src = full global tensor on the host).
 static int upload_tensor(rama_ctx* c, int i, const float* src, cudaStream_t st) {
   const TensorPlan& p = c->plan[i];
@@ -468,6 +496,7 @@ static int upload_tensor(rama_ctx* c, int i, const float* src, cudaStream_t st) 
 extern "C" int rama_ctx_load_host(rama_ctx* c, const rama_config* cfg, const float* const tensors[RAMA_T_COUNT]) {
   if (!c || !cfg || !tensors) return fail(RAMA_E_INVALID, "NULL argument");
   std::lock_guard<std::mutex> lk(c->mu);
+  RK(reload_allowed(c));
   CK(cudaSetDevice(c->device));
   RK(set_config(c, cfg));
   RK(alloc_weights(c));
@@ -505,29 +534,32 @@ static int load_file_pipelined(rama_ctx* c, int fd, const std::vector<LoadPiece>
       return fail(RAMA_E_CUDA, "pinned staging ring: %s", cudaGetErrorString(cudaGetLastError()));
     }
   }
-  // slot state: 0 free, 1 being filled, 2 ready (filled), 3 in flight (DMA issued, `done` recorded)
+  // Slot (i % kBuf) is used by pieces i, i+kBuf, i+2·kBuf, …  Two counters per slot enforce that order whatever the
+  // scheduling of the reader threads (a reader that claimed piece i and was descheduled must not find its slot taken by
+  // the reader of piece i+kBuf): issued[slot] = pieces of this slot whose DMA has been issued, filled[slot] = pieces of
+  // this slot read from the file.  Piece i (the k-th use of its slot, k = i / kBuf) may be read only when issued == k
+  // (and after that DMA has drained the buffer); the main loop issues it only when filled == k + 1.
   std::mutex mu;
   std::condition_variable cv;
-  std::vector<int> state(kBuf, 0);
+  std::vector<size_t> issued(kBuf, 0), filled(kBuf, 0);
   std::atomic<size_t> next{0};
   std::atomic<int> io_error{0};
   const size_t n = pieces.size();
-  auto reader = [&](int) {
+  const int reader_delay_us = env_int("RAMA_LOAD_TEST_DELAY_US", 0);  // test hook: widen the claim → fill window
+  auto reader = [&](int t) {
     cudaSetDevice(c->device);
     for (;;) {
       const size_t i = next.fetch_add(1);
       if (i >= n || io_error.load()) return;
       const int slot = (int)(i % kBuf);
+      const size_t k = i / kBuf;
+      if (reader_delay_us > 0 && (i + t) % 3 == 0) std::this_thread::sleep_for(std::chrono::microseconds(reader_delay_us));
       {
         std::unique_lock<std::mutex> lk(mu);
-        // piece i may use its slot once piece i-kBuf has been issued and its DMA has finished
-        cv.wait(lk, [&] { return state[slot] == 0 || state[slot] == 3 || io_error.load(); });
+        cv.wait(lk, [&] { return issued[slot] == k || io_error.load(); });
         if (io_error.load()) return;
-        const bool wait_dma = state[slot] == 3;
-        state[slot] = 1;
-        lk.unlock();
-        if (wait_dma) cudaEventSynchronize(done[slot]);
       }
+      if (k > 0) cudaEventSynchronize(done[slot]);  // the DMA of piece i - kBuf has left the buffer
       const LoadPiece& p = pieces[i];
       size_t got = 0;
       const size_t want = p.rows * p.row_bytes;
@@ -538,12 +570,11 @@ static int load_file_pipelined(rama_ctx* c, int fd, const std::vector<LoadPiece>
       }
       {
         std::lock_guard<std::mutex> lk(mu);
-        state[slot] = 2;
+        filled[slot] = k + 1;
       }
       cv.notify_all();
     }
   };
-  // pieces are claimed in order by fetch_add, so slot (i % kBuf) is always filled by piece i after piece i-kBuf
   std::vector<std::thread> th;
   for (int t = 0; t < kReaders; ++t) th.emplace_back(reader, t);
   const auto t0 = std::chrono::steady_clock::now();
@@ -551,9 +582,10 @@ static int load_file_pipelined(rama_ctx* c, int fd, const std::vector<LoadPiece>
   int rc = RAMA_OK;
   for (size_t i = 0; i < n && rc == RAMA_OK; ++i) {
     const int slot = (int)(i % kBuf);
+    const size_t k = i / kBuf;
     {
       std::unique_lock<std::mutex> lk(mu);
-      cv.wait(lk, [&] { return state[slot] == 2 || io_error.load(); });
+      cv.wait(lk, [&] { return filled[slot] == k + 1 || io_error.load(); });
     }
     if (io_error.load()) { rc = fail(RAMA_E_IO, "short read from the checkpoint file"); break; }
     const LoadPiece& p = pieces[i];
@@ -568,7 +600,7 @@ static int load_file_pipelined(rama_ctx* c, int fd, const std::vector<LoadPiece>
     bytes += p.rows * p.col_bytes;
     {
       std::lock_guard<std::mutex> lk(mu);
-      state[slot] = 3;
+      issued[slot] = k + 1;
     }
     cv.notify_all();
   }
@@ -595,12 +627,17 @@ extern "C" int rama_ctx_load_file(rama_ctx* c, const char* path) {
   }
   posix_fadvise(fd, 0, 0, POSIX_FADV_SEQUENTIAL);
   // header: 7 LE i32; vocab > 0 ⇒ shared classifier (mod.rs:140-166)
+  if (h[5] == INT32_MIN) {  // |vocab| does not fit an i32 (untrusted file; -INT_MIN is undefined behaviour)
+    close(fd);
+    return fail(RAMA_E_INVALID, "%s: vocabulary size out of range", path);
+  }
   rama_config cfg{h[0], h[1], h[2], h[3], h[4], h[5] > 0 ? h[5] : -h[5], h[6], h[5] > 0 ? 1 : 0};
   int rc;
   {
     std::lock_guard<std::mutex> lk(c->mu);
     cudaSetDevice(c->device);
-    rc = set_config(c, &cfg);
+    rc = reload_allowed(c);
+    if (rc == RAMA_OK) rc = set_config(c, &cfg);
     if (rc == RAMA_OK) {
       size_t need = 28;
       for (int i = 0; i < RAMA_T_COUNT; ++i) need += c->plan[i].global_elems() * 4;
@@ -614,7 +651,8 @@ extern "C" int rama_ctx_load_file(rama_ctx* c, const char* path) {
       for (int i = 0; i < RAMA_T_COUNT; ++i) {
         const TensorPlan& p = c->plan[i];
         if (p.local_elems()) {
-          const size_t row_bytes = p.C * 4, max_rows = std::max<size_t>(1, ((size_t)32 << 20) / row_bytes);
+          const size_t piece_bytes = std::min<size_t>((size_t)32 << 20, (size_t)std::max(1, env_int("RAMA_LOAD_PIECE_KB", 32 << 10)) << 10);
+          const size_t row_bytes = p.C * 4, max_rows = std::max<size_t>(1, piece_bytes / row_bytes);
           for (size_t l = 0; l < p.Lc; ++l) {
             for (size_t r = 0; r < p.Rl; r += max_rows) {
               const size_t nr = std::min(max_rows, p.Rl - r);
@@ -645,6 +683,7 @@ extern "C" int rama_ctx_load_synthetic(rama_ctx* c, const rama_config* cfg, uint
                                        const float* freq_real, const float* freq_imag) {
   if (!c || !cfg || !scale || !offset || !freq_real || !freq_imag) return fail(RAMA_E_INVALID, "NULL argument");
   std::lock_guard<std::mutex> lk(c->mu);
+  RK(reload_allowed(c));
   CK(cudaSetDevice(c->device));
   RK(set_config(c, cfg));
   RK(alloc_weights(c));
@@ -901,21 +940,27 @@ extern "C" int rama_session_create(rama_ctx* c, rama_session** out) {
       return rc;
     }
   }
+  c->n_objects.fetch_add(1);
   *out = s;
   return RAMA_OK;
 }
 
 extern "C" int rama_session_destroy(rama_session* s) {
   if (!s) return RAMA_OK;
-  std::lock_guard<std::mutex> cap_lk(s->ctx->cap_mu);
+  rama_ctx* c = s->ctx;
+  std::lock_guard<std::mutex> cap_lk(c->cap_mu);
+  if (s->fence) { cudaSetDevice(c->device); cudaEventSynchronize(s->fence->ev); s->fence.reset(); }
   session_free(s);
+  c->n_objects.fetch_sub(1);
   return RAMA_OK;
 }
 
 extern "C" int rama_session_sync(rama_session* s) {
   if (!s) return fail(RAMA_E_INVALID, "NULL session");
   CK(cudaSetDevice(s->ctx->device));
+  CK(session_enter(s));
   CK(cudaStreamSynchronize(s->stream));
+  s->async_pending = false;
   return RAMA_OK;
 }
 
@@ -923,6 +968,7 @@ extern "C" int rama_session_reset(rama_session* s) {
   if (!s) return fail(RAMA_E_INVALID, "NULL session");
   rama_ctx* c = s->ctx;
   CK(cudaSetDevice(c->device));
+  CK(session_enter(s));
   const size_t kv = (size_t)c->L * c->T * c->Dq * sizeof(float);
   CK(cudaMemsetAsync(s->key_cache, 0, kv, s->stream));
   CK(cudaMemsetAsync(s->value_cache, 0, kv, s->stream));
@@ -936,6 +982,7 @@ extern "C" int rama_session_reset(rama_session* s) {
 extern "C" int rama_session_set_debug(rama_session* s, int keep_att) {
   if (!s) return fail(RAMA_E_INVALID, "NULL session");
   CK(cudaSetDevice(s->ctx->device));
+  CK(session_enter(s));
   CK(cudaStreamSynchronize(s->stream));
   if (s->keep_att != keep_att) {  // the captured graphs bake the att pointer in
     for (auto& gm : s->g) for (auto& g : gm) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
@@ -1306,6 +1353,7 @@ extern "C" int rama_forward(rama_session* s, int32_t token, int32_t pos) {
     return fail(RAMA_E_STATE, "pos %d outside [0, seq_len=%d)", pos, c->T);
   if (token < 0 || token >= c->V) return fail(RAMA_E_INVALID, "token %d outside the vocabulary", token);
   CK(cudaSetDevice(c->device));
+  CK(session_enter(s));
   const int bk = set_attn_bucket(s, pos);
   if (!s->g[0][bk]) RK(capture(s, 0, &s->g[0][bk]));
   StepCtrl* h = &s->h_ring[s->ring_i];
@@ -1321,6 +1369,7 @@ extern "C" int rama_forward(rama_session* s, int32_t token, int32_t pos) {
   CK(cudaGraphLaunch(s->g[0][bk], s->stream));
   s->logits_gathered = false;
   s->parts_valid = true;
+  s->async_pending = true;
   return RAMA_OK;
 }
 
@@ -1336,6 +1385,7 @@ static int gather_logits(rama_session* s) {
 static int read_ret(rama_session* s, int32_t* next) {
   CK(cudaMemcpyAsync(s->h_ret, &s->ctrl->next, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, s->stream));
   CK(cudaStreamSynchronize(s->stream));
+  s->async_pending = false;
   if (s->h_ret[1] == 1) return fail(RAMA_E_STATE, "token id outside the vocabulary reached the device step");
   if (s->h_ret[1] == 2) return fail(RAMA_E_STATE, "top-p candidate list is empty (the reference panics here, infer.rs:66)");
   if (s->h_ret[1] == 3) return fail(RAMA_E_NCCL, "timed out waiting for a tensor-parallel peer's partial results");
@@ -1348,6 +1398,7 @@ extern "C" int rama_sample(rama_session* s, float temperature, float topp, int32
   if (!s || !next) return fail(RAMA_E_INVALID, "NULL argument");
   rama_ctx* c = s->ctx;
   CK(cudaSetDevice(c->device));
+  CK(session_enter(s));
   const bool greedy = temperature == 0.0f;
   if (!greedy) RK(gather_logits(s));
   const int n_part = c->world > 1 ? c->world * c->sm_count : c->sm_count;
@@ -1374,6 +1425,7 @@ extern "C" int rama_generate(rama_session* s, const int32_t* prompt, int32_t n_p
   for (int i = 0; i < n_prompt; ++i)
     if (prompt[i] < 0 || prompt[i] >= c->V) return fail(RAMA_E_INVALID, "prompt token %d outside the vocabulary", prompt[i]);
   CK(cudaSetDevice(c->device));
+  CK(session_enter(s));
   const int gi = temperature == 0.0f ? 0 : 1;
   for (int i = 0; i < steps; i += kAttnChunk) {  // make sure every bucket this run touches is captured before timing
     const int bk = set_attn_bucket(s, i);
@@ -1433,6 +1485,7 @@ extern "C" int rama_profile_step(rama_session* s, int32_t token, int32_t pos, fl
   if (pos < 0 || pos >= c->T) return fail(RAMA_E_STATE, "pos %d outside [0, seq_len=%d)", pos, c->T);
   if (token < 0 || token >= c->V) return fail(RAMA_E_INVALID, "token outside the vocabulary");
   CK(cudaSetDevice(c->device));
+  CK(session_enter(s));
   RK(init_parts(s));
   set_attn_bucket(s, pos);
   StepCtrl* h = &s->h_ring[s->ring_i];
@@ -1468,6 +1521,7 @@ extern "C" int rama_step_trace(rama_session* s, int32_t token, int32_t pos, long
   const int n = 2 * (5 * c->L + 1) + 1;
   if (cap < n) return fail(RAMA_E_INVALID, "need room for %d stamps", n);
   CK(cudaSetDevice(c->device));
+  CK(session_enter(s));
   long long* d = nullptr;
   CK(cudaMalloc((void**)&d, n * sizeof(long long)));
   StepCtrl* h = &s->h_ring[s->ring_i];
@@ -1492,6 +1546,7 @@ extern "C" int rama_logits_to_host(rama_session* s, float* dst, size_t n) {
   rama_ctx* c = s->ctx;
   if (n < (size_t)c->V) return fail(RAMA_E_INVALID, "buffer too small");
   CK(cudaSetDevice(c->device));
+  CK(session_enter(s));
   RK(gather_logits(s));
   CK(cudaMemcpyAsync(dst, s->logits, (size_t)c->V * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
   CK(cudaStreamSynchronize(s->stream));
@@ -1502,6 +1557,7 @@ extern "C" int rama_state_to_host(rama_session* s, int buf, float* dst, size_t n
   if (!s) return fail(RAMA_E_INVALID, "NULL session");
   rama_ctx* c = s->ctx;
   CK(cudaSetDevice(c->device));
+  CK(session_enter(s));
   const float* src = nullptr;
   size_t have = 0;
   switch (buf) {
@@ -1761,6 +1817,7 @@ extern "C" int rama_prefill(rama_session* s, const int32_t* tokens, int32_t n, i
                             float ms_kind[RAMA_PK_COUNT], int32_t* n_launch) {
   if (!s || !tokens) return fail(RAMA_E_INVALID, "NULL argument");
   CK(cudaSetDevice(s->ctx->device));
+  CK(session_enter(s));
   CK(cudaEventRecord(s->ev0, s->stream));
   RK(prefill_run(s, tokens, n, pos0, ms_kind, n_launch));
   CK(cudaEventRecord(s->ev1, s->stream));
@@ -1804,6 +1861,7 @@ struct rama_batch {
   std::vector<cudaGraphExec_t> graphs;  // by batch size
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int launches = 0;
+  std::shared_ptr<BatchFence> fence;    // re-recorded after every step; the sessions of the step hold a reference
 };
 
 // split-K factor: the smallest one that fills ≥ 92 % of the CTA slots of its last wave (every extra split writes and
@@ -1862,6 +1920,12 @@ extern "C" int rama_batch_create(rama_ctx* c, int32_t max_seqs, rama_batch** out
     return fail(RAMA_E_CUDA, "batch allocation: %s", cudaGetErrorString(e));
   }
   b->graphs.assign(max_seqs + 1, nullptr);
+  b->fence = std::make_shared<BatchFence>();
+  if (cudaEventCreateWithFlags(&b->fence->ev, cudaEventDisableTiming) != cudaSuccess) {
+    rama_batch_destroy(b);
+    return fail(RAMA_E_CUDA, "batch fence event");
+  }
+  c->n_objects.fetch_add(1);
   *out = b;
   return RAMA_OK;
 }
@@ -1880,6 +1944,7 @@ extern "C" int rama_batch_destroy(rama_batch* b) {
   if (b->ev0) cudaEventDestroy(b->ev0);
   if (b->ev1) cudaEventDestroy(b->ev1);
   if (b->stream) cudaStreamDestroy(b->stream);
+  if (b->fence) b->ctx->n_objects.fetch_sub(1);  // counted only once fully created
   delete b;
   return RAMA_OK;
 }
@@ -2011,6 +2076,15 @@ extern "C" int rama_forward_batch(rama_batch* b, rama_session* const* sessions, 
     hs[i] = BatchSeq{s->key_cache, s->value_cache, s->logits, s->ctrl, pos[i], tokens[i]};
     s->logits_gathered = true;   // under TP the batched step leaves the full vocabulary in every session
     s->parts_valid = false;
+    // stream ordering, both ways: the step waits for work the session still has in flight on its own stream (an async
+    // rama_forward), and the session's next own operation waits for this step (session_enter)
+    if (s->fence && s->fence != b->fence) CK(cudaStreamWaitEvent(b->stream, s->fence->ev, 0));  // last touched by another batch
+    if (s->async_pending) {
+      CK(cudaEventRecord(s->ev1, s->stream));
+      CK(cudaStreamWaitEvent(b->stream, s->ev1, 0));
+      s->async_pending = false;
+    }
+    s->fence = b->fence;
   }
   CK(cudaMemcpyAsync(b->d_seqs, hs, (size_t)n * sizeof(BatchSeq), cudaMemcpyHostToDevice, b->stream));
   if (!b->graphs[n]) {
@@ -2028,6 +2102,7 @@ extern "C" int rama_forward_batch(rama_batch* b, rama_session* const* sessions, 
     b->launches = nl;
   }
   CK(cudaGraphLaunch(b->graphs[n], b->stream));
+  CK(cudaEventRecord(b->fence->ev, b->stream));
   return RAMA_OK;
 }
 
@@ -2044,6 +2119,12 @@ extern "C" int rama_sample_batch(rama_batch* b, rama_session* const* sessions, i
     rama_session* s = sessions[i];
     b->h_sp[i] = SampleParams{s->logits, nullptr, 0, 0, c->V, s->ctrl, nullptr, nullptr, s->sort_keys, temperature, topp, 0, PeerIn{}};
     hs[i] = BatchSeq{s->key_cache, s->value_cache, s->logits, s->ctrl, 0, 0};
+    if (s->fence && s->fence != b->fence) CK(cudaStreamWaitEvent(b->stream, s->fence->ev, 0));
+    if (s->async_pending) {  // logits written by an asynchronous rama_forward on the session's own stream
+      CK(cudaEventRecord(s->ev1, s->stream));
+      CK(cudaStreamWaitEvent(b->stream, s->ev1, 0));
+      s->async_pending = false;
+    }
   }
   CK(cudaMemcpyAsync(b->d_sp, b->h_sp, (size_t)n * sizeof(SampleParams), cudaMemcpyHostToDevice, b->stream));
   // d_seqs still describes this batch when sample follows forward; rewrite only if the caller passes other sessions

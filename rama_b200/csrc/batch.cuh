@@ -37,8 +37,10 @@ __global__ void __launch_bounds__(256) batch_embed_kernel(const BatchSeq* __rest
   const BatchSeq sq = seqs[blockIdx.x];
   int token = sq.token;
   if (threadIdx.x == 0) {
+    // the error flag describes THIS step (rama_sample_batch reads it per step): a session handed back to a pool and reused
+    // must not carry an earlier request's error
     sq.ctrl->pos = sq.pos; sq.ctrl->token = token; sq.ctrl->chained = 0;
-    if (token < 0 || token >= vocab) sq.ctrl->error = 1;
+    sq.ctrl->error = (token < 0 || token >= vocab) ? 1 : 0;
   }
   if (token < 0 || token >= vocab) token = 0;
   const float4* src = reinterpret_cast<const float4*>(emb + (size_t)token * D);

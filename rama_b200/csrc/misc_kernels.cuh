@@ -45,8 +45,11 @@ struct SampleParams {
   const int32_t* prompt;    // chained mode
   int32_t* out_tokens;      // chained mode: out_tokens[pos] = next
   unsigned long long* keys; // scratch [2][V] composite sort keys (top-p path)
-  float temperature, topp;  // used when !ctrl->chained (host-driven rama_sample)
-  int use_ctrl_params;      // 1: take temperature/topp from ctrl (chained generate)
+  float temperature, topp;  // used when !chained (host-driven rama_sample)
+  int chained;              // 1 (only from rama_generate and the graphs it captures): device-resident loop — temperature/topp
+                            // from ctrl, prompt forcing, token feedback and pos advance on the device.  A launch parameter, not
+                            // device state: a later rama_sample / rama_prefill / rama_sample_batch on the same session must not
+                            // inherit it (stale ctrl->pos would index out_tokens out of bounds)
   PeerIn pin;               // pin.P > 0: part is an LL array [P*n_per][2] written by every rank's classifier
 };
 
@@ -117,8 +120,8 @@ __device__ __forceinline__ void sample_body(const SampleParams& p) {
   __shared__ float s_cum;
   __shared__ unsigned long long s_sort[kSortSmem];  // 32 KB: sort tile / walk staging
   StepCtrl* ctrl = p.ctrl;
-  const float temperature = p.use_ctrl_params ? ctrl->temperature : p.temperature;
-  const float topp = p.use_ctrl_params ? ctrl->topp : p.topp;
+  const float temperature = p.chained ? ctrl->temperature : p.temperature;
+  const float topp = p.chained ? ctrl->topp : p.topp;
   const int V = p.V;
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
   int* redi = reinterpret_cast<int*>(red + kWarp);
@@ -254,7 +257,7 @@ __device__ __forceinline__ void sample_body(const SampleParams& p) {
 
   if (threadIdx.x == 0) {
     int next = s_next;
-    if (ctrl->chained) {
+    if (p.chained) {
       const int pos = ctrl->pos;
       if (pos < ctrl->n_prompt) next = p.prompt[pos];  // prompt forcing (mod.rs:190-191)
       p.out_tokens[pos] = next;

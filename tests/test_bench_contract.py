@@ -31,6 +31,21 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert "workload" in d["config"] and "stories15M" in d["config"]["workload"]
 
 
+def test_reference_arm_under_torchrun_uses_all_cores_and_stays_bounded():
+    """torchrun exports OMP_NUM_THREADS=1 when nproc > 1 (round 1: the oracle then ran single-threaded and the arm timed
+    out at N = 2/4/8).  Rank 0 must still use every host core, size its sample from the time budget and print the same
+    `config` keys as the CUDA arm."""
+    env = dict(os.environ, RANK="0", LOCAL_RANK="0", WORLD_SIZE="2", OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, BENCH, "--impl", "reference", "--gpus", "2", "--model", "stories15M", "--steps", "3",
+                        "--warmup", "1"], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    (d,) = _json_lines(r.stdout)
+    assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
+    assert d["n_gpus"] == 2 and d["steps"] == 3 and d["warmup"] == 1
+    assert sorted(d["config"]) == ["l2", "parallelism", "seed", "workload"] and d["config"]["parallelism"] == "tp2"
+    assert d["ms_per_step"] * (d["steps"] + d["warmup"]) < 60e3
+
+
 def test_reference_arm_other_ranks_exit_quietly():
     env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2")
     r = subprocess.run([sys.executable, BENCH, "--impl", "reference", "--gpus", "2", "--model", "stories15M"], capture_output=True,

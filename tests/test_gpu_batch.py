@@ -86,25 +86,42 @@ def test_batch_errors():
 
 
 def test_batch_64_at_7b_layer_shapes():
-    """BASELINE config 5 geometry (dim 4096, ffn 11008, 32 heads, 64 concurrent sequences) on 2 layers."""
+    """BASELINE config 5 geometry (dim 4096, ffn 11008, 32 heads, 64 concurrent sequences) on 2 layers: the batched
+    tensor-core step against the CPU ORACLE (every sequence's own forward() stream, lib.rs:127-160) for six sequences
+    spread over the batch, and against the per-token CUDA path."""
     cfg = ck.CONFIGS["l7-2layer"]
+    spec = ck.SynthSpec()
     gpu = GPU(0)
-    gpu.load_synthetic(cfg, ck.SynthSpec())
+    gpu.load_synthetic(cfg, spec)
+    om = ref.Model(cfg, ref.synth_tensors(cfg, spec))  # bit-identical to the device generator
     B, steps = 64, 6
     rng = np.random.default_rng(1)
     streams = [[1] + [int(t) for t in rng.integers(0, cfg.vocab_size, steps)] for _ in range(B)]
     bat = [Session(gpu) for _ in range(B)]
     check = [0, 17, 63]
+    oracle_check = [0, 9, 17, 31, 46, 63]
     solo = {i: Session(gpu) for i in check}
+    ost = {i: ref.State(om) for i in oracle_check}
     batch = Batch(gpu, 64)
     for k in range(steps):
         batch.forward(bat, [streams[i][k] for i in range(B)], [k] * B)
         for i in check:
             solo[i].forward(streams[i][k], k)
+        for i in oracle_check:
+            ref.forward(om, ost[i], streams[i][k], k)
     batch.sync()
+    for i in oracle_check:
+        assert rel_err(bat[i].logits(), ost[i].logits) < LOGIT_TOL, i
+        ko = ost[i].key_cache.reshape(cfg.n_layers, cfg.seq_len, -1)[:, :steps]
+        vo = ost[i].value_cache.reshape(cfg.n_layers, cfg.seq_len, -1)[:, :steps]
+        kb = bat[i].state("key_cache").reshape(cfg.n_layers, cfg.seq_len, -1)[:, :steps]
+        vb = bat[i].state("value_cache").reshape(cfg.n_layers, cfg.seq_len, -1)[:, :steps]
+        assert rel_err(kb, ko) < 1e-4 and rel_err(vb, vo) < 1e-4, i
     for i in check:
         assert rel_err(bat[i].logits(), solo[i].logits()) < LOGIT_TOL, i
     nxt = batch.sample(bat, 0.0, 0.9)
+    for i in oracle_check:
+        assert nxt[i] == int(np.flatnonzero(ost[i].logits == ost[i].logits.max())[-1]), i
     for i in check:
         assert nxt[i] == solo[i].sample(0.0, 0.9)
     print("launches per batched step", batch.launches_per_step())

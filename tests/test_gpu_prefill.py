@@ -88,24 +88,34 @@ def test_prefill_errors():
 
 
 def test_prefill_512_at_7b_layer_shapes():
-    """BASELINE config 4 geometry (dim 4096, ffn 11008, 32 heads, 512 prompt tokens) on 2 layers:
-    prefill vs 512 per-token steps of the decode path."""
+    """BASELINE config 4 geometry (dim 4096, ffn 11008, 32 heads, 512 prompt tokens) on 2 layers: the tensor-core
+    prefill against the CPU ORACLE run token by token over the same 512 rows (K = 4096 / 11008 contractions — where a
+    tcgen05 accumulation drift would show), and against 512 per-token steps of the decode path."""
     cfg = ck.CONFIGS["l7-2layer"]
+    spec = ck.SynthSpec()
     gpu = GPU(0)
-    gpu.load_synthetic(cfg, ck.SynthSpec())
+    gpu.load_synthetic(cfg, spec)
+    om = ref.Model(cfg, ref.synth_tensors(cfg, spec))  # same integer recipe as the device generator (bit-identical)
+    os_ = ref.State(om)
     rng = np.random.default_rng(7)
     n = 512
     toks = [1] + [int(t) for t in rng.integers(0, cfg.vocab_size, n - 1)]
     a, b = Session(gpu), Session(gpu)
     for pos, t in enumerate(toks):
         a.forward(t, pos)
+        ref.forward(om, os_, t, pos)
     ms, kinds, launches = b.prefill(toks, 0, profile=True)
     print("prefill-512 l7-2layer ms", ms, kinds, launches)
     ka, va = _kv(a, cfg, n)
     kb, vb = _kv(b, cfg, n)
+    ko = os_.key_cache.reshape(cfg.n_layers, cfg.seq_len, -1)[:, :n]
+    vo = os_.value_cache.reshape(cfg.n_layers, cfg.seq_len, -1)[:, :n]
+    assert rel_err(kb, ko) < 1e-4 and rel_err(vb, vo) < 1e-4          # every cache row of every layer vs the oracle
+    assert rel_err(b.logits(), os_.logits) < LOGIT_TOL                # last-position logits vs the oracle
     assert rel_err(kb, ka) < 1e-4 and rel_err(vb, va) < 1e-4
     assert rel_err(b.logits(), a.logits()) < LOGIT_TOL
-    assert b.sample(0.0, 0.9) == a.sample(0.0, 0.9)
+    want = int(np.flatnonzero(os_.logits == os_.logits.max())[-1])    # later index wins (cpu.rs:165)
+    assert b.sample(0.0, 0.9) == want == a.sample(0.0, 0.9)
     a.close(); b.close(); gpu.close()
 
 
