@@ -26,7 +26,6 @@ constexpr int kAttnThreads = 256;
 constexpr int kAttnWarps = kAttnThreads / kWarp;
 constexpr int kAttnPerWarp = 4;                          // timesteps per warp
 constexpr int kAttnChunk = kAttnWarps * kAttnPerWarp;    // 32 timesteps per CTA
-constexpr int kAttnMaxHs = 128;
 
 struct AttnParams {
   const float* q;            // [H_loc*hs]
@@ -170,7 +169,7 @@ __device__ __forceinline__ void attn_decode_body(const AttnParams& p, int pos) {
   }
 }
 
-__global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnParams p, int use_pdl) {
+static __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnParams p, int use_pdl) {
   if (use_pdl) pdl_launch_dependents();
   if (p.prefetch && threadIdx.x == 0) {  // weights do not depend on the previous kernel
     const size_t n_cta = (size_t)gridDim.x * gridDim.y, me = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
@@ -200,7 +199,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnPar
 // wait only q and row `pos` remain to be fetched.
 constexpr int kAttnClusterMax = 8;  // portable cluster size
 
-__global__ void __launch_bounds__(kAttnThreads, 2) attn_cluster_kernel(const AttnParams p, int use_pdl) {
+static __global__ void __launch_bounds__(kAttnThreads, 2) attn_cluster_kernel(const AttnParams p, int use_pdl) {
   namespace cg = cooperative_groups;
   constexpr int NW = kAttnWarps;
   __shared__ float s_m[NW], s_l[NW];
@@ -375,7 +374,7 @@ struct AttnWoParams {
   int Dq, hs, D, J;
 };
 
-__global__ void __launch_bounds__(kAttnWoThreads) attn_wo_kernel(const AttnWoParams p, int use_pdl) {
+static __global__ void __launch_bounds__(kAttnWoThreads) attn_wo_kernel(const AttnWoParams p, int use_pdl) {
   __shared__ float s_m[kAttnWoWarps], s_l[kAttnWoWarps];
   __shared__ __align__(16) float s_acc[kAttnWoWarps][kAttnMaxHs];
   __shared__ __align__(16) float s_xb[kAttnMaxHs];
@@ -473,7 +472,7 @@ __global__ void __launch_bounds__(kAttnWoThreads) attn_wo_kernel(const AttnWoPar
 // Rows of hs ≤ 64 floats take half a warp: two rows per 128-bit warp load.
 constexpr int kAwcRowLoads = 8;  // 128-bit wo loads per lane held in registers across the attention
 
-__global__ void __launch_bounds__(kAttnThreads, 2) attn_wo_cluster_kernel(const AttnWoParams p, int use_pdl) {
+static __global__ void __launch_bounds__(kAttnThreads, 2) attn_wo_cluster_kernel(const AttnWoParams p, int use_pdl) {
   namespace cg = cooperative_groups;
   constexpr int NW = kAttnWarps;
   __shared__ float s_m[NW], s_l[NW];

@@ -21,7 +21,7 @@ struct BatchSeq {  // one sequence of a batched step (device array, rewritten by
 };
 
 // out[i] = Σ_s part[s][i], s ascending
-__global__ void sum_partials_kernel(float* __restrict__ out, const float* __restrict__ part, size_t n, int S) {
+static __global__ void sum_partials_kernel(float* __restrict__ out, const float* __restrict__ part, size_t n, int S) {
   pdl_launch_dependents(); pdl_wait();  // (no-ops unless launched with programmatic stream serialization)
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     float a = 0.f;
@@ -31,7 +31,7 @@ __global__ void sum_partials_kernel(float* __restrict__ out, const float* __rest
 }
 
 // x[b] = token_embedding_table[token_b] (infer.rs:13); mirrors (token,pos) into the session's control block
-__global__ void __launch_bounds__(256) batch_embed_kernel(const BatchSeq* __restrict__ seqs, const float* __restrict__ emb,
+static __global__ void __launch_bounds__(256) batch_embed_kernel(const BatchSeq* __restrict__ seqs, const float* __restrict__ emb,
                                                           float* __restrict__ x, int D, int vocab) {
   pdl_launch_dependents(); pdl_wait();  // (no-ops unless launched with programmatic stream serialization)
   const BatchSeq sq = seqs[blockIdx.x];
@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(256) batch_embed_kernel(const BatchSeq* __rest
 // ≙ array_add (cpu.rs:16-21) + rmsnorm (cpu.rs:99-117); one 1024-thread CTA per sequence, the S partial loads of an
 // element issued back to back (the kernel is pure latency: 64 CTAs, a few KB each)
 constexpr int kBatchNormThreads = 1024;
-__global__ void __launch_bounds__(kBatchNormThreads) batch_addnorm_kernel(float* __restrict__ x, const float* __restrict__ y,
+static __global__ void __launch_bounds__(kBatchNormThreads) batch_addnorm_kernel(float* __restrict__ x, const float* __restrict__ y,
                                                                           int S, size_t slab, const float* __restrict__ w,
                                                                           float* __restrict__ xn, int D) {
   pdl_launch_dependents(); pdl_wait();  // (no-ops unless launched with programmatic stream serialization)
@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(kBatchNormThreads) batch_addnorm_kernel(float*
 
 // [wq;wk;wv] partials [3][S][B][Dq] → sum, RoPE on q,k at the sequence's own position (cpu.rs:74-97),
 // q → Q[b], k/v → the session's cache row pos_b of this layer (infer.rs:31-33).  Grid (B, ceil(Dq/2/256)).
-__global__ void __launch_bounds__(256) batch_qkv_finish_kernel(const float* __restrict__ part, int S, size_t slab,
+static __global__ void __launch_bounds__(256) batch_qkv_finish_kernel(const float* __restrict__ part, int S, size_t slab,
                                                                const BatchSeq* __restrict__ seqs, size_t layer_off,
                                                                float* __restrict__ q, const float* __restrict__ freq_real,
                                                                const float* __restrict__ freq_imag, int Dq, int hs2) {
@@ -136,7 +136,7 @@ struct AttnBatchParams {
   size_t layer_off;
   int T, Dq, hs, n_split, H;
 };
-__global__ void __launch_bounds__(kAttnThreads) attn_decode_batch_kernel(const AttnBatchParams bp) {
+static __global__ void __launch_bounds__(kAttnThreads) attn_decode_batch_kernel(const AttnBatchParams bp) {
   pdl_launch_dependents(); pdl_wait();  // (no-ops unless launched with programmatic stream serialization)
   const int b = blockIdx.z;
   const BatchSeq sq = bp.seqs[b];
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_batch_kernel(const A
 }
 
 // [w1;w3] partials [2][S][B][F] → hb[b][j] = (h1·(1/(1+exp(−h1))))·h3   (cpu.rs:54-64)
-__global__ void __launch_bounds__(256) batch_swiglu_finish_kernel(const float* __restrict__ part, int S, size_t slab,
+static __global__ void __launch_bounds__(256) batch_swiglu_finish_kernel(const float* __restrict__ part, int S, size_t slab,
                                                                   float* __restrict__ hb, int F, int B) {
   pdl_launch_dependents(); pdl_wait();  // (no-ops unless launched with programmatic stream serialization)
   const size_t n = (size_t)B * F;
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(256) batch_swiglu_finish_kernel(const float* _
 }
 
 // tensor parallelism: staging [P][B][Vl] (all-gathered) → every session's full logits [V]
-__global__ void __launch_bounds__(256) batch_logits_scatter_kernel(const float* __restrict__ staging,
+static __global__ void __launch_bounds__(256) batch_logits_scatter_kernel(const float* __restrict__ staging,
                                                                    const BatchSeq* __restrict__ seqs, int Vl, int P, int B) {
   pdl_launch_dependents(); pdl_wait();  // (no-ops unless launched with programmatic stream serialization)
   const int b = blockIdx.y;
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(256) batch_logits_scatter_kernel(const float* 
 }
 
 // classifier partials [S][B][Vl] → staging[b][Vl] (tensor parallelism: this rank's block of the all-gather buffer)
-__global__ void __launch_bounds__(256) batch_cls_stage_kernel(const float* __restrict__ part, int S, size_t slab,
+static __global__ void __launch_bounds__(256) batch_cls_stage_kernel(const float* __restrict__ part, int S, size_t slab,
                                                               float* __restrict__ out, int Vl) {
   pdl_launch_dependents(); pdl_wait();  // (no-ops unless launched with programmatic stream serialization)
   const int b = blockIdx.y;
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(256) batch_cls_stage_kernel(const float* __res
 }
 
 // classifier partials [S][B][Vl] → the session's logits[v0 .. v0+Vl)
-__global__ void __launch_bounds__(256) batch_cls_finish_kernel(const float* __restrict__ part, int S, size_t slab,
+static __global__ void __launch_bounds__(256) batch_cls_finish_kernel(const float* __restrict__ part, int S, size_t slab,
                                                                const BatchSeq* __restrict__ seqs, int Vl, int v0) {
   pdl_launch_dependents(); pdl_wait();  // (no-ops unless launched with programmatic stream serialization)
   const int b = blockIdx.y;
@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(256) batch_cls_finish_kernel(const float* __re
 }
 
 // after sample_batch_kernel: next[b] = ctrl_b->next, err[b] = ctrl_b->error
-__global__ void batch_collect_kernel(const BatchSeq* __restrict__ seqs, int32_t* __restrict__ out, int B) {
+static __global__ void batch_collect_kernel(const BatchSeq* __restrict__ seqs, int32_t* __restrict__ out, int B) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b < B) {
     out[2 * b] = seqs[b].ctrl->next;

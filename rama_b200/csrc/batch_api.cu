@@ -1,0 +1,330 @@
+// batch_api.cu — batched multi-sequence decode (host side): one step for n sessions (server path, lib.rs:127-160).
+#include "internal.cuh"
+
+#include "gemm_host.cuh"
+#include "batch.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// batched multi-sequence decode (server path, lib.rs:127-160): one step for n sessions
+// ------------------------------------------------------------------------------------------------
+extern "C" int rama_batch_destroy(rama_batch* b);
+constexpr int kBatchMax = 64;    // one 64-column MMA tile of sequences
+constexpr int kBatchRing = 8;
+// batched-decode GEMM tile: 128 weight rows × 64 sequences, 2 stages, chunks of 2 k-blocks; two CTAs fit an SM
+// (64 KB of shared memory and 256 TMEM columns each) and interleave their pipelines
+#define BATCH_GEMM launch_gemm_tf32x3<64, 2, 4, 0>  // 128-k chunks as in prefill (CH = 2: 9.18 ms per 64-sequence step)
+constexpr int kBatchCtasPerSm = GemmSmem<64, 2, 0>::kCtasPerSm;
+
+struct rama_batch {
+  rama_ctx* ctx = nullptr;
+  int cap = 0, n_split = 1;
+  cudaStream_t stream = nullptr;
+  float *x = nullptr, *xn = nullptr, *q = nullptr, *att = nullptr, *h = nullptr, *part = nullptr, *attn_ws = nullptr;
+  float *red = nullptr, *lstage = nullptr;  // tensor parallelism: all-reduce buffer [B][D], logits all-gather staging [P][B][Vl]
+  unsigned int* tickets = nullptr;
+  size_t part_floats = 0;
+  BatchSeq* d_seqs = nullptr;
+  BatchSeq* h_seqs = nullptr;        // pinned ring [kBatchRing][cap]
+  SampleParams* d_sp = nullptr;
+  SampleParams* h_sp = nullptr;      // pinned [cap]
+  int32_t* d_next = nullptr;
+  int32_t* h_next = nullptr;         // pinned [2·cap]
+  int ring_i = 0;
+  std::vector<cudaGraphExec_t> graphs;  // by batch size
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int launches = 0;
+  std::shared_ptr<BatchFence> fence;    // re-recorded after every step; the sessions of the step hold a reference
+};
+
+// split-K factor: the smallest one that fills ≥ 92 % of the CTA slots of its last wave (every extra split writes and
+// re-reads another [n][rows] partial), else the best-filling one; ≥ 8 k-blocks per split
+static int pick_ksplit(const rama_ctx* c, int tiles, int K) {
+  const int total_kb = (K + kGemmBK - 1) / kGemmBK;
+  const int slots = c->sm_count * kBatchCtasPerSm;  // CTAs resident at once
+  int best = 1;
+  double best_eff = 0.0;
+  for (int S = 1; S <= 16; ++S) {
+    if (S > 1 && total_kb / S < 8) break;
+    const int units = tiles * S, waves = (units + slots - 1) / slots;
+    const double eff = (double)units / ((double)waves * slots);
+    if (eff >= 0.92) return S;
+    if (eff > best_eff + 0.02) { best_eff = eff; best = S; }
+  }
+  return best;
+}
+
+extern "C" int rama_batch_create(rama_ctx* c, int32_t max_seqs, rama_batch** out) {
+  if (!c || !out) return fail(RAMA_E_INVALID, "NULL argument");
+  if (!c->loaded) return fail(RAMA_E_STATE, "no weights loaded");
+  if (max_seqs < 1 || max_seqs > kBatchMax) return fail(RAMA_E_INVALID, "max_seqs must be in [1, %d]", kBatchMax);
+  CK(cudaSetDevice(c->device));
+  std::lock_guard<std::mutex> cap_lk(c->cap_mu);
+  rama_batch* b = new rama_batch();
+  b->ctx = c;
+  b->cap = max_seqs;
+  b->n_split = (c->T + kAttnChunk - 1) / kAttnChunk;
+  const size_t B = max_seqs, D = c->D, Dq = c->Dq, Fl = c->Fl;
+  // partial buffer: the largest of [3][S][B][Dq], [S][B][D], [2][S][B][Fl], [S][B][Vl] over the chosen split factors
+  auto tiles = [](int rows) { return (rows + kGemmBM - 1) / kGemmBM; };
+  size_t pf = 0;
+  pf = std::max(pf, (size_t)3 * pick_ksplit(c, 3 * tiles(c->Dq), c->D) * B * Dq);
+  pf = std::max(pf, (size_t)pick_ksplit(c, tiles(c->D), c->Dq) * B * D);
+  pf = std::max(pf, (size_t)2 * pick_ksplit(c, 2 * tiles(c->Fl), c->D) * B * Fl);
+  pf = std::max(pf, (size_t)pick_ksplit(c, tiles(c->D), c->Fl) * B * D);
+  pf = std::max(pf, (size_t)pick_ksplit(c, tiles(c->Vl), c->D) * B * c->Vl);
+  b->part_floats = pf;
+  cudaError_t e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
+#define A(call) if (e == cudaSuccess) e = (call)
+  A(dalloc(&b->x, B * D)); A(dalloc(&b->xn, B * D)); A(dalloc(&b->q, B * Dq)); A(dalloc(&b->att, B * Dq));
+  A(dalloc(&b->h, B * Fl)); A(dalloc(&b->part, pf));
+  if (c->world > 1) { A(dalloc(&b->red, B * D)); A(dalloc(&b->lstage, (size_t)c->world * B * c->Vl)); }
+  A(dalloc(&b->attn_ws, B * c->Hl * b->n_split * (c->hs + 2)));
+  A(dalloc(&b->tickets, B * c->Hl));
+  A(dalloc(&b->d_seqs, B)); A(dalloc(&b->d_sp, B)); A(dalloc(&b->d_next, 2 * B));
+  A(cudaHostAlloc((void**)&b->h_seqs, kBatchRing * B * sizeof(BatchSeq), cudaHostAllocDefault));
+  A(cudaHostAlloc((void**)&b->h_sp, B * sizeof(SampleParams), cudaHostAllocDefault));
+  A(cudaHostAlloc((void**)&b->h_next, 2 * B * sizeof(int32_t), cudaHostAllocDefault));
+  A(cudaEventCreate(&b->ev0)); A(cudaEventCreate(&b->ev1));
+  A(cudaDeviceSynchronize());
+#undef A
+  if (e != cudaSuccess) {
+    rama_batch_destroy(b);
+    return fail(RAMA_E_CUDA, "batch allocation: %s", cudaGetErrorString(e));
+  }
+  b->graphs.assign(max_seqs + 1, nullptr);
+  b->fence = std::make_shared<BatchFence>();
+  if (cudaEventCreateWithFlags(&b->fence->ev, cudaEventDisableTiming) != cudaSuccess) {
+    rama_batch_destroy(b);
+    return fail(RAMA_E_CUDA, "batch fence event");
+  }
+  c->n_objects.fetch_add(1);
+  *out = b;
+  return RAMA_OK;
+}
+
+extern "C" int rama_batch_destroy(rama_batch* b) {
+  if (!b) return RAMA_OK;
+  cudaSetDevice(b->ctx->device);
+  if (b->stream) cudaStreamSynchronize(b->stream);
+  std::lock_guard<std::mutex> cap_lk(b->ctx->cap_mu);
+  for (auto g : b->graphs) if (g) cudaGraphExecDestroy(g);
+  void* bufs[] = {b->x, b->xn, b->q, b->att, b->h, b->part, b->attn_ws, b->tickets, b->d_seqs, b->d_sp, b->d_next, b->red, b->lstage};
+  for (void* p : bufs) if (p) cudaFree(p);
+  if (b->h_seqs) cudaFreeHost(b->h_seqs);
+  if (b->h_sp) cudaFreeHost(b->h_sp);
+  if (b->h_next) cudaFreeHost(b->h_next);
+  if (b->ev0) cudaEventDestroy(b->ev0);
+  if (b->ev1) cudaEventDestroy(b->ev1);
+  if (b->stream) cudaStreamDestroy(b->stream);
+  if (b->fence) b->ctx->n_objects.fetch_sub(1);  // counted only once fully created
+  delete b;
+  return RAMA_OK;
+}
+
+// enqueue one batched step for n sequences (everything per-sequence is read from b->d_seqs on the device,
+// so the captured graph of a batch size serves every step)
+static int enqueue_batch_step(rama_batch* b, int n, int* n_launch) {
+  rama_ctx* c = b->ctx;
+  cudaStream_t st = b->stream;
+  const int D = c->D, Dq = c->Dq, Fl = c->Fl, T = c->T, hs = c->hs, L = c->L, Vl = c->Vl;
+  const float* const* W = c->w;
+  int launches = 0;
+  const bool pdl = c->use_pdl && env_int("RAMA_BATCH_PDL", 1);
+  auto tiles = [](int rows) { return (rows + kGemmBM - 1) / kGemmBM; };
+#define LK(call)                                                                                              \
+  do {                                                                                                        \
+    cudaError_t e_ = (call);                                                                                  \
+    if (e_ == cudaSuccess) e_ = cudaGetLastError();                                                           \
+    ++launches;                                                                                               \
+    if (e_ != cudaSuccess) return fail(RAMA_E_CUDA, "batched step launch %s: %s", #call, cudaGetErrorString(e_)); \
+  } while (0)
+  LK(launch_k(pdl, batch_embed_kernel, dim3(n), dim3(256), st, b->d_seqs, W[RAMA_T_TOKEN_EMBEDDING], b->x, D, c->V));
+  GemmOperand X{b->xn, (size_t)n, (size_t)D};
+  int S_prev = 0;  // split factor of the pending residual partials in b->part (0: none)
+  const float* pending = b->part;
+  // tensor parallelism: row-parallel wo / w2 leave a partial [n][D] on every rank — sum the split-K partials, all-reduce
+  // over NVLink (NCCL, 1 MB at 64 sequences), and hand the reduced buffer to the next addnorm as a single "split"
+  auto reduce_ranks = [&](int& S) -> int {
+    if (c->world <= 1) return RAMA_OK;
+    LK(launch_k(pdl, sum_partials_kernel, dim3(c->sm_count * 2), dim3(256), st, b->red, (const float*)b->part, (size_t)n * D, S));
+    NK(g_nccl.AllReduce(b->red, b->red, (size_t)n * D, kNcclFloat32, kNcclSum, c->comm, st));
+    ++launches;
+    S = 1;
+    pending = b->red;
+    return RAMA_OK;
+  };
+  for (int l = 0; l < L; ++l) {
+    const size_t layer_off = (size_t)l * T * Dq;
+    // x += pending w2 output; xn = rmsnorm(x)   (infer.rs:19, :47 of the previous layer)
+    LK(launch_k(pdl, batch_addnorm_kernel, dim3(n), dim3(kBatchNormThreads), st, b->x, S_prev ? pending : nullptr, S_prev,
+                (size_t)n * D, W[RAMA_T_RMS_ATT] + (size_t)l * D, b->xn, D));
+    {  // [wq;wk;wv] (weights = the 128-row operand, the batch = the 64-column operand)   (infer.rs:20-23)
+      GemmOperand A[3] = {{W[RAMA_T_WQ] + (size_t)l * Dq * D, (size_t)Dq, (size_t)D},
+                          {W[RAMA_T_WK] + (size_t)l * Dq * D, (size_t)Dq, (size_t)D},
+                          {W[RAMA_T_WV] + (size_t)l * Dq * D, (size_t)Dq, (size_t)D}};
+      const int S = pick_ksplit(c, 3 * tiles(Dq), D);
+      EpiStoreT epi{b->part, Dq, n, S, (size_t)n * Dq};
+      LK((BATCH_GEMM(st, A, 3, &X, 1, Dq, n, D, 0, S, epi, pdl)));
+      LK(launch_k(pdl, batch_qkv_finish_kernel, dim3(n, (Dq / 2 + 255) / 256), dim3(256), st, b->part, S, (size_t)n * Dq, b->d_seqs, layer_off, b->q, W[RAMA_T_FREQ_REAL], W[RAMA_T_FREQ_IMAG], Dq, hs / 2));
+    }
+    {  // attention per sequence   (infer.rs:34)
+      AttnBatchParams ap{b->d_seqs, b->q, b->att, b->attn_ws, b->tickets, layer_off, T, Dq, hs, b->n_split, c->Hl};
+      LK(launch_k(pdl, attn_decode_batch_kernel, dim3(c->Hl, std::min(b->n_split, 2), n), dim3(kAttnThreads), st, ap));  // CTAs stride over the chunks
+    }
+    int S_wo;
+    {  // wo   (infer.rs:35)
+      GemmOperand A{W[RAMA_T_WO] + (size_t)l * D * Dq, (size_t)D, (size_t)Dq};
+      GemmOperand Bm{b->att, (size_t)n, (size_t)Dq};
+      S_wo = pick_ksplit(c, tiles(D), Dq);
+      EpiStoreT epi{b->part, D, n, S_wo, (size_t)n * D};
+      LK((BATCH_GEMM(st, &A, 1, &Bm, 1, D, n, Dq, 0, S_wo, epi, pdl)));
+      RK(reduce_ranks(S_wo));
+    }
+    // x += wo output; xn = rmsnorm(x)   (infer.rs:37-38)
+    LK(launch_k(pdl, batch_addnorm_kernel, dim3(n), dim3(kBatchNormThreads), st, b->x, pending, S_wo, (size_t)n * D, W[RAMA_T_RMS_FFN] + (size_t)l * D, b->xn, D));
+    {  // [w1;w3] → SwiGLU   (infer.rs:39-45)
+      GemmOperand A[2] = {{W[RAMA_T_W1] + (size_t)l * Fl * D, (size_t)Fl, (size_t)D},
+                          {W[RAMA_T_W3] + (size_t)l * Fl * D, (size_t)Fl, (size_t)D}};
+      const int S = pick_ksplit(c, 2 * tiles(Fl), D);
+      EpiStoreT epi{b->part, Fl, n, S, (size_t)n * Fl};
+      LK((BATCH_GEMM(st, A, 2, &X, 1, Fl, n, D, 0, S, epi, pdl)));
+      LK(launch_k(pdl, batch_swiglu_finish_kernel, dim3(std::min(c->sm_count * 4, (n * Fl + 255) / 256)), dim3(256), st, b->part, S, (size_t)n * Fl, b->h, Fl, n));
+    }
+    {  // w2   (infer.rs:46)
+      GemmOperand A{W[RAMA_T_W2] + (size_t)l * D * Fl, (size_t)D, (size_t)Fl};
+      GemmOperand Bm{b->h, (size_t)n, (size_t)Fl};
+      S_prev = pick_ksplit(c, tiles(D), Fl);
+      EpiStoreT epi{b->part, D, n, S_prev, (size_t)n * D};
+      LK((BATCH_GEMM(st, &A, 1, &Bm, 1, D, n, Fl, 0, S_prev, epi, pdl)));
+      RK(reduce_ranks(S_prev));
+    }
+  }
+  // x += w2 output; final rmsnorm; classifier → each session's logits   (infer.rs:49-51)
+  LK(launch_k(pdl, batch_addnorm_kernel, dim3(n), dim3(kBatchNormThreads), st, b->x, pending, S_prev, (size_t)n * D, W[RAMA_T_RMS_FINAL], b->xn, D));
+  {
+    GemmOperand A{c->wcls, (size_t)Vl, (size_t)D};
+    const int S = pick_ksplit(c, tiles(Vl), D);
+    EpiStoreT epi{b->part, Vl, n, S, (size_t)n * Vl};
+    LK((BATCH_GEMM(st, &A, 1, &X, 1, Vl, n, D, 0, S, epi, pdl)));
+    if (c->world > 1) {  // vocabulary rows are split: gather every rank's block, then scatter into the sessions' logits
+      float* mine = b->lstage + (size_t)c->rank * n * Vl;
+      LK(launch_k(pdl, batch_cls_stage_kernel, dim3(std::min(64, (Vl + 255) / 256), n), dim3(256), st, b->part, S, (size_t)n * Vl, mine, Vl));
+      NK(g_nccl.AllGather(mine, b->lstage, (size_t)n * Vl, kNcclFloat32, c->comm, st));
+      ++launches;
+      LK(launch_k(pdl, batch_logits_scatter_kernel, dim3(std::min(64, (c->V + 255) / 256), n), dim3(256), st, b->lstage, b->d_seqs, Vl, c->world, n));
+    } else {
+      LK(launch_k(pdl, batch_cls_finish_kernel, dim3(std::min(64, (Vl + 255) / 256), n), dim3(256), st, b->part, S, (size_t)n * Vl, b->d_seqs, Vl, c->v0));
+    }
+  }
+#undef LK
+  if (n_launch) *n_launch = launches;
+  return RAMA_OK;
+}
+
+static int batch_check_sessions(rama_batch* b, rama_session* const* sessions, int32_t n) {
+  if (n < 1 || n > b->cap) return fail(RAMA_E_INVALID, "batch of %d sequences outside [1, %d]", n, b->cap);
+  for (int i = 0; i < n; ++i) {
+    if (!sessions[i] || sessions[i]->ctx != b->ctx) return fail(RAMA_E_INVALID, "session %d is NULL or belongs to another context", i);
+    for (int j = 0; j < i; ++j)
+      if (sessions[j] == sessions[i]) return fail(RAMA_E_INVALID, "session %d appears twice in the batch", i);
+  }
+  return RAMA_OK;
+}
+
+extern "C" int rama_forward_batch(rama_batch* b, rama_session* const* sessions, const int32_t* tokens,
+                                  const int32_t* pos, int32_t n) {
+  if (!b || !sessions || !tokens || !pos) return fail(RAMA_E_INVALID, "NULL argument");
+  rama_ctx* c = b->ctx;
+  RK(batch_check_sessions(b, sessions, n));
+  for (int i = 0; i < n; ++i) {
+    if (pos[i] < 0 || pos[i] >= c->T) return fail(RAMA_E_STATE, "pos %d of sequence %d outside [0, seq_len=%d)", pos[i], i, c->T);
+    if (tokens[i] < 0 || tokens[i] >= c->V) return fail(RAMA_E_INVALID, "token %d of sequence %d outside the vocabulary", tokens[i], i);
+  }
+  CK(cudaSetDevice(c->device));
+  BatchSeq* hs = b->h_seqs + (size_t)b->ring_i * b->cap;
+  if (++b->ring_i == kBatchRing) { b->ring_i = 0; CK(cudaStreamSynchronize(b->stream)); }
+  for (int i = 0; i < n; ++i) {
+    rama_session* s = sessions[i];
+    hs[i] = BatchSeq{s->key_cache, s->value_cache, s->logits, s->ctrl, pos[i], tokens[i]};
+    s->logits_gathered = true;   // under TP the batched step leaves the full vocabulary in every session
+    s->parts_valid = false;
+    // stream ordering, both ways: the step waits for work the session still has in flight on its own stream (an async
+    // rama_forward), and the session's next own operation waits for this step (session_enter)
+    if (s->fence && s->fence != b->fence) CK(cudaStreamWaitEvent(b->stream, s->fence->ev, 0));  // last touched by another batch
+    if (s->async_pending) {
+      CK(cudaEventRecord(s->ev1, s->stream));
+      CK(cudaStreamWaitEvent(b->stream, s->ev1, 0));
+      s->async_pending = false;
+    }
+    s->fence = b->fence;
+  }
+  CK(cudaMemcpyAsync(b->d_seqs, hs, (size_t)n * sizeof(BatchSeq), cudaMemcpyHostToDevice, b->stream));
+  if (!b->graphs[n]) {
+    std::lock_guard<std::mutex> cap_lk(c->cap_mu);
+    cudaGraph_t g = nullptr;
+    CK(cudaStreamBeginCapture(b->stream, cudaStreamCaptureModeRelaxed));
+    int nl = 0;
+    int rc = enqueue_batch_step(b, n, &nl);
+    cudaError_t e = cudaStreamEndCapture(b->stream, &g);
+    if (rc != RAMA_OK) { if (g) cudaGraphDestroy(g); return rc; }
+    if (e != cudaSuccess) return fail(RAMA_E_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&b->graphs[n], g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) return fail(RAMA_E_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+    b->launches = nl;
+  }
+  CK(cudaGraphLaunch(b->graphs[n], b->stream));
+  CK(cudaEventRecord(b->fence->ev, b->stream));
+  return RAMA_OK;
+}
+
+extern "C" int rama_sample_batch(rama_batch* b, rama_session* const* sessions, int32_t n, float temperature,
+                                 float topp, int32_t* next) {
+  if (!b || !sessions || !next) return fail(RAMA_E_INVALID, "NULL argument");
+  rama_ctx* c = b->ctx;
+  RK(batch_check_sessions(b, sessions, n));
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(b->stream));  // h_sp / h_next are single-buffered
+  BatchSeq* hs = b->h_seqs + (size_t)b->ring_i * b->cap;
+  if (++b->ring_i == kBatchRing) b->ring_i = 0;
+  for (int i = 0; i < n; ++i) {
+    rama_session* s = sessions[i];
+    b->h_sp[i] = SampleParams{s->logits, nullptr, 0, 0, c->V, s->ctrl, nullptr, nullptr, s->sort_keys, temperature, topp, 0, PeerIn{}};
+    hs[i] = BatchSeq{s->key_cache, s->value_cache, s->logits, s->ctrl, 0, 0};
+    if (s->fence && s->fence != b->fence) CK(cudaStreamWaitEvent(b->stream, s->fence->ev, 0));
+    if (s->async_pending) {  // logits written by an asynchronous rama_forward on the session's own stream
+      CK(cudaEventRecord(s->ev1, s->stream));
+      CK(cudaStreamWaitEvent(b->stream, s->ev1, 0));
+      s->async_pending = false;
+    }
+  }
+  CK(cudaMemcpyAsync(b->d_sp, b->h_sp, (size_t)n * sizeof(SampleParams), cudaMemcpyHostToDevice, b->stream));
+  // d_seqs still describes this batch when sample follows forward; rewrite only if the caller passes other sessions
+  CK(cudaMemcpyAsync(b->d_seqs, hs, (size_t)n * sizeof(BatchSeq), cudaMemcpyHostToDevice, b->stream));
+  sample_batch_kernel<<<n, kSampleThreads, 0, b->stream>>>(b->d_sp);
+  CK(cudaGetLastError());
+  batch_collect_kernel<<<1, 64, 0, b->stream>>>(b->d_seqs, b->d_next, n);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(b->h_next, b->d_next, (size_t)2 * n * sizeof(int32_t), cudaMemcpyDeviceToHost, b->stream));
+  CK(cudaStreamSynchronize(b->stream));
+  for (int i = 0; i < n; ++i) {
+    if (b->h_next[2 * i + 1] == 1) return fail(RAMA_E_STATE, "token id outside the vocabulary reached the device step (sequence %d)", i);
+    if (b->h_next[2 * i + 1] == 2) return fail(RAMA_E_STATE, "top-p candidate list is empty (the reference panics here, infer.rs:66) (sequence %d)", i);
+    next[i] = b->h_next[2 * i];
+  }
+  return RAMA_OK;
+}
+
+extern "C" int rama_batch_sync(rama_batch* b) {
+  if (!b) return fail(RAMA_E_INVALID, "NULL batch");
+  CK(cudaSetDevice(b->ctx->device));
+  CK(cudaStreamSynchronize(b->stream));
+  return RAMA_OK;
+}
+
+extern "C" int rama_batch_launches_per_step(const rama_batch* b, int32_t* n) {
+  if (!b || !n) return fail(RAMA_E_INVALID, "NULL argument");
+  *n = b->launches;
+  return RAMA_OK;
+}
+

@@ -6,6 +6,7 @@
 namespace rama {
 
 constexpr int kWarp = 32;
+constexpr int kAttnMaxHs = 128;  // largest head_size the attention kernels hold per head (checked at load)
 
 // Device-resident step control block (one per session).  Kernels read pos/token from here so
 // that one captured CUDA graph can be replayed for every position.

@@ -1,0 +1,349 @@
+// internal.cuh — declarations shared by the translation units of the library (host side of the C ABI,
+// include/rama_b200.h): error plumbing, the run-time-resolved NCCL table, context / session structures, the GEMV
+// dispatch templates and the few helpers that cross translation units.  Nothing here is part of the ABI.
+#pragma once
+#include "../../include/rama_b200.h"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <thread>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "gemv.cuh"
+#include "misc_kernels.cuh"
+
+using namespace rama;
+
+// ---- errors (ctx.cu) ----
+int fail(int code, const char* fmt, ...);
+int env_int(const char* name, int dflt);
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return fail(RAMA_E_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+  } while (0)
+#define RK(call)                     \
+  do {                               \
+    int r_ = (call);                 \
+    if (r_ != RAMA_OK) return r_;    \
+  } while (0)
+// ------------------------------------------------------------------------------------------------
+// NCCL, resolved at run time (only when tp->world > 1) so that the single-GPU path has no
+// dependency on it and the process shares whatever libnccl.so.2 is already loaded.
+// ------------------------------------------------------------------------------------------------
+struct NcclId { char internal[128]; };
+typedef void* NcclComm;
+struct NcclApi {
+  void* h = nullptr;
+  int (*GetUniqueId)(NcclId*) = nullptr;
+  int (*CommInitRank)(NcclComm*, int, NcclId, int) = nullptr;
+  int (*CommDestroy)(NcclComm) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, NcclComm, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+extern NcclApi g_nccl;
+constexpr int kNcclFloat32 = 7, kNcclSum = 0;
+int nccl_load();
+#define NK(call)                                                                                   \
+  do {                                                                                             \
+    int e_ = (call);                                                                               \
+    if (e_ != 0) return fail(RAMA_E_NCCL, "%s:%d %s: %s", __FILE__, __LINE__, #call, g_nccl.GetErrorString(e_)); \
+  } while (0)
+// ------------------------------------------------------------------------------------------------
+// structures
+// ------------------------------------------------------------------------------------------------
+struct TensorPlan {  // local window [Lc][Rl][Cl] of the global tensor [Lc][R][C] at (r0, c0)
+  size_t Lc = 1, R = 0, C = 0, r0 = 0, Rl = 0, c0 = 0, Cl = 0;
+  size_t local_elems() const { return Lc * Rl * Cl; }
+  size_t global_elems() const { return Lc * R * C; }
+};
+
+struct rama_ctx {
+  int device = 0, sm_count = 148;
+  int rank = 0, world = 1;
+  NcclComm comm = nullptr;
+  bool loaded = false;
+  rama_config cfg{};
+  int D = 0, F = 0, L = 0, H = 0, V = 0, T = 0, hs = 0;  // global
+  int Dq = 0, Fl = 0, Hl = 0, Vl = 0, v0 = 0;            // this rank's shard
+  TensorPlan plan[RAMA_T_COUNT];
+  float* w[RAMA_T_COUNT] = {nullptr};
+  const float* wcls = nullptr;  // this rank's classifier rows (own tensor, or a window of the embedding)
+  cudaStream_t op_stream = nullptr;
+  int use_pdl = 0;
+  int variant_override = -1;
+  int p2p = 0;  // TP exchange: 1 = fused peer-memory all-reduce (default), 0 = NCCL collectives
+  int staged = 1;      // RAMA_GEMV_STAGED=0 disables the shared-memory-staged GEMV for small slabs
+  int embed_kernel = 1;  // RAMA_EMBED_KERNEL=0: fold the embedding gather into the layer-0 QKV prologue (ProNorm::emb)
+  int stage_max_kb = 110;  // RAMA_GEMV_STAGE_KB: largest x + slab the staged GEMV takes (≤ 110: two CTAs per SM; ≤ 208: one)
+  int attn_cluster = 1;  // RAMA_ATTN=split selects the global-memory split merge (attn_decode_kernel) at every context length
+  int persistent = 0;  // RAMA_STEP=persistent: the decode step as one persistent cooperative kernel (step_kernel.cuh);
+                       // default: one fused kernel per op group in a CUDA graph (measured faster)
+  std::mutex mu;
+  // A stream capture is invalidated by a device-wide synchronisation (cudaDeviceSynchronize, default-stream work,
+  // cudaFree) issued by ANOTHER host thread of the same context — the server creates and drops sessions while other
+  // request threads capture their step graphs.  Captures and those device-wide operations take this lock.
+  std::mutex cap_mu;
+  std::atomic<int> n_objects{0};  // live sessions + batches: their captured graphs hold the weight pointers, so no reload
+};
+
+// A batched step runs on the batch's stream, the per-session entry points on the session's own stream.  The batch
+// re-records ONE event after every step it launches; each session of that step keeps a reference and makes its own
+// stream wait on it before its next operation (waiting on a later record of the same event is merely conservative).
+struct BatchFence {
+  cudaEvent_t ev = nullptr;
+  ~BatchFence() { if (ev) cudaEventDestroy(ev); }
+};
+
+struct rama_session {
+  rama_ctx* ctx = nullptr;
+  cudaStream_t stream = nullptr;
+  float *x0 = nullptr, *x1 = nullptr, *xfinal = nullptr, *xb = nullptr, *xb2 = nullptr, *w2out = nullptr;
+  float *hb = nullptr, *hb2 = nullptr, *q = nullptr, *k = nullptr, *v = nullptr, *att = nullptr;
+  float *logits = nullptr;  // [V]; this rank's rows live at logits + v0
+  float *key_cache = nullptr, *value_cache = nullptr;
+  float* attn_ws = nullptr;
+  unsigned int* tickets = nullptr;
+  ArgPart* part = nullptr;      // [world * sm_count] greedy partials (single GPU / NCCL mode)
+  unsigned* seq = nullptr;      // device step counter (epoch source of the fused TP exchange)
+  unsigned long long* bar = nullptr;  // persistent step kernel: [0] grid-barrier arrivals, [1] steps completed
+  bool persistent = false;
+  int cls_grid = 0;             // CTAs of the classifier launch (slots that get written)
+  // fused TP exchange: one IPC-exported block per session {flags[3][P] | parts[P][SMs] | inbox[2][P][D]}
+  char* peer_mem = nullptr;
+  char* peer_base[kMaxPeers] = {nullptr};  // every rank's block, peer-mapped (own block at [rank])
+  size_t off_parts = 0, off_inbox = 0, peer_bytes = 0;
+  bool p2p = false;
+  unsigned long long* sort_keys = nullptr;
+  StepCtrl* ctrl = nullptr;     // device
+  int32_t *d_prompt = nullptr, *d_out = nullptr;
+  StepCtrl* h_ring = nullptr;   // pinned ring for host-driven (token,pos)
+  int ring_i = 0;
+  int32_t* h_ret = nullptr;     // pinned {next, error}
+  // step graphs per attention grid bucket (chunks-per-head CTAs for the position range): [mode][bucket],
+  // mode 0 = forward, 1 = chained greedy, 2 = chained sampled
+  cudaGraphExec_t g[3][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+  int attn_gy = 1;              // gridDim.y of the attention launch being enqueued
+  int attn_bk = 0;              // its bucket (0: positions < 256)
+  float* wo_part = nullptr;     // [H][D] per-head wo partials of the fused attention+wo kernel (small models), or null
+  int attn_wo_mode = 0;         // 1: attn_wo_cluster_kernel, 2: attn_wo_kernel, 0: separate launches
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int keep_att = 0;
+  int n_split = 1;
+  int host_mode_set = 0;
+  int launches = 0;
+  bool logits_gathered = false;
+  bool parts_valid = true;       // the classifier GEMV's per-CTA argmax partials describe the current logits
+  // prefill workspace (allocated on first use): activations of one chunk of prompt rows
+  int pf_cap = 0;                // rows per chunk
+  int pf_min = 16;               // rama_generate: prompts of at least this many rows (BOS included) are prefilled
+  float *pf_x = nullptr, *pf_xn = nullptr, *pf_q = nullptr, *pf_att = nullptr, *pf_y = nullptr, *pf_h = nullptr;
+  int32_t* pf_tokens = nullptr;
+  std::shared_ptr<BatchFence> fence;  // set by rama_forward_batch: work of another stream this session must wait for
+  bool async_pending = false;         // work enqueued on s->stream since it was last synchronised (a batch must wait for it)
+};
+
+// called first by every per-session entry point: order this session's stream after the batched step that touched it
+inline cudaError_t session_enter(rama_session* s) {
+  if (!s->fence) return cudaSuccess;
+  cudaError_t e = cudaStreamWaitEvent(s->stream, s->fence->ev, 0);
+  s->fence.reset();
+  return e;
+}
+
+// ------------------------------------------------------------------------------------------------
+// GEMV dispatch
+// ------------------------------------------------------------------------------------------------
+constexpr int kNumVariants = 8;
+constexpr int kVariantStaged = 100;  // gemv_smem_kernel
+struct Variant { int WK, RP, U; };
+inline const Variant kVariants[kNumVariants] = {{16, 2, 2}, {8, 2, 4}, {4, 2, 4}, {1, 2, 4},
+                                                {16, 4, 2}, {8, 4, 2}, {2, 2, 4}, {16, 1, 4}};
+constexpr size_t kMaxDynSmem = 200 * 1024;
+
+template <int WK, int RP, int U, class Pro, class Rows, class Epi>
+inline cudaError_t launch_gemv_t(int grid, cudaStream_t st, int pdl, const Pro& pro, const Rows& rows,
+                                 const Epi& epi, int K4, int n_pairs) {
+  auto kern = gemv_fused_kernel<WK, RP, U, Pro, Rows, Epi>;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [&] {
+    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
+  });
+  if (attr_err != cudaSuccess) return attr_err;
+  const size_t smem = gemv_smem_bytes(K4, n_pairs, grid, WK);
+  if (smem > kMaxDynSmem) return cudaErrorInvalidValue;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kGemvThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  if (pdl) {
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+  }
+  return cudaLaunchKernelEx(&cfg, kern, pro, rows, epi, K4, n_pairs, pdl);
+}
+
+// bytes of shared memory the staged variant needs for this launch (x + the largest CTA slab)
+inline size_t gemv_stage_bytes(int K4, int n_pairs, int grid, int rows_per_pair) {
+  const int maxp = (n_pairs + grid - 1) / grid;
+  return (size_t)K4 * 16 + (size_t)maxp * rows_per_pair * K4 * 16;
+}
+
+template <class Pro, class Rows, class Epi>
+inline cudaError_t launch_gemv_staged(int grid, cudaStream_t st, int pdl, const Pro& pro, const Rows& rows, const Epi& epi,
+                                      int K4, int n_pairs) {
+  auto kern = gemv_smem_kernel<Pro, Rows, Epi>;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [&] {
+    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemvSmemStageMaxSolo);
+  });
+  if (attr_err != cudaSuccess) return attr_err;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kGemvThreads);
+  cfg.dynamicSmemBytes = gemv_stage_bytes(K4, n_pairs, grid, 2);
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  if (pdl) {
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+  }
+  return cudaLaunchKernelEx(&cfg, kern, pro, rows, epi, K4, n_pairs, pdl);
+}
+
+template <class Pro, class Rows, class Epi>
+inline cudaError_t launch_gemv(int variant, int grid, cudaStream_t st, int pdl, const Pro& pro,
+                               const Rows& rows, const Epi& epi, int K4, int n_pairs) {
+  // small slabs (the small models): whole slab staged in shared memory ahead of the dependency (gemv_smem_kernel)
+  if (variant == kVariantStaged) return launch_gemv_staged(grid, st, pdl, pro, rows, epi, K4, n_pairs);
+  switch (variant) {
+    case 0: return launch_gemv_t<16, 2, 2>(grid, st, pdl, pro, rows, epi, K4, n_pairs);
+    case 1: return launch_gemv_t<8, 2, 4>(grid, st, pdl, pro, rows, epi, K4, n_pairs);
+    case 2: return launch_gemv_t<4, 2, 4>(grid, st, pdl, pro, rows, epi, K4, n_pairs);
+    case 3: return launch_gemv_t<1, 2, 4>(grid, st, pdl, pro, rows, epi, K4, n_pairs);
+    case 4: return launch_gemv_t<16, 4, 2>(grid, st, pdl, pro, rows, epi, K4, n_pairs);
+    case 5: return launch_gemv_t<8, 4, 2>(grid, st, pdl, pro, rows, epi, K4, n_pairs);
+    case 6: return launch_gemv_t<2, 2, 4>(grid, st, pdl, pro, rows, epi, K4, n_pairs);
+    case 7: return launch_gemv_t<16, 1, 4>(grid, st, pdl, pro, rows, epi, K4, n_pairs);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+inline int pick_variant(const rama_ctx* c, int K4, int n_pairs = 0) {
+  if (c->variant_override >= 0 && c->variant_override < kNumVariants) return c->variant_override;
+  if (c->staged && n_pairs > 0 && gemv_stage_bytes(K4, n_pairs, c->sm_count, 2) <= (size_t)c->stage_max_kb * 1024 &&
+      n_pairs >= c->sm_count)
+    return kVariantStaged;
+  if (K4 >= 1024) return 1;
+  if (K4 >= 512) return 2;
+  if (K4 >= 128) return 6;
+  return 3;
+}
+inline int pick_grid(const rama_ctx* c, int variant, int n_pairs) {
+  if (variant == kVariantStaged) return c->sm_count;
+  const int rp = kVariants[variant].RP;
+  return std::max(1, std::min(c->sm_count, (n_pairs + rp - 1) / rp));
+}
+
+template <class Tp>
+inline cudaError_t dalloc(Tp** p, size_t n) {
+  cudaError_t e = cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(Tp));
+  if (e == cudaSuccess) e = cudaMemset(*p, 0, std::max<size_t>(n, 1) * sizeof(Tp));
+  return e;
+}
+
+constexpr int kRing = 64;
+
+inline PeerOut peer_out(const rama_session* s, int stage, int layer) {  // stage 0 = wo, 1 = w2
+  PeerOut po{};
+  const rama_ctx* c = s->ctx;
+  if (!s->p2p) return po;
+  po.P = c->world; po.seq = s->seq; po.L = c->L + 1; po.layer = layer;
+  for (int r = 0; r < c->world; ++r)
+    po.inbox[r] = reinterpret_cast<uint2*>(s->peer_base[r] + s->off_inbox) + ((size_t)stage * c->world + c->rank) * c->D;
+  return po;
+}
+inline PeerIn peer_in(const rama_session* s, int stage, int layer) {
+  PeerIn pi{};
+  const rama_ctx* c = s->ctx;
+  if (!s->p2p) return pi;
+  pi.inbox = reinterpret_cast<const uint2*>(s->peer_mem + s->off_inbox) + (size_t)stage * c->world * c->D;
+  pi.seq = s->seq; pi.error = &s->ctrl->error;
+  pi.P = c->world; pi.n = c->D; pi.L = c->L + 1; pi.layer = layer;
+  return pi;
+}
+inline PeerOut peer_out_parts(const rama_session* s) {  // classifier partials, "layer" L
+  PeerOut po{};
+  const rama_ctx* c = s->ctx;
+  if (!s->p2p) return po;
+  po.P = c->world; po.seq = s->seq; po.L = c->L + 1; po.layer = c->L;
+  for (int r = 0; r < c->world; ++r)
+    po.inbox[r] = reinterpret_cast<uint2*>(s->peer_base[r] + s->off_parts) + (size_t)c->rank * c->sm_count * 2;
+  return po;
+}
+inline PeerIn peer_in_parts(const rama_session* s) {
+  PeerIn pi{};
+  const rama_ctx* c = s->ctx;
+  if (!s->p2p) return pi;
+  pi.inbox = reinterpret_cast<const uint2*>(s->peer_mem + s->off_parts);
+  pi.seq = s->seq; pi.error = &s->ctrl->error;
+  pi.P = c->world; pi.n = c->sm_count; pi.L = c->L + 1; pi.layer = c->L;
+  return pi;
+}
+
+// ------------------------------------------------------------------------------------------------
+// prompt prefill (tensor cores): ≙ the prompt part of generate()'s loop, mod.rs:187-192
+// ------------------------------------------------------------------------------------------------
+// kernel launch with the programmatic-stream-serialization attribute (PDL): the next kernel's CTAs start while this one
+// drains; every kernel of the batched step executes griddepcontrol.wait before it touches memory (batch.cuh)
+template <class... P, class... A>
+inline cudaError_t launch_k(bool pdl, void (*kern)(P...), dim3 grid, dim3 block, cudaStream_t st, A&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  if (pdl) {
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+  }
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<A>(args)...);
+}
+
+
+// ---- helpers that cross translation units ----
+int init_parts(rama_session* s);                        // session.cu
+int gather_logits(rama_session* s);                     // session.cu
+int read_ret(rama_session* s, int32_t* next);           // session.cu
+int prefill_run(rama_session* s, const int32_t* tokens, int32_t n, int32_t pos0, float ms_kind[RAMA_PK_COUNT],
+                int32_t* n_launch);                     // prefill.cu

@@ -7,7 +7,7 @@
 namespace rama {
 
 // ---- step begin: x ← token_embedding_table[token] (infer.rs:13) ---------------------------------
-__global__ void __launch_bounds__(256) step_begin_kernel(StepCtrl* ctrl, unsigned* seq,
+static __global__ void __launch_bounds__(256) step_begin_kernel(StepCtrl* ctrl, unsigned* seq,
                                                          const float* __restrict__ emb,
                                                          float* __restrict__ x, int D, int vocab,
                                                          int use_pdl) {
@@ -63,7 +63,7 @@ __device__ __forceinline__ unsigned long long sample_key(float p, int idx) {
 // shared memory (the common case: a trained model leaves few candidates above the cutoff); larger
 // candidate sets (flat distributions, e.g. random weights) run the wide strides through L2.
 constexpr int kSortSmem = 4096;
-__device__ void bitonic_sort_cta(unsigned long long* a, int n_pow2, unsigned long long* sm) {
+static __device__ void bitonic_sort_cta(unsigned long long* a, int n_pow2, unsigned long long* sm) {
   if (n_pow2 <= kSortSmem) {
     for (int i = threadIdx.x; i < n_pow2; i += kSampleThreads) sm[i] = a[i];
     __syncthreads();
@@ -268,38 +268,38 @@ __device__ __forceinline__ void sample_body(const SampleParams& p) {
   }
 }
 
-__global__ void __launch_bounds__(kSampleThreads) sample_kernel(const SampleParams p, int use_pdl) {
+static __global__ void __launch_bounds__(kSampleThreads) sample_kernel(const SampleParams p, int use_pdl) {
   if (use_pdl) { pdl_launch_dependents(); pdl_wait(); }
   sample_body(p);
 }
 
 // one CTA per sequence of a batch (server path: concurrent requests, lib.rs:127-160)
-__global__ void __launch_bounds__(kSampleThreads) sample_batch_kernel(const SampleParams* __restrict__ ps) {
+static __global__ void __launch_bounds__(kSampleThreads) sample_batch_kernel(const SampleParams* __restrict__ ps) {
   const SampleParams p = ps[blockIdx.x];
   sample_body(p);
 }
 
 // ---- element-wise Device ops (trait parity; the fused step does not launch these) -----------------
-__global__ void op_array_add_kernel(float* t, const float* s, size_t n) {  // cpu.rs:16-21
+static __global__ void op_array_add_kernel(float* t, const float* s, size_t n) {  // cpu.rs:16-21
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     t[i] = t[i] + s[i];
 }
-__global__ void op_array_mult_kernel(float* t, const float* s, size_t n) {  // cpu.rs:59-64
+static __global__ void op_array_mult_kernel(float* t, const float* s, size_t n) {  // cpu.rs:59-64
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     t[i] = t[i] * s[i];
 }
-__global__ void op_sinu_kernel(float* o, size_t n) {  // cpu.rs:54-57
+static __global__ void op_sinu_kernel(float* o, size_t n) {  // cpu.rs:54-57
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const float a = o[i];
     o[i] = a * (1.0f / (1.0f + expf(-a)));
   }
 }
-__global__ void op_copy_kernel(float* t, const float* s, size_t n) {  // cpu.rs:66-72
+static __global__ void op_copy_kernel(float* t, const float* s, size_t n) {  // cpu.rs:66-72
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     t[i] = s[i];
 }
 // cpu.rs:99-117, one CTA.  o may alias x.
-__global__ void __launch_bounds__(1024) op_rmsnorm_kernel(float* o, const float* x, const float* w, int n) {
+static __global__ void __launch_bounds__(1024) op_rmsnorm_kernel(float* o, const float* x, const float* w, int n) {
   __shared__ float red[kWarp];
   float ss = 0.f;
   for (int i = threadIdx.x; i < n; i += 1024) ss = fmaf(x[i], x[i], ss);
@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(1024) op_rmsnorm_kernel(float* o, const float*
   for (int i = threadIdx.x; i < n; i += 1024) o[i] = w[i] * (v * x[i]);
 }
 // cpu.rs:74-97: one head of q and k
-__global__ void op_apply_position_kernel(float* q, float* k, const float* pr, const float* pi, int hs2) {
+static __global__ void op_apply_position_kernel(float* q, float* k, const float* pr, const float* pi, int hs2) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= hs2) return;
   const float c = pr[i], s = pi[i];
@@ -320,7 +320,7 @@ __global__ void op_apply_position_kernel(float* q, float* k, const float* pr, co
   k[2 * i + 1] = __fadd_rn(__fmul_rn(k0, s), __fmul_rn(k1, c));
 }
 // cpu.rs:119-125, one CTA
-__global__ void __launch_bounds__(1024) op_softmax_kernel(float* x, int n) {
+static __global__ void __launch_bounds__(1024) op_softmax_kernel(float* x, int n) {
   __shared__ float red[kWarp];
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
   float mx = -INFINITY;
@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(1024) op_softmax_kernel(float* x, int n) {
 }
 // general o_cols > 1 matmul (device.rs:13) — not on the decode path (which only uses o_cols = 1);
 // kept so the trait is complete.  One thread per output, serial k.
-__global__ void op_matmul_general_kernel(float* o, const float* a, const float* b, int width, int o_rows,
+static __global__ void op_matmul_general_kernel(float* o, const float* a, const float* b, int width, int o_rows,
                                          int o_cols) {
   const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (idx >= (size_t)o_rows * o_cols) return;
@@ -365,7 +365,7 @@ __device__ __forceinline__ unsigned sum16(unsigned long long h) {
   return (unsigned)(h & 0xFFFF) + (unsigned)((h >> 16) & 0xFFFF) + (unsigned)((h >> 32) & 0xFFFF) +
          (unsigned)(h >> 48);
 }
-__global__ void synth_fill_kernel(float* dst, unsigned long long n, unsigned long long key, ShardMap m,
+static __global__ void synth_fill_kernel(float* dst, unsigned long long n, unsigned long long key, ShardMap m,
                                   unsigned long long start, float scale, float offset) {
   for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
        i += (unsigned long long)gridDim.x * blockDim.x) {

@@ -14,7 +14,7 @@
 namespace rama {
 
 // ---- x[m] = token_embedding_table[token[m]] (infer.rs:13, for every prompt position) -----------------
-__global__ void __launch_bounds__(256) prefill_embed_kernel(const int32_t* __restrict__ tokens, const float* __restrict__ emb,
+static __global__ void __launch_bounds__(256) prefill_embed_kernel(const int32_t* __restrict__ tokens, const float* __restrict__ emb,
                                                             float* __restrict__ x, int D, int vocab, int32_t* error,
                                                             unsigned* seq) {
   pdl_launch_dependents(); pdl_wait();  // (no-ops unless launched with programmatic stream serialization)
@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(256) prefill_embed_kernel(const int32_t* __res
 
 // ---- x[m] += y[m] (pending residual, may be null);  xn[m] = w · (rsqrt-scale · x[m]) -------------------
 // one CTA per row; ≙ array_add (cpu.rs:16-21) folded in front of rmsnorm (cpu.rs:99-117)
-__global__ void __launch_bounds__(256) prefill_addnorm_kernel(float* __restrict__ x, const float* __restrict__ y,
+static __global__ void __launch_bounds__(256) prefill_addnorm_kernel(float* __restrict__ x, const float* __restrict__ y,
                                                               const float* __restrict__ w, float* __restrict__ xn, int D) {
   pdl_launch_dependents(); pdl_wait();  // (no-ops unless launched with programmatic stream serialization)
   __shared__ float red[2 * kWarp];
@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(kPfThreads) prefill_attn_kernel(const PrefillA
 }
 
 // last prompt row → the decode path's residual buffer: x0 = x[M-1] + y[M-1]
-__global__ void prefill_last_row_kernel(const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ x0,
+static __global__ void prefill_last_row_kernel(const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ x0,
                                         int D) {
   pdl_launch_dependents(); pdl_wait();  // (no-ops unless launched with programmatic stream serialization)
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < D; i += gridDim.x * blockDim.x) x0[i] = x[i] + y[i];

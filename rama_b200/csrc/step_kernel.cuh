@@ -1,7 +1,7 @@
 // step_kernel.cuh — the whole decode step (infer.rs:8-53 + greedy Device::sample, cpu.rs:155-168) as ONE
 // persistent cooperative launch.
 //
-// The multi-kernel step (api.cu enqueue_step) costs ~3-4 µs per kernel boundary even inside a CUDA graph
+// The multi-kernel step (session.cu enqueue_step) costs ~3-4 µs per kernel boundary even inside a CUDA graph
 // with programmatic dependent launch; with 1 + 5·L + 1 kernels per token that is what bounds the small
 // models (stories110M: 62 kernels × 4.7 µs against 67 µs of weight streaming) and tensor parallelism at
 // 8 GPUs.  Here the same prologue / row / epilogue functors (gemv.cuh) and the flash-decode work item
@@ -194,7 +194,7 @@ struct StepEpiCls {  // logits + per-CTA greedy partial (ties → higher index, 
   }
 };
 
-__global__ void __launch_bounds__(kGemvThreads, 1) decode_step_kernel(const __grid_constant__ StepParams p) {
+static __global__ void __launch_bounds__(kGemvThreads, 1) decode_step_kernel(const __grid_constant__ StepParams p) {
   extern __shared__ float4 gemv_smem[];
   __shared__ float red[2 * kWarp];
   float4* xs = gemv_smem;

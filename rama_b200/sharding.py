@@ -1,4 +1,4 @@
-"""Tensor-parallel shard plan (host mirror of set_config() in csrc/api.cu).
+"""Tensor-parallel shard plan (host mirror of set_config() in csrc/ctx.cu).
 
 New relative to the reference, which is single-device (gpu.rs:215).  Classic Megatron layout on
 llama2.c's row-major [out][in] matrices — the inverse of what the reference's

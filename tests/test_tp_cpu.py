@@ -30,7 +30,7 @@ def _allreduce(a):
 
 
 def _tp_forward(cfg, sh, st, token, pos, rank, world):
-    """One decode step on this rank's shard (mirrors enqueue_step() in csrc/api.cu)."""
+    """One decode step on this rank's shard (mirrors enqueue_step() in csrc/session.cu)."""
     import ctypes as C
     D, F, H, T = cfg.dim, cfg.hidden_dim, cfg.n_heads, cfg.seq_len
     hs, Dq, Fl, Vl, Hl = cfg.head_size, D // world, F // world, cfg.vocab_size // world, H // world
