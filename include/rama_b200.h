@@ -78,6 +78,17 @@ int rama_device_count(int* n);
 int rama_ctx_create(int device, const rama_tp* tp, rama_ctx** out);
 int rama_ctx_destroy(rama_ctx* ctx);
 int rama_tp_unique_id(uint8_t out[128]);
+/* ≙ GPU::new() for a caller that is ONE process with ONE device handle — the reference's engine binary and server
+ * (engine/src/main.rs:70-98, engine/src/lib.rs:99-119) cannot launch a rank per GPU.  The returned context owns
+ * n_gpus devices (devices[] or, when NULL, 0..n_gpus-1; all pairs must be peer-addressable) and is accepted by every
+ * entry point below exactly like a single-device context: loads shard the weights over the devices (column-parallel
+ * wq/wk/wv/w1/w3, row-parallel wo/w2, vocabulary-split classifier), a session holds one KV-cache shard per device, and
+ * rama_forward / rama_generate / rama_prefill / rama_forward_batch drive every device's captured step from the calling
+ * thread (one library-owned host thread per device issues its launches).  The devices exchange through NVLink peer
+ * memory inside the kernels; NCCL is not involved.  Op-level calls (rama_op_*, rama_dev_*) run on the first device;
+ * rama_state_to_host returns the first device's shard of sharded buffers (logits and x are complete).
+ * n_gpus == 1 returns a plain single-device context. */
+int rama_ctx_create_multi(int32_t n_gpus, const int32_t* devices, rama_ctx** out);
 
 /* ≙ Config::from_file + TransformerWeights::from_file + ::from_weight
  * (mod.rs:140-166, ram.rs:27-51, hbm.rs:55-90): mmap the v0 .bin, stream it through pinned
@@ -149,7 +160,10 @@ int rama_session_set_prefill(rama_session* s, int32_t min_rows);
  * session's logits buffer holds its logits, exactly as after rama_forward(session, token, pos), so
  * rama_sample / rama_logits_to_host work per session; rama_sample_batch samples all of them in one launch.
  * A batch object owns the workspace and the stream; sessions in a batch must not be used concurrently
- * through their own entry points.  Single GPU in this version. */
+ * through their own entry points (one after the other is fine: the library orders the batch's stream and the
+ * sessions' streams with events, no explicit rama_batch_sync / rama_session_sync is needed in between).
+ * Works on one GPU, under tensor parallelism with one process per GPU (every rank calls it with its own sessions,
+ * collectively) and on a multi-device context of rama_ctx_create_multi. */
 typedef struct rama_batch rama_batch;
 int rama_batch_create(rama_ctx* ctx, int32_t max_seqs /* ≤ 64 */, rama_batch** out);
 int rama_batch_destroy(rama_batch* b);

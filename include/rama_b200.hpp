@@ -233,7 +233,18 @@ struct Device {
 class GPU final : public Device<DevBuf> {
  public:
   rama_ctx* ctx = nullptr;
-  GPU() { ck(rama_ctx_create(0, nullptr, &ctx)); }  // ≙ GPU::new(): device 0, no NVRTC / cuBLAS
+  // ≙ GPU::new(): no NVRTC / cuBLAS.  RAMA_GPUS=N (or GPU(N)) makes the one handle a tensor-parallel context over devices
+  // 0..N-1 of this process (rama_ctx_create_multi) — callers stay unchanged, exactly as with one device.
+  GPU() : GPU(gpus_from_env()) {}
+  explicit GPU(int n_gpus) {
+    if (n_gpus > 1) ck(rama_ctx_create_multi(n_gpus, nullptr, &ctx));
+    else ck(rama_ctx_create(0, nullptr, &ctx));
+  }
+  static int gpus_from_env() {
+    const char* v = std::getenv("RAMA_GPUS");
+    const int n = v && *v ? std::atoi(v) : 1;
+    return n < 1 ? 1 : n;
+  }
   ~GPU() override { if (ctx) rama_ctx_destroy(ctx); }
   GPU(const GPU&) = delete;
   GPU& operator=(const GPU&) = delete;

@@ -18,6 +18,7 @@ pub const RAMA_T_COUNT: usize = 14;
 extern "C" {
     pub fn rama_last_error() -> *const c_char;
     pub fn rama_ctx_create(device: c_int, tp: *const rama_tp, out: *mut *mut rama_ctx) -> c_int;
+    pub fn rama_ctx_create_multi(n_gpus: i32, devices: *const i32, out: *mut *mut rama_ctx) -> c_int;
     pub fn rama_ctx_destroy(ctx: *mut rama_ctx) -> c_int;
     pub fn rama_ctx_load_file(ctx: *mut rama_ctx, path: *const c_char) -> c_int;
     pub fn rama_ctx_load_host(ctx: *mut rama_ctx, cfg: *const rama_config, tensors: *const *const c_float) -> c_int;

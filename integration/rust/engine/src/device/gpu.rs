@@ -43,9 +43,16 @@ unsafe impl Send for GPU {}
 unsafe impl Sync for GPU {}
 
 impl GPU {
+    /// `RAMA_GPUS=N` makes this one handle tensor-parallel over devices 0..N-1 of the process
+    /// (rama_ctx_create_multi): main.rs and lib.rs keep calling `GPU::new()` unchanged.
     pub fn new() -> Self {
+        let n: i32 = std::env::var("RAMA_GPUS").ok().and_then(|v| v.parse().ok()).unwrap_or(1);
         let mut ctx = std::ptr::null_mut();
-        ck(unsafe { rama_ctx_create(0, std::ptr::null(), &mut ctx) });
+        if n > 1 {
+            ck(unsafe { rama_ctx_create_multi(n, std::ptr::null(), &mut ctx) });
+        } else {
+            ck(unsafe { rama_ctx_create(0, std::ptr::null(), &mut ctx) });
+        }
         Self { ctx, lock: Mutex::new(()) }
     }
     pub fn alloc(&self, host: &[f32]) -> DevBuf {

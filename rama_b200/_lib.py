@@ -46,6 +46,7 @@ _SIGS = {
     "rama_last_error": ([], C.c_char_p),
     "rama_device_count": ([C.POINTER(C.c_int)], C.c_int),
     "rama_ctx_create": ([C.c_int, C.POINTER(CTp), C.POINTER(vp)], C.c_int),
+    "rama_ctx_create_multi": ([C.c_int32, ip, C.POINTER(vp)], C.c_int),
     "rama_ctx_destroy": ([vp], C.c_int),
     "rama_tp_unique_id": ([C.POINTER(C.c_uint8)], C.c_int),
     "rama_ctx_load_file": ([vp, C.c_char_p], C.c_int),

@@ -18,6 +18,7 @@ struct BatchSeq {  // one sequence of a batched step (device array, rewritten by
   float* logits;       // the session's logits [V]
   StepCtrl* ctrl;      // the session's control block (pos/token mirrored there; sampler output)
   int32_t pos, token;
+  float* logits_peer[kMaxPeers];  // tensor parallelism over peer memory: the same session's logits on every rank
 };
 
 // out[i] = Σ_s part[s][i], s ascending
@@ -32,8 +33,9 @@ static __global__ void sum_partials_kernel(float* __restrict__ out, const float*
 
 // x[b] = token_embedding_table[token_b] (infer.rs:13); mirrors (token,pos) into the session's control block
 static __global__ void __launch_bounds__(256) batch_embed_kernel(const BatchSeq* __restrict__ seqs, const float* __restrict__ emb,
-                                                          float* __restrict__ x, int D, int vocab) {
+                                                          float* __restrict__ x, int D, int vocab, unsigned* step_counter) {
   pdl_launch_dependents(); pdl_wait();  // (no-ops unless launched with programmatic stream serialization)
+  if (step_counter && blockIdx.x == 0 && threadIdx.x == 0) *step_counter += 1u;  // epoch source of the step's TP exchanges
   const BatchSeq sq = seqs[blockIdx.x];
   int token = sq.token;
   if (threadIdx.x == 0) {
@@ -203,6 +205,22 @@ static __global__ void __launch_bounds__(256) batch_cls_finish_kernel(const floa
     float a = 0.f;
     for (int s = 0; s < S; ++s) a += part[(size_t)s * slab + (size_t)b * Vl + i];
     dst[i] = a;
+  }
+}
+
+// the same under the peer exchange: the slice goes into the session's logits on EVERY rank (vocabulary all-gather by
+// remote stores; a tp_barrier_kernel afterwards makes all slices visible before the samplers run)
+static __global__ void __launch_bounds__(256) batch_cls_push_kernel(const float* __restrict__ part, int S, size_t slab,
+                                                             const BatchSeq* __restrict__ seqs, int Vl, int v0, int P) {
+  pdl_launch_dependents(); pdl_wait();  // (no-ops unless launched with programmatic stream serialization)
+  const int b = blockIdx.y;
+  const BatchSeq sq = seqs[b];
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < Vl; i += gridDim.x * 256) {
+    float a = 0.f;
+    for (int s = 0; s < S; ++s) a += part[(size_t)s * slab + (size_t)b * Vl + i];
+#pragma unroll
+    for (int r = 0; r < kMaxPeers; ++r)
+      if (r < P) sq.logits_peer[r][v0 + i] = a;
   }
 }
 

@@ -28,12 +28,20 @@ struct rama_batch {
   SampleParams* d_sp = nullptr;
   SampleParams* h_sp = nullptr;      // pinned [cap]
   int32_t* d_next = nullptr;
+  int32_t* d_err = nullptr;          // device error word of the TP exchange (3 = a peer timed out)
   int32_t* h_next = nullptr;         // pinned [2·cap]
   int ring_i = 0;
   std::vector<cudaGraphExec_t> graphs;  // by batch size
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int launches = 0;
   std::shared_ptr<BatchFence> fence;    // re-recorded after every step; the sessions of the step hold a reference
+  // tensor parallelism over peer memory (tp_exchange.cuh): inbox[P][S_max][bpr_max][D] | xn[cap][D] | flags[3][P] | done | step counter
+  bool p2p = false;
+  PeerBlock blk;
+  size_t off_xn = 0, off_flags = 0, off_done = 0, off_step = 0;
+  int s_max = 1;
+  // single-process group batch: one batch per rank
+  std::vector<rama_batch*> ranks;
 };
 
 // split-K factor: the smallest one that fills ≥ 92 % of the CTA slots of its last wave (every extra split writes and
@@ -53,10 +61,8 @@ static int pick_ksplit(const rama_ctx* c, int tiles, int K) {
   return best;
 }
 
-extern "C" int rama_batch_create(rama_ctx* c, int32_t max_seqs, rama_batch** out) {
-  if (!c || !out) return fail(RAMA_E_INVALID, "NULL argument");
-  if (!c->loaded) return fail(RAMA_E_STATE, "no weights loaded");
-  if (max_seqs < 1 || max_seqs > kBatchMax) return fail(RAMA_E_INVALID, "max_seqs must be in [1, %d]", kBatchMax);
+static int batch_create_rank(rama_ctx* c, int32_t max_seqs, rama_batch** out, bool connect) {
+  if (c->tp_sim) return fail(RAMA_E_STATE, "RAMA_TP_SIM measures the decode step only");
   CK(cudaSetDevice(c->device));
   std::lock_guard<std::mutex> cap_lk(c->cap_mu);
   rama_batch* b = new rama_batch();
@@ -75,12 +81,14 @@ extern "C" int rama_batch_create(rama_ctx* c, int32_t max_seqs, rama_batch** out
   b->part_floats = pf;
   cudaError_t e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
 #define A(call) if (e == cudaSuccess) e = (call)
-  A(dalloc(&b->x, B * D)); A(dalloc(&b->xn, B * D)); A(dalloc(&b->q, B * Dq)); A(dalloc(&b->att, B * Dq));
+  b->p2p = c->world > 1 && c->p2p;
+  A(dalloc(&b->x, B * D)); A(dalloc(&b->q, B * Dq)); A(dalloc(&b->att, B * Dq));
+  if (!b->p2p) A(dalloc(&b->xn, B * D));
   A(dalloc(&b->h, B * Fl)); A(dalloc(&b->part, pf));
-  if (c->world > 1) { A(dalloc(&b->red, B * D)); A(dalloc(&b->lstage, (size_t)c->world * B * c->Vl)); }
+  if (c->world > 1 && !b->p2p) { A(dalloc(&b->red, B * D)); A(dalloc(&b->lstage, (size_t)c->world * B * c->Vl)); }
   A(dalloc(&b->attn_ws, B * c->Hl * b->n_split * (c->hs + 2)));
   A(dalloc(&b->tickets, B * c->Hl));
-  A(dalloc(&b->d_seqs, B)); A(dalloc(&b->d_sp, B)); A(dalloc(&b->d_next, 2 * B));
+  A(dalloc(&b->d_seqs, B)); A(dalloc(&b->d_sp, B)); A(dalloc(&b->d_next, 2 * B)); A(dalloc(&b->d_err, 1));
   A(cudaHostAlloc((void**)&b->h_seqs, kBatchRing * B * sizeof(BatchSeq), cudaHostAllocDefault));
   A(cudaHostAlloc((void**)&b->h_sp, B * sizeof(SampleParams), cudaHostAllocDefault));
   A(cudaHostAlloc((void**)&b->h_next, 2 * B * sizeof(int32_t), cudaHostAllocDefault));
@@ -90,6 +98,19 @@ extern "C" int rama_batch_create(rama_ctx* c, int32_t max_seqs, rama_batch** out
   if (e != cudaSuccess) {
     rama_batch_destroy(b);
     return fail(RAMA_E_CUDA, "batch allocation: %s", cudaGetErrorString(e));
+  }
+  if (b->p2p) {
+    auto al = [](size_t v) { return (v + 255) / 256 * 256; };
+    b->s_max = std::max(pick_ksplit(c, tiles(c->D), c->Dq), pick_ksplit(c, tiles(c->D), c->Fl));
+    const size_t bpr_max = (B + c->world - 1) / c->world;
+    b->off_xn = al((size_t)c->world * b->s_max * bpr_max * D * sizeof(float));
+    b->off_flags = al(b->off_xn + B * D * sizeof(float));
+    b->off_done = al(b->off_flags + (size_t)3 * c->world * sizeof(unsigned));
+    b->off_step = b->off_done + 256;
+    int rc = peer_block_alloc(c, b->off_step + 256, &b->blk);
+    if (rc == RAMA_OK && connect) rc = peer_block_connect(c, &b->blk, b->stream);
+    if (rc != RAMA_OK) { rama_batch_destroy(b); return rc; }
+    b->xn = reinterpret_cast<float*>(b->blk.local + b->off_xn);
   }
   b->graphs.assign(max_seqs + 1, nullptr);
   b->fence = std::make_shared<BatchFence>();
@@ -102,13 +123,50 @@ extern "C" int rama_batch_create(rama_ctx* c, int32_t max_seqs, rama_batch** out
   return RAMA_OK;
 }
 
+extern "C" int rama_batch_create(rama_ctx* c, int32_t max_seqs, rama_batch** out) {
+  if (!c || !out) return fail(RAMA_E_INVALID, "NULL argument");
+  if (!c->loaded) return fail(RAMA_E_STATE, "no weights loaded");
+  if (max_seqs < 1 || max_seqs > kBatchMax) return fail(RAMA_E_INVALID, "max_seqs must be in [1, %d]", kBatchMax);
+  if (c->ranks.empty()) return batch_create_rank(c, max_seqs, out, true);
+  rama_batch* g = new rama_batch();  // single-process group: one batch per rank, exchange blocks cross-wired
+  g->ctx = c;
+  g->cap = max_seqs;
+  for (rama_ctx* rc : c->ranks) {
+    rama_batch* rb = nullptr;
+    int r = batch_create_rank(rc, max_seqs, &rb, false);
+    if (r != RAMA_OK) {
+      for (rama_batch* x : g->ranks) rama_batch_destroy(x);
+      delete g;
+      return r;
+    }
+    g->ranks.push_back(rb);
+  }
+  std::vector<PeerBlock*> blocks;
+  for (rama_batch* r : g->ranks) blocks.push_back(&r->blk);
+  peer_blocks_connect_group(blocks.data(), (int)blocks.size());
+  c->n_objects.fetch_add(1);
+  *out = g;
+  return RAMA_OK;
+}
+
 extern "C" int rama_batch_destroy(rama_batch* b) {
   if (!b) return RAMA_OK;
+  if (!b->ranks.empty()) {
+    for (rama_batch* r : b->ranks) { cudaSetDevice(r->ctx->device); cudaStreamSynchronize(r->stream); }
+    for (rama_batch* r : b->ranks) rama_batch_destroy(r);
+    b->ctx->n_objects.fetch_sub(1);
+    delete b;
+    return RAMA_OK;
+  }
   cudaSetDevice(b->ctx->device);
   if (b->stream) cudaStreamSynchronize(b->stream);
   std::lock_guard<std::mutex> cap_lk(b->ctx->cap_mu);
   for (auto g : b->graphs) if (g) cudaGraphExecDestroy(g);
-  void* bufs[] = {b->x, b->xn, b->q, b->att, b->h, b->part, b->attn_ws, b->tickets, b->d_seqs, b->d_sp, b->d_next, b->red, b->lstage};
+  if (b->p2p) {
+    peer_block_free(b->ctx, &b->blk, b->stream, b->x);
+    b->xn = nullptr;  // lived inside the block
+  }
+  void* bufs[] = {b->x, b->xn, b->q, b->att, b->h, b->part, b->attn_ws, b->tickets, b->d_seqs, b->d_sp, b->d_next, b->red, b->lstage, b->d_err};
   for (void* p : bufs) if (p) cudaFree(p);
   if (b->h_seqs) cudaFreeHost(b->h_seqs);
   if (b->h_sp) cudaFreeHost(b->h_sp);
@@ -138,14 +196,47 @@ static int enqueue_batch_step(rama_batch* b, int n, int* n_launch) {
     ++launches;                                                                                               \
     if (e_ != cudaSuccess) return fail(RAMA_E_CUDA, "batched step launch %s: %s", #call, cudaGetErrorString(e_)); \
   } while (0)
-  LK(launch_k(pdl, batch_embed_kernel, dim3(n), dim3(256), st, b->d_seqs, W[RAMA_T_TOKEN_EMBEDDING], b->x, D, c->V));
+  const bool xchg = b->p2p;
+  unsigned* step_counter = xchg ? reinterpret_cast<unsigned*>(b->blk.local + b->off_step) : nullptr;
+  LK(launch_k(pdl, batch_embed_kernel, dim3(n), dim3(256), st, b->d_seqs, W[RAMA_T_TOKEN_EMBEDDING], b->x, D, c->V, step_counter));
   GemmOperand X{b->xn, (size_t)n, (size_t)D};
+  // Tensor parallelism over peer memory (tp_exchange.cuh): sequences dealt in blocks of bpr; the wo / w2 GEMMs push their
+  // split-K partials to the owners, tp_addnorm sums ranks × splits in fixed order, normalises and stores into every rank's xn.
+  const int P = c->world;
+  const int bpr = xchg ? (n + P - 1) / P : n;
+  const int row0 = std::min(n, c->rank * bpr), n_rows = std::max(0, std::min(n - row0, bpr));
+  const unsigned n_epochs = 2u * (unsigned)L + 2u;  // exchanges of one step (wo, w2 per layer; + the logits barrier)
+  unsigned xi = 0;                                   // index of the next exchange inside the step
+  TpPeers tpp{};
+  if (xchg) {
+    tpp.P = P; tpp.me = c->rank;
+    for (int r = 0; r < P; ++r) tpp.flags[r] = reinterpret_cast<unsigned*>(b->blk.base[r] + b->off_flags);
+  }
+  auto pusher = [&](int S) {
+    EpiPushT e{};
+    for (int r = 0; r < P; ++r) e.inbox[r] = reinterpret_cast<float*>(b->blk.base[r]);
+    e.bpr = bpr; e.me = c->rank; e.ldc = D; e.N = n; e.ksplit = S;
+    return e;
+  };
+  auto exchange = [&](int S, const float* norm_w) -> int {
+    TpAddNormParams ap{};
+    ap.x = b->x; ap.inbox = reinterpret_cast<const float*>(b->blk.local);
+    ap.n_slab = P * S; ap.slab_stride = (size_t)bpr * D; ap.w = norm_w;
+    for (int r = 0; r < P; ++r) { ap.xn[r] = reinterpret_cast<float*>(b->blk.base[r] + b->off_xn); ap.xlast[r] = nullptr; }
+    ap.last_row = -1; ap.row0 = row0; ap.n_rows = n_rows; ap.rpr = bpr; ap.D = D;
+    ap.tp = tpp;
+    ap.epoch = TpEpoch{step_counter, n_epochs, ++xi};
+    ap.done = reinterpret_cast<unsigned*>(b->blk.local + b->off_done);
+    ap.error = &b->d_err[0];
+    LK(launch_k(pdl, tp_addnorm_kernel, dim3(std::max(1, n_rows)), dim3(kTpNormThreads), st, ap));
+    return RAMA_OK;
+  };
   int S_prev = 0;  // split factor of the pending residual partials in b->part (0: none)
   const float* pending = b->part;
   // tensor parallelism: row-parallel wo / w2 leave a partial [n][D] on every rank — sum the split-K partials, all-reduce
   // over NVLink (NCCL, 1 MB at 64 sequences), and hand the reduced buffer to the next addnorm as a single "split"
   auto reduce_ranks = [&](int& S) -> int {
-    if (c->world <= 1) return RAMA_OK;
+    if (c->world <= 1 || xchg) return RAMA_OK;
     LK(launch_k(pdl, sum_partials_kernel, dim3(c->sm_count * 2), dim3(256), st, b->red, (const float*)b->part, (size_t)n * D, S));
     NK(g_nccl.AllReduce(b->red, b->red, (size_t)n * D, kNcclFloat32, kNcclSum, c->comm, st));
     ++launches;
@@ -156,6 +247,8 @@ static int enqueue_batch_step(rama_batch* b, int n, int* n_launch) {
   for (int l = 0; l < L; ++l) {
     const size_t layer_off = (size_t)l * T * Dq;
     // x += pending w2 output; xn = rmsnorm(x)   (infer.rs:19, :47 of the previous layer)
+    if (xchg && l > 0) RK(exchange(S_prev, W[RAMA_T_RMS_ATT] + (size_t)l * D));
+    else
     LK(launch_k(pdl, batch_addnorm_kernel, dim3(n), dim3(kBatchNormThreads), st, b->x, S_prev ? pending : nullptr, S_prev,
                 (size_t)n * D, W[RAMA_T_RMS_ATT] + (size_t)l * D, b->xn, D));
     {  // [wq;wk;wv] (weights = the 128-row operand, the batch = the 64-column operand)   (infer.rs:20-23)
@@ -176,11 +269,17 @@ static int enqueue_batch_step(rama_batch* b, int n, int* n_launch) {
       GemmOperand A{W[RAMA_T_WO] + (size_t)l * D * Dq, (size_t)D, (size_t)Dq};
       GemmOperand Bm{b->att, (size_t)n, (size_t)Dq};
       S_wo = pick_ksplit(c, tiles(D), Dq);
-      EpiStoreT epi{b->part, D, n, S_wo, (size_t)n * D};
-      LK((BATCH_GEMM(st, &A, 1, &Bm, 1, D, n, Dq, 0, S_wo, epi, pdl)));
+      if (xchg) {
+        LK((BATCH_GEMM(st, &A, 1, &Bm, 1, D, n, Dq, 0, S_wo, pusher(S_wo), pdl)));
+      } else {
+        EpiStoreT epi{b->part, D, n, S_wo, (size_t)n * D};
+        LK((BATCH_GEMM(st, &A, 1, &Bm, 1, D, n, Dq, 0, S_wo, epi, pdl)));
+      }
       RK(reduce_ranks(S_wo));
     }
     // x += wo output; xn = rmsnorm(x)   (infer.rs:37-38)
+    if (xchg) RK(exchange(S_wo, W[RAMA_T_RMS_FFN] + (size_t)l * D));
+    else
     LK(launch_k(pdl, batch_addnorm_kernel, dim3(n), dim3(kBatchNormThreads), st, b->x, pending, S_wo, (size_t)n * D, W[RAMA_T_RMS_FFN] + (size_t)l * D, b->xn, D));
     {  // [w1;w3] → SwiGLU   (infer.rs:39-45)
       GemmOperand A[2] = {{W[RAMA_T_W1] + (size_t)l * Fl * D, (size_t)Fl, (size_t)D},
@@ -194,19 +293,28 @@ static int enqueue_batch_step(rama_batch* b, int n, int* n_launch) {
       GemmOperand A{W[RAMA_T_W2] + (size_t)l * D * Fl, (size_t)D, (size_t)Fl};
       GemmOperand Bm{b->h, (size_t)n, (size_t)Fl};
       S_prev = pick_ksplit(c, tiles(D), Fl);
-      EpiStoreT epi{b->part, D, n, S_prev, (size_t)n * D};
-      LK((BATCH_GEMM(st, &A, 1, &Bm, 1, D, n, Fl, 0, S_prev, epi, pdl)));
+      if (xchg) {
+        LK((BATCH_GEMM(st, &A, 1, &Bm, 1, D, n, Fl, 0, S_prev, pusher(S_prev), pdl)));
+      } else {
+        EpiStoreT epi{b->part, D, n, S_prev, (size_t)n * D};
+        LK((BATCH_GEMM(st, &A, 1, &Bm, 1, D, n, Fl, 0, S_prev, epi, pdl)));
+      }
       RK(reduce_ranks(S_prev));
     }
   }
   // x += w2 output; final rmsnorm; classifier → each session's logits   (infer.rs:49-51)
+  if (xchg) RK(exchange(S_prev, W[RAMA_T_RMS_FINAL]));
+  else
   LK(launch_k(pdl, batch_addnorm_kernel, dim3(n), dim3(kBatchNormThreads), st, b->x, pending, S_prev, (size_t)n * D, W[RAMA_T_RMS_FINAL], b->xn, D));
   {
     GemmOperand A{c->wcls, (size_t)Vl, (size_t)D};
     const int S = pick_ksplit(c, tiles(Vl), D);
     EpiStoreT epi{b->part, Vl, n, S, (size_t)n * Vl};
     LK((BATCH_GEMM(st, &A, 1, &X, 1, Vl, n, D, 0, S, epi, pdl)));
-    if (c->world > 1) {  // vocabulary rows are split: gather every rank's block, then scatter into the sessions' logits
+    if (xchg) {  // vocabulary rows are split: every rank stores its slice into the sessions' logits on every rank, then a barrier
+      LK(launch_k(pdl, batch_cls_push_kernel, dim3(std::min(64, (Vl + 255) / 256), n), dim3(256), st, b->part, S, (size_t)n * Vl, b->d_seqs, Vl, c->v0, P));
+      LK(launch_k(pdl, tp_barrier_kernel, dim3(1), dim3(32), st, tpp, TpEpoch{step_counter, n_epochs, n_epochs}, &b->d_err[0]));
+    } else if (c->world > 1) {  // NCCL mode: gather every rank's block, then scatter into the sessions' logits
       float* mine = b->lstage + (size_t)c->rank * n * Vl;
       LK(launch_k(pdl, batch_cls_stage_kernel, dim3(std::min(64, (Vl + 255) / 256), n), dim3(256), st, b->part, S, (size_t)n * Vl, mine, Vl));
       NK(g_nccl.AllGather(mine, b->lstage, (size_t)n * Vl, kNcclFloat32, c->comm, st));
@@ -231,9 +339,26 @@ static int batch_check_sessions(rama_batch* b, rama_session* const* sessions, in
   return RAMA_OK;
 }
 
+// group batch: the rank-r batch steps the rank-r sessions
+static int group_sessions(rama_batch* b, rama_session* const* sessions, int32_t n, std::vector<std::vector<rama_session*>>& per_rank) {
+  if (n < 1 || n > b->cap) return fail(RAMA_E_INVALID, "batch of %d sequences outside [1, %d]", n, b->cap);
+  per_rank.assign(b->ranks.size(), std::vector<rama_session*>((size_t)n));
+  for (int i = 0; i < n; ++i) {
+    if (!sessions[i] || sessions[i]->ctx != b->ctx || sessions[i]->ranks.size() != b->ranks.size())
+      return fail(RAMA_E_INVALID, "session %d is NULL or belongs to another context", i);
+    for (size_t r = 0; r < b->ranks.size(); ++r) per_rank[r][i] = sessions[i]->ranks[r];
+  }
+  return RAMA_OK;
+}
+
 extern "C" int rama_forward_batch(rama_batch* b, rama_session* const* sessions, const int32_t* tokens,
                                   const int32_t* pos, int32_t n) {
   if (!b || !sessions || !tokens || !pos) return fail(RAMA_E_INVALID, "NULL argument");
+  if (!b->ranks.empty()) {
+    std::vector<std::vector<rama_session*>> pr;
+    RK(group_sessions(b, sessions, n, pr));
+    return group_run(b->ctx, [&](int r) { return rama_forward_batch(b->ranks[r], pr[r].data(), tokens, pos, n); });
+  }
   rama_ctx* c = b->ctx;
   RK(batch_check_sessions(b, sessions, n));
   for (int i = 0; i < n; ++i) {
@@ -245,7 +370,11 @@ extern "C" int rama_forward_batch(rama_batch* b, rama_session* const* sessions, 
   if (++b->ring_i == kBatchRing) { b->ring_i = 0; CK(cudaStreamSynchronize(b->stream)); }
   for (int i = 0; i < n; ++i) {
     rama_session* s = sessions[i];
-    hs[i] = BatchSeq{s->key_cache, s->value_cache, s->logits, s->ctrl, pos[i], tokens[i]};
+    hs[i] = BatchSeq{s->key_cache, s->value_cache, s->logits, s->ctrl, pos[i], tokens[i], {nullptr}};
+    if (b->p2p) {
+      if (!s->p2p) return fail(RAMA_E_STATE, "session %d was not created for the peer exchange", i);
+      for (int r = 0; r < c->world; ++r) hs[i].logits_peer[r] = reinterpret_cast<float*>(s->blk.base[r] + s->off_logits);
+    }
     s->logits_gathered = true;   // under TP the batched step leaves the full vocabulary in every session
     s->parts_valid = false;
     // stream ordering, both ways: the step waits for work the session still has in flight on its own stream (an async
@@ -281,6 +410,12 @@ extern "C" int rama_forward_batch(rama_batch* b, rama_session* const* sessions, 
 extern "C" int rama_sample_batch(rama_batch* b, rama_session* const* sessions, int32_t n, float temperature,
                                  float topp, int32_t* next) {
   if (!b || !sessions || !next) return fail(RAMA_E_INVALID, "NULL argument");
+  if (!b->ranks.empty()) {  // every rank holds every session's full logits: rank 0 samples
+    std::vector<std::vector<rama_session*>> pr;
+    RK(group_sessions(b, sessions, n, pr));
+    RK(group_run(b->ctx, [&](int r) { return r == 0 ? RAMA_OK : rama_batch_sync(b->ranks[r]); }));
+    return rama_sample_batch(b->ranks[0], pr[0].data(), n, temperature, topp, next);
+  }
   rama_ctx* c = b->ctx;
   RK(batch_check_sessions(b, sessions, n));
   CK(cudaSetDevice(c->device));
@@ -290,7 +425,7 @@ extern "C" int rama_sample_batch(rama_batch* b, rama_session* const* sessions, i
   for (int i = 0; i < n; ++i) {
     rama_session* s = sessions[i];
     b->h_sp[i] = SampleParams{s->logits, nullptr, 0, 0, c->V, s->ctrl, nullptr, nullptr, s->sort_keys, temperature, topp, 0, PeerIn{}};
-    hs[i] = BatchSeq{s->key_cache, s->value_cache, s->logits, s->ctrl, 0, 0};
+    hs[i] = BatchSeq{s->key_cache, s->value_cache, s->logits, s->ctrl, 0, 0, {nullptr}};
     if (s->fence && s->fence != b->fence) CK(cudaStreamWaitEvent(b->stream, s->fence->ev, 0));
     if (s->async_pending) {  // logits written by an asynchronous rama_forward on the session's own stream
       CK(cudaEventRecord(s->ev1, s->stream));
@@ -307,6 +442,11 @@ extern "C" int rama_sample_batch(rama_batch* b, rama_session* const* sessions, i
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(b->h_next, b->d_next, (size_t)2 * n * sizeof(int32_t), cudaMemcpyDeviceToHost, b->stream));
   CK(cudaStreamSynchronize(b->stream));
+  if (b->p2p) {
+    int32_t xerr = 0;
+    CK(cudaMemcpy(&xerr, b->d_err, sizeof(xerr), cudaMemcpyDeviceToHost));
+    if (xerr == 3) return fail(RAMA_E_NCCL, "timed out waiting for a tensor-parallel peer in the batched step");
+  }
   for (int i = 0; i < n; ++i) {
     if (b->h_next[2 * i + 1] == 1) return fail(RAMA_E_STATE, "token id outside the vocabulary reached the device step (sequence %d)", i);
     if (b->h_next[2 * i + 1] == 2) return fail(RAMA_E_STATE, "top-p candidate list is empty (the reference panics here, infer.rs:66) (sequence %d)", i);
@@ -317,6 +457,7 @@ extern "C" int rama_sample_batch(rama_batch* b, rama_session* const* sessions, i
 
 extern "C" int rama_batch_sync(rama_batch* b) {
   if (!b) return fail(RAMA_E_INVALID, "NULL batch");
+  if (!b->ranks.empty()) return group_run(b->ctx, [&](int r) { return rama_batch_sync(b->ranks[r]); });
   CK(cudaSetDevice(b->ctx->device));
   CK(cudaStreamSynchronize(b->stream));
   return RAMA_OK;
@@ -324,6 +465,7 @@ extern "C" int rama_batch_sync(rama_batch* b) {
 
 extern "C" int rama_batch_launches_per_step(const rama_batch* b, int32_t* n) {
   if (!b || !n) return fail(RAMA_E_INVALID, "NULL argument");
+  if (!b->ranks.empty()) return rama_batch_launches_per_step(b->ranks[0], n);
   *n = b->launches;
   return RAMA_OK;
 }

@@ -3,7 +3,24 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#ifndef __CUDACC_RTC__
+#include <atomic>
+#endif
+
 namespace rama {
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-DEVICE setting: a process that drives several devices
+// (rama_ctx_create_multi) must apply it on each of them, not once per process.  `mask` = one bit per device done.
+inline cudaError_t ensure_dyn_smem(const void* kern, int bytes, std::atomic<unsigned long long>& mask) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (mask.load(std::memory_order_acquire) & bit) return cudaSuccess;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) mask.fetch_or(bit, std::memory_order_release);
+  return e;
+}
 
 constexpr int kWarp = 32;
 constexpr int kAttnMaxHs = 128;  // largest head_size the attention kernels hold per head (checked at load)
@@ -73,6 +90,34 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 // L2 prefetch of a contiguous byte range (bytes % 16 == 0, 16-byte aligned), issued by one thread.
 __device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+// ---- thread-block cluster helpers (distributed shared memory) -------------------------------------
+__device__ __forceinline__ unsigned cluster_ctarank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ unsigned cluster_nctarank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+// address of the same shared-memory location in CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t dsmem_addr(const void* local_smem, unsigned rank) {
+  uint32_t a = (uint32_t)__cvta_generic_to_shared(local_smem), r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void dsmem_st_f4(uint32_t addr, const float4& v) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void dsmem_st_f1(uint32_t addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {  // every thread of every CTA of the cluster
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 // ---- peer-memory exchange (tensor parallelism over NVLink; see gemv.cuh PeerOut/PeerIn) -----------

@@ -88,6 +88,7 @@ extern "C" int rama_ctx_create(int device, const rama_tp* tp, rama_ctx** out) {
   c->use_pdl = env_int("RAMA_PDL", 1);
   c->variant_override = env_int("RAMA_GEMV_VARIANT", -1);
   c->staged = env_int("RAMA_GEMV_STAGED", 1);
+  c->tp_cluster = env_int("RAMA_TP_CLUSTER", 4);
   c->embed_kernel = env_int("RAMA_EMBED_KERNEL", 1);  // the fold measured +0.3 % (stories15M 10173 → 10201 tok/s): a tiny kernel in a PDL chain is almost free
   c->stage_max_kb = std::max(0, std::min((int)(kGemvSmemStageMaxSolo / 1024), env_int("RAMA_GEMV_STAGE_KB", 110)));
   {
@@ -113,6 +114,10 @@ extern "C" int rama_ctx_create(int device, const rama_tp* tp, rama_ctx** out) {
     c->rank = tp->rank;
     c->world = tp->world;
   }
+  if (c->world == 1) {
+    const int sim = env_int("RAMA_TP_SIM", 0);
+    if (sim > 1 && sim <= kMaxPeers) { c->world = sim; c->rank = 0; c->p2p = 1; c->tp_sim = 1; c->persistent = 0; }
+  }
   cudaError_t e = cudaStreamCreateWithFlags(&c->op_stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { delete c; return fail(RAMA_E_CUDA, "stream: %s", cudaGetErrorString(e)); }
   *out = c;
@@ -130,6 +135,11 @@ static void free_weights(rama_ctx* c) {
 
 extern "C" int rama_ctx_destroy(rama_ctx* c) {
   if (!c) return RAMA_OK;
+  if (is_group(c)) {
+    group_destroy(c);
+    delete c;
+    return RAMA_OK;
+  }
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   free_weights(c);
@@ -224,8 +234,19 @@ static int upload_tensor(rama_ctx* c, int i, const float* src, cudaStream_t st) 
   return RAMA_OK;
 }
 
+// a group loads every rank's shard concurrently (each rank thread reads / generates only the rows it keeps)
+template <class F>
+static int group_load(rama_ctx* g, F&& load_rank) {
+  if (g->n_objects.load() > 0) return fail(RAMA_E_STATE, "sessions or batches of this context are alive: destroy them before loading weights again");
+  g->loaded = false;
+  RK(group_run(g, [&](int r) { return load_rank(g->ranks[r]); }));
+  group_adopt_config(g);
+  return RAMA_OK;
+}
+
 extern "C" int rama_ctx_load_host(rama_ctx* c, const rama_config* cfg, const float* const tensors[RAMA_T_COUNT]) {
   if (!c || !cfg || !tensors) return fail(RAMA_E_INVALID, "NULL argument");
+  if (is_group(c)) return group_load(c, [&](rama_ctx* rc) { return rama_ctx_load_host(rc, cfg, tensors); });
   std::lock_guard<std::mutex> lk(c->mu);
   RK(reload_allowed(c));
   CK(cudaSetDevice(c->device));
@@ -348,6 +369,7 @@ static double g_last_load_gbps = 0.0;
 
 extern "C" int rama_ctx_load_file(rama_ctx* c, const char* path) {
   if (!c || !path) return fail(RAMA_E_INVALID, "NULL argument");
+  if (is_group(c)) return group_load(c, [&](rama_ctx* rc) { return rama_ctx_load_file(rc, path); });
   int fd = open(path, O_RDONLY);
   if (fd < 0) return fail(RAMA_E_IO, "cannot open %s", path);
   struct stat st;
@@ -413,6 +435,8 @@ extern "C" int rama_ctx_load_synthetic(rama_ctx* c, const rama_config* cfg, uint
                                        const float scale[RAMA_T_COUNT], const float offset[RAMA_T_COUNT],
                                        const float* freq_real, const float* freq_imag) {
   if (!c || !cfg || !scale || !offset || !freq_real || !freq_imag) return fail(RAMA_E_INVALID, "NULL argument");
+  if (is_group(c))
+    return group_load(c, [&](rama_ctx* rc) { return rama_ctx_load_synthetic(rc, cfg, seed, scale, offset, freq_real, freq_imag); });
   std::lock_guard<std::mutex> lk(c->mu);
   RK(reload_allowed(c));
   CK(cudaSetDevice(c->device));
@@ -451,6 +475,7 @@ extern "C" int rama_ctx_config(const rama_ctx* c, rama_config* out) {
 
 extern "C" int rama_ctx_weight_to_host(rama_ctx* c, int tensor, float* dst, size_t n, size_t* n_out) {
   if (!c || tensor < 0 || tensor >= RAMA_T_COUNT) return fail(RAMA_E_INVALID, "bad argument");
+  if (is_group(c)) c = c->ranks[0];  // rank 0's shard
   if (!c->loaded) return fail(RAMA_E_STATE, "no weights loaded");
   const size_t have = c->plan[tensor].local_elems();
   if (n_out) *n_out = have;
@@ -463,6 +488,17 @@ extern "C" int rama_ctx_weight_to_host(rama_ctx* c, int tensor, float* dst, size
 
 extern "C" int rama_ctx_mem_info(rama_ctx* c, size_t* free_bytes, size_t* total_bytes) {
   if (!c || !free_bytes || !total_bytes) return fail(RAMA_E_INVALID, "NULL argument");
+  if (is_group(c)) {  // what every rank can still allocate
+    size_t f = ~(size_t)0, t = 0;
+    for (rama_ctx* rc : c->ranks) {
+      size_t fr, tr;
+      RK(rama_ctx_mem_info(rc, &fr, &tr));
+      f = std::min(f, fr);
+      t = tr;
+    }
+    *free_bytes = f; *total_bytes = t;
+    return RAMA_OK;
+  }
   CK(cudaSetDevice(c->device));
   CK(cudaMemGetInfo(free_bytes, total_bytes));
   return RAMA_OK;
@@ -470,6 +506,16 @@ extern "C" int rama_ctx_mem_info(rama_ctx* c, size_t* free_bytes, size_t* total_
 
 extern "C" int rama_ctx_weight_bytes(const rama_ctx* c, size_t* bytes) {
   if (!c || !bytes) return fail(RAMA_E_INVALID, "NULL argument");
+  if (is_group(c)) {
+    size_t t = 0;
+    for (const rama_ctx* rc : c->ranks) {
+      size_t b = 0;
+      RK(rama_ctx_weight_bytes(rc, &b));
+      t += b;
+    }
+    *bytes = t;
+    return RAMA_OK;
+  }
   size_t t = 0;
   for (int i = 0; i < RAMA_T_COUNT; ++i) t += c->plan[i].local_elems() * 4;
   *bytes = t;

@@ -62,9 +62,8 @@ cudaError_t launch_gemm_tf32x3(cudaStream_t st, const GemmOperand* A, int n_a, c
   constexpr int BK = kGemmBK;
   static_assert(SM::kTotal <= 227 * 1024, "tile does not fit shared memory");
   auto kern = gemm_tf32x3_kernel<BN, STAGES, CH, NX, Epi, AS>;
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal); });
+  static std::atomic<unsigned long long> attr_done{0};
+  const cudaError_t attr_err = ensure_dyn_smem((const void*)kern, SM::kTotal, attr_done);
   if (attr_err != cudaSuccess) return attr_err;
   if (M <= 0 || N <= 0 || K <= 0 || K % 4 || n_a < 1 || n_a > 3 || n_b < 1 || n_b > 3 || ksplit < 1) return cudaErrorInvalidValue;
   if (n_a > 1 && (n_b > 1 || Epi::kDual)) return cudaErrorInvalidValue;

@@ -23,6 +23,7 @@ namespace rama {
 constexpr int kGemvThreads = 512;
 constexpr int kGemvWarps = kGemvThreads / kWarp;
 constexpr int kPdlPrefetchBytes = 192 * 1024;  // per CTA: ≈ what HBM delivers to one SM in ~4 µs
+constexpr int kMaxClusterShare = 4;            // cluster size of the shared peer reduction (ProNorm)
 
 struct ArgPart {  // greedy partial: best value and its global vocabulary index
   float v;
@@ -99,6 +100,7 @@ struct ProNorm {
   StepCtrl* ctrl = nullptr;
   unsigned* seq = nullptr;     // step counter: epoch source of the TP exchange
   int vocab = 0;
+  int cluster_share = 0;       // launched as clusters: the CTAs of a cluster split the peer reduction (see operator())
   // The norm weights never depend on the previous kernel: the first N float4 per thread are loaded BEFORE
   // griddepcontrol.wait (one L2 round trip off the critical path of every norm-prologue kernel).
   template <int N>
@@ -130,19 +132,30 @@ struct ProNorm {
     const float4* a4 = reinterpret_cast<const float4*>(add);
     const bool peers = pin.P > 0 && add != nullptr;
     const unsigned ep = peers ? pin.epoch() : 0u;
+    // Tensor parallelism, launched as thread-block clusters (cluster_share): the CTAs of a cluster split the vector — CTA r
+    // reads the P LL partials of ITS slice only (1/CS of the L2 reads and of the spinning; at P = 8 every CTA of a plain launch
+    // pulls 256 KB through L2, 148 CTAs at once), adds them in rank order and stores the slice into every sibling's xs over
+    // DSMEM; one cluster barrier later every CTA holds the whole vector and the CS partial sums of squares.
+    const unsigned CS = (peers && cluster_share) ? cluster_nctarank() : 1u;
+    const unsigned cr = CS > 1 ? cluster_ctarank() : 0u;
+    const int lo = (int)((long long)K4 * cr / CS), hi = (int)((long long)K4 * (cr + 1) / CS);
+    const bool first_cluster = blockIdx.x < CS;  // the cluster (or CTA) that also writes the RunState copies
+    uint32_t sib[kMaxClusterShare];
+#pragma unroll
+    for (int j = 0; j < kMaxClusterShare; ++j) sib[j] = (CS > 1 && j < (int)CS) ? dsmem_addr(xs, j) : 0u;
     float ss = 0.f;
-    for (int i = threadIdx.x; i < K4; i += kGemvThreads) {
+    for (int i = lo + threadIdx.x; i < hi; i += kGemvThreads) {
       float4 v = __ldcg(x4 + i);
       if (peers) {
         // issue every rank's two 16-byte LL loads first (independent), then validate the epochs;
         // only an element that has not arrived yet falls into the spinning reload
-        uint4 lo[kMaxPeers], hi[kMaxPeers];
+        uint4 lo_[kMaxPeers], hi_[kMaxPeers];
 #pragma unroll
         for (int r = 0; r < kMaxPeers; ++r) {
           if (r < pin.P) {
             const uint2* e = pin.inbox + (size_t)r * pin.n + 4 * i;
-            lo[r] = ld_ll2(e);
-            hi[r] = ld_ll2(e + 2);
+            lo_[r] = ld_ll2(e);
+            hi_[r] = ld_ll2(e + 2);
           }
         }
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -150,14 +163,14 @@ struct ProNorm {
         for (int r = 0; r < kMaxPeers; ++r) {  // rank order: same association on every rank
           if (r < pin.P) {
             const uint2* e = pin.inbox + (size_t)r * pin.n + 4 * i;
-            if (lo[r].y != ep || lo[r].w != ep) lo[r] = ld_ll2_wait(e, ep, pin.error);
-            if (hi[r].y != ep || hi[r].w != ep) hi[r] = ld_ll2_wait(e + 2, ep, pin.error);
-            a.x += __uint_as_float(lo[r].x); a.y += __uint_as_float(lo[r].z);
-            a.z += __uint_as_float(hi[r].x); a.w += __uint_as_float(hi[r].z);
+            if (lo_[r].y != ep || lo_[r].w != ep) lo_[r] = ld_ll2_wait(e, ep, pin.error);
+            if (hi_[r].y != ep || hi_[r].w != ep) hi_[r] = ld_ll2_wait(e + 2, ep, pin.error);
+            a.x += __uint_as_float(lo_[r].x); a.y += __uint_as_float(lo_[r].z);
+            a.z += __uint_as_float(hi_[r].x); a.w += __uint_as_float(hi_[r].z);
           }
         }
         v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
-        if (blockIdx.x == 0) reinterpret_cast<float4*>(const_cast<float*>(add))[i] = a;  // RunState.xb2 / xb
+        if (first_cluster) reinterpret_cast<float4*>(const_cast<float*>(add))[i] = a;  // RunState.xb2 / xb
       } else if (add) {
         float4 a = __ldcg(a4 + i);
         for (int h = 1; h < n_add; ++h) {
@@ -167,14 +180,33 @@ struct ProNorm {
         v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
         if (add_out && blockIdx.x == 0) reinterpret_cast<float4*>(add_out)[i] = a;
       }
-      xs[i] = v;
+      if (CS > 1) {
+#pragma unroll
+        for (int j = 0; j < kMaxClusterShare; ++j)
+          if (j < (int)CS) dsmem_st_f4(sib[j] + (uint32_t)i * 16u, v);  // own copy included
+      } else {
+        xs[i] = v;
+      }
       ss = dot4(v, v, ss);
-      if (blockIdx.x == 0) reinterpret_cast<float4*>(xout)[i] = v;
+      if (first_cluster) reinterpret_cast<float4*>(xout)[i] = v;
     }
     ss = block_sum<kGemvThreads>(ss, red);
+    if (CS > 1) {
+      // red[40 .. 40+CS): the slices' sums of squares, written by each owner into every CTA of the cluster
+      if (threadIdx.x == 0) {
+#pragma unroll
+        for (int j = 0; j < kMaxClusterShare; ++j)
+          if (j < (int)CS) dsmem_st_f1(dsmem_addr(red + 40 + cr, j), ss);
+      }
+      cluster_sync_all();  // slices and partial sums of every sibling have landed (release / acquire at cluster scope)
+      ss = 0.f;
+#pragma unroll
+      for (int j = 0; j < kMaxClusterShare; ++j)
+        if (j < (int)CS) ss += red[40 + j];  // slice order: identical on every CTA and every rank
+    }
     const float scale = 1.0f / sqrtf(ss / (float)(K4 * 4) + 1e-5f);
     const float4* w4 = reinterpret_cast<const float4*>(w);
-    auto apply = [&](int i, const float4 g) {  // same i as above: no sync needed
+    auto apply = [&](int i, const float4 g) {  // CS == 1: same i as above, no sync needed; CS > 1: after the cluster barrier
       float4 v = xs[i];
       v.x = g.x * (scale * v.x); v.y = g.y * (scale * v.y);
       v.z = g.z * (scale * v.z); v.w = g.w * (scale * v.w);
@@ -383,17 +415,32 @@ struct EpiCls {
   float bv;
   int bi;
   PeerOut po;          // po.P > 0: the partial goes to every rank's part array (po.inbox[r] = its slot base)
+  // po.P > 0 and lpeer[0] != null: the logits slice itself is stored into EVERY rank's full logits array [V] (peer-mapped), so
+  // the vocabulary all-gather is part of this epilogue; the LL partial written by finish() — after a system-scope fence — tells
+  // a reader that this CTA's slice has arrived (sample_body / peer_parts_wait_kernel wait for all of them).
+  float* lpeer[kMaxPeers];
   __device__ __forceinline__ void prepare() {}
   __device__ __forceinline__ void prefetch(int) {}
   __device__ __forceinline__ void operator()(int p, float v0, float v1) {
-    logits[2 * p] = v0;
-    argmax_merge(bv, bi, v0, row_offset + 2 * p);
-    if (2 * p + 1 < n_rows) {
-      logits[2 * p + 1] = v1;
-      argmax_merge(bv, bi, v1, row_offset + 2 * p + 1);
+    const bool two = 2 * p + 1 < n_rows;
+    if (po.P > 0 && lpeer[0]) {
+      const int g = row_offset + 2 * p;
+#pragma unroll
+      for (int r = 0; r < kMaxPeers; ++r) {
+        if (r < po.P) {
+          if (two && !(g & 1)) *reinterpret_cast<float2*>(lpeer[r] + g) = make_float2(v0, v1);
+          else { lpeer[r][g] = v0; if (two) lpeer[r][g + 1] = v1; }
+        }
+      }
+    } else {
+      logits[2 * p] = v0;
+      if (two) logits[2 * p + 1] = v1;
     }
+    argmax_merge(bv, bi, v0, row_offset + 2 * p);
+    if (two) argmax_merge(bv, bi, v1, row_offset + 2 * p + 1);
   }
   __device__ __forceinline__ void finish(float* red) {
+    if (po.P > 0) __threadfence_system();  // this thread's remote logits stores before the CTA's partial (the arrival flag)
     // block argmax: warp shuffle then 16 warps through shared memory
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {

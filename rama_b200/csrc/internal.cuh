@@ -21,6 +21,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -29,6 +30,7 @@
 #include "common.cuh"
 #include "gemv.cuh"
 #include "misc_kernels.cuh"
+#include "tp_exchange.cuh"
 
 using namespace rama;
 
@@ -97,6 +99,12 @@ struct rama_ctx {
   int embed_kernel = 1;  // RAMA_EMBED_KERNEL=0: fold the embedding gather into the layer-0 QKV prologue (ProNorm::emb)
   int stage_max_kb = 110;  // RAMA_GEMV_STAGE_KB: largest x + slab the staged GEMV takes (≤ 110: two CTAs per SM; ≤ 208: one)
   int attn_cluster = 1;  // RAMA_ATTN=split selects the global-memory split merge (attn_decode_kernel) at every context length
+  // RAMA_TP_SIM=P (measurement tool, single GPU, no `tp`): this device behaves like rank 0 of P — 1/P shards, the peer
+  // exchange with every "peer" slot delivered locally (P remote stores become P local ones, the consumer still reduces P
+  // LL partials).  Results are meaningless (the same partial P times); kernel shapes, bytes and the dependent chain are
+  // those of one rank of a P-GPU run minus NVLink latency and rank skew: what ncu and the in-graph timeline can see.
+  int tp_sim = 0;
+  int tp_cluster = 4;  // RAMA_TP_CLUSTER: cluster size of the shared peer reduction in the norm prologues (0/1: off)
   int persistent = 0;  // RAMA_STEP=persistent: the decode step as one persistent cooperative kernel (step_kernel.cuh);
                        // default: one fused kernel per op group in a CUDA graph (measured faster)
   std::mutex mu;
@@ -105,7 +113,28 @@ struct rama_ctx {
   // request threads capture their step graphs.  Captures and those device-wide operations take this lock.
   std::mutex cap_mu;
   std::atomic<int> n_objects{0};  // live sessions + batches: their captured graphs hold the weight pointers, so no reload
+  // Single-process tensor parallelism (rama_ctx_create_multi): a GROUP context owns one rank context per device
+  // (`ranks`, each with `group` pointing back); every entry point that takes the group handle drives all ranks from
+  // the calling thread.  Rank contexts of a group use the peer-memory exchange with directly addressable peer
+  // pointers (cudaDeviceEnablePeerAccess) — no NCCL, no IPC.
+  std::vector<rama_ctx*> ranks;
+  rama_ctx* group = nullptr;
+  struct GroupPool* pool = nullptr;  // group only: one host thread per rank (group.cu)
 };
+
+// A device allocation that every rank of the TP group can address (NVLink peer memory): CUDA IPC between the processes
+// of a torchrun launch, plain peer access inside a single-process group.
+struct PeerBlock {
+  char* local = nullptr;
+  char* base[kMaxPeers] = {nullptr};  // every rank's block as seen from this rank (base[rank] == local)
+  size_t bytes = 0;
+  bool ipc = false;                   // peers were opened with cudaIpcOpenMemHandle (must be closed)
+};
+int peer_block_alloc(rama_ctx* c, size_t bytes, PeerBlock* b);                 // local allocation, zero-filled (session.cu)
+int peer_block_connect(rama_ctx* c, PeerBlock* b, cudaStream_t st);            // collective over the processes; group ranks: no-op
+void peer_block_free(rama_ctx* c, PeerBlock* b, cudaStream_t st, float* scratch);  // collective (barrier before the owner frees)
+void peer_blocks_connect_group(PeerBlock* const* blocks, int P);               // single process: cross-wire P blocks
+
 
 // A batched step runs on the batch's stream, the per-session entry points on the session's own stream.  The batch
 // re-records ONE event after every step it launches; each session of that step keeps a reference and makes its own
@@ -129,11 +158,19 @@ struct rama_session {
   unsigned long long* bar = nullptr;  // persistent step kernel: [0] grid-barrier arrivals, [1] steps completed
   bool persistent = false;
   int cls_grid = 0;             // CTAs of the classifier launch (slots that get written)
-  // fused TP exchange: one IPC-exported block per session {flags[3][P] | parts[P][SMs] | inbox[2][P][D]}
-  char* peer_mem = nullptr;
-  char* peer_base[kMaxPeers] = {nullptr};  // every rank's block, peer-mapped (own block at [rank])
-  size_t off_parts = 0, off_inbox = 0, peer_bytes = 0;
+  // fused TP exchange: one peer-addressable block per session
+  //   parts[P][SMs][2] (LL) | inbox[2][P][D] (LL) | logits[V] | x0[D] | bulk flags[3][P] | bulk done counter
+  // (logits and x0 live here so that peers can store into them: classifier slices, last prefill row)
+  PeerBlock blk;
+  size_t off_parts = 0, off_inbox = 0, off_logits = 0, off_x0 = 0, off_flags = 0, off_done = 0;
   bool p2p = false;
+  unsigned bulk_epoch = 0;      // host counter of bulk exchanges on this session (prefill); identical on every rank
+  PeerBlock pf_blk;             // prefill exchange buffers (allocated with the prefill workspace): inbox[P][rpr][D] | xn[cap][D]
+  size_t pf_off_xn = 0;
+  int pf_rpr_max = 0;
+  // single-process group session: one session per rank, driven together
+  std::vector<rama_session*> ranks;
+  rama_session* parent = nullptr;
   unsigned long long* sort_keys = nullptr;
   StepCtrl* ctrl = nullptr;     // device
   int32_t *d_prompt = nullptr, *d_out = nullptr;
@@ -159,6 +196,7 @@ struct rama_session {
   int pf_min = 16;               // rama_generate: prompts of at least this many rows (BOS included) are prefilled
   float *pf_x = nullptr, *pf_xn = nullptr, *pf_q = nullptr, *pf_att = nullptr, *pf_y = nullptr, *pf_h = nullptr;
   int32_t* pf_tokens = nullptr;
+  int32_t* h_tokens = nullptr;   // pinned staging of a prompt (a pageable source could make the async copy wait for the stream)
   std::shared_ptr<BatchFence> fence;  // set by rama_forward_batch: work of another stream this session must wait for
   bool async_pending = false;         // work enqueued on s->stream since it was last synchronised (a batch must wait for it)
 };
@@ -181,30 +219,54 @@ inline const Variant kVariants[kNumVariants] = {{16, 2, 2}, {8, 2, 4}, {4, 2, 4}
                                                 {16, 4, 2}, {8, 4, 2}, {2, 2, 4}, {16, 1, 4}};
 constexpr size_t kMaxDynSmem = 200 * 1024;
 
+inline void set_cluster_share(ProNorm& p, int on) { p.cluster_share = on; }
+inline void set_cluster_share(ProPlain&, int) {}
+
+// want_cluster > 1 (tensor parallelism, prologues that reduce peer partials): launch as thread-block clusters so that the
+// CTAs of a cluster share the reduction (ProNorm).  The cluster size is the largest power of two ≤ want_cluster whose
+// clusters still cover (almost) every SM in ONE wave — a CTA of this kernel owns an SM, and clusters cannot span GPCs.
 template <int WK, int RP, int U, class Pro, class Rows, class Epi>
-inline cudaError_t launch_gemv_t(int grid, cudaStream_t st, int pdl, const Pro& pro, const Rows& rows,
-                                 const Epi& epi, int K4, int n_pairs) {
+inline cudaError_t launch_gemv_t(int grid, cudaStream_t st, int pdl, const Pro& pro_in, const Rows& rows,
+                                 const Epi& epi, int K4, int n_pairs, int want_cluster = 0) {
   auto kern = gemv_fused_kernel<WK, RP, U, Pro, Rows, Epi>;
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [&] {
-    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
-  });
+  static std::atomic<unsigned long long> attr_done{0};
+  const cudaError_t attr_err = ensure_dyn_smem((const void*)kern, (int)kMaxDynSmem, attr_done);
   if (attr_err != cudaSuccess) return attr_err;
+  Pro pro = pro_in;
+  cudaLaunchConfig_t cfg{};
+  cfg.blockDim = dim3(kGemvThreads);
+  cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  int na = 0, cs = 1;
+  for (int c = std::min(want_cluster, kMaxClusterShare); c >= 2; c >>= 1) {
+    const int g = grid / c * c;
+    if (g < c) continue;
+    cfg.gridDim = dim3(g);
+    cfg.dynamicSmemBytes = gemv_smem_bytes(K4, n_pairs, g, WK);
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = c; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n_active = 0;
+    if (cudaOccupancyMaxActiveClusters(&n_active, kern, &cfg) != cudaSuccess) { cudaGetLastError(); continue; }
+    if ((double)n_active * c >= 0.97 * g) {
+      cs = c;
+      grid = std::min(g, n_active * c);
+      na = 1;
+      break;
+    }
+  }
+  set_cluster_share(pro, cs > 1);
   const size_t smem = gemv_smem_bytes(K4, n_pairs, grid, WK);
   if (smem > kMaxDynSmem) return cudaErrorInvalidValue;
-  cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kGemvThreads);
   cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute at[1];
   if (pdl) {
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
   }
+  cfg.attrs = at;
+  cfg.numAttrs = na;
   return cudaLaunchKernelEx(&cfg, kern, pro, rows, epi, K4, n_pairs, pdl);
 }
 
@@ -218,11 +280,8 @@ template <class Pro, class Rows, class Epi>
 inline cudaError_t launch_gemv_staged(int grid, cudaStream_t st, int pdl, const Pro& pro, const Rows& rows, const Epi& epi,
                                       int K4, int n_pairs) {
   auto kern = gemv_smem_kernel<Pro, Rows, Epi>;
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [&] {
-    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemvSmemStageMaxSolo);
-  });
+  static std::atomic<unsigned long long> attr_done{0};
+  const cudaError_t attr_err = ensure_dyn_smem((const void*)kern, (int)kGemvSmemStageMaxSolo, attr_done);
   if (attr_err != cudaSuccess) return attr_err;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
@@ -241,18 +300,18 @@ inline cudaError_t launch_gemv_staged(int grid, cudaStream_t st, int pdl, const 
 
 template <class Pro, class Rows, class Epi>
 inline cudaError_t launch_gemv(int variant, int grid, cudaStream_t st, int pdl, const Pro& pro,
-                               const Rows& rows, const Epi& epi, int K4, int n_pairs) {
+                               const Rows& rows, const Epi& epi, int K4, int n_pairs, int want_cluster = 0) {
   // small slabs (the small models): whole slab staged in shared memory ahead of the dependency (gemv_smem_kernel)
   if (variant == kVariantStaged) return launch_gemv_staged(grid, st, pdl, pro, rows, epi, K4, n_pairs);
   switch (variant) {
-    case 0: return launch_gemv_t<16, 2, 2>(grid, st, pdl, pro, rows, epi, K4, n_pairs);
-    case 1: return launch_gemv_t<8, 2, 4>(grid, st, pdl, pro, rows, epi, K4, n_pairs);
-    case 2: return launch_gemv_t<4, 2, 4>(grid, st, pdl, pro, rows, epi, K4, n_pairs);
-    case 3: return launch_gemv_t<1, 2, 4>(grid, st, pdl, pro, rows, epi, K4, n_pairs);
-    case 4: return launch_gemv_t<16, 4, 2>(grid, st, pdl, pro, rows, epi, K4, n_pairs);
-    case 5: return launch_gemv_t<8, 4, 2>(grid, st, pdl, pro, rows, epi, K4, n_pairs);
-    case 6: return launch_gemv_t<2, 2, 4>(grid, st, pdl, pro, rows, epi, K4, n_pairs);
-    case 7: return launch_gemv_t<16, 1, 4>(grid, st, pdl, pro, rows, epi, K4, n_pairs);
+    case 0: return launch_gemv_t<16, 2, 2>(grid, st, pdl, pro, rows, epi, K4, n_pairs, want_cluster);
+    case 1: return launch_gemv_t<8, 2, 4>(grid, st, pdl, pro, rows, epi, K4, n_pairs, want_cluster);
+    case 2: return launch_gemv_t<4, 2, 4>(grid, st, pdl, pro, rows, epi, K4, n_pairs, want_cluster);
+    case 3: return launch_gemv_t<1, 2, 4>(grid, st, pdl, pro, rows, epi, K4, n_pairs, want_cluster);
+    case 4: return launch_gemv_t<16, 4, 2>(grid, st, pdl, pro, rows, epi, K4, n_pairs, want_cluster);
+    case 5: return launch_gemv_t<8, 4, 2>(grid, st, pdl, pro, rows, epi, K4, n_pairs, want_cluster);
+    case 6: return launch_gemv_t<2, 2, 4>(grid, st, pdl, pro, rows, epi, K4, n_pairs, want_cluster);
+    case 7: return launch_gemv_t<16, 1, 4>(grid, st, pdl, pro, rows, epi, K4, n_pairs, want_cluster);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -288,14 +347,14 @@ inline PeerOut peer_out(const rama_session* s, int stage, int layer) {  // stage
   if (!s->p2p) return po;
   po.P = c->world; po.seq = s->seq; po.L = c->L + 1; po.layer = layer;
   for (int r = 0; r < c->world; ++r)
-    po.inbox[r] = reinterpret_cast<uint2*>(s->peer_base[r] + s->off_inbox) + ((size_t)stage * c->world + c->rank) * c->D;
+    po.inbox[r] = reinterpret_cast<uint2*>(s->blk.base[r] + s->off_inbox) + ((size_t)stage * c->world + (c->tp_sim ? r : c->rank)) * c->D;
   return po;
 }
 inline PeerIn peer_in(const rama_session* s, int stage, int layer) {
   PeerIn pi{};
   const rama_ctx* c = s->ctx;
   if (!s->p2p) return pi;
-  pi.inbox = reinterpret_cast<const uint2*>(s->peer_mem + s->off_inbox) + (size_t)stage * c->world * c->D;
+  pi.inbox = reinterpret_cast<const uint2*>(s->blk.local + s->off_inbox) + (size_t)stage * c->world * c->D;
   pi.seq = s->seq; pi.error = &s->ctrl->error;
   pi.P = c->world; pi.n = c->D; pi.L = c->L + 1; pi.layer = layer;
   return pi;
@@ -306,14 +365,14 @@ inline PeerOut peer_out_parts(const rama_session* s) {  // classifier partials, 
   if (!s->p2p) return po;
   po.P = c->world; po.seq = s->seq; po.L = c->L + 1; po.layer = c->L;
   for (int r = 0; r < c->world; ++r)
-    po.inbox[r] = reinterpret_cast<uint2*>(s->peer_base[r] + s->off_parts) + (size_t)c->rank * c->sm_count * 2;
+    po.inbox[r] = reinterpret_cast<uint2*>(s->blk.base[r] + s->off_parts) + (size_t)(c->tp_sim ? r : c->rank) * c->sm_count * 2;
   return po;
 }
 inline PeerIn peer_in_parts(const rama_session* s) {
   PeerIn pi{};
   const rama_ctx* c = s->ctx;
   if (!s->p2p) return pi;
-  pi.inbox = reinterpret_cast<const uint2*>(s->peer_mem + s->off_parts);
+  pi.inbox = reinterpret_cast<const uint2*>(s->blk.local + s->off_parts);
   pi.seq = s->seq; pi.error = &s->ctrl->error;
   pi.P = c->world; pi.n = c->sm_count; pi.L = c->L + 1; pi.layer = c->L;
   return pi;
@@ -341,9 +400,40 @@ inline cudaError_t launch_k(bool pdl, void (*kern)(P...), dim3 grid, dim3 block,
 }
 
 
+// the classifier epilogue stores every logits slice into every rank's array (no all-gather afterwards)
+inline bool logits_pushed(const rama_session* s) { return s->p2p && !s->persistent; }
+
+// classifier epilogue of the decode path (and of prefill's last row): local slice + greedy partial; under the peer
+// exchange the slice goes into every rank's logits array (EpiCls::lpeer)
+inline EpiCls make_epi_cls(const rama_session* s) {
+  const rama_ctx* c = s->ctx;
+  EpiCls e{s->logits + c->v0, s->part + (size_t)c->rank * c->sm_count, c->Vl, c->v0, -INFINITY, -1, peer_out_parts(s), {nullptr}};
+  if (logits_pushed(s))
+    for (int r = 0; r < c->world; ++r) e.lpeer[r] = reinterpret_cast<float*>(s->blk.base[r] + s->off_logits);
+  return e;
+}
+
+// bulk exchange (tp_exchange.cuh) over a session's block: flags / done counter live in the session block
+inline TpPeers tp_peers(const rama_session* s) {
+  TpPeers t{};
+  const rama_ctx* c = s->ctx;
+  t.P = c->world; t.me = c->rank;
+  for (int r = 0; r < c->world; ++r) t.flags[r] = reinterpret_cast<unsigned*>(s->blk.base[r] + s->off_flags);
+  return t;
+}
+
+// ---- single-process group (group.cu) ----
+int group_run(rama_ctx* g, const std::function<int(int)>& fn);  // fn(rank index) on every rank's thread; first failure
+void group_destroy(rama_ctx* g);
+void group_adopt_config(rama_ctx* g);
+inline bool is_group(const rama_ctx* c) { return !c->ranks.empty(); }
+inline rama_ctx* rank0(rama_ctx* c) { return c->ranks.empty() ? c : c->ranks[0]; }
+
 // ---- helpers that cross translation units ----
 int init_parts(rama_session* s);                        // session.cu
 int gather_logits(rama_session* s);                     // session.cu
 int read_ret(rama_session* s, int32_t* next);           // session.cu
 int prefill_run(rama_session* s, const int32_t* tokens, int32_t n, int32_t pos0, float ms_kind[RAMA_PK_COUNT],
-                int32_t* n_launch);                     // prefill.cu
+                int32_t* n_launch);                     // prefill_api.cu
+int prefill_alloc_ws(rama_session* s);                  // prefill_api.cu
+int group_prefill_prepare(rama_session* g);             // prefill_api.cu

@@ -126,6 +126,17 @@ __device__ __forceinline__ void sample_body(const SampleParams& p) {
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
   int* redi = reinterpret_cast<int*>(red + kWarp);
 
+  if (temperature != 0.0f && p.pin.P > 0) {
+    // the vocabulary slices of the other ranks are stored into this rank's logits by their classifier epilogues: every
+    // CTA's LL partial (written after a system-scope fence) proves that CTA's slice has arrived
+    const unsigned ep = p.pin.epoch();
+    for (int i = threadIdx.x; i < p.n_part; i += kSampleThreads) {
+      if ((i % p.pin.n) >= p.n_live) continue;
+      ld_ll2_wait(p.pin.inbox + 2 * (size_t)i, ep, p.pin.error);
+    }
+    __threadfence_system();
+    __syncthreads();
+  }
   if (temperature == 0.0f) {
     float bv = -INFINITY;
     int bi = -1;
@@ -271,6 +282,17 @@ __device__ __forceinline__ void sample_body(const SampleParams& p) {
 static __global__ void __launch_bounds__(kSampleThreads) sample_kernel(const SampleParams p, int use_pdl) {
   if (use_pdl) { pdl_launch_dependents(); pdl_wait(); }
   sample_body(p);
+}
+
+// Tensor parallelism, host reads of the logits (rama_logits_to_host): wait until every classifier CTA of every rank has
+// delivered its slice (its LL partial carries this step's epoch), then the stream-ordered copy may read the array.
+static __global__ void __launch_bounds__(kSampleThreads) peer_parts_wait_kernel(const PeerIn pin, int n_part, int n_live) {
+  const unsigned ep = pin.epoch();
+  for (int i = threadIdx.x; i < n_part; i += kSampleThreads) {
+    if ((i % pin.n) >= n_live) continue;
+    ld_ll2_wait(pin.inbox + 2 * (size_t)i, ep, pin.error);
+  }
+  __threadfence_system();
 }
 
 // one CTA per sequence of a batch (server path: concurrent requests, lib.rs:127-160)

@@ -11,6 +11,7 @@
 // ------------------------------------------------------------------------------------------------
 extern "C" int rama_dev_alloc(rama_ctx* c, size_t n, float** out) {
   if (!c || !out) return fail(RAMA_E_INVALID, "NULL argument");
+  c = rank0(c);
   CK(cudaSetDevice(c->device));
   CK(cudaMalloc((void**)out, std::max<size_t>(n, 1) * sizeof(float)));
   // RunState::from_config zero-fills (ram.rs:7-23).  On the op stream (non-blocking: it does not
@@ -21,12 +22,14 @@ extern "C" int rama_dev_alloc(rama_ctx* c, size_t n, float** out) {
 }
 extern "C" int rama_dev_free(rama_ctx* c, float* p) {
   if (!c) return fail(RAMA_E_INVALID, "NULL ctx");
+  c = rank0(c);
   CK(cudaSetDevice(c->device));
   CK(cudaFree(p));
   return RAMA_OK;
 }
 extern "C" int rama_dev_h2d(rama_ctx* c, float* dst, const float* src, size_t n) {
   if (!c || (!dst && n) || (!src && n)) return fail(RAMA_E_INVALID, "NULL argument");
+  c = rank0(c);
   CK(cudaSetDevice(c->device));
   CK(cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyHostToDevice, c->op_stream));
   CK(cudaStreamSynchronize(c->op_stream));
@@ -34,6 +37,7 @@ extern "C" int rama_dev_h2d(rama_ctx* c, float* dst, const float* src, size_t n)
 }
 extern "C" int rama_dev_d2h(rama_ctx* c, float* dst, const float* src, size_t n) {
   if (!c || (!dst && n) || (!src && n)) return fail(RAMA_E_INVALID, "NULL argument");
+  c = rank0(c);
   CK(cudaSetDevice(c->device));
   CK(cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyDeviceToHost, c->op_stream));
   CK(cudaStreamSynchronize(c->op_stream));
@@ -41,6 +45,7 @@ extern "C" int rama_dev_d2h(rama_ctx* c, float* dst, const float* src, size_t n)
 }
 extern "C" int rama_ctx_sync(rama_ctx* c) {
   if (!c) return fail(RAMA_E_INVALID, "NULL ctx");
+  c = rank0(c);
   CK(cudaSetDevice(c->device));
   CK(cudaStreamSynchronize(c->op_stream));
   return RAMA_OK;
@@ -49,8 +54,10 @@ extern "C" int rama_ctx_sync(rama_ctx* c) {
 static int ew_grid(const rama_ctx* c, size_t n) {
   return (int)std::max<size_t>(1, std::min<size_t>((n + 255) / 256, (size_t)c->sm_count * 8));
 }
+// (a group context runs the single-device Device ops on its first rank's device)
 #define OP_PRE(c)                                         \
   if (!(c)) return fail(RAMA_E_INVALID, "NULL ctx");      \
+  (c) = rank0(c);                                         \
   CK(cudaSetDevice((c)->device));
 
 extern "C" int rama_op_array_add(rama_ctx* c, float* t, const float* s, size_t n) {

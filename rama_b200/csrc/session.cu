@@ -5,6 +5,82 @@
 #include "attention.cuh"
 #include "step_kernel.cuh"
 
+#include <array>
+
+// ------------------------------------------------------------------------------------------------
+// peer-addressable blocks (NVLink peer memory)
+// ------------------------------------------------------------------------------------------------
+int peer_block_alloc(rama_ctx* c, size_t bytes, PeerBlock* b) {
+  if (c->world > kMaxPeers) return fail(RAMA_E_INVALID, "tp world %d > %d", c->world, kMaxPeers);
+  b->bytes = (bytes + 255) / 256 * 256;
+  CK(cudaMalloc((void**)&b->local, b->bytes));
+  CK(cudaMemset(b->local, 0, b->bytes));  // epoch 0 is never used
+  CK(cudaDeviceSynchronize());
+  for (int r = 0; r < kMaxPeers; ++r) b->base[r] = nullptr;
+  b->base[c->rank] = b->local;
+  return RAMA_OK;
+}
+
+// Processes of a torchrun launch: swap CUDA IPC handles through NCCL and map every peer's block.  Collective.
+int peer_block_connect(rama_ctx* c, PeerBlock* b, cudaStream_t st) {
+  if (c->group) return RAMA_OK;  // single-process group: the group cross-wires its ranks' blocks (peer_blocks_connect_group)
+  if (c->tp_sim) {               // measurement mode: every "peer" is this device
+    for (int r = 0; r < c->world; ++r) b->base[r] = b->local;
+    return RAMA_OK;
+  }
+  const int P = c->world;
+  cudaIpcMemHandle_t mine;
+  CK(cudaIpcGetMemHandle(&mine, b->local));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  char* d_h = nullptr;
+  CK(cudaMalloc((void**)&d_h, 64 * (size_t)P + 64));
+  CK(cudaMemcpy(d_h + 64 * (size_t)c->rank, &mine, 64, cudaMemcpyHostToDevice));
+  CK(cudaDeviceSynchronize());  // `st` is non-blocking: make the staged copy land first
+  int e = g_nccl.AllGather(d_h + 64 * (size_t)c->rank, d_h, 16, kNcclFloat32, c->comm, st);
+  if (e) { cudaFree(d_h); return fail(RAMA_E_NCCL, "handle all-gather: %s", g_nccl.GetErrorString(e)); }
+  CK(cudaStreamSynchronize(st));
+  std::vector<cudaIpcMemHandle_t> all(P);
+  CK(cudaMemcpy(all.data(), d_h, 64 * (size_t)P, cudaMemcpyDeviceToHost));
+  for (int r = 0; r < P; ++r) {
+    if (r == c->rank) continue;
+    void* p = nullptr;
+    cudaError_t ce = cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess);
+    if (ce != cudaSuccess) {
+      cudaFree(d_h);
+      return fail(RAMA_E_CUDA, "cudaIpcOpenMemHandle(rank %d): %s (set RAMA_TP_COMM=nccl to fall back)", r, cudaGetErrorString(ce));
+    }
+    b->base[r] = (char*)p;
+  }
+  b->ipc = true;
+  // nobody may write into a peer block before its owner has zeroed it: barrier
+  e = g_nccl.AllReduce(d_h + 64 * (size_t)P, d_h + 64 * (size_t)P, 1, kNcclFloat32, kNcclSum, c->comm, st);
+  if (e) { cudaFree(d_h); return fail(RAMA_E_NCCL, "barrier: %s", g_nccl.GetErrorString(e)); }
+  CK(cudaStreamSynchronize(st));
+  CK(cudaFree(d_h));
+  return RAMA_OK;
+}
+
+void peer_blocks_connect_group(PeerBlock* const* blocks, int P) {
+  for (int r = 0; r < P; ++r)
+    for (int q = 0; q < P; ++q) blocks[r]->base[q] = blocks[q]->local;
+}
+
+// Collective between processes: every rank must have unmapped the block before its owner frees it.  (A group frees its
+// ranks' blocks only after every device has been synchronised.)
+void peer_block_free(rama_ctx* c, PeerBlock* b, cudaStream_t st, float* scratch) {
+  if (!b->local) return;
+  if (b->ipc) {
+    for (int r = 0; r < c->world; ++r)
+      if (r != c->rank && b->base[r]) cudaIpcCloseMemHandle(b->base[r]);
+    if (c->comm && scratch) {
+      g_nccl.AllReduce(scratch, scratch, 1, kNcclFloat32, kNcclSum, c->comm, st);
+      cudaStreamSynchronize(st);
+    }
+  }
+  cudaFree(b->local);
+  *b = PeerBlock{};
+}
+
 // ------------------------------------------------------------------------------------------------
 // session
 // ------------------------------------------------------------------------------------------------
@@ -15,14 +91,10 @@ static void session_free(rama_session* s) {
   for (auto& gm : s->g) for (auto& g : gm) if (g) cudaGraphExecDestroy(g);
   if (s->p2p) {
     rama_ctx* c = s->ctx;
-    for (int r = 0; r < c->world; ++r)
-      if (r != c->rank && s->peer_base[r]) cudaIpcCloseMemHandle(s->peer_base[r]);
-    // every rank must have unmapped this block before its owner frees it: barrier through NCCL
-    if (c->comm && s->xb2) {
-      g_nccl.AllReduce(s->xb2, s->xb2, 1, kNcclFloat32, kNcclSum, c->comm, s->stream);
-      cudaStreamSynchronize(s->stream);
-    }
-    if (s->peer_mem) cudaFree(s->peer_mem);
+    peer_block_free(c, &s->pf_blk, s->stream, s->xb2);
+    peer_block_free(c, &s->blk, s->stream, s->xb2);
+    s->logits = nullptr; s->x0 = nullptr;  // lived inside the block
+    s->pf_xn = nullptr;
   }
   void* bufs[] = {s->x0, s->x1, s->xfinal, s->xb, s->xb2, s->w2out, s->hb, s->hb2, s->q, s->k, s->v, s->att,
                   s->logits, s->key_cache, s->value_cache, s->attn_ws, s->tickets, s->part, s->sort_keys,
@@ -31,59 +103,33 @@ static void session_free(rama_session* s) {
   for (void* b : bufs) if (b) cudaFree(b);
   if (s->h_ring) cudaFreeHost(s->h_ring);
   if (s->h_ret) cudaFreeHost(s->h_ret);
+  if (s->h_tokens) cudaFreeHost(s->h_tokens);
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
   if (s->stream) cudaStreamDestroy(s->stream);
   delete s;
 }
 
-
-// Collective over the TP group: allocate this session's exchange block, swap CUDA IPC handles through
-// NCCL and map every peer's block (NVLink P2P).  Layout (LL elements = {payload, epoch} uint2):
-//   uint2 parts[P][SMs][2] | uint2 inbox[2 stages][P][D]
-static int setup_peer_exchange(rama_session* s) {
+// The session's exchange block.  Layout (LL elements = {payload, epoch} uint2):
+//   uint2 parts[P][SMs][2] | uint2 inbox[2 stages][P][D] | float logits[V] | float x0[D] | unsigned flags[3][P] | unsigned done
+static int setup_peer_exchange(rama_session* s, bool connect) {
   rama_ctx* c = s->ctx;
   const int P = c->world;
-  if (P > kMaxPeers) return fail(RAMA_E_INVALID, "tp world %d > %d", P, kMaxPeers);
+  auto al = [](size_t v) { return (v + 255) / 256 * 256; };
   s->off_parts = 0;
-  s->off_inbox = ((size_t)P * c->sm_count * 2 * sizeof(uint2) + 255) / 256 * 256;
-  s->peer_bytes = s->off_inbox + (size_t)2 * P * c->D * sizeof(uint2);
-  CK(cudaMalloc((void**)&s->peer_mem, s->peer_bytes));
-  CK(cudaMemset(s->peer_mem, 0, s->peer_bytes));  // epoch 0 is never used
-  CK(cudaDeviceSynchronize());
-  cudaIpcMemHandle_t mine;
-  CK(cudaIpcGetMemHandle(&mine, s->peer_mem));
-  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-  char* d_h = nullptr;
-  CK(cudaMalloc((void**)&d_h, 64 * (size_t)P));
-  CK(cudaMemcpy(d_h + 64 * (size_t)c->rank, &mine, 64, cudaMemcpyHostToDevice));
-  CK(cudaDeviceSynchronize());  // s->stream is non-blocking: make the staged copy land first
-  int e = g_nccl.AllGather(d_h + 64 * (size_t)c->rank, d_h, 16, kNcclFloat32, c->comm, s->stream);
-  if (e) { cudaFree(d_h); return fail(RAMA_E_NCCL, "handle all-gather: %s", g_nccl.GetErrorString(e)); }
-  CK(cudaStreamSynchronize(s->stream));
-  std::vector<cudaIpcMemHandle_t> all(P);
-  CK(cudaMemcpy(all.data(), d_h, 64 * (size_t)P, cudaMemcpyDeviceToHost));
-  CK(cudaFree(d_h));
-  for (int r = 0; r < P; ++r) {
-    if (r == c->rank) { s->peer_base[r] = s->peer_mem; continue; }
-    void* p = nullptr;
-    cudaError_t ce = cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess);
-    if (ce != cudaSuccess)
-      return fail(RAMA_E_CUDA, "cudaIpcOpenMemHandle(rank %d): %s (set RAMA_TP_COMM=nccl to fall back)", r,
-                  cudaGetErrorString(ce));
-    s->peer_base[r] = (char*)p;
-  }
-  // nobody may write into a peer block before its owner has zeroed it: barrier
-  e = g_nccl.AllReduce(s->xb2, s->xb2, 1, kNcclFloat32, kNcclSum, c->comm, s->stream);
-  if (e) return fail(RAMA_E_NCCL, "barrier: %s", g_nccl.GetErrorString(e));
-  CK(cudaStreamSynchronize(s->stream));
-  CK(cudaMemsetAsync(s->xb2, 0, sizeof(float), s->stream));
+  s->off_inbox = al((size_t)P * c->sm_count * 2 * sizeof(uint2));
+  s->off_logits = al(s->off_inbox + (size_t)2 * P * c->D * sizeof(uint2));
+  s->off_x0 = al(s->off_logits + (size_t)c->V * sizeof(float));
+  s->off_flags = al(s->off_x0 + (size_t)c->D * sizeof(float));
+  s->off_done = al(s->off_flags + (size_t)3 * P * sizeof(unsigned));
+  RK(peer_block_alloc(c, s->off_done + 256, &s->blk));
+  s->logits = reinterpret_cast<float*>(s->blk.local + s->off_logits);
+  s->x0 = reinterpret_cast<float*>(s->blk.local + s->off_x0);
+  if (connect) RK(peer_block_connect(c, &s->blk, s->stream));
   return RAMA_OK;
 }
 
-extern "C" int rama_session_create(rama_ctx* c, rama_session** out) {
-  if (!c || !out) return fail(RAMA_E_INVALID, "NULL argument");
-  if (!c->loaded) return fail(RAMA_E_STATE, "no weights loaded");
+static int session_create_rank(rama_ctx* c, rama_session** out, bool connect) {
   CK(cudaSetDevice(c->device));
   std::lock_guard<std::mutex> cap_lk(c->cap_mu);
   rama_session* s = new rama_session();
@@ -96,26 +142,23 @@ extern "C" int rama_session_create(rama_ctx* c, rama_session** out) {
   const size_t D = c->D, Dq = c->Dq, Fl = c->Fl, V = c->V, T = c->T, L = c->L;
   size_t vp2 = 1;
   while (vp2 < V) vp2 <<= 1;
+  s->p2p = c->world > 1 && c->p2p;
   cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
 #define A(call) if (e == cudaSuccess) e = (call)
-  A(dalloc(&s->x0, D)); A(dalloc(&s->x1, D)); A(dalloc(&s->xfinal, D));
+  if (!s->p2p) { A(dalloc(&s->x0, D)); A(dalloc(&s->logits, V)); }  // p2p: inside the exchange block (peers store into them)
+  A(dalloc(&s->x1, D)); A(dalloc(&s->xfinal, D));
   A(dalloc(&s->xb, Dq)); A(dalloc(&s->xb2, D)); A(dalloc(&s->w2out, D));
   A(dalloc(&s->hb, Fl)); A(dalloc(&s->hb2, Fl));
   A(dalloc(&s->q, Dq)); A(dalloc(&s->k, Dq)); A(dalloc(&s->v, Dq));
   A(dalloc(&s->att, (size_t)c->Hl * T));
-  A(dalloc(&s->logits, V));
   A(dalloc(&s->key_cache, L * T * Dq)); A(dalloc(&s->value_cache, L * T * Dq));
   A(dalloc(&s->attn_ws, (size_t)c->Hl * s->n_split * (c->hs + 2)));
   A(dalloc(&s->tickets, (size_t)c->Hl));
-  s->p2p = c->world > 1 && c->p2p;
-  s->persistent = c->persistent && (c->world == 1 || s->p2p);
+  s->persistent = c->persistent && !c->group && (c->world == 1 || s->p2p);
   if (s->persistent) s->cls_grid = c->sm_count;  // every CTA of the persistent kernel writes a classifier partial
   A(dalloc(&s->part, (size_t)c->world * c->sm_count));
   A(dalloc(&s->seq, 1));
   A(dalloc(&s->bar, 2));
-  // small models: attention + wo as one kernel with per-head partial outputs (attention.cuh attn_wo_kernel)
-  // (measured: a win up to stories15M's size — 8425 → 9340 tok/s; at stories110M the redundant per-CTA attention and the
-  // 12-way partial sum cost more than the saved launch — 3757 → 3536 — so dim ≤ 512 only)
   // Attention + wo as ONE launch (per-head partial outputs of wo, summed by the next prologue) — opt-in since the cluster
   // attention kernel: RAMA_ATTN_WO = 0 (default) separate launches, 1 = attn_wo_cluster_kernel, 2 = attn_wo_kernel (per-CTA
   // redundant attention); RAMA_ATTN_WO_MAXDIM moves the size limit of mode 1.  Measured on B200 (tok/s):
@@ -148,9 +191,8 @@ extern "C" int rama_session_create(rama_ctx* c, rama_session** out) {
     return fail(RAMA_E_CUDA, "session allocation: %s", cudaGetErrorString(e));
   }
   if (s->p2p) {
-    int rc = setup_peer_exchange(s);
+    int rc = setup_peer_exchange(s, connect);
     if (rc != RAMA_OK) {
-      s->p2p = false;
       session_free(s);
       return rc;
     }
@@ -160,18 +202,64 @@ extern "C" int rama_session_create(rama_ctx* c, rama_session** out) {
   return RAMA_OK;
 }
 
-extern "C" int rama_session_destroy(rama_session* s) {
-  if (!s) return RAMA_OK;
+static void session_destroy_rank(rama_session* s) {
   rama_ctx* c = s->ctx;
   std::lock_guard<std::mutex> cap_lk(c->cap_mu);
   if (s->fence) { cudaSetDevice(c->device); cudaEventSynchronize(s->fence->ev); s->fence.reset(); }
   session_free(s);
   c->n_objects.fetch_sub(1);
+}
+
+// every stream of every rank idle: nothing is in flight towards a peer block any more
+static void group_quiesce(rama_session* g) {
+  for (rama_session* r : g->ranks) {
+    cudaSetDevice(r->ctx->device);
+    cudaStreamSynchronize(r->stream);
+  }
+}
+
+extern "C" int rama_session_create(rama_ctx* c, rama_session** out) {
+  if (!c || !out) return fail(RAMA_E_INVALID, "NULL argument");
+  if (!c->loaded) return fail(RAMA_E_STATE, "no weights loaded");
+  if (c->ranks.empty()) return session_create_rank(c, out, true);
+  // single-process group: one session per rank, exchange blocks cross-wired directly
+  rama_session* g = new rama_session();
+  g->ctx = c;
+  for (rama_ctx* rc : c->ranks) {
+    rama_session* rs = nullptr;
+    int rc_ = session_create_rank(rc, &rs, false);
+    if (rc_ != RAMA_OK) {
+      for (rama_session* x : g->ranks) session_destroy_rank(x);
+      delete g;
+      return rc_;
+    }
+    rs->parent = g;
+    g->ranks.push_back(rs);
+  }
+  std::vector<PeerBlock*> blocks;
+  for (rama_session* r : g->ranks) blocks.push_back(&r->blk);
+  peer_blocks_connect_group(blocks.data(), (int)blocks.size());
+  c->n_objects.fetch_add(1);
+  *out = g;
+  return RAMA_OK;
+}
+
+extern "C" int rama_session_destroy(rama_session* s) {
+  if (!s) return RAMA_OK;
+  if (!s->ranks.empty()) {
+    group_quiesce(s);
+    for (rama_session* r : s->ranks) session_destroy_rank(r);
+    s->ctx->n_objects.fetch_sub(1);
+    delete s;
+    return RAMA_OK;
+  }
+  session_destroy_rank(s);
   return RAMA_OK;
 }
 
 extern "C" int rama_session_sync(rama_session* s) {
   if (!s) return fail(RAMA_E_INVALID, "NULL session");
+  if (!s->ranks.empty()) return group_run(s->ctx, [&](int r) { return rama_session_sync(s->ranks[r]); });
   CK(cudaSetDevice(s->ctx->device));
   CK(session_enter(s));
   CK(cudaStreamSynchronize(s->stream));
@@ -181,6 +269,7 @@ extern "C" int rama_session_sync(rama_session* s) {
 
 extern "C" int rama_session_reset(rama_session* s) {
   if (!s) return fail(RAMA_E_INVALID, "NULL session");
+  if (!s->ranks.empty()) return group_run(s->ctx, [&](int r) { return rama_session_reset(s->ranks[r]); });
   rama_ctx* c = s->ctx;
   CK(cudaSetDevice(c->device));
   CK(session_enter(s));
@@ -196,6 +285,7 @@ extern "C" int rama_session_reset(rama_session* s) {
 
 extern "C" int rama_session_set_debug(rama_session* s, int keep_att) {
   if (!s) return fail(RAMA_E_INVALID, "NULL session");
+  if (!s->ranks.empty()) return group_run(s->ctx, [&](int r) { return rama_session_set_debug(s->ranks[r], keep_att); });
   CK(cudaSetDevice(s->ctx->device));
   CK(session_enter(s));
   CK(cudaStreamSynchronize(s->stream));
@@ -270,7 +360,7 @@ static int enqueue_step_persistent(rama_session* s, cudaStream_t st, int mode, i
   p.wk_d = wk_for(c->D / 4); p.wk_wo = wk_for(c->Dq / 4); p.wk_w2 = wk_for(c->Fl / 4);
   p.mode = mode == 1 ? 1 : 0;
   p.rank = c->rank; p.world = s->p2p ? c->world : 1;
-  for (int r = 0; r < kMaxPeers; ++r) p.peer_base[r] = r < c->world ? s->peer_base[r] : nullptr;
+  for (int r = 0; r < kMaxPeers; ++r) p.peer_base[r] = r < c->world ? s->blk.base[r] : nullptr;
   p.off_inbox = s->off_inbox; p.off_parts = s->off_parts;
   const int grid = c->sm_count;
   size_t smem = 0;
@@ -278,11 +368,8 @@ static int enqueue_step_persistent(rama_session* s, cudaStream_t st, int mode, i
   need(c->D / 4, 3 * c->Dq / 2, p.wk_d); need(c->Dq / 4, c->D / 2, p.wk_wo); need(c->D / 4, c->Fl, p.wk_d);
   need(c->Fl / 4, c->D / 2, p.wk_w2); need(c->D / 4, (c->Vl + 1) / 2, p.wk_d);
   if (smem > kMaxDynSmem) return fail(RAMA_E_INVALID, "persistent step: %zu bytes of shared memory needed", smem);
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [&] {
-    attr_err = cudaFuncSetAttribute(decode_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
-  });
+  static std::atomic<unsigned long long> attr_done{0};
+  const cudaError_t attr_err = ensure_dyn_smem((const void*)decode_step_kernel, (int)kMaxDynSmem, attr_done);
   if (attr_err != cudaSuccess) return fail(RAMA_E_CUDA, "persistent step attribute: %s", cudaGetErrorString(attr_err));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
@@ -358,7 +445,7 @@ static int enqueue_step(rama_session* s, cudaStream_t st, int mode, StepTrace* t
       q.pre(RAMA_K_QKV);
       // the cluster attention kernel reads older K/V rows ahead of its wait: release it after this kernel's own wait
       const int pdl_flags = q.pdl ? ((attn_cluster || fuse_cluster) ? 3 : 1) : 0;
-      q.post(launch_gemv(var, pick_grid(c, var, np), st, pdl_flags, pro, rows, epi, D / 4, np));
+      q.post(launch_gemv(var, pick_grid(c, var, np), st, pdl_flags, pro, rows, epi, D / 4, np, (s->p2p && l > 0) ? c->tp_cluster : 0));
     }
     if (fuse_attn_wo) {
       // ---- attention + wo in one launch, per-head partial outputs (infer.rs:34-35) ----
@@ -441,7 +528,7 @@ static int enqueue_step(rama_session* s, cudaStream_t st, int mode, StepTrace* t
       EpiSwiGLU epi{s->hb, s->hb2};
       const int np = Fl, var = pick_variant(c, D / 4, np);
       q.pre(RAMA_K_W13);
-      q.post(launch_gemv(var, pick_grid(c, var, np), st, q.pdl, pro, rows, epi, D / 4, np));
+      q.post(launch_gemv(var, pick_grid(c, var, np), st, q.pdl, pro, rows, epi, D / 4, np, s->p2p ? c->tp_cluster : 0));
     }
     // ---- w2 (infer.rs:46); residual add (:47) folded into the next prologue ----
     {
@@ -464,12 +551,11 @@ static int enqueue_step(rama_session* s, cudaStream_t st, int mode, StepTrace* t
   {
     ProNorm pro{s->x0, s->w2out, s->x1, W[RAMA_T_RMS_FINAL], s->xfinal, peer_in(s, 1, L - 1)};
     RowsPlain rows{c->wcls, D, c->Vl};
-    EpiCls epi{s->logits + c->v0, s->part + (size_t)c->rank * c->sm_count, c->Vl, c->v0, -INFINITY, -1,
-               peer_out_parts(s)};
+    EpiCls epi = make_epi_cls(s);
     const int np = (c->Vl + 1) / 2, var = pick_variant(c, D / 4);
     cls_grid = pick_grid(c, var, np);
     q.pre(RAMA_K_CLS);
-    q.post(launch_gemv(var, cls_grid, st, q.pdl, pro, rows, epi, D / 4, np));
+    q.post(launch_gemv(var, cls_grid, st, q.pdl, pro, rows, epi, D / 4, np));  // (no cluster launch: every one of the cls_grid partial slots must be written)
   }
   int n_part = cls_grid;
   if (c->world > 1) {
@@ -484,7 +570,7 @@ static int enqueue_step(rama_session* s, cudaStream_t st, int mode, StepTrace* t
       q.post(cudaSuccess);
     }
     n_part = c->world * c->sm_count;
-    if (mode == 2) {
+    if (mode == 2 && !logits_pushed(s)) {
       q.pre(RAMA_K_COMM);
       e = g_nccl.AllGather(s->logits + c->v0, s->logits, (size_t)c->Vl, kNcclFloat32, c->comm, st);
       if (e && !q.nccl_err) q.nccl_err = e;
@@ -514,11 +600,15 @@ static int enqueue_step(rama_session* s, cudaStream_t st, int mode, StepTrace* t
 }
 
 // unused partial slots (a CTA-less tail when the classifier grid < sm_count) must read as "empty"
+static __global__ void fill_parts_kernel(ArgPart* part, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) part[i] = ArgPart{-INFINITY, -1};
+}
 int init_parts(rama_session* s) {
   rama_ctx* c = s->ctx;
-  std::vector<ArgPart> h((size_t)c->world * c->sm_count, ArgPart{-INFINITY, -1});
-  CK(cudaMemcpyAsync(s->part, h.data(), h.size() * sizeof(ArgPart), cudaMemcpyHostToDevice, s->stream));
-  CK(cudaStreamSynchronize(s->stream));
+  const int n = c->world * c->sm_count;
+  fill_parts_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(s->part, n);
+  CK(cudaGetLastError());
   return RAMA_OK;
 }
 
@@ -553,6 +643,7 @@ static int capture(rama_session* s, int mode, cudaGraphExec_t* out) {
 
 extern "C" int rama_session_launches_per_step(const rama_session* s, int* n) {
   if (!s || !n) return fail(RAMA_E_INVALID, "NULL argument");
+  if (!s->ranks.empty()) return rama_session_launches_per_step(s->ranks[0], n);
   const rama_ctx* c = s->ctx;
   if (s->persistent) { *n = 1; return RAMA_OK; }  // the whole greedy step is one persistent cooperative launch
   // embed + L·(qkv, attn, wo, w13, w2) + cls + sample (+ collectives under TP); attention + wo are one launch
@@ -563,6 +654,7 @@ extern "C" int rama_session_launches_per_step(const rama_session* s, int* n) {
 
 extern "C" int rama_forward(rama_session* s, int32_t token, int32_t pos) {
   if (!s) return fail(RAMA_E_INVALID, "NULL session");
+  if (!s->ranks.empty()) return group_run(s->ctx, [&](int r) { return rama_forward(s->ranks[r], token, pos); });
   rama_ctx* c = s->ctx;
   if (pos < 0 || pos >= c->T)  // the reference panics on the cache slice (infer.rs:32)
     return fail(RAMA_E_STATE, "pos %d outside [0, seq_len=%d)", pos, c->T);
@@ -588,10 +680,20 @@ extern "C" int rama_forward(rama_session* s, int32_t token, int32_t pos) {
   return RAMA_OK;
 }
 
+// Full vocabulary in s->logits, stream-ordered.  Peer exchange: the classifier epilogues of all ranks store their slices
+// into every rank's array, so this only waits for their arrival; NCCL mode: all-gather of the slices.
 int gather_logits(rama_session* s) {
   rama_ctx* c = s->ctx;
   if (c->world > 1 && !s->logits_gathered) {
-    NK(g_nccl.AllGather(s->logits + c->v0, s->logits, (size_t)c->Vl, kNcclFloat32, c->comm, s->stream));
+    if (logits_pushed(s)) {
+      if (s->parts_valid) {
+        peer_parts_wait_kernel<<<1, kSampleThreads, 0, s->stream>>>(peer_in_parts(s), c->world * c->sm_count, s->cls_grid);
+        CK(cudaGetLastError());
+      }
+    } else {
+      if (!c->comm) return fail(RAMA_E_STATE, "logits all-gather needs NCCL (persistent step kernel inside a single-process group)");
+      NK(g_nccl.AllGather(s->logits + c->v0, s->logits, (size_t)c->Vl, kNcclFloat32, c->comm, s->stream));
+    }
     s->logits_gathered = true;
   }
   return RAMA_OK;
@@ -611,6 +713,9 @@ int read_ret(rama_session* s, int32_t* next) {
 
 extern "C" int rama_sample(rama_session* s, float temperature, float topp, int32_t* next) {
   if (!s || !next) return fail(RAMA_E_INVALID, "NULL argument");
+  // group: every rank holds every rank's greedy partials and the full logits — rank 0 samples (host-driven loop: the
+  // token comes back through the next rama_forward on every rank)
+  if (!s->ranks.empty()) return rama_sample(s->ranks[0], temperature, topp, next);
   rama_ctx* c = s->ctx;
   CK(cudaSetDevice(c->device));
   CK(session_enter(s));
@@ -631,6 +736,17 @@ extern "C" int rama_sample(rama_session* s, float temperature, float topp, int32
 extern "C" int rama_generate(rama_session* s, const int32_t* prompt, int32_t n_prompt, int32_t steps,
                              float temperature, float topp, int32_t* out_tokens, float* elapsed_ms) {
   if (!s || (n_prompt > 0 && !prompt) || !out_tokens) return fail(RAMA_E_INVALID, "NULL argument");
+  if (!s->ranks.empty()) {
+    // every rank runs the device-resident loop (each samples the same token from the same exchanged partials); rank 0's
+    // stream of tokens and its device time are returned
+    if (s->ranks[0]->pf_min > 0 && n_prompt + 1 >= s->ranks[0]->pf_min) RK(group_prefill_prepare(s));
+    std::vector<std::vector<int32_t>> scratch(s->ranks.size());
+    return group_run(s->ctx, [&](int r) {
+      if (r == 0) return rama_generate(s->ranks[0], prompt, n_prompt, steps, temperature, topp, out_tokens, elapsed_ms);
+      scratch[r].resize((size_t)std::max(steps, 1));
+      return rama_generate(s->ranks[r], prompt, n_prompt, steps, temperature, topp, scratch[r].data(), nullptr);
+    });
+  }
   rama_ctx* c = s->ctx;
   if (steps < 0 || steps > c->T)  // mod.rs has no guard: the reference panics past seq_len
     return fail(RAMA_E_STATE, "steps %d exceeds seq_len %d", steps, c->T);
@@ -694,6 +810,14 @@ extern "C" int rama_generate(rama_session* s, const int32_t* prompt, int32_t n_p
 extern "C" int rama_profile_step(rama_session* s, int32_t token, int32_t pos, float ms[RAMA_K_COUNT],
                                  int32_t launches[RAMA_K_COUNT]) {
   if (!s || !ms || !launches) return fail(RAMA_E_INVALID, "NULL argument");
+  if (!s->ranks.empty()) {  // rank 0's timings; the other ranks run the same un-graphed step (the exchange needs them)
+    std::vector<std::array<float, RAMA_K_COUNT>> m(s->ranks.size());
+    std::vector<std::array<int32_t, RAMA_K_COUNT>> l(s->ranks.size());
+    return group_run(s->ctx, [&](int r) {
+      return r == 0 ? rama_profile_step(s->ranks[0], token, pos, ms, launches)
+                    : rama_profile_step(s->ranks[r], token, pos, m[r].data(), l[r].data());
+    });
+  }
   rama_ctx* c = s->ctx;
   if (pos < 0 || pos >= c->T) return fail(RAMA_E_STATE, "pos %d outside [0, seq_len=%d)", pos, c->T);
   if (token < 0 || token >= c->V) return fail(RAMA_E_INVALID, "token outside the vocabulary");
@@ -728,6 +852,7 @@ extern "C" int rama_profile_step(rama_session* s, int32_t token, int32_t pos, fl
 // (2·(5L+1)+1 stamps).  Tool for tools/step_trace.py.
 extern "C" int rama_step_trace(rama_session* s, int32_t token, int32_t pos, long long* stamps, int32_t cap, int32_t* n_out) {
   if (!s || !stamps || !n_out) return fail(RAMA_E_INVALID, "NULL argument");
+  if (!s->ranks.empty()) return fail(RAMA_E_STATE, "the persistent step kernel is not used by a single-process group");
   rama_ctx* c = s->ctx;
   if (!s->persistent) return fail(RAMA_E_STATE, "session does not use the persistent step kernel");
   if (pos < 0 || pos >= c->T || token < 0 || token >= c->V) return fail(RAMA_E_INVALID, "token/pos out of range");
@@ -756,6 +881,7 @@ extern "C" int rama_step_trace(rama_session* s, int32_t token, int32_t pos, long
 
 extern "C" int rama_logits_to_host(rama_session* s, float* dst, size_t n) {
   if (!s || !dst) return fail(RAMA_E_INVALID, "NULL argument");
+  if (!s->ranks.empty()) return rama_logits_to_host(s->ranks[0], dst, n);  // every rank holds the full vocabulary
   rama_ctx* c = s->ctx;
   if (n < (size_t)c->V) return fail(RAMA_E_INVALID, "buffer too small");
   CK(cudaSetDevice(c->device));
@@ -768,6 +894,7 @@ extern "C" int rama_logits_to_host(rama_session* s, float* dst, size_t n) {
 
 extern "C" int rama_state_to_host(rama_session* s, int buf, float* dst, size_t n, size_t* n_out) {
   if (!s) return fail(RAMA_E_INVALID, "NULL session");
+  if (!s->ranks.empty()) return rama_state_to_host(s->ranks[0], buf, dst, n, n_out);  // rank 0's shard (logits, x: complete)
   rama_ctx* c = s->ctx;
   CK(cudaSetDevice(c->device));
   CK(session_enter(s));

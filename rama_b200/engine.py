@@ -120,6 +120,20 @@ class GPU:
         self.cfg: Optional[Config] = None
         self.rank, self.world = (tp[0], tp[1]) if tp is not None else (0, 1)
 
+    @classmethod
+    def multi(cls, n_gpus: int, devices: Optional[Sequence[int]] = None) -> "GPU":
+        """One handle over n_gpus devices of this process (rama_ctx_create_multi): tensor parallelism for callers that,
+        like the reference's engine binary and server, are a single process holding a single `GPU`."""
+        self = cls.__new__(cls)
+        self.h = C.c_void_p()
+        arr = None
+        if devices is not None:
+            arr = (C.c_int32 * n_gpus)(*[int(d) for d in devices])
+        check(_lib.lib().rama_ctx_create_multi(n_gpus, arr, C.byref(self.h)))
+        self.cfg = None
+        self.rank, self.world = 0, n_gpus
+        return self
+
     @staticmethod
     def unique_id() -> bytes:
         buf = (C.c_uint8 * 128)()

@@ -1,7 +1,7 @@
 // engine_main.cpp — the engine CLI (≙ engine/src/main.rs with `--features gpu`) on the C++ mirror of the reference
 // interface (include/rama_b200.hpp): same flags, same call sequence, same output.
 //
-//   engine -m <model.bin> -t <tokenizer.bin> [-p prompt] [-s steps=255] [-r temperature=1.0] [-l topp=0.9] [--per-op]
+//   engine -m <model.bin> -t <tokenizer.bin> [-p prompt] [-s steps=255] [-r temperature=1.0] [-l topp=0.9] [--per-op] [--gpus N]
 //
 // main.rs:61-105: Config::from_file → GPU::new() → TransformerWeights::from_file/from_weight → RunState::from_config/
 // from_state → views → Tokenizer::new → generate(...) → "elapsed: S.mmm s, avg tok/s: (step-1)/elapsed".
@@ -22,11 +22,12 @@ struct Args {  // main.rs:20-50
   unsigned step = 255;
   float temperature = 1.0f, topp = 0.9f;
   bool per_op = false;
+  int gpus = 0;  // 0: RAMA_GPUS or 1; N > 1: one tensor-parallel handle over devices 0..N-1 of this process
 };
 
 static void usage() {
   std::fprintf(stderr,
-               "Usage: engine -m <MODEL> -t <TOKENIZER> [-p <PROMPT>] [-s <STEP>] [-r <TEMPERATURE>] [-l <TOPP>] [-o <MODE>] [--per-op]\n");
+               "Usage: engine -m <MODEL> -t <TOKENIZER> [-p <PROMPT>] [-s <STEP>] [-r <TEMPERATURE>] [-l <TOPP>] [-o <MODE>] [--per-op] [--gpus <N>]\n");
 }
 
 static bool parse(int argc, char** argv, Args& a) {
@@ -44,6 +45,7 @@ static bool parse(int argc, char** argv, Args& a) {
     else if (k == "-r" || k == "--temperature") a.temperature = std::strtof(v, nullptr);
     else if (k == "-l" || k == "--topp") a.topp = std::strtof(v, nullptr);
     else if (k == "-o" || k == "--mode") a.mode = v;
+    else if (k == "--gpus") a.gpus = std::atoi(v);
     else return false;
   }
   return !a.model.empty() && !a.tokenizer.empty();
@@ -57,7 +59,9 @@ int main(int argc, char** argv) {
     if (!rd) throw Panic(RAMA_E_IO, "cannot open " + args.model);  // File::open(path).unwrap()
     const Config config = Config::from_file(rd);
 
-    const GPU device;  // GPU::new()
+    // GPU::new(); --gpus N (or RAMA_GPUS=N): the same single handle, tensor-parallel over N devices of this process
+    if (args.gpus > 1 && args.per_op) throw Panic(RAMA_E_INVALID, "--per-op runs the single-device Device ops; drop --gpus");
+    const GPU device(args.gpus > 0 ? args.gpus : GPU::gpus_from_env());
 
     TransformerWeights<HostVec> host_weights;
     TransformerWeights<DevBuf> weights;

@@ -24,3 +24,15 @@ def test_tp_generate_matches_oracle(world):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "TP-OK" in r.stdout
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_single_process_group_matches_oracle(world):
+    """rama_ctx_create_multi: one process, one handle, `world` devices (what a `--features gpu` caller of the reference
+    can use) — decode, sampling, prefill and batched decode against the oracle."""
+    if _ngpu() < world:
+        pytest.skip(f"needs {world} GPUs")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "tp_single.py"), str(world)], capture_output=True, text=True,
+                       timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert f"TP1P-OK {world}" in r.stdout
