@@ -194,6 +194,15 @@ enum rama_kernel_kind {
 };
 int rama_profile_step(rama_session* s, int32_t token, int32_t pos, float ms[RAMA_K_COUNT],
                       int32_t launches[RAMA_K_COUNT]);
+/* In-graph timeline of one decode step: the step is captured into a CUDA graph exactly like the production one (programmatic
+ * dependent launch included) with a %globaltimer slot per kernel; CTA 0 of kernel i stamps stamps_ns[4i + 0] entry,
+ * [4i + 1] dependency resolved (the previous kernel of the chain has completed), [4i + 2] prologue done (activations in shared
+ * memory; under tensor parallelism: every peer's partial has arrived), [4i + 3] its own end — nanoseconds relative to the first
+ * stamp of the last of `reps` replays; kinds[i] is the rama_kernel_kind.  mode 0 = forward, 1 = + greedy sampler.
+ * cap ≥ 5·n_layers + 3.  Collective under tensor parallelism.  (rama_profile_step's event pairs include launch latency and
+ * remove all overlap; this is the attribution to trust.) */
+int rama_step_timeline(rama_session* s, int32_t token, int32_t pos, int32_t mode, int32_t reps, double* stamps_ns,
+                       int32_t* kinds, int32_t cap, int32_t* n_out);
 
 /* Phase timeline of one persistent step (tools/step_trace.py): SM-clock stamps of CTA 0 at kernel entry and
  * before/after each of the 5L+1 grid barriers. */

@@ -78,6 +78,7 @@ _SIGS = {
     "rama_session_launches_per_step": ([vp, C.POINTER(C.c_int)], C.c_int),
     "rama_step_trace": ([vp, C.c_int32, C.c_int32, C.POINTER(C.c_longlong), C.c_int32, ip], C.c_int),
     "rama_profile_step": ([vp, C.c_int32, C.c_int32, fp, ip], C.c_int),
+    "rama_step_timeline": ([vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_double), ip, C.c_int32, ip], C.c_int),
     "rama_tokenizer_load": ([C.c_char_p, C.c_int32, C.POINTER(vp)], C.c_int),
     "rama_tokenizer_free": ([vp], C.c_int),
     "rama_tokenizer_info": ([vp, ip, ip], C.c_int),

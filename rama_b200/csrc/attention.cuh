@@ -169,7 +169,9 @@ __device__ __forceinline__ void attn_decode_body(const AttnParams& p, int pos) {
   }
 }
 
-static __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnParams p, int use_pdl) {
+static __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnParams p, int use_pdl, unsigned long long* trace = nullptr) {
+  const bool tr = trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0;  // rama_step_timeline
+  if (tr) trace[0] = globaltimer_ns();
   if (use_pdl) pdl_launch_dependents();
   if (p.prefetch && threadIdx.x == 0) {  // weights do not depend on the previous kernel
     const size_t n_cta = (size_t)gridDim.x * gridDim.y, me = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
@@ -181,7 +183,9 @@ static __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const 
     }
   }
   if (use_pdl) pdl_wait();
+  if (tr) trace[1] = trace[2] = globaltimer_ns();
   attn_decode_body(p, p.pos_override >= 0 ? p.pos_override : p.ctrl->pos);
+  if (tr) trace[3] = globaltimer_ns();
 }
 
 // ---- flash-decode with the splits of a head in ONE thread-block cluster ---------------------------------------
@@ -199,7 +203,9 @@ static __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const 
 // wait only q and row `pos` remain to be fetched.
 constexpr int kAttnClusterMax = 8;  // portable cluster size
 
-static __global__ void __launch_bounds__(kAttnThreads, 2) attn_cluster_kernel(const AttnParams p, int use_pdl) {
+static __global__ void __launch_bounds__(kAttnThreads, 2) attn_cluster_kernel(const AttnParams p, int use_pdl, unsigned long long* trace = nullptr) {
+  const bool tr = trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0;  // rama_step_timeline
+  if (tr) trace[0] = globaltimer_ns();
   namespace cg = cooperative_groups;
   constexpr int NW = kAttnWarps;
   __shared__ float s_m[NW], s_l[NW];
@@ -246,6 +252,7 @@ static __global__ void __launch_bounds__(kAttnThreads, 2) attn_cluster_kernel(co
 
   if (use_pdl & 1) pdl_wait();
   if ((use_pdl & 3) == 3) pdl_launch_dependents();
+  if (tr) trace[1] = trace[2] = globaltimer_ns();
 
   const float4 q4 = active ? __ldcg(reinterpret_cast<const float4*>(p.q + col) + lane) : zero4;
 #pragma unroll
@@ -352,6 +359,7 @@ static __global__ void __launch_bounds__(kAttnThreads, 2) attn_cluster_kernel(co
     }
   }
   cluster.sync();  // no CTA may exit while a sibling still reads its shared memory
+  if (tr) trace[3] = globaltimer_ns();
 }
 
 // ---- attention + wo in one launch (small models, short contexts) ---------------------------------------------

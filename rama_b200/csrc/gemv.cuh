@@ -101,6 +101,17 @@ struct ProNorm {
   unsigned* seq = nullptr;     // step counter: epoch source of the TP exchange
   int vocab = 0;
   int cluster_share = 0;       // launched as clusters: the CTAs of a cluster split the peer reduction (see operator())
+  // Two-phase peer reduction (P ≥ 4): the first red_n CTAs each reduce ONE slice of the vector (P LL partials + the residual)
+  // and publish it — again as LL elements, so no fence — in this local buffer; every CTA then reads the reduced vector:
+  // 32 KB per CTA at D = 4096 instead of P · 32 KB (measured on one rank's share of a TP = 8 step, RAMA_TP_SIM: the plain
+  // prologue spends 7.2 µs pulling 148 × 256 KB through L2, cluster pairs 5.1 µs).
+  uint2* red_ll = nullptr;     // local [K] LL elements of this stage, or null
+  int red_n = 0;
+  // The kernel runs WITHOUT griddepcontrol.wait (use_pdl bit 3): the arrival of the peers' partials — this rank's own
+  // included — is the dependency.  The residual stream is then read only AFTER an element of the partial has arrived: a CTA of
+  // this rank's producing GEMV has stored it, so that kernel had passed ITS wait and everything older (the kernel that wrote
+  // the residual stream) is complete and visible.
+  int x_after_peers = 0;
   // The norm weights never depend on the previous kernel: the first N float4 per thread are loaded BEFORE
   // griddepcontrol.wait (one L2 round trip off the critical path of every norm-prologue kernel).
   template <int N>
@@ -140,12 +151,58 @@ struct ProNorm {
     const unsigned cr = CS > 1 ? cluster_ctarank() : 0u;
     const int lo = (int)((long long)K4 * cr / CS), hi = (int)((long long)K4 * (cr + 1) / CS);
     const bool first_cluster = blockIdx.x < CS;  // the cluster (or CTA) that also writes the RunState copies
+    const bool cta0 = blockIdx.x == 0;
     uint32_t sib[kMaxClusterShare];
 #pragma unroll
     for (int j = 0; j < kMaxClusterShare; ++j) sib[j] = (CS > 1 && j < (int)CS) ? dsmem_addr(xs, j) : 0u;
     float ss = 0.f;
+    if (peers && red_ll) {
+      const int NR = min((int)gridDim.x, red_n);
+      if ((int)blockIdx.x < NR) {  // phase 1: reduce slice blockIdx.x
+        const int s_lo = (int)((long long)K4 * blockIdx.x / NR), s_hi = (int)((long long)K4 * (blockIdx.x + 1) / NR);
+        for (int i = s_lo + threadIdx.x; i < s_hi; i += kGemvThreads) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (!x_after_peers) v = __ldcg(x4 + i);
+          uint4 lo_[kMaxPeers], hi_[kMaxPeers];
+#pragma unroll
+          for (int r = 0; r < kMaxPeers; ++r) {
+            if (r < pin.P) {
+              const uint2* e = pin.inbox + (size_t)r * pin.n + 4 * i;
+              lo_[r] = ld_ll2(e);
+              hi_[r] = ld_ll2(e + 2);
+            }
+          }
+          float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int r = 0; r < kMaxPeers; ++r) {  // rank order: same association on every rank
+            if (r < pin.P) {
+              const uint2* e = pin.inbox + (size_t)r * pin.n + 4 * i;
+              if ((lo_[r].y != ep || lo_[r].w != ep)) lo_[r] = ld_ll2_wait(e, ep, pin.error);
+              if ((hi_[r].y != ep || hi_[r].w != ep)) hi_[r] = ld_ll2_wait(e + 2, ep, pin.error);
+              a.x += __uint_as_float(lo_[r].x); a.y += __uint_as_float(lo_[r].z);
+              a.z += __uint_as_float(hi_[r].x); a.w += __uint_as_float(hi_[r].z);
+            }
+          }
+          if (x_after_peers) v = __ldcg(x4 + i);
+          v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+          st_ll2(red_ll + 4 * i, __float_as_uint(v.x), __float_as_uint(v.y), ep);
+          st_ll2(red_ll + 4 * i + 2, __float_as_uint(v.z), __float_as_uint(v.w), ep);
+          reinterpret_cast<float4*>(const_cast<float*>(add))[i] = a;  // RunState.xb2 / xb
+        }
+      }
+      for (int i = threadIdx.x; i < K4; i += kGemvThreads) {  // phase 2: the reduced vector (residual included)
+        uint4 l = ld_ll2(red_ll + 4 * i), h = ld_ll2(red_ll + 4 * i + 2);
+        if ((l.y != ep || l.w != ep)) l = ld_ll2_wait(red_ll + 4 * i, ep, pin.error);
+        if ((h.y != ep || h.w != ep)) h = ld_ll2_wait(red_ll + 4 * i + 2, ep, pin.error);
+        const float4 v = make_float4(__uint_as_float(l.x), __uint_as_float(l.z), __uint_as_float(h.x), __uint_as_float(h.z));
+        xs[i] = v;
+        ss = dot4(v, v, ss);
+        if (cta0) reinterpret_cast<float4*>(xout)[i] = v;
+      }
+    } else
     for (int i = lo + threadIdx.x; i < hi; i += kGemvThreads) {
-      float4 v = __ldcg(x4 + i);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (!(peers && x_after_peers)) v = __ldcg(x4 + i);
       if (peers) {
         // issue every rank's two 16-byte LL loads first (independent), then validate the epochs;
         // only an element that has not arrived yet falls into the spinning reload
@@ -163,12 +220,13 @@ struct ProNorm {
         for (int r = 0; r < kMaxPeers; ++r) {  // rank order: same association on every rank
           if (r < pin.P) {
             const uint2* e = pin.inbox + (size_t)r * pin.n + 4 * i;
-            if (lo_[r].y != ep || lo_[r].w != ep) lo_[r] = ld_ll2_wait(e, ep, pin.error);
-            if (hi_[r].y != ep || hi_[r].w != ep) hi_[r] = ld_ll2_wait(e + 2, ep, pin.error);
+            if ((lo_[r].y != ep || lo_[r].w != ep)) lo_[r] = ld_ll2_wait(e, ep, pin.error);
+            if ((hi_[r].y != ep || hi_[r].w != ep)) hi_[r] = ld_ll2_wait(e + 2, ep, pin.error);
             a.x += __uint_as_float(lo_[r].x); a.y += __uint_as_float(lo_[r].z);
             a.z += __uint_as_float(hi_[r].x); a.w += __uint_as_float(hi_[r].z);
           }
         }
+        if (x_after_peers) v = __ldcg(x4 + i);
         v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
         if (first_cluster) reinterpret_cast<float4*>(const_cast<float*>(add))[i] = a;  // RunState.xb2 / xb
       } else if (add) {
@@ -178,7 +236,7 @@ struct ProNorm {
           a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
         }
         v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
-        if (add_out && blockIdx.x == 0) reinterpret_cast<float4*>(add_out)[i] = a;
+        if (add_out && cta0) reinterpret_cast<float4*>(add_out)[i] = a;
       }
       if (CS > 1) {
 #pragma unroll
@@ -211,7 +269,7 @@ struct ProNorm {
       v.x = g.x * (scale * v.x); v.y = g.y * (scale * v.y);
       v.z = g.z * (scale * v.z); v.w = g.w * (scale * v.w);
       xs[i] = v;
-      if (xnorm && blockIdx.x == 0) reinterpret_cast<float4*>(xnorm)[i] = v;
+      if (xnorm && cta0) reinterpret_cast<float4*>(xnorm)[i] = v;
     };
 #pragma unroll
     for (int j = 0; j < N; ++j) {
@@ -543,7 +601,12 @@ __host__ __device__ inline size_t gemv_smem_bytes(int K4, int n_pairs, int grid,
 
 template <int WK, int RP, int U, class Pro, class Rows, class Epi>
 __global__ void __launch_bounds__(kGemvThreads, 1)
-gemv_fused_kernel(const Pro pro, const Rows rows, const Epi epi_in, int K4, int n_pairs, int use_pdl) {
+gemv_fused_kernel(const Pro pro, const Rows rows, const Epi epi_in, int K4, int n_pairs, int use_pdl,
+                  unsigned long long* trace) {
+  // trace (rama_step_timeline, else null): CTA 0 stamps %globaltimer at entry, after griddepcontrol.wait (= the previous kernel
+  // of the chain has completed), after the prologue (activations in shared memory; under TP: all peer partials arrived) and at its end
+  const bool tr = trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+  if (tr) trace[0] = globaltimer_ns();
   extern __shared__ float4 gemv_smem[];
   __shared__ float red[2 * kWarp];
   float4* xs = gemv_smem;
@@ -570,14 +633,20 @@ gemv_fused_kernel(const Pro pro, const Rows rows, const Epi epi_in, int K4, int 
       if (bytes >= 16) l2_prefetch_bulk(ptr, (uint32_t)(bytes & ~(size_t)15));
     }
   }
-  if (use_pdl & 1) pdl_wait();
-  if ((use_pdl & 3) == 3) pdl_launch_dependents();
+  // bit 3 (tensor parallelism, prologues fed by the peer exchange): no griddepcontrol.wait — the epochs of the peers' partials
+  // carry the dependency (ProNorm::x_after_peers), so the CTA reduces the partials as they arrive, under the producer's tail
+  const bool no_wait = (use_pdl & 8) != 0;
+  if ((use_pdl & 1) && !no_wait) pdl_wait();
+  if ((use_pdl & 3) == 3 && !no_wait) pdl_launch_dependents();
+  if (tr) trace[1] = globaltimer_ns();
 
   Epi epi = epi_in;
   epi.prepare();
   pro(xs, K4, red, pre);
+  if ((use_pdl & 3) == 3 && no_wait) pdl_launch_dependents();  // everything older than this kernel is complete now
   if ((int)threadIdx.x < np) epi.prefetch(p0 + threadIdx.x);  // this thread's (first) epilogue pair
   __syncthreads();
+  if (tr) trace[2] = globaltimer_ns();
   gemv_pairs<WK, RP, U>(rows, K4, p0, np, xs, part);
   __syncthreads();
 
@@ -591,6 +660,7 @@ gemv_fused_kernel(const Pro pro, const Rows rows, const Epi epi_in, int K4, int 
     epi(p0 + i, v0, v1);
   }
   epi.finish(red);
+  if (tr) trace[3] = globaltimer_ns();
 }
 
 // this CTA's balanced contiguous range of pairs
@@ -618,7 +688,10 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 
 template <class Pro, class Rows, class Epi>
 __global__ void __launch_bounds__(kGemvThreads, 2)
-gemv_smem_kernel(const Pro pro, const Rows rows, const Epi epi_in, int K4, int n_pairs, int use_pdl) {
+gemv_smem_kernel(const Pro pro, const Rows rows, const Epi epi_in, int K4, int n_pairs, int use_pdl,
+                 unsigned long long* trace) {
+  const bool tr = trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0;  // (stamps as in gemv_fused_kernel)
+  if (tr) trace[0] = globaltimer_ns();
   extern __shared__ float4 gemv_smem[];
   __shared__ float red[2 * kWarp];
   __shared__ __align__(8) unsigned long long bar_storage;
@@ -643,11 +716,13 @@ gemv_smem_kernel(const Pro pro, const Rows rows, const Epi epi_in, int K4, int n
   const auto pre = pro.template preload<1>(K4);
   if (use_pdl & 1) pdl_wait();
   if ((use_pdl & 3) == 3) pdl_launch_dependents();
+  if (tr) trace[1] = globaltimer_ns();
 
   Epi epi = epi_in;
   epi.prepare();
   pro(xs, K4, red, pre);
   __syncthreads();  // xs complete; also makes the mbarrier init visible to every waiter
+  if (tr) trace[2] = globaltimer_ns();
   {
     uint32_t done = 0;
     while (!done)
@@ -671,6 +746,7 @@ gemv_smem_kernel(const Pro pro, const Rows rows, const Epi epi_in, int K4, int n
     if (lane == 0) epi(p0 + i, a0, a1);
   }
   epi.finish(red);
+  if (tr) trace[3] = globaltimer_ns();
 }
 
 // ---- the same streaming core with a run-time k-split (persistent step kernel: one instantiation per

@@ -93,6 +93,9 @@ struct rama_ctx {
   const float* wcls = nullptr;  // this rank's classifier rows (own tensor, or a window of the embedding)
   cudaStream_t op_stream = nullptr;
   int use_pdl = 0;
+  int tp_nowait = 0;  // RAMA_TP_NOWAIT=1: the GEMVs fed by the peer exchange skip griddepcontrol.wait (gemv.cuh use_pdl bit 3) — measured on
+                      // one rank's share of a TP step (RAMA_TP_SIM): +1 % at P = 2/4, −4 % at P = 8 (the spinning consumers compete with the
+                      // producer's tail for L2): off by default
   int variant_override = -1;
   int p2p = 0;  // TP exchange: 1 = fused peer-memory all-reduce (default), 0 = NCCL collectives
   int staged = 1;      // RAMA_GEMV_STAGED=0 disables the shared-memory-staged GEMV for small slabs
@@ -104,6 +107,8 @@ struct rama_ctx {
   // LL partials).  Results are meaningless (the same partial P times); kernel shapes, bytes and the dependent chain are
   // those of one rank of a P-GPU run minus NVLink latency and rank skew: what ncu and the in-graph timeline can see.
   int tp_sim = 0;
+  int tp_reduce = -1;  // RAMA_TP_REDUCE: how a norm prologue reduces the P peer partials — 0 every CTA reads all of them, 1 the CTAs
+                       // of a cluster share the reads (tp_cluster), 2 two-phase through a local LL buffer; -1 (default): 1
   int tp_cluster = 4;  // RAMA_TP_CLUSTER: cluster size of the shared peer reduction in the norm prologues (0/1: off)
   int persistent = 0;  // RAMA_STEP=persistent: the decode step as one persistent cooperative kernel (step_kernel.cuh);
                        // default: one fused kernel per op group in a CUDA graph (measured faster)
@@ -165,6 +170,7 @@ struct rama_session {
   size_t off_parts = 0, off_inbox = 0, off_logits = 0, off_x0 = 0, off_flags = 0, off_done = 0;
   bool p2p = false;
   unsigned bulk_epoch = 0;      // host counter of bulk exchanges on this session (prefill); identical on every rank
+  uint2* red_ll = nullptr;      // two-phase peer reduction: local [2 stages][D] LL elements (gemv.cuh ProNorm::red_ll)
   PeerBlock pf_blk;             // prefill exchange buffers (allocated with the prefill workspace): inbox[P][rpr][D] | xn[cap][D]
   size_t pf_off_xn = 0;
   int pf_rpr_max = 0;
@@ -227,7 +233,8 @@ inline void set_cluster_share(ProPlain&, int) {}
 // clusters still cover (almost) every SM in ONE wave — a CTA of this kernel owns an SM, and clusters cannot span GPCs.
 template <int WK, int RP, int U, class Pro, class Rows, class Epi>
 inline cudaError_t launch_gemv_t(int grid, cudaStream_t st, int pdl, const Pro& pro_in, const Rows& rows,
-                                 const Epi& epi, int K4, int n_pairs, int want_cluster = 0) {
+                                 const Epi& epi, int K4, int n_pairs, int want_cluster = 0,
+                                 unsigned long long* trace = nullptr) {
   auto kern = gemv_fused_kernel<WK, RP, U, Pro, Rows, Epi>;
   static std::atomic<unsigned long long> attr_done{0};
   const cudaError_t attr_err = ensure_dyn_smem((const void*)kern, (int)kMaxDynSmem, attr_done);
@@ -267,7 +274,7 @@ inline cudaError_t launch_gemv_t(int grid, cudaStream_t st, int pdl, const Pro& 
   }
   cfg.attrs = at;
   cfg.numAttrs = na;
-  return cudaLaunchKernelEx(&cfg, kern, pro, rows, epi, K4, n_pairs, pdl);
+  return cudaLaunchKernelEx(&cfg, kern, pro, rows, epi, K4, n_pairs, pdl, trace);
 }
 
 // bytes of shared memory the staged variant needs for this launch (x + the largest CTA slab)
@@ -278,7 +285,7 @@ inline size_t gemv_stage_bytes(int K4, int n_pairs, int grid, int rows_per_pair)
 
 template <class Pro, class Rows, class Epi>
 inline cudaError_t launch_gemv_staged(int grid, cudaStream_t st, int pdl, const Pro& pro, const Rows& rows, const Epi& epi,
-                                      int K4, int n_pairs) {
+                                      int K4, int n_pairs, unsigned long long* trace = nullptr) {
   auto kern = gemv_smem_kernel<Pro, Rows, Epi>;
   static std::atomic<unsigned long long> attr_done{0};
   const cudaError_t attr_err = ensure_dyn_smem((const void*)kern, (int)kGemvSmemStageMaxSolo, attr_done);
@@ -295,23 +302,24 @@ inline cudaError_t launch_gemv_staged(int grid, cudaStream_t st, int pdl, const 
     cfg.attrs = at;
     cfg.numAttrs = 1;
   }
-  return cudaLaunchKernelEx(&cfg, kern, pro, rows, epi, K4, n_pairs, pdl);
+  return cudaLaunchKernelEx(&cfg, kern, pro, rows, epi, K4, n_pairs, pdl, trace);
 }
 
 template <class Pro, class Rows, class Epi>
 inline cudaError_t launch_gemv(int variant, int grid, cudaStream_t st, int pdl, const Pro& pro,
-                               const Rows& rows, const Epi& epi, int K4, int n_pairs, int want_cluster = 0) {
+                               const Rows& rows, const Epi& epi, int K4, int n_pairs, int want_cluster = 0,
+                               unsigned long long* trace = nullptr) {
   // small slabs (the small models): whole slab staged in shared memory ahead of the dependency (gemv_smem_kernel)
-  if (variant == kVariantStaged) return launch_gemv_staged(grid, st, pdl, pro, rows, epi, K4, n_pairs);
+  if (variant == kVariantStaged) return launch_gemv_staged(grid, st, pdl, pro, rows, epi, K4, n_pairs, trace);
   switch (variant) {
-    case 0: return launch_gemv_t<16, 2, 2>(grid, st, pdl, pro, rows, epi, K4, n_pairs, want_cluster);
-    case 1: return launch_gemv_t<8, 2, 4>(grid, st, pdl, pro, rows, epi, K4, n_pairs, want_cluster);
-    case 2: return launch_gemv_t<4, 2, 4>(grid, st, pdl, pro, rows, epi, K4, n_pairs, want_cluster);
-    case 3: return launch_gemv_t<1, 2, 4>(grid, st, pdl, pro, rows, epi, K4, n_pairs, want_cluster);
-    case 4: return launch_gemv_t<16, 4, 2>(grid, st, pdl, pro, rows, epi, K4, n_pairs, want_cluster);
-    case 5: return launch_gemv_t<8, 4, 2>(grid, st, pdl, pro, rows, epi, K4, n_pairs, want_cluster);
-    case 6: return launch_gemv_t<2, 2, 4>(grid, st, pdl, pro, rows, epi, K4, n_pairs, want_cluster);
-    case 7: return launch_gemv_t<16, 1, 4>(grid, st, pdl, pro, rows, epi, K4, n_pairs, want_cluster);
+    case 0: return launch_gemv_t<16, 2, 2>(grid, st, pdl, pro, rows, epi, K4, n_pairs, want_cluster, trace);
+    case 1: return launch_gemv_t<8, 2, 4>(grid, st, pdl, pro, rows, epi, K4, n_pairs, want_cluster, trace);
+    case 2: return launch_gemv_t<4, 2, 4>(grid, st, pdl, pro, rows, epi, K4, n_pairs, want_cluster, trace);
+    case 3: return launch_gemv_t<1, 2, 4>(grid, st, pdl, pro, rows, epi, K4, n_pairs, want_cluster, trace);
+    case 4: return launch_gemv_t<16, 4, 2>(grid, st, pdl, pro, rows, epi, K4, n_pairs, want_cluster, trace);
+    case 5: return launch_gemv_t<8, 4, 2>(grid, st, pdl, pro, rows, epi, K4, n_pairs, want_cluster, trace);
+    case 6: return launch_gemv_t<2, 2, 4>(grid, st, pdl, pro, rows, epi, K4, n_pairs, want_cluster, trace);
+    case 7: return launch_gemv_t<16, 1, 4>(grid, st, pdl, pro, rows, epi, K4, n_pairs, want_cluster, trace);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -399,6 +407,21 @@ inline cudaError_t launch_k(bool pdl, void (*kern)(P...), dim3 grid, dim3 block,
   return cudaLaunchKernelEx(&cfg, kern, std::forward<A>(args)...);
 }
 
+
+// how this session's norm prologues reduce the peer partials (rama_ctx::tp_reduce)
+inline int tp_reduce_mode(const rama_session* s) {
+  const rama_ctx* c = s->ctx;
+  if (!s->p2p) return 0;
+  if (c->tp_reduce >= 0) return c->tp_reduce;
+  return 1;  // measured (RAMA_TP_SIM, tok/s at P = 8 / 4 / 2): mode 0 779 / 617 / 400, mode 1 866 / 642 / 406, mode 2 869 / 627 / 398
+}
+// returns the extra use_pdl bits of the launch (bit 3: no griddepcontrol.wait, the peer epochs carry the dependency)
+inline int set_peer_reduce(const rama_session* s, ProNorm& pro, int stage, int pdl) {
+  if (!s->p2p) return 0;
+  if (tp_reduce_mode(s) == 2 && s->red_ll) { pro.red_ll = s->red_ll + (size_t)stage * s->ctx->D; pro.red_n = 64; }
+  if (pdl && s->ctx->tp_nowait) { pro.x_after_peers = 1; return 8; }
+  return 0;
+}
 
 // the classifier epilogue stores every logits slice into every rank's array (no all-gather afterwards)
 inline bool logits_pushed(const rama_session* s) { return s->p2p && !s->persistent; }

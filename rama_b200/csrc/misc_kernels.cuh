@@ -10,8 +10,11 @@ namespace rama {
 static __global__ void __launch_bounds__(256) step_begin_kernel(StepCtrl* ctrl, unsigned* seq,
                                                          const float* __restrict__ emb,
                                                          float* __restrict__ x, int D, int vocab,
-                                                         int use_pdl) {
+                                                         int use_pdl, unsigned long long* trace = nullptr) {
+  const bool tr = trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0;  // rama_step_timeline
+  if (tr) trace[0] = globaltimer_ns();
   if (use_pdl) { pdl_launch_dependents(); pdl_wait(); }
+  if (tr) trace[1] = trace[2] = trace[3] = globaltimer_ns();
   if (blockIdx.x == 0 && threadIdx.x == 0) *seq += 1u;  // step counter: epoch source of the TP exchange
   int token = ctrl->token;
   if (token < 0 || token >= vocab) {  // the reference would panic on the slice (infer.rs:13)
@@ -279,9 +282,14 @@ __device__ __forceinline__ void sample_body(const SampleParams& p) {
   }
 }
 
-static __global__ void __launch_bounds__(kSampleThreads) sample_kernel(const SampleParams p, int use_pdl) {
+static __global__ void __launch_bounds__(kSampleThreads) sample_kernel(const SampleParams p, int use_pdl,
+                                                                       unsigned long long* trace = nullptr) {
+  const bool tr = trace != nullptr && threadIdx.x == 0;  // rama_step_timeline
+  if (tr) trace[0] = globaltimer_ns();
   if (use_pdl) { pdl_launch_dependents(); pdl_wait(); }
+  if (tr) trace[1] = trace[2] = globaltimer_ns();
   sample_body(p);
+  if (tr) trace[3] = globaltimer_ns();
 }
 
 // Tensor parallelism, host reads of the logits (rama_logits_to_host): wait until every classifier CTA of every rank has

@@ -98,7 +98,7 @@ static void session_free(rama_session* s) {
   }
   void* bufs[] = {s->x0, s->x1, s->xfinal, s->xb, s->xb2, s->w2out, s->hb, s->hb2, s->q, s->k, s->v, s->att,
                   s->logits, s->key_cache, s->value_cache, s->attn_ws, s->tickets, s->part, s->sort_keys,
-                  s->ctrl, s->d_prompt, s->d_out, s->seq, s->bar, s->wo_part, s->pf_x, s->pf_xn, s->pf_q, s->pf_att, s->pf_y, s->pf_h,
+                  s->ctrl, s->d_prompt, s->d_out, s->seq, s->bar, s->wo_part, s->red_ll, s->pf_x, s->pf_xn, s->pf_q, s->pf_att, s->pf_y, s->pf_h,
                   s->pf_tokens};
   for (void* b : bufs) if (b) cudaFree(b);
   if (s->h_ring) cudaFreeHost(s->h_ring);
@@ -157,6 +157,7 @@ static int session_create_rank(rama_ctx* c, rama_session** out, bool connect) {
   s->persistent = c->persistent && !c->group && (c->world == 1 || s->p2p);
   if (s->persistent) s->cls_grid = c->sm_count;  // every CTA of the persistent kernel writes a classifier partial
   A(dalloc(&s->part, (size_t)c->world * c->sm_count));
+  if (s->p2p) A(dalloc(&s->red_ll, (size_t)2 * D));
   A(dalloc(&s->seq, 1));
   A(dalloc(&s->bar, 2));
   // Attention + wo as ONE launch (per-head partial outputs of wo, summed by the next prologue) — opt-in since the cluster
@@ -312,6 +313,14 @@ struct StepEnq {
   int pdl;
   cudaError_t err = cudaSuccess;
   int nccl_err = 0;
+  // in-graph timeline (rama_step_timeline): every kernel of the step gets a 4-stamp slot of this device buffer
+  unsigned long long* tl = nullptr;
+  std::vector<int>* tl_kinds = nullptr;
+  unsigned long long* slot(int kind) {
+    if (!tl) return nullptr;
+    tl_kinds->push_back(kind);
+    return tl + 4 * (tl_kinds->size() - 1);
+  }
   void pre(int kind) {
     if (tr) {
       cudaEvent_t a;
@@ -400,10 +409,12 @@ static int enqueue_step_persistent(rama_session* s, cudaStream_t st, int mode, i
 }
 
 // mode: 0 = forward only (logits + greedy partials), 1 = + chained greedy sampler, 2 = + chained top-p
-static int enqueue_step(rama_session* s, cudaStream_t st, int mode, StepTrace* tr, int* n_launch) {
+static int enqueue_step(rama_session* s, cudaStream_t st, int mode, StepTrace* tr, int* n_launch,
+                        unsigned long long* tl = nullptr, std::vector<int>* tl_kinds = nullptr) {
   rama_ctx* c = s->ctx;
   if (s->persistent && !tr) return enqueue_step_persistent(s, st, mode, n_launch);
   StepEnq q{s, st, tr};
+  q.tl = tl; q.tl_kinds = tl_kinds;
   // PDL edges are only used inside captured graphs / plain streams without event timing
   q.pdl = tr ? 0 : c->use_pdl;
   const int D = c->D, Dq = c->Dq, Fl = c->Fl, T = c->T, hs = c->hs, L = c->L;
@@ -429,7 +440,7 @@ static int enqueue_step(rama_session* s, cudaStream_t st, int mode, StepTrace* t
       at[0].val.programmaticStreamSerializationAllowed = 1;
       cfg.attrs = at; cfg.numAttrs = 1;
     }
-    q.post(cudaLaunchKernelEx(&cfg, step_begin_kernel, s->ctrl, s->seq, W[RAMA_T_TOKEN_EMBEDDING], s->x0, D, c->V, q.pdl));
+    q.post(cudaLaunchKernelEx(&cfg, step_begin_kernel, s->ctrl, s->seq, W[RAMA_T_TOKEN_EMBEDDING], s->x0, D, c->V, q.pdl, q.slot(RAMA_K_EMBED)));
   }
 
   for (int l = 0; l < L; ++l) {
@@ -437,6 +448,8 @@ static int enqueue_step(rama_session* s, cudaStream_t st, int mode, StepTrace* t
     {
       ProNorm pro{s->x0, l == 0 ? nullptr : s->w2out, s->x1, W[RAMA_T_RMS_ATT] + (size_t)l * D, nullptr, peer_in(s, 1, l - 1)};
       if (l == 0 && !embed_kernel) { pro.emb = W[RAMA_T_TOKEN_EMBEDDING]; pro.ctrl = s->ctrl; pro.seq = s->seq; pro.vocab = c->V; }
+      const int nowait = l > 0 ? set_peer_reduce(s, pro, 1, q.pdl) : 0;
+      const int want_cluster = (s->p2p && l > 0 && tp_reduce_mode(s) == 1) ? c->tp_cluster : 0;
       RowsQKV rows{W[RAMA_T_WQ] + (size_t)l * Dq * D, W[RAMA_T_WK] + (size_t)l * Dq * D,
                    W[RAMA_T_WV] + (size_t)l * Dq * D, D, Dq / 2};
       EpiQKV epi{s->q, s->k, s->v, s->key_cache + (size_t)l * T * Dq, s->value_cache + (size_t)l * T * Dq,
@@ -444,8 +457,8 @@ static int enqueue_step(rama_session* s, cudaStream_t st, int mode, StepTrace* t
       const int np = 3 * Dq / 2, var = pick_variant(c, D / 4, np);
       q.pre(RAMA_K_QKV);
       // the cluster attention kernel reads older K/V rows ahead of its wait: release it after this kernel's own wait
-      const int pdl_flags = q.pdl ? ((attn_cluster || fuse_cluster) ? 3 : 1) : 0;
-      q.post(launch_gemv(var, pick_grid(c, var, np), st, pdl_flags, pro, rows, epi, D / 4, np, (s->p2p && l > 0) ? c->tp_cluster : 0));
+      const int pdl_flags = (q.pdl ? ((attn_cluster || fuse_cluster) ? 3 : 1) : 0) | nowait;
+      q.post(launch_gemv(var, pick_grid(c, var, np), st, pdl_flags, pro, rows, epi, D / 4, np, want_cluster, q.slot(RAMA_K_QKV)));
     }
     if (fuse_attn_wo) {
       // ---- attention + wo in one launch, per-head partial outputs (infer.rs:34-35) ----
@@ -501,8 +514,9 @@ static int enqueue_step(rama_session* s, cudaStream_t st, int mode, StepTrace* t
       }
       cfg.attrs = at; cfg.numAttrs = na;
       q.pre(RAMA_K_ATTN);
-      if (attn_cluster) q.post(cudaLaunchKernelEx(&cfg, attn_cluster_kernel, ap, q.pdl));
-      else q.post(cudaLaunchKernelEx(&cfg, attn_decode_kernel, ap, q.pdl));
+      unsigned long long* tslot = q.slot(RAMA_K_ATTN);
+      if (attn_cluster) q.post(cudaLaunchKernelEx(&cfg, attn_cluster_kernel, ap, q.pdl, tslot));
+      else q.post(cudaLaunchKernelEx(&cfg, attn_decode_kernel, ap, q.pdl, tslot));
     }
     // ---- wo (infer.rs:35); the residual add (:37) is folded into the next prologue ----
     {
@@ -511,7 +525,7 @@ static int enqueue_step(rama_session* s, cudaStream_t st, int mode, StepTrace* t
       EpiStore epi{s->xb2, D, peer_out(s, 0, l)};
       const int np = D / 2, var = pick_variant(c, Dq / 4, np);
       q.pre(RAMA_K_WO);
-      q.post(launch_gemv(var, pick_grid(c, var, np), st, q.pdl, pro, rows, epi, Dq / 4, np));
+      q.post(launch_gemv(var, pick_grid(c, var, np), st, q.pdl, pro, rows, epi, Dq / 4, np, 0, q.slot(RAMA_K_WO)));
     }
     if (c->world > 1 && !s->p2p) {
       q.pre(RAMA_K_COMM);
@@ -524,11 +538,12 @@ static int enqueue_step(rama_session* s, cudaStream_t st, int mode, StepTrace* t
     {
       ProNorm pro{s->x1, s->xb2, s->x0, W[RAMA_T_RMS_FFN] + (size_t)l * D, nullptr, peer_in(s, 0, l)};
       if (fuse_attn_wo) { pro.add = s->wo_part; pro.n_add = c->H; pro.add_out = s->xb2; }
+      const int nowait = set_peer_reduce(s, pro, 0, q.pdl);
       RowsW13 rows{W[RAMA_T_W1] + (size_t)l * Fl * D, W[RAMA_T_W3] + (size_t)l * Fl * D, D};
       EpiSwiGLU epi{s->hb, s->hb2};
       const int np = Fl, var = pick_variant(c, D / 4, np);
       q.pre(RAMA_K_W13);
-      q.post(launch_gemv(var, pick_grid(c, var, np), st, q.pdl, pro, rows, epi, D / 4, np, s->p2p ? c->tp_cluster : 0));
+      q.post(launch_gemv(var, pick_grid(c, var, np), st, q.pdl | nowait, pro, rows, epi, D / 4, np, (s->p2p && tp_reduce_mode(s) == 1) ? c->tp_cluster : 0, q.slot(RAMA_K_W13)));
     }
     // ---- w2 (infer.rs:46); residual add (:47) folded into the next prologue ----
     {
@@ -537,7 +552,7 @@ static int enqueue_step(rama_session* s, cudaStream_t st, int mode, StepTrace* t
       EpiStore epi{s->w2out, D, peer_out(s, 1, l)};
       const int np = D / 2, var = pick_variant(c, Fl / 4, np);
       q.pre(RAMA_K_W2);
-      q.post(launch_gemv(var, pick_grid(c, var, np), st, q.pdl, pro, rows, epi, Fl / 4, np));
+      q.post(launch_gemv(var, pick_grid(c, var, np), st, q.pdl, pro, rows, epi, Fl / 4, np, 0, q.slot(RAMA_K_W2)));
     }
     if (c->world > 1 && !s->p2p) {
       q.pre(RAMA_K_COMM);
@@ -550,12 +565,13 @@ static int enqueue_step(rama_session* s, cudaStream_t st, int mode, StepTrace* t
   int cls_grid;
   {
     ProNorm pro{s->x0, s->w2out, s->x1, W[RAMA_T_RMS_FINAL], s->xfinal, peer_in(s, 1, L - 1)};
+    const int nowait = set_peer_reduce(s, pro, 1, q.pdl);
     RowsPlain rows{c->wcls, D, c->Vl};
     EpiCls epi = make_epi_cls(s);
     const int np = (c->Vl + 1) / 2, var = pick_variant(c, D / 4);
     cls_grid = pick_grid(c, var, np);
     q.pre(RAMA_K_CLS);
-    q.post(launch_gemv(var, cls_grid, st, q.pdl, pro, rows, epi, D / 4, np));  // (no cluster launch: every one of the cls_grid partial slots must be written)
+    q.post(launch_gemv(var, cls_grid, st, q.pdl | nowait, pro, rows, epi, D / 4, np, 0, q.slot(RAMA_K_CLS)));  // (no cluster launch: every one of the cls_grid partial slots must be written)
   }
   int n_part = cls_grid;
   if (c->world > 1) {
@@ -591,7 +607,7 @@ static int enqueue_step(rama_session* s, cudaStream_t st, int mode, StepTrace* t
       cfg.attrs = at; cfg.numAttrs = 1;
     }
     q.pre(RAMA_K_SAMPLE);
-    q.post(cudaLaunchKernelEx(&cfg, sample_kernel, sp, q.pdl));
+    q.post(cudaLaunchKernelEx(&cfg, sample_kernel, sp, q.pdl, q.slot(RAMA_K_SAMPLE)));
   }
   if (n_launch) *n_launch = q.launches;
   if (q.nccl_err) return fail(RAMA_E_NCCL, "nccl collective in step: %s", g_nccl.GetErrorString(q.nccl_err));
@@ -846,6 +862,83 @@ extern "C" int rama_profile_step(rama_session* s, int32_t token, int32_t pos, fl
   if (rc != RAMA_OK) return rc;
   if (e != cudaSuccess) return fail(RAMA_E_CUDA, "profile step: %s", cudaGetErrorString(e));
   return RAMA_OK;
+}
+
+// In-graph per-kernel timeline of one decode step.  rama_profile_step times every launch with an event pair on an un-graphed
+// stream — launch latency included, no overlap between kernels — and so overstates each kernel by ~20 %; here the step is captured
+// into a CUDA graph exactly like the production one (same launch attributes, programmatic dependent launch included) with a
+// %globaltimer slot per kernel: CTA 0 of each kernel stamps entry, "dependency resolved" (after griddepcontrol.wait), "prologue
+// done" (activations in shared memory; under TP: every peer partial has arrived) and its own end.  The graph is replayed `reps`
+// times at the same (token, pos); the stamps of the last replay are returned in nanoseconds relative to the first stamp.
+// Under tensor parallelism every rank calls this collectively (a group context fans it out; rank 0's stamps are returned).
+extern "C" int rama_step_timeline(rama_session* s, int32_t token, int32_t pos, int32_t mode, int32_t reps, double* stamps_ns,
+                                  int32_t* kinds, int32_t cap, int32_t* n_out) {
+  if (!s || !stamps_ns || !kinds || !n_out) return fail(RAMA_E_INVALID, "NULL argument");
+  if (!s->ranks.empty()) {
+    std::vector<std::vector<double>> st(s->ranks.size(), std::vector<double>((size_t)4 * std::max(cap, 1)));
+    std::vector<std::vector<int32_t>> kd(s->ranks.size(), std::vector<int32_t>((size_t)std::max(cap, 1)));
+    std::vector<int32_t> nn(s->ranks.size(), 0);
+    return group_run(s->ctx, [&](int r) {
+      return r == 0 ? rama_step_timeline(s->ranks[0], token, pos, mode, reps, stamps_ns, kinds, cap, n_out)
+                    : rama_step_timeline(s->ranks[r], token, pos, mode, reps, st[r].data(), kd[r].data(), cap, &nn[r]);
+    });
+  }
+  rama_ctx* c = s->ctx;
+  if (s->persistent) return fail(RAMA_E_STATE, "the persistent step kernel has its own phase trace (rama_step_trace)");
+  if (pos < 0 || pos >= c->T || token < 0 || token >= c->V) return fail(RAMA_E_INVALID, "token/pos out of range");
+  if (mode < 0 || mode > 1 || reps < 1) return fail(RAMA_E_INVALID, "mode must be 0 (forward) or 1 (+ greedy sampler), reps ≥ 1");
+  CK(cudaSetDevice(c->device));
+  CK(session_enter(s));
+  const int max_k = 1 + 5 * c->L + 2;
+  if (cap < max_k) return fail(RAMA_E_INVALID, "need room for %d kernels", max_k);
+  unsigned long long* d = nullptr;
+  CK(cudaMalloc((void**)&d, (size_t)max_k * 4 * sizeof(unsigned long long)));
+  CK(cudaMemset(d, 0, (size_t)max_k * 4 * sizeof(unsigned long long)));
+  set_attn_bucket(s, pos);
+  std::vector<int> kk;
+  cudaGraphExec_t ge = nullptr;
+  int rc = RAMA_OK;
+  {
+    std::lock_guard<std::mutex> cap_lk(c->cap_mu);
+    rc = init_parts(s);
+    cudaGraph_t g = nullptr;
+    if (rc == RAMA_OK && cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) rc = fail(RAMA_E_CUDA, "begin capture");
+    if (rc == RAMA_OK) {
+      int n = 0;
+      rc = enqueue_step(s, s->stream, mode, nullptr, &n, d, &kk);
+      cudaError_t e = cudaStreamEndCapture(s->stream, &g);
+      if (rc == RAMA_OK && e != cudaSuccess) rc = fail(RAMA_E_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+      if (rc == RAMA_OK && cudaGraphInstantiate(&ge, g, 0) != cudaSuccess) rc = fail(RAMA_E_CUDA, "cudaGraphInstantiate");
+      if (g) cudaGraphDestroy(g);
+    }
+  }
+  if (rc == RAMA_OK) {
+    for (int i = 0; i < reps && rc == RAMA_OK; ++i) {
+      StepCtrl* h = &s->h_ring[s->ring_i];
+      if (++s->ring_i == kRing) { s->ring_i = 0; cudaStreamSynchronize(s->stream); }
+      memset(h, 0, sizeof(*h));
+      h->pos = pos; h->token = token; h->chained = 0;
+      if (cudaMemcpyAsync(s->ctrl, h, sizeof(StepCtrl), cudaMemcpyHostToDevice, s->stream) != cudaSuccess ||
+          cudaGraphLaunch(ge, s->stream) != cudaSuccess)
+        rc = fail(RAMA_E_CUDA, "timeline replay: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    if (cudaStreamSynchronize(s->stream) != cudaSuccess) rc = fail(RAMA_E_CUDA, "timeline sync: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+  if (rc == RAMA_OK) {
+    std::vector<unsigned long long> hst((size_t)kk.size() * 4);
+    if (cudaMemcpy(hst.data(), d, hst.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess)
+      rc = fail(RAMA_E_CUDA, "timeline copy");
+    unsigned long long t0 = ~0ull;
+    for (unsigned long long v : hst) if (v && v < t0) t0 = v;
+    for (size_t i = 0; i < hst.size(); ++i) stamps_ns[i] = hst[i] ? (double)(hst[i] - t0) : -1.0;
+    for (size_t i = 0; i < kk.size(); ++i) kinds[i] = kk[i];
+    *n_out = (int32_t)kk.size();
+  }
+  if (ge) cudaGraphExecDestroy(ge);
+  cudaFree(d);
+  s->logits_gathered = false;
+  s->parts_valid = true;
+  return rc;
 }
 
 // Phase timeline of one persistent step: clock64() of CTA 0 at kernel entry and before/after each grid barrier

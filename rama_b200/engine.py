@@ -405,6 +405,36 @@ class Session:
         return {k: (ms[i], ln[i]) for i, k in enumerate(_lib.KERNEL_KINDS)}
 
 
+def step_timeline(session: "Session", token: int, pos: int, mode: int = 0, reps: int = 5):
+    """In-graph per-kernel timeline of one decode step (rama_step_timeline).  Returns a list of dicts
+    {kind, entry, ready, pro, end} (ns relative to the first stamp) in launch order."""
+    cap = 5 * session.cfg.n_layers + 8
+    st = (C.c_double * (4 * cap))()
+    kd = (C.c_int32 * cap)()
+    n = C.c_int32()
+    check(_lib.lib().rama_step_timeline(session.h, token, pos, mode, reps, st, kd, cap, C.byref(n)))
+    return [{"kind": _lib.KERNEL_KINDS[kd[i]], "entry": st[4 * i], "ready": st[4 * i + 1], "pro": st[4 * i + 2], "end": st[4 * i + 3]}
+            for i in range(n.value)]
+
+
+def summarize_timeline(tl) -> Dict[str, Dict[str, float]]:
+    """Per kernel kind, microseconds per step: `chain` = dependency-resolved of this kernel → dependency-resolved of the next
+    (the kernel's share of the step's critical path), split into `prologue` (ready → activations staged / peer partials
+    arrived), `body` (→ CTA 0 done) and `tail` (→ next kernel's dependency resolved: the other CTAs, the grid drain and the
+    dependent-launch hand-over); `early` = how long the kernel was resident before its dependency resolved."""
+    out: Dict[str, Dict[str, float]] = {}
+    for i, k in enumerate(tl):
+        nxt = tl[i + 1]["ready"] if i + 1 < len(tl) else k["end"]
+        a = out.setdefault(k["kind"], {"n": 0, "chain": 0.0, "prologue": 0.0, "body": 0.0, "tail": 0.0, "early": 0.0})
+        a["n"] += 1
+        a["chain"] += (nxt - k["ready"]) * 1e-3
+        a["prologue"] += (k["pro"] - k["ready"]) * 1e-3
+        a["body"] += (k["end"] - k["pro"]) * 1e-3
+        a["tail"] += (nxt - k["end"]) * 1e-3
+        a["early"] += (k["ready"] - k["entry"]) * 1e-3
+    return out
+
+
 class Tokenizer:
     """≙ tokenizer::bpe::Tokenizer (bpe.rs:9-97) + decode() (bpe.rs:102-116) over the C ABI (host code)."""
 

@@ -20,12 +20,15 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("gloo")  # only to hand out the NCCL id; the data path is the library's NCCL
-    cases = [(m, n, st) for m in ("p2p", "nccl", "p2p+persistent") for n, st in (("tiny", 40), ("tiny-sep", 30), ("l7-2layer", 12))]
+    cases = [(m, n, st) for m in ("p2p", "nccl", "p2p+persistent", "p2p+reduce0", "p2p+reduce1", "p2p+reduce2")
+             for n, st in (("tiny", 40), ("tiny-sep", 30), ("l7-2layer", 12))]
     for mode, name, steps in cases:
         # read at rama_ctx_create: fused peer-memory exchange vs NCCL collectives; one kernel per op group vs the
         # persistent cooperative step kernel
         os.environ["RAMA_TP_COMM"] = mode.split("+")[0]
         os.environ["RAMA_STEP"] = "persistent" if mode.endswith("persistent") else "kernels"
+        # how the norm prologues reduce the peer partials: every CTA reads all / cluster-shared / two-phase via a local LL buffer
+        os.environ["RAMA_TP_REDUCE"] = mode[-1] if "reduce" in mode else "-1"
         cfg = ck.CONFIGS[name]
         if cfg.n_heads % world:
             continue
