@@ -40,6 +40,7 @@ struct AttnParams {
   int T, Dq, hs, n_split;
   const float* prefetch;     // next kernel's weights (or nullptr)
   size_t prefetch_bytes;
+  float* out_lo = nullptr;   // optional: tf32 remainder of `out` (the pre-split B operand of the batched wo GEMM)
 };
 
 // One (head h, chunk) work item of the flash-decode pass for the sequence described by p, executed by a
@@ -147,7 +148,9 @@ __device__ __forceinline__ void attn_item(const AttnParams& p, int pos, int h, i
 #pragma unroll 4
     for (int c = 0; c < n_chunks; ++c)
       a += __ldcg(wh + (size_t)c * (hs + 2) + 2 + i) * expf(__ldcg(wh + (size_t)c * (hs + 2)) - M);
-    p.out[(size_t)h * hs + i] = a / L;
+    const float o = a / L;
+    p.out[(size_t)h * hs + i] = o;
+    if (p.out_lo) p.out_lo[(size_t)h * hs + i] = tf32_lo(o);
   }
   if (p.att) {
     for (int t = threadIdx.x; t < n; t += kThreads) {

@@ -54,9 +54,10 @@ static __global__ void __launch_bounds__(256) batch_embed_kernel(const BatchSeq*
 // ≙ array_add (cpu.rs:16-21) + rmsnorm (cpu.rs:99-117); one 1024-thread CTA per sequence, the S partial loads of an
 // element issued back to back (the kernel is pure latency: 64 CTAs, a few KB each)
 constexpr int kBatchNormThreads = 1024;
+// xn_lo (optional): the tf32 remainder plane of xn — xn is the pre-split B operand of the next GEMM (gemm_tf32x3.cuh, PS)
 static __global__ void __launch_bounds__(kBatchNormThreads) batch_addnorm_kernel(float* __restrict__ x, const float* __restrict__ y,
                                                                           int S, size_t slab, const float* __restrict__ w,
-                                                                          float* __restrict__ xn, int D) {
+                                                                          float* __restrict__ xn, int D, float* __restrict__ xn_lo) {
   pdl_launch_dependents(); pdl_wait();  // (no-ops unless launched with programmatic stream serialization)
   __shared__ float red[2 * kWarp];
   const int b = blockIdx.x;
@@ -90,9 +91,12 @@ static __global__ void __launch_bounds__(kBatchNormThreads) batch_addnorm_kernel
   const float scale = 1.0f / sqrtf(ss / (float)D + 1e-5f);
   const float4* w4 = reinterpret_cast<const float4*>(w);
   float4* o = reinterpret_cast<float4*>(xn + (size_t)b * D);
+  float4* ol = xn_lo ? reinterpret_cast<float4*>(xn_lo + (size_t)b * D) : nullptr;
   for (int i = threadIdx.x; i < (D >> 2); i += kBatchNormThreads) {
     const float4 v = xr[i], g = w4[i];
-    o[i] = make_float4(g.x * (scale * v.x), g.y * (scale * v.y), g.z * (scale * v.z), g.w * (scale * v.w));
+    const float4 r = make_float4(g.x * (scale * v.x), g.y * (scale * v.y), g.z * (scale * v.z), g.w * (scale * v.w));
+    o[i] = r;
+    if (ol) ol[i] = tf32_lo4(r);
   }
 }
 
@@ -137,6 +141,7 @@ struct AttnBatchParams {
   unsigned int* tickets; // [B][H]
   size_t layer_off;
   int T, Dq, hs, n_split, H;
+  float* out_lo;         // optional [B][Dq]: tf32 remainder plane of `out` (pre-split B operand of the wo GEMM)
 };
 static __global__ void __launch_bounds__(kAttnThreads) attn_decode_batch_kernel(const AttnBatchParams bp) {
   pdl_launch_dependents(); pdl_wait();  // (no-ops unless launched with programmatic stream serialization)
@@ -153,12 +158,13 @@ static __global__ void __launch_bounds__(kAttnThreads) attn_decode_batch_kernel(
   p.ctrl = nullptr; p.pos_override = sq.pos;
   p.T = bp.T; p.Dq = bp.Dq; p.hs = bp.hs; p.n_split = bp.n_split;
   p.prefetch = nullptr; p.prefetch_bytes = 0;
+  p.out_lo = bp.out_lo ? bp.out_lo + (size_t)b * bp.Dq : nullptr;
   attn_decode_body(p, sq.pos);
 }
 
 // [w1;w3] partials [2][S][B][F] → hb[b][j] = (h1·(1/(1+exp(−h1))))·h3   (cpu.rs:54-64)
 static __global__ void __launch_bounds__(256) batch_swiglu_finish_kernel(const float* __restrict__ part, int S, size_t slab,
-                                                                  float* __restrict__ hb, int F, int B) {
+                                                                  float* __restrict__ hb, int F, int B, float* __restrict__ hb_lo) {
   pdl_launch_dependents(); pdl_wait();  // (no-ops unless launched with programmatic stream serialization)
   const size_t n = (size_t)B * F;
   for (size_t i = blockIdx.x * (size_t)256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
@@ -167,7 +173,9 @@ static __global__ void __launch_bounds__(256) batch_swiglu_finish_kernel(const f
       h1 += part[(size_t)s * slab + i];
       h3 += part[(size_t)(S + s) * slab + i];
     }
-    hb[i] = (h1 * (1.0f / (1.0f + expf(-h1)))) * h3;
+    const float r = (h1 * (1.0f / (1.0f + expf(-h1)))) * h3;
+    hb[i] = r;
+    if (hb_lo) hb_lo[i] = tf32_lo(r);  // pre-split B operand of the w2 GEMM
   }
 }
 

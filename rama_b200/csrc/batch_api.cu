@@ -12,8 +12,18 @@ constexpr int kBatchMax = 64;    // one 64-column MMA tile of sequences
 constexpr int kBatchRing = 8;
 // batched-decode GEMM tile: 128 weight rows × 64 sequences, 2 stages, chunks of 2 k-blocks; two CTAs fit an SM
 // (64 KB of shared memory and 256 TMEM columns each) and interleave their pipelines
-#define BATCH_GEMM launch_gemm_tf32x3<64, 2, 4, 0>  // 128-k chunks as in prefill (CH = 2: 9.18 ms per 64-sequence step)
-constexpr int kBatchCtasPerSm = GemmSmem<64, 2, 0>::kCtasPerSm;
+// Round 2 experiment (RAMA_BATCH_PS=1, off by default): pre-split activations (gemm_tf32x3.cuh PS mode) — the producing kernels
+// write the tf32 remainder plane next to the activations, the GEMM's workers only split the weight k-blocks, two MMAs per k-step
+// instead of three, one CTA per SM with a deep weight ring (kBatchAS × 16 KB in flight per SM).  Parity-green, and measured
+// SLOWER than the round-1 tile (10.5 vs 9.2 ms per 64-sequence step): the role timeline shows the single issuer thread as the
+// bound (907 clk per k-block, 600 of them issuing 8 MMAs), where two round-1 CTAs per SM reach 762 clk per k-block and SM —
+// and the second operand plane doubles the L2 → SM traffic of the activations.  DESIGN.md §4.8.
+constexpr int kBatchAS = 8;
+#define BATCH_GEMM_R1 launch_gemm_tf32x3<64, 2, 4, 0>
+#define BATCH_GEMM_PS launch_gemm_tf32x3<64, 4, 4, 0, kBatchAS, 1>
+constexpr int kBatchCtasPerSmR1 = GemmSmem<64, 2, 0>::kCtasPerSm;
+constexpr int kBatchCtasPerSmPS = GemmSmem<64, 4, 0, kBatchAS, 1>::kCtasPerSm;
+constexpr int kBatchPlane = kBatchMax;  // rows between an activation matrix and its remainder plane
 
 struct rama_batch {
   rama_ctx* ctx = nullptr;
@@ -46,9 +56,13 @@ struct rama_batch {
 
 // split-K factor: the smallest one that fills ≥ 92 % of the CTA slots of its last wave (every extra split writes and
 // re-reads another [n][rows] partial), else the best-filling one; ≥ 8 k-blocks per split
+static int batch_ps(const rama_ctx*) {
+  static const int v = env_int("RAMA_BATCH_PS", 0);
+  return v;
+}
 static int pick_ksplit(const rama_ctx* c, int tiles, int K) {
   const int total_kb = (K + kGemmBK - 1) / kGemmBK;
-  const int slots = c->sm_count * kBatchCtasPerSm;  // CTAs resident at once
+  const int slots = c->sm_count * (batch_ps(c) ? kBatchCtasPerSmPS : kBatchCtasPerSmR1);  // CTAs resident at once
   int best = 1;
   double best_eff = 0.0;
   for (int S = 1; S <= 16; ++S) {
@@ -82,9 +96,11 @@ static int batch_create_rank(rama_ctx* c, int32_t max_seqs, rama_batch** out, bo
   cudaError_t e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
 #define A(call) if (e == cudaSuccess) e = (call)
   b->p2p = c->world > 1 && c->p2p;
-  A(dalloc(&b->x, B * D)); A(dalloc(&b->q, B * Dq)); A(dalloc(&b->att, B * Dq));
-  if (!b->p2p) A(dalloc(&b->xn, B * D));
-  A(dalloc(&b->h, B * Fl)); A(dalloc(&b->part, pf));
+  // xn / att / h are B operands of the GEMMs: [2·64][K] — rows 0..63 the activations, rows 64..127 their tf32 remainders
+  constexpr size_t R2 = 2 * kBatchPlane;
+  A(dalloc(&b->x, B * D)); A(dalloc(&b->q, B * Dq)); A(dalloc(&b->att, R2 * Dq));
+  if (!b->p2p) A(dalloc(&b->xn, R2 * D));
+  A(dalloc(&b->h, R2 * Fl)); A(dalloc(&b->part, pf));
   if (c->world > 1 && !b->p2p) { A(dalloc(&b->red, B * D)); A(dalloc(&b->lstage, (size_t)c->world * B * c->Vl)); }
   A(dalloc(&b->attn_ws, B * c->Hl * b->n_split * (c->hs + 2)));
   A(dalloc(&b->tickets, B * c->Hl));
@@ -104,7 +120,7 @@ static int batch_create_rank(rama_ctx* c, int32_t max_seqs, rama_batch** out, bo
     b->s_max = std::max(pick_ksplit(c, tiles(c->D), c->Dq), pick_ksplit(c, tiles(c->D), c->Fl));
     const size_t bpr_max = (B + c->world - 1) / c->world;
     b->off_xn = al((size_t)c->world * b->s_max * bpr_max * D * sizeof(float));
-    b->off_flags = al(b->off_xn + B * D * sizeof(float));
+    b->off_flags = al(b->off_xn + 2 * kBatchPlane * D * sizeof(float));
     b->off_done = al(b->off_flags + (size_t)3 * c->world * sizeof(unsigned));
     b->off_step = b->off_done + 256;
     int rc = peer_block_alloc(c, b->off_step + 256, &b->blk);
@@ -199,7 +215,16 @@ static int enqueue_batch_step(rama_batch* b, int n, int* n_launch) {
   const bool xchg = b->p2p;
   unsigned* step_counter = xchg ? reinterpret_cast<unsigned*>(b->blk.local + b->off_step) : nullptr;
   LK(launch_k(pdl, batch_embed_kernel, dim3(n), dim3(256), st, b->d_seqs, W[RAMA_T_TOKEN_EMBEDDING], b->x, D, c->V, step_counter));
-  GemmOperand X{b->xn, (size_t)n, (size_t)D};
+  const bool ps = batch_ps(c) != 0;
+  // the batch's activation operands: n rows, or (pre-split) the [128][K] matrix of activations + remainder plane
+  const size_t brows = ps ? 2 * kBatchPlane : (size_t)n;
+  GemmOperand X{b->xn, brows, (size_t)D};
+  float* const xn_lo = ps ? b->xn + (size_t)kBatchPlane * D : nullptr;
+  float* const att_lo = ps ? b->att + (size_t)kBatchPlane * Dq : nullptr;
+  float* const h_lo = ps ? b->h + (size_t)kBatchPlane * Fl : nullptr;
+  auto gemm = [&](const GemmOperand* A, int n_a, const GemmOperand* Bop, int rows, int K, int S, const auto& epi) -> cudaError_t {
+    return ps ? BATCH_GEMM_PS(st, A, n_a, Bop, 1, rows, n, K, 0, S, epi, pdl) : BATCH_GEMM_R1(st, A, n_a, Bop, 1, rows, n, K, 0, S, epi, pdl);
+  };
   // Tensor parallelism over peer memory (tp_exchange.cuh): sequences dealt in blocks of bpr; the wo / w2 GEMMs push their
   // split-K partials to the owners, tp_addnorm sums ranks × splits in fixed order, normalises and stores into every rank's xn.
   const int P = c->world;
@@ -224,6 +249,7 @@ static int enqueue_batch_step(rama_batch* b, int n, int* n_launch) {
     ap.n_slab = P * S; ap.slab_stride = (size_t)bpr * D; ap.w = norm_w;
     for (int r = 0; r < P; ++r) { ap.xn[r] = reinterpret_cast<float*>(b->blk.base[r] + b->off_xn); ap.xlast[r] = nullptr; }
     ap.last_row = -1; ap.row0 = row0; ap.n_rows = n_rows; ap.rpr = bpr; ap.D = D;
+    ap.lo_off = ps ? (size_t)kBatchPlane * D : 0;
     ap.tp = tpp;
     ap.epoch = TpEpoch{step_counter, n_epochs, ++xi};
     ap.done = reinterpret_cast<unsigned*>(b->blk.local + b->off_done);
@@ -250,54 +276,54 @@ static int enqueue_batch_step(rama_batch* b, int n, int* n_launch) {
     if (xchg && l > 0) RK(exchange(S_prev, W[RAMA_T_RMS_ATT] + (size_t)l * D));
     else
     LK(launch_k(pdl, batch_addnorm_kernel, dim3(n), dim3(kBatchNormThreads), st, b->x, S_prev ? pending : nullptr, S_prev,
-                (size_t)n * D, W[RAMA_T_RMS_ATT] + (size_t)l * D, b->xn, D));
+                (size_t)n * D, W[RAMA_T_RMS_ATT] + (size_t)l * D, b->xn, D, xn_lo));
     {  // [wq;wk;wv] (weights = the 128-row operand, the batch = the 64-column operand)   (infer.rs:20-23)
       GemmOperand A[3] = {{W[RAMA_T_WQ] + (size_t)l * Dq * D, (size_t)Dq, (size_t)D},
                           {W[RAMA_T_WK] + (size_t)l * Dq * D, (size_t)Dq, (size_t)D},
                           {W[RAMA_T_WV] + (size_t)l * Dq * D, (size_t)Dq, (size_t)D}};
       const int S = pick_ksplit(c, 3 * tiles(Dq), D);
       EpiStoreT epi{b->part, Dq, n, S, (size_t)n * Dq};
-      LK((BATCH_GEMM(st, A, 3, &X, 1, Dq, n, D, 0, S, epi, pdl)));
+      LK(gemm(A, 3, &X, Dq, D, S, epi));
       LK(launch_k(pdl, batch_qkv_finish_kernel, dim3(n, (Dq / 2 + 255) / 256), dim3(256), st, b->part, S, (size_t)n * Dq, b->d_seqs, layer_off, b->q, W[RAMA_T_FREQ_REAL], W[RAMA_T_FREQ_IMAG], Dq, hs / 2));
     }
     {  // attention per sequence   (infer.rs:34)
-      AttnBatchParams ap{b->d_seqs, b->q, b->att, b->attn_ws, b->tickets, layer_off, T, Dq, hs, b->n_split, c->Hl};
+      AttnBatchParams ap{b->d_seqs, b->q, b->att, b->attn_ws, b->tickets, layer_off, T, Dq, hs, b->n_split, c->Hl, att_lo};
       LK(launch_k(pdl, attn_decode_batch_kernel, dim3(c->Hl, std::min(b->n_split, 2), n), dim3(kAttnThreads), st, ap));  // CTAs stride over the chunks
     }
     int S_wo;
     {  // wo   (infer.rs:35)
       GemmOperand A{W[RAMA_T_WO] + (size_t)l * D * Dq, (size_t)D, (size_t)Dq};
-      GemmOperand Bm{b->att, (size_t)n, (size_t)Dq};
+      GemmOperand Bm{b->att, brows, (size_t)Dq};
       S_wo = pick_ksplit(c, tiles(D), Dq);
       if (xchg) {
-        LK((BATCH_GEMM(st, &A, 1, &Bm, 1, D, n, Dq, 0, S_wo, pusher(S_wo), pdl)));
+        LK(gemm(&A, 1, &Bm, D, Dq, S_wo, pusher(S_wo)));
       } else {
         EpiStoreT epi{b->part, D, n, S_wo, (size_t)n * D};
-        LK((BATCH_GEMM(st, &A, 1, &Bm, 1, D, n, Dq, 0, S_wo, epi, pdl)));
+        LK(gemm(&A, 1, &Bm, D, Dq, S_wo, epi));
       }
       RK(reduce_ranks(S_wo));
     }
     // x += wo output; xn = rmsnorm(x)   (infer.rs:37-38)
     if (xchg) RK(exchange(S_wo, W[RAMA_T_RMS_FFN] + (size_t)l * D));
     else
-    LK(launch_k(pdl, batch_addnorm_kernel, dim3(n), dim3(kBatchNormThreads), st, b->x, pending, S_wo, (size_t)n * D, W[RAMA_T_RMS_FFN] + (size_t)l * D, b->xn, D));
+    LK(launch_k(pdl, batch_addnorm_kernel, dim3(n), dim3(kBatchNormThreads), st, b->x, pending, S_wo, (size_t)n * D, W[RAMA_T_RMS_FFN] + (size_t)l * D, b->xn, D, xn_lo));
     {  // [w1;w3] → SwiGLU   (infer.rs:39-45)
       GemmOperand A[2] = {{W[RAMA_T_W1] + (size_t)l * Fl * D, (size_t)Fl, (size_t)D},
                           {W[RAMA_T_W3] + (size_t)l * Fl * D, (size_t)Fl, (size_t)D}};
       const int S = pick_ksplit(c, 2 * tiles(Fl), D);
       EpiStoreT epi{b->part, Fl, n, S, (size_t)n * Fl};
-      LK((BATCH_GEMM(st, A, 2, &X, 1, Fl, n, D, 0, S, epi, pdl)));
-      LK(launch_k(pdl, batch_swiglu_finish_kernel, dim3(std::min(c->sm_count * 4, (n * Fl + 255) / 256)), dim3(256), st, b->part, S, (size_t)n * Fl, b->h, Fl, n));
+      LK(gemm(A, 2, &X, Fl, D, S, epi));
+      LK(launch_k(pdl, batch_swiglu_finish_kernel, dim3(std::min(c->sm_count * 4, (n * Fl + 255) / 256)), dim3(256), st, b->part, S, (size_t)n * Fl, b->h, Fl, n, h_lo));
     }
     {  // w2   (infer.rs:46)
       GemmOperand A{W[RAMA_T_W2] + (size_t)l * D * Fl, (size_t)D, (size_t)Fl};
-      GemmOperand Bm{b->h, (size_t)n, (size_t)Fl};
+      GemmOperand Bm{b->h, brows, (size_t)Fl};
       S_prev = pick_ksplit(c, tiles(D), Fl);
       if (xchg) {
-        LK((BATCH_GEMM(st, &A, 1, &Bm, 1, D, n, Fl, 0, S_prev, pusher(S_prev), pdl)));
+        LK(gemm(&A, 1, &Bm, D, Fl, S_prev, pusher(S_prev)));
       } else {
         EpiStoreT epi{b->part, D, n, S_prev, (size_t)n * D};
-        LK((BATCH_GEMM(st, &A, 1, &Bm, 1, D, n, Fl, 0, S_prev, epi, pdl)));
+        LK(gemm(&A, 1, &Bm, D, Fl, S_prev, epi));
       }
       RK(reduce_ranks(S_prev));
     }
@@ -305,12 +331,12 @@ static int enqueue_batch_step(rama_batch* b, int n, int* n_launch) {
   // x += w2 output; final rmsnorm; classifier → each session's logits   (infer.rs:49-51)
   if (xchg) RK(exchange(S_prev, W[RAMA_T_RMS_FINAL]));
   else
-  LK(launch_k(pdl, batch_addnorm_kernel, dim3(n), dim3(kBatchNormThreads), st, b->x, pending, S_prev, (size_t)n * D, W[RAMA_T_RMS_FINAL], b->xn, D));
+  LK(launch_k(pdl, batch_addnorm_kernel, dim3(n), dim3(kBatchNormThreads), st, b->x, pending, S_prev, (size_t)n * D, W[RAMA_T_RMS_FINAL], b->xn, D, xn_lo));
   {
     GemmOperand A{c->wcls, (size_t)Vl, (size_t)D};
     const int S = pick_ksplit(c, tiles(Vl), D);
     EpiStoreT epi{b->part, Vl, n, S, (size_t)n * Vl};
-    LK((BATCH_GEMM(st, &A, 1, &X, 1, Vl, n, D, 0, S, epi, pdl)));
+    LK(gemm(&A, 1, &X, Vl, D, S, epi));
     if (xchg) {  // vocabulary rows are split: every rank stores its slice into the sessions' logits on every rank, then a barrier
       LK(launch_k(pdl, batch_cls_push_kernel, dim3(std::min(64, (Vl + 255) / 256), n), dim3(256), st, b->part, S, (size_t)n * Vl, b->d_seqs, Vl, c->v0, P));
       LK(launch_k(pdl, tp_barrier_kernel, dim3(1), dim3(32), st, tpp, TpEpoch{step_counter, n_epochs, n_epochs}, &b->d_err[0]));

@@ -47,6 +47,11 @@ __device__ __forceinline__ float4 ldg_stream(const float4* p) {
   return r;
 }
 
+// Exact remainder of an f32 after the tensor core's tf32 truncation (it ignores the 13 low mantissa bits): the lo plane of a
+// pre-split B operand (gemm_tf32x3.cuh, PS mode); the raw value itself serves as the hi operand.
+__device__ __forceinline__ float tf32_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+__device__ __forceinline__ float4 tf32_lo4(const float4& v) { return make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w)); }
+
 __device__ __forceinline__ float dot4(const float4& a, const float4& b, float acc) {
   acc = fmaf(a.x, b.x, acc);
   acc = fmaf(a.y, b.y, acc);

@@ -45,6 +45,7 @@ inline bool make_tmap_2d(CUtensorMap* m, const float* base, size_t rows, size_t 
            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+inline int g_gemm_pf_rows = -1;   // RAMA_GEMM_PFROWS (read once): k-blocks per L2 row burst of the streamed A operand (0: box prefetch, RAMA_GEMM_PF)
 inline int g_gemm_pf_ahead = -1;  // RAMA_GEMM_PF (read once): k-blocks of L2 prefetch ahead of the ring when the A operand streams from HBM
 inline long long* g_gemm_trace = nullptr;  // debug: set by rama_debug_gemm_trace (device buffer [128][8]) or null
 
@@ -55,13 +56,13 @@ struct GemmOperand {  // a K-major f32 matrix [rows][K], row pitch ld
 
 // C (per group g) = A[ga] · B[gb]ᵀ.  n_a > 1: groups differ in A (weights as the 128-row operand, batched decode);
 // n_b > 1: groups differ in B (prefill QKV); a dual epilogue stacks B[0] on B[1] inside one tile.
-template <int BN, int STAGES, int CH, int NX, int AS = 0, class Epi>
+template <int BN, int STAGES, int CH, int NX, int AS = 0, int PS = 0, int NACC = 2, class Epi>
 cudaError_t launch_gemm_tf32x3(cudaStream_t st, const GemmOperand* A, int n_a, const GemmOperand* B, int n_b, int M,
                                int N, int K, int hi_round, int ksplit, const Epi& epi, bool pdl = false) {
-  using SM = GemmSmem<BN, STAGES, NX, AS>;
+  using SM = GemmSmem<BN, STAGES, NX, AS, PS, NACC>;
   constexpr int BK = kGemmBK;
   static_assert(SM::kTotal <= 227 * 1024, "tile does not fit shared memory");
-  auto kern = gemm_tf32x3_kernel<BN, STAGES, CH, NX, Epi, AS>;
+  auto kern = gemm_tf32x3_kernel<BN, STAGES, CH, NX, Epi, AS, PS, NACC>;
   static std::atomic<unsigned long long> attr_done{0};
   const cudaError_t attr_err = ensure_dyn_smem((const void*)kern, SM::kTotal, attr_done);
   if (attr_err != cudaSuccess) return attr_err;
@@ -69,7 +70,7 @@ cudaError_t launch_gemm_tf32x3(cudaStream_t st, const GemmOperand* A, int n_a, c
   if (n_a > 1 && (n_b > 1 || Epi::kDual)) return cudaErrorInvalidValue;
   GemmMaps maps;
   memset(&maps, 0, sizeof(maps));
-  constexpr int box_n = Epi::kDual ? BN / 2 : BN;
+  constexpr int box_n = Epi::kDual ? BN / 2 : (PS ? 2 * BN : BN);  // PS: the B operand is the pre-split [2·BN][K] matrix
   for (int i = 0; i < 3; ++i) {
     const GemmOperand& a = A[i < n_a ? i : 0];
     const GemmOperand& b = B[i < n_b ? i : 0];
@@ -81,9 +82,18 @@ cudaError_t launch_gemm_tf32x3(cudaStream_t st, const GemmOperand* A, int n_a, c
     g_gemm_pf_ahead = v && *v ? atoi(v) : 2;  // measured on B200 (batched-decode GEMMs, µs): 0 → 70.4/126.5/63.1, 2 → 66.6/119.1/59.8, 8 → 75.9/133.0/68.6
   }
   // only where A is the streamed operand (weights as the 128-row operand: BN = 64, batched decode)
-  GemmShape shp{M, N, K, hi_round, ksplit, n_a > 1 ? 1 : 0, BN == 64 ? g_gemm_pf_ahead : 0, g_gemm_trace};
+  if (g_gemm_pf_rows < 0) {
+    const char* v = getenv("RAMA_GEMM_PFROWS");
+    // measured on B200 (7B decode shapes, round-1 tile): 0 (box prefetch) 9.35 ms per 64-sequence step, 8 → 12.2, 16 → 11.2:
+    // the bursts lose — kept as a run-time option only
+    g_gemm_pf_rows = v && *v ? atoi(v) : 0;
+  }
+  const int pf_rows = BN == 64 ? g_gemm_pf_rows : 0;
+  GemmShape shp{M, N, K, hi_round, ksplit, n_a > 1 ? 1 : 0, (BN == 64 && pf_rows == 0) ? g_gemm_pf_ahead : 0, pf_rows,
+                {A[0].p, A[n_a > 1 ? 1 : 0].p, A[n_a > 2 ? 2 : 0].p}, (long long)A[0].ld, g_gemm_trace};
   const int groups = Epi::kDual ? 1 : std::max(n_a, n_b);
-  dim3 grid((M + kGemmBM - 1) / kGemmBM, (N + box_n - 1) / box_n, groups * ksplit);
+  constexpr int tile_n = Epi::kDual ? BN / 2 : BN;
+  dim3 grid((M + kGemmBM - 1) / kGemmBM, (N + tile_n - 1) / tile_n, groups * ksplit);
   if (grid.y > 65535) return cudaErrorInvalidValue;
   if (pdl) {  // programmatic dependent launch: barrier init / TMEM allocation overlap the previous kernel's tail
     cudaLaunchConfig_t cfg{};

@@ -189,6 +189,13 @@ struct GemmShape {
   int ksplit;      // split-K: blockIdx.z = group·ksplit + split; split s reduces k-blocks [s·nkb/ksplit, (s+1)·nkb/ksplit)
   int group_on_a;  // grouped launch: 1 = groups differ in the A operand (weights as A: batched decode), 0 = in B
   int pf_ahead;    // > 0: the producer L2-prefetches the A box (weights streaming from HBM) this many k-blocks ahead
+  // pf_rows > 0 (instead of pf_ahead): the idle lanes of the producer warp prefetch the A rows into L2 in contiguous bursts of
+  // pf_rows k-blocks (pf_rows · 128 bytes per row), one burst ahead of the TMA loads.  A TMA box touches 128 rows × 128 bytes —
+  // 128 different DRAM pages for 16 KB, and the next 128 bytes of each row only a k-block period later, when the page is long
+  // closed; the bursts make HBM see ≥ 1 KB per opened page and the boxes then hit L2.
+  int pf_rows;
+  const float* a_base[3];  // the A matrices (per group) as plain pointers, for the bursts
+  long long a_ld;          // their row pitch in floats
   long long* trace;  // debug (tools/gemm_trace.py): CTA (0,0,0) stamps clock64() per k-block and role, [128][8]; else nullptr
 };
 
@@ -198,20 +205,31 @@ constexpr int kGemmBK = 32;  // floats per k-block = one 128-byte swizzle row
 // own ring of AS slots that a slot leaves as soon as the workers have split it into TMEM, while the B tile (raw + lo) and the TMEM
 // A slot keep the STAGES-deep ring that the MMAs release.  The long-latency HBM loads then run AS k-blocks ahead inside the same
 // shared-memory budget (AS = 4, STAGES = 2 at BN = 64: 64 + 32 KB = the 96 KB of two coupled 48 KB... stages).
-template <int BN, int STAGES, int NX = 0, int AS = 0>
+// PS = 1 ("pre-split B", batched decode): the B operand arrives already split by the kernel that produced it — a [2·BN][K]
+// matrix whose rows 0..BN-1 are the raw activations (= the hi operand: the tensor core ignores the 13 low mantissa bits) and
+// rows BN..2BN-1 the exact remainders lo = x − trunc_tf32(x).  One TMA box of 2·BN rows per k-block, no worker touches B, and
+// the two products that share A_hi are ONE instruction of width 2·BN (a small-N tcgen05.mma has a floor of ≈55 clk where
+// N = 128 costs 64): per 8-wide k-step  acc[:, 0:2BN] += A_hi · [B_hi | B_lo],  acc[:, 0:BN] += A_lo · B_hi  — 119 clk instead
+// of 3 × 55.  The epilogue adds the two column halves.  Requires the decoupled A ring (AS > 0) and BN = 64.
+template <int BN, int STAGES, int NX = 0, int AS = 0, int PS = 0, int NACC = 2>
 struct GemmSmem {
   static constexpr int kABytes = kGemmBM * kGemmBK * 4;         // raw A k-block (only the workers read it)
-  static constexpr int kBBytes = BN * kGemmBK * 4;              // raw B k-block = hi operand
+  static constexpr int kBBytes = (PS ? 2 * BN : BN) * kGemmBK * 4;  // raw B k-block = hi operand (PS: hi rows then lo rows)
   static constexpr int kTxBytes = kABytes + kBBytes;
-  static constexpr int kStageBytes = AS > 0 ? 2 * kBBytes : kABytes + 2 * kBBytes;  // (+ B lo); coupled: A in front of B
+  static constexpr int kStageBytes = PS ? kBBytes : (AS > 0 ? 2 * kBBytes : kABytes + 2 * kBBytes);  // (+ B lo); coupled: A in front of B
   static constexpr int kARingBytes = AS * kABytes;              // decoupled A ring in front of the stages
   static constexpr int kBOff = AS > 0 ? 0 : kABytes;            // B hi inside a stage
   static constexpr int kBarOff = kARingBytes + STAGES * kStageBytes;
   static constexpr int kNumBars = 3 * STAGES + 4 + 2 * AS;      // full/ready/empty per stage, accfull[2], accfree[2], a_full/a_empty[AS]
   static constexpr int kTotal = kBarOff + kNumBars * 8 + 16 + 1024 /* alignment slack */;
   // TMEM: [0,BN) acc 0 | [BN,2BN) acc 1 | NX cross-term accumulators | then per stage 32 columns A hi + 32 columns A lo
-  static constexpr int kAccCols = (2 + NX) * BN;
+  static constexpr int kAccN = PS ? 2 * BN : BN;                // columns of one accumulator
+  // NACC = 1: a single accumulator instead of the ping-pong pair (the MMAs of the next chunk wait for the drain; meant for
+  // two CTAs per SM, whose pipelines fill each other's bubbles) — halves the accumulator columns
+  static constexpr int kAccCols = (NACC + NX) * kAccN;
+  static_assert(NACC == 1 || NACC == 2, "one accumulator or a ping-pong pair");
   static constexpr int kTmemNeed = kAccCols + 64 * STAGES;
+  static_assert(!PS || (AS > 0 && NX == 0 && BN == 64), "pre-split B: decoupled A ring, BN = 64, no cross accumulators");
   static_assert(kTmemNeed <= 512, "accumulators + A stages exceed tensor memory");
   static_assert(AS % 2 == 0, "the two worker groups alternate k-blocks: an A slot must always belong to the same group");
   static constexpr int kTmemCols = kTmemNeed <= 128 ? 128 : (kTmemNeed <= 256 ? 256 : 512);  // power of two
@@ -241,10 +259,12 @@ struct GemmSmem {
 // where m is the global row, n the first global column of the 32-column chunk; the whole warp calls it
 // (valid = m < M) so an epilogue may shuffle between rows.
 
-template <int BN, int STAGES, int CH, int NX, class Epi, int AS = 0>
-__global__ void __launch_bounds__(kGemmThreads, (GemmSmem<BN, STAGES, NX, AS>::kCtasPerSm))
+template <int BN, int STAGES, int CH, int NX, class Epi, int AS = 0, int PS = 0, int NACC = 2>
+__global__ void __launch_bounds__(kGemmThreads, (GemmSmem<BN, STAGES, NX, AS, PS, NACC>::kCtasPerSm))
 gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, const Epi epi_in) {
-  using SM = GemmSmem<BN, STAGES, NX, AS>;
+  using SM = GemmSmem<BN, STAGES, NX, AS, PS, NACC>;
+  static_assert(NACC == 2 || NX == 0, "cross accumulators sit behind the ping-pong pair");
+  constexpr int AN = SM::kAccN;  // accumulator width in TMEM columns
   constexpr int BK = kGemmBK;
   static_assert(BN == 64 || BN == 128, "BN");
   // the two worker groups take alternate k-blocks: with an even stage count a stage always belongs to the same group,
@@ -262,6 +282,7 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, c
   const uint32_t bar_afull = bar_accfree + 16;             // [AS] raw A k-block landed            (decoupled A ring only)
   const uint32_t bar_aempty = bar_afull + 8 * AS;          // [AS] the group's four warps have read it
   const uint32_t tmem_slot = bar_aempty + 8 * AS;
+  volatile int* pf_progress = reinterpret_cast<volatile int*>(gemm_smem_raw + (base - smem_u32(gemm_smem_raw)) + SM::kBarOff + SM::kNumBars * 8 + 8);
   const uint32_t stage0 = base + SM::kARingBytes;          // first (B) stage
   uint8_t* gen_base = gemm_smem_raw + (base - smem_u32(gemm_smem_raw));
 
@@ -283,6 +304,7 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, c
   const CUtensorMap* mapB0 = &maps.b[(Epi::kDual || shp.group_on_a) ? 0 : group];
 
   if (warp == 0 && lane == 0) {
+    *pf_progress = 0;
     tma_prefetch_desc(mapA);
     tma_prefetch_desc(mapB0);
     if (Epi::kDual) tma_prefetch_desc(&maps.b[1]);
@@ -311,6 +333,19 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, c
 
   if (warp == 0) {
     // ===== TMA producer =====
+    if (shp.pf_rows > 0 && lane > 0) {  // lanes 1..31: row bursts into L2, one burst ahead of lane 0's loads
+      const float* ab = shp.a_base[shp.group_on_a ? group : 0];
+      const int R = shp.pf_rows;
+      const int nburst = (num_kb + R - 1) / R;
+      for (int c = 0; c < nburst; ++c) {
+        while (c >= 2 && *pf_progress < (c - 1) * R) __nanosleep(64);  // bursts 0 and 1 right away
+        const int k0 = (kb_begin + c * R) * BK;
+        const int kn = min(R * BK, shp.K - k0);
+        if (kn > 0)
+          for (int r = lane - 1; r < kGemmBM; r += 31)
+            if (m0 + r < shp.M) l2_prefetch_bulk(ab + (size_t)(m0 + r) * (size_t)shp.a_ld + k0, (uint32_t)kn * 4u);
+      }
+    }
     // (the role loops are single threads on the critical path of a k-block: running counters, no divisions)
     if constexpr (AS > 0) {
       // two independent rings fed by one polling thread: A (weights, HBM latency) runs up to AS k-blocks ahead and is gated by
@@ -331,6 +366,7 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, c
               mbar_arrive_expect_tx(bar_afull + 8 * sa, SM::kABytes);
               tma_load_2d(base + sa * SM::kABytes, mapA, bar_afull + 8 * sa, (kb_begin + ka) * BK, m0);
               ++ka;
+              *pf_progress = ka;
             }
           }
           if (kbb < num_kb) {
@@ -355,6 +391,7 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, c
           tma_prefetch_l2_2d(mapA, kc + (STAGES + shp.pf_ahead) * BK, m0);
         mbar_wait(be, ph);
         RAMA_GEMM_TR(kb, 0);
+        *pf_progress = kb;
         mbar_arrive_expect_tx(bf, SM::kTxBytes);
         tma_load_2d(st, mapA, bf, kc, m0);
         if (Epi::kDual) {
@@ -373,6 +410,7 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, c
     // (constant high word, base low word + a small offset) — one 32-bit add per operand.
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_tf32<BN>();
+      constexpr uint32_t idesc2 = umma_idesc_tf32<2 * BN <= 256 ? 2 * BN : BN>();  // PS: A_hi · [B_hi | B_lo]
       const uint64_t d0 = umma_smem_desc<BK>(stage0 + SM::kBOff);  // B hi of stage 0, k-step 0
       const uint32_t d_hi32 = (uint32_t)(d0 >> 32), d_lo32 = (uint32_t)d0;
       auto desc = [&](uint32_t lo) { return ((uint64_t)d_hi32 << 32) | lo; };
@@ -380,9 +418,10 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, c
       uint32_t ph = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
         const bool first = in_ch == 0, last = (in_ch == CH - 1) || kb == num_kb - 1;
-        const uint32_t acc = tmem + (ch & 1) * BN;
-        if (first && ch >= 2) {  // acc[ch&1] still holds chunk ch-2 until the workers have drained it
-          mbar_wait(bar_accfree + 8 * (ch & 1), ((ch >> 1) - 1) & 1);  // (the fence after the `ready` wait below covers this one too)
+        const int ab = NACC == 2 ? (ch & 1) : 0;  // accumulator of this chunk
+        const uint32_t acc = tmem + ab * AN;
+        if (first && ch >= NACC) {  // it still holds chunk ch-NACC until the workers have drained it
+          mbar_wait(bar_accfree + 8 * ab, (NACC == 2 ? (ch >> 1) - 1 : ch - 1) & 1);  // (the fence after the `ready` wait below covers this one too)
           RAMA_GEMM_TR(kb, 7);
         }
         mbar_wait(bar_ready + 8 * s, ph);
@@ -391,7 +430,17 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, c
         const uint32_t bh = d_lo32 + s * (SM::kStageBytes >> 4), bl = bh + (SM::kBBytes >> 4);
         const uint32_t a_hi = tmem_a + 64 * s, a_lo = a_hi + 32;
         // 8 tf32 = 32 bytes = 2 descriptor units inside the swizzle row; TMEM A: 8 columns per k-step
-        if constexpr (NX == 0) {
+        if constexpr (PS) {
+          // Measured (role timeline, 8 MMAs per k-block): alternating N = 128 / N = 64 instructions issue at ≈82 clk each — a
+          // change of instruction shape costs a bubble.  So the four wide products go first, then the narrow ones (PS = 1), or
+          // every product is wide (PS = 2: A_lo · [B_hi | B_lo] also adds the lo·lo term — 64 clk instead of 55, one shape).
+#pragma unroll
+          for (int ks = 0; ks < BK / 8; ++ks)
+            umma_tf32_ts(acc, a_hi + 8 * ks, desc(bh + 2 * ks), idesc2, !(first && ks == 0));  // both column halves (initialises them)
+#pragma unroll
+          for (int ks = 0; ks < BK / 8; ++ks)
+            umma_tf32_ts(acc, a_lo + 8 * ks, desc(bh + 2 * ks), PS == 2 ? idesc2 : idesc, 1);  // PS = 1: rows 0..BN-1 of the tile = B_hi
+        } else if constexpr (NX == 0) {
 #pragma unroll
           for (int ks = 0; ks < BK / 8; ++ks) {
             umma_tf32_ts(acc, a_lo + 8 * ks, desc(bh + 2 * ks), idesc, !(first && ks == 0));  // small terms first
@@ -416,7 +465,7 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, c
           XA(2, 1); XB(2); XA(3, 1); XB(3);
         }
         umma_commit(bar_empty + 8 * s);  // smem stage + TMEM A stage reusable once these MMAs have read them
-        if (last) umma_commit(bar_accfull + 8 * (ch & 1));
+        if (last) umma_commit(bar_accfull + 8 * ab);
         RAMA_GEMM_TR(kb, 4);
         if (++s == STAGES) { s = 0; ph ^= 1; }
         if (++in_ch == CH) { in_ch = 0; ++ch; }
@@ -437,17 +486,22 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, c
 
     int drained = 0;
     auto drain = [&](int c) {  // acc += acc_tmem[c&1] (chunk c), then hand the buffer back
-      const int b = c & 1;
+      const int b = NACC == 2 ? (c & 1) : 0;
       if (quarter == 0 && lane == 0) RAMA_GEMM_TR(2 * c + half, 5);
-      mbar_wait(bar_accfull + 8 * b, (c >> 1) & 1);
+      mbar_wait(bar_accfull + 8 * b, (NACC == 2 ? (c >> 1) : c) & 1);
       tc_fence_after();
       if (quarter == 0 && lane == 0) RAMA_GEMM_TR(2 * c + half, 6);
 #pragma unroll
       for (int j = 0; j < NSEG; ++j) {
         float v[32];
-        tmem_ld_32x32(trow + b * BN + seg_col(j), v);
+        tmem_ld_32x32(trow + b * AN + seg_col(j), v);
 #pragma unroll
         for (int i = 0; i < 32; ++i) acc[j][i] += v[i];
+        if constexpr (PS) {  // the A_hi · B_lo products live in the upper column half
+          tmem_ld_32x32(trow + b * AN + BN + seg_col(j), v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc[j][i] += v[i];
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -501,7 +555,7 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, c
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_aempty + 8 * (kb % AS));
       }
-      {
+      if constexpr (!PS) {
         const float4* braw = reinterpret_cast<const float4*>(st + SM::kBOff);
         float4* bhi = reinterpret_cast<float4*>(const_cast<uint8_t*>(st) + SM::kBOff);
         float4* blo = reinterpret_cast<float4*>(const_cast<uint8_t*>(st) + SM::kBOff + SM::kBBytes);
@@ -525,7 +579,7 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, c
           blo[i] = l;
         }
       }
-      fence_proxy_async_smem();  // generic-proxy writes → visible to the tensor core's async proxy
+      if constexpr (!PS) fence_proxy_async_smem();  // generic-proxy writes → visible to the tensor core's async proxy
       tmem_st_wait();            // A halves have landed in TMEM
       tc_fence_before();
       __syncwarp();

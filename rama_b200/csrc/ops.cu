@@ -218,6 +218,15 @@ extern "C" int rama_bench_gemv(rama_ctx* c, float* o, const float* w, const floa
   return RAMA_OK;
 }
 
+// rows 0..N-1 of dst = src, rows plane.. = the tf32 remainders (pre-split B operand, gemm_tf32x3.cuh PS mode)
+static __global__ void split_rows_kernel(float* __restrict__ dst, const float* __restrict__ src, size_t N, size_t K, size_t plane) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < N * K; i += (size_t)gridDim.x * blockDim.x) {
+    const float v = src[i];
+    dst[i] = v;
+    dst[plane + i] = tf32_lo(v);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // tensor-core contraction (tcgen05, 3xTF32): C[M][N] = A[M][K] · B[N][K]^T
 // ------------------------------------------------------------------------------------------------
@@ -244,6 +253,21 @@ extern "C" int rama_op_matmul_nt(rama_ctx* c, float* out, const float* a, const 
       case 3: e = launch_gemm_tf32x3<64, 2, 2, 0>(c->op_stream, &A, 1, &B, 1, m, n, k, hi_round, ksplit, epi); break;  // 2 CTAs/SM
       case 4: e = launch_gemm_tf32x3<64, 2, 4, 0>(c->op_stream, &A, 1, &B, 1, m, n, k, hi_round, ksplit, epi); break;  // + 128-k chunks
       case 5: e = launch_gemm_tf32x3<64, 2, 2, 0, 4>(c->op_stream, &A, 1, &B, 1, m, n, k, hi_round, ksplit, epi); break;  // decoupled A ring
+      case 6: case 7: case 8: case 9: {  // pre-split B (the batched-decode tile of round 2): build the [128][K] activations + remainder matrix first
+        if (N > 64) return fail(RAMA_E_INVALID, "matmul_nt: the pre-split variant takes N ≤ 64 columns");
+        float* bs = nullptr;
+        CK(cudaMallocAsync((void**)&bs, (size_t)128 * K * sizeof(float), c->op_stream));
+        CK(cudaMemsetAsync(bs, 0, (size_t)128 * K * sizeof(float), c->op_stream));
+        split_rows_kernel<<<c->sm_count * 2, 256, 0, c->op_stream>>>(bs, b, N, K, (size_t)64 * K);
+        GemmOperand Bs{bs, 128, K};
+        if (variant == 6) e = launch_gemm_tf32x3<64, 4, 4, 0, 8, 1>(c->op_stream, &A, 1, &Bs, 1, m, n, k, hi_round, ksplit, epi);
+        else if (variant == 7) e = launch_gemm_tf32x3<64, 4, 4, 0, 8, 2>(c->op_stream, &A, 1, &Bs, 1, m, n, k, hi_round, ksplit, epi);  // all products wide
+        // two CTAs per SM: one accumulator, two B / TMEM-A stages and a 4-slot weight ring each (96 KB, 256 TMEM columns)
+        else if (variant == 8) e = launch_gemm_tf32x3<64, 2, 4, 0, 4, 1, 1>(c->op_stream, &A, 1, &Bs, 1, m, n, k, hi_round, ksplit, epi);
+        else e = launch_gemm_tf32x3<64, 2, 4, 0, 4, 2, 1>(c->op_stream, &A, 1, &Bs, 1, m, n, k, hi_round, ksplit, epi);
+        CK(cudaFreeAsync(bs, c->op_stream));
+        break;
+      }
       default: return fail(RAMA_E_INVALID, "matmul_nt: unknown transposed variant %d", variant);
     }
     if (ksplit > 1) {

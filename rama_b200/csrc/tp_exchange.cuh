@@ -79,6 +79,7 @@ struct TpAddNormParams {
   size_t slab_stride;     // floats between slabs (rpr · D)
   const float* w;         // rmsnorm weight, or null: residual add only (last exchange of a prefill pass)
   float* xn[kMaxPeers];   // every rank's normalised-activation buffer [rows][D] (peer-mapped)
+  size_t lo_off;          // > 0: also store the tf32 remainder of the row at xn + lo_off (pre-split B operand, batched decode)
   float* xlast[kMaxPeers];  // optional: every rank's x0[D] receives the updated residual of global row last_row
   int last_row;
   int row0, n_rows, rpr;  // this rank owns global rows [row0, row0 + n_rows)
@@ -144,6 +145,12 @@ static __global__ void __launch_bounds__(kTpNormThreads) tp_addnorm_kernel(const
 #pragma unroll
         for (int q = 0; q < kMaxPeers; ++q)  // all-gather by remote stores: the row lands in every rank's xn
           if (q < p.tp.P) reinterpret_cast<float4*>(p.xn[q] + (size_t)m * p.D)[c] = o;
+        if (p.lo_off) {
+          const float4 ol = tf32_lo4(o);
+#pragma unroll
+          for (int q = 0; q < kMaxPeers; ++q)
+            if (q < p.tp.P) reinterpret_cast<float4*>(p.xn[q] + p.lo_off + (size_t)m * p.D)[c] = ol;
+        }
       }
     }
   }

@@ -47,11 +47,19 @@ def test_matmul_nt_f32_accuracy(gpu, shape, variant):
     assert err < max(8 * ref_err, 6e-6), (err, ref_err)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9])  # 6-9: pre-split B operand (the batched-decode tiles of round 2)
 @pytest.mark.parametrize("shape", [(4096, 64, 4096), (11008, 64, 4096), (4096, 64, 11008), (288, 3, 288), (1000, 17, 64)])
 def test_matmul_nt_transposed_store(gpu, shape, variant):
     M, N, K = shape
     err, ref_err = run(gpu, M, N, K, variant, 2)
+    assert err < max(8 * ref_err, 6e-6), (err, ref_err)
+
+
+@pytest.mark.parametrize("variant", [4, 6, 8])
+@pytest.mark.parametrize("ksplit", [2, 5])
+def test_matmul_nt_transposed_split_k(gpu, variant, ksplit):
+    """split-K partials summed in fixed order (flags bits 8..15 = split factor), uneven k-block counts per split"""
+    err, ref_err = run(gpu, 4096, 64, 4096 + 96, variant, 2 | (ksplit << 8))
     assert err < max(8 * ref_err, 6e-6), (err, ref_err)
 
 
