@@ -237,16 +237,18 @@ static int enqueue_batch_step(rama_batch* b, int n, int* n_launch) {
     tpp.P = P; tpp.me = c->rank;
     for (int r = 0; r < P; ++r) tpp.flags[r] = reinterpret_cast<unsigned*>(b->blk.base[r] + b->off_flags);
   }
-  auto pusher = [&](int S) {
-    EpiPushT e{};
-    for (int r = 0; r < P; ++r) e.inbox[r] = reinterpret_cast<float*>(b->blk.base[r]);
-    e.bpr = bpr; e.me = c->rank; e.ldc = D; e.N = n; e.ksplit = S;
-    return e;
+  // this rank's split-K partials [S][n][D] → summed, every reduced row stored once into its owner's inbox (slab = this rank)
+  auto sum_push = [&](int S) -> int {
+    TpInboxes ib{};
+    for (int r = 0; r < P; ++r) ib.p[r] = reinterpret_cast<float*>(b->blk.base[r]);
+    LK(launch_k(pdl, tp_sum_push_kernel, dim3((D / 4 + 255) / 256, n), dim3(256), st, (const float*)b->part, S, (size_t)n * D, ib, bpr, c->rank, D));
+    return RAMA_OK;
   };
   auto exchange = [&](int S, const float* norm_w) -> int {
     TpAddNormParams ap{};
     ap.x = b->x; ap.inbox = reinterpret_cast<const float*>(b->blk.local);
-    ap.n_slab = P * S; ap.slab_stride = (size_t)bpr * D; ap.w = norm_w;
+    (void)S;
+    ap.n_slab = P; ap.slab_stride = (size_t)bpr * D; ap.w = norm_w;
     for (int r = 0; r < P; ++r) { ap.xn[r] = reinterpret_cast<float*>(b->blk.base[r] + b->off_xn); ap.xlast[r] = nullptr; }
     ap.last_row = -1; ap.row0 = row0; ap.n_rows = n_rows; ap.rpr = bpr; ap.D = D;
     ap.lo_off = ps ? (size_t)kBatchPlane * D : 0;
@@ -295,12 +297,9 @@ static int enqueue_batch_step(rama_batch* b, int n, int* n_launch) {
       GemmOperand A{W[RAMA_T_WO] + (size_t)l * D * Dq, (size_t)D, (size_t)Dq};
       GemmOperand Bm{b->att, brows, (size_t)Dq};
       S_wo = pick_ksplit(c, tiles(D), Dq);
-      if (xchg) {
-        LK(gemm(&A, 1, &Bm, D, Dq, S_wo, pusher(S_wo)));
-      } else {
-        EpiStoreT epi{b->part, D, n, S_wo, (size_t)n * D};
-        LK(gemm(&A, 1, &Bm, D, Dq, S_wo, epi));
-      }
+      EpiStoreT epi{b->part, D, n, S_wo, (size_t)n * D};
+      LK(gemm(&A, 1, &Bm, D, Dq, S_wo, epi));
+      if (xchg) RK(sum_push(S_wo));
       RK(reduce_ranks(S_wo));
     }
     // x += wo output; xn = rmsnorm(x)   (infer.rs:37-38)
@@ -319,12 +318,9 @@ static int enqueue_batch_step(rama_batch* b, int n, int* n_launch) {
       GemmOperand A{W[RAMA_T_W2] + (size_t)l * D * Fl, (size_t)D, (size_t)Fl};
       GemmOperand Bm{b->h, brows, (size_t)Fl};
       S_prev = pick_ksplit(c, tiles(D), Fl);
-      if (xchg) {
-        LK(gemm(&A, 1, &Bm, D, Fl, S_prev, pusher(S_prev)));
-      } else {
-        EpiStoreT epi{b->part, D, n, S_prev, (size_t)n * D};
-        LK(gemm(&A, 1, &Bm, D, Fl, S_prev, epi));
-      }
+      EpiStoreT epi{b->part, D, n, S_prev, (size_t)n * D};
+      LK(gemm(&A, 1, &Bm, D, Fl, S_prev, epi));
+      if (xchg) RK(sum_push(S_prev));
       RK(reduce_ranks(S_prev));
     }
   }

@@ -56,13 +56,13 @@ struct GemmOperand {  // a K-major f32 matrix [rows][K], row pitch ld
 
 // C (per group g) = A[ga] · B[gb]ᵀ.  n_a > 1: groups differ in A (weights as the 128-row operand, batched decode);
 // n_b > 1: groups differ in B (prefill QKV); a dual epilogue stacks B[0] on B[1] inside one tile.
-template <int BN, int STAGES, int CH, int NX, int AS = 0, int PS = 0, int NACC = 2, class Epi>
+template <int BN, int STAGES, int CH, int NX, int AS = 0, int PS = 0, int NACC = 2, int PAIR = 0, class Epi>
 cudaError_t launch_gemm_tf32x3(cudaStream_t st, const GemmOperand* A, int n_a, const GemmOperand* B, int n_b, int M,
                                int N, int K, int hi_round, int ksplit, const Epi& epi, bool pdl = false) {
-  using SM = GemmSmem<BN, STAGES, NX, AS, PS, NACC>;
+  using SM = GemmSmem<BN, STAGES, NX, AS, PS, NACC, PAIR>;
   constexpr int BK = kGemmBK;
   static_assert(SM::kTotal <= 227 * 1024, "tile does not fit shared memory");
-  auto kern = gemm_tf32x3_kernel<BN, STAGES, CH, NX, Epi, AS, PS, NACC>;
+  auto kern = gemm_tf32x3_kernel<BN, STAGES, CH, NX, Epi, AS, PS, NACC, PAIR>;
   static std::atomic<unsigned long long> attr_done{0};
   const cudaError_t attr_err = ensure_dyn_smem((const void*)kern, SM::kTotal, attr_done);
   if (attr_err != cudaSuccess) return attr_err;
@@ -70,7 +70,8 @@ cudaError_t launch_gemm_tf32x3(cudaStream_t st, const GemmOperand* A, int n_a, c
   if (n_a > 1 && (n_b > 1 || Epi::kDual)) return cudaErrorInvalidValue;
   GemmMaps maps;
   memset(&maps, 0, sizeof(maps));
-  constexpr int box_n = Epi::kDual ? BN / 2 : (PS ? 2 * BN : BN);  // PS: the B operand is the pre-split [2·BN][K] matrix
+  // PS: the B operand is the pre-split [2·BN][K] matrix; PAIR: each CTA of the pair loads half of the B tile
+  constexpr int box_n = (Epi::kDual || PAIR) ? BN / 2 : (PS ? 2 * BN : BN);
   for (int i = 0; i < 3; ++i) {
     const GemmOperand& a = A[i < n_a ? i : 0];
     const GemmOperand& b = B[i < n_b ? i : 0];
@@ -94,18 +95,28 @@ cudaError_t launch_gemm_tf32x3(cudaStream_t st, const GemmOperand* A, int n_a, c
   const int groups = Epi::kDual ? 1 : std::max(n_a, n_b);
   constexpr int tile_n = Epi::kDual ? BN / 2 : BN;
   dim3 grid((M + kGemmBM - 1) / kGemmBM, (N + tile_n - 1) / tile_n, groups * ksplit);
+  if (PAIR) grid.x = (grid.x + 1) / 2 * 2;  // whole pairs: a CTA beyond M loads zeros (TMA out-of-bounds fill) and stores nothing
   if (grid.y > 65535) return cudaErrorInvalidValue;
-  if (pdl) {  // programmatic dependent launch: barrier init / TMEM allocation overlap the previous kernel's tail
+  if (pdl || PAIR) {  // programmatic dependent launch: barrier init / TMEM allocation overlap the previous kernel's tail
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;
     cfg.blockDim = dim3(kGemmThreads);
     cfg.dynamicSmemBytes = SM::kTotal;
     cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute at[2];
+    int na = 0;
+    if (pdl) {
+      at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[na].val.programmaticStreamSerializationAllowed = 1;
+      ++na;
+    }
+    if (PAIR) {  // the two CTAs of a pair sit on the two SMs of one TPC
+      at[na].id = cudaLaunchAttributeClusterDimension;
+      at[na].val.clusterDim.x = 2; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+      ++na;
+    }
     cfg.attrs = at;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = na;
     return cudaLaunchKernelEx(&cfg, kern, maps, shp, epi);
   }
   kern<<<grid, kGemmThreads, SM::kTotal, st>>>(maps, shp, epi);

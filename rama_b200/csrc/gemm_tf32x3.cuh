@@ -35,6 +35,12 @@
 
 namespace rama {
 
+// epilogues that re-tile their 32×32 block through shared memory declare a `float* scratch` member (tp_exchange.cuh EpiPushNT)
+template <class T, class = void>
+struct epi_has_scratch { static constexpr bool value = false; };
+template <class T>
+struct epi_has_scratch<T, decltype((void)((T*)nullptr)->scratch)> { static constexpr bool value = true; };
+
 constexpr int kGemmBM = 128;
 constexpr int kGemmWorkerWarps = 8;
 constexpr int kGemmThreads = (2 + kGemmWorkerWarps) * kWarp;  // 320
@@ -158,6 +164,54 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// ---- CTA pair (cta_group::2): two CTAs of a cluster on the two SMs of a TPC issue ONE MMA of M = 256 ----------------------
+// mbarrier arrive on the barrier at the same shared-memory offset in CTA `rank` of this cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t local_bar, unsigned rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_bar), "r"(rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(r) : "memory");
+}
+// wait on a local barrier whose arrivals may come from the peer CTA (cluster-scope acquire)
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAITC_%=:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONEC_%=;\n\t"
+      "bra WAITC_%=;\n\t"
+      "DONEC_%=:\n\t"
+      "}" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t smem_dst) {  // one whole warp in EACH CTA of the pair, same smem_dst
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "n"(COLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {  // one whole warp in each CTA
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+// D[tmem, both CTAs: 128 rows each] (+)= A[tmem, 128 rows per CTA] · B[smem desc: N/2 rows in each CTA], issued by the leader
+__device__ __forceinline__ void umma_tf32_ts_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  const uint32_t z = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(z)
+      : "memory");
+}
+// arrive on the barrier at this offset in BOTH CTAs of the pair once all MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((unsigned short)3)
+               : "memory");
+}
+
 // K-major shared-memory matrix descriptor (sm_100 format): rows of BK·4 bytes, 8-row groups of
 // 8·BK·4 bytes back to back, swizzle = row bytes (64 B or 128 B).  `addr` is the tile base
 // (1024-byte aligned) plus the k-step offset inside the swizzle row.
@@ -171,10 +225,10 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t addr) {
          (1ull << 46) /* descriptor version: Blackwell */ | (layout << 61);
 }
 
-template <int BN>
+template <int BN, int BM = kGemmBM>
 __host__ __device__ constexpr uint32_t umma_idesc_tf32() {
   // c_format F32 (bit 4), a/b_format TF32 = 2 (bits 7-9, 10-12), both K-major, N>>3 at 17, M>>4 at 24
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kGemmBM >> 4) << 24);
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
 // ---- kernel parameters ------------------------------------------------------------------------------
@@ -211,10 +265,15 @@ constexpr int kGemmBK = 32;  // floats per k-block = one 128-byte swizzle row
 // the two products that share A_hi are ONE instruction of width 2·BN (a small-N tcgen05.mma has a floor of ≈55 clk where
 // N = 128 costs 64): per 8-wide k-step  acc[:, 0:2BN] += A_hi · [B_hi | B_lo],  acc[:, 0:BN] += A_lo · B_hi  — 119 clk instead
 // of 3 × 55.  The epilogue adds the two column halves.  Requires the decoupled A ring (AS > 0) and BN = 64.
-template <int BN, int STAGES, int NX = 0, int AS = 0, int PS = 0, int NACC = 2>
+// PAIR = 1 (prefill, BN = 128): a CTA pair computes a 256×BN tile with tcgen05.mma.cta_group::2 — each CTA keeps its own 128 rows
+// of A in TMEM and only HALF of the B k-block (BN/2 rows: raw + lo) in shared memory; the pair's tensor cores share the halves.
+// Shared-memory bytes per k-block and SM fall from 128 KB to 80 KB (TMA 24, worker reads 24, B_lo 8, MMA 24), below what the
+// MMAs need (the single-CTA tile is bound by the shared-memory port at 109 of 128 B/clk).
+template <int BN, int STAGES, int NX = 0, int AS = 0, int PS = 0, int NACC = 2, int PAIR = 0>
 struct GemmSmem {
   static constexpr int kABytes = kGemmBM * kGemmBK * 4;         // raw A k-block (only the workers read it)
-  static constexpr int kBBytes = (PS ? 2 * BN : BN) * kGemmBK * 4;  // raw B k-block = hi operand (PS: hi rows then lo rows)
+  static constexpr int kBBytes = (PS ? 2 * BN : (PAIR ? BN / 2 : BN)) * kGemmBK * 4;  // raw B k-block = hi operand (PS: hi rows then lo rows; PAIR: this CTA's half)
+  static_assert(!PAIR || (AS == 0 && PS == 0 && NX == 0 && BN == 128 && NACC == 2), "CTA pair: the coupled BN = 128 tile");
   static constexpr int kTxBytes = kABytes + kBBytes;
   static constexpr int kStageBytes = PS ? kBBytes : (AS > 0 ? 2 * kBBytes : kABytes + 2 * kBBytes);  // (+ B lo); coupled: A in front of B
   static constexpr int kARingBytes = AS * kABytes;              // decoupled A ring in front of the stages
@@ -259,10 +318,15 @@ struct GemmSmem {
 // where m is the global row, n the first global column of the 32-column chunk; the whole warp calls it
 // (valid = m < M) so an epilogue may shuffle between rows.
 
-template <int BN, int STAGES, int CH, int NX, class Epi, int AS = 0, int PS = 0, int NACC = 2>
-__global__ void __launch_bounds__(kGemmThreads, (GemmSmem<BN, STAGES, NX, AS, PS, NACC>::kCtasPerSm))
+template <int BN, int STAGES, int CH, int NX, class Epi, int AS = 0, int PS = 0, int NACC = 2, int PAIR = 0>
+__global__ void __launch_bounds__(kGemmThreads, (GemmSmem<BN, STAGES, NX, AS, PS, NACC, PAIR>::kCtasPerSm))
 gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, const Epi epi_in) {
-  using SM = GemmSmem<BN, STAGES, NX, AS, PS, NACC>;
+  using SM = GemmSmem<BN, STAGES, NX, AS, PS, NACC, PAIR>;
+  // CTA pair: rank inside the 2-CTA cluster (0 = the leader, which issues the MMAs for both)
+  const unsigned crank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = crank == 0;
+  constexpr int kWorkersPerReady = (kGemmWorkerWarps / 2) * (PAIR ? 2 : 1);  // arrivals that complete a stage's `ready`
+  constexpr int kWorkersPerFree = kGemmWorkerWarps * (PAIR ? 2 : 1);         // … an accumulator's `accfree`
   static_assert(NACC == 2 || NX == 0, "cross accumulators sit behind the ping-pong pair");
   constexpr int AN = SM::kAccN;  // accumulator width in TMEM columns
   constexpr int BK = kGemmBK;
@@ -310,12 +374,12 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, c
     if (Epi::kDual) tma_prefetch_desc(&maps.b[1]);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_ready + 8 * s, kGemmWorkerWarps / 2);  // the four warps of the group that owns the k-block
+      mbar_init(bar_ready + 8 * s, kWorkersPerReady);  // the four warps of the group that owns the k-block (pair: of both CTAs)
       mbar_init(bar_empty + 8 * s, 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_accfull + 8 * b, 1);
-      mbar_init(bar_accfree + 8 * b, kGemmWorkerWarps);
+      mbar_init(bar_accfree + 8 * b, kWorkersPerFree);
     }
     for (int a = 0; a < AS; ++a) {
       mbar_init(bar_afull + 8 * a, 1);
@@ -323,9 +387,13 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, c
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<SM::kTmemCols>(tmem_slot);
+  if (warp == 1) {
+    if constexpr (PAIR) tmem_alloc_pair<SM::kTmemCols>(tmem_slot);
+    else tmem_alloc<SM::kTmemCols>(tmem_slot);
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();  // the peer's barriers are initialised before anyone arrives on them remotely
+  else __syncthreads();
   tc_fence_after();
   pdl_wait();  // the operands (and the buffers the epilogue overwrites) belong to the previous kernel until here
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen_base + SM::kBarOff + SM::kNumBars * 8);
@@ -394,7 +462,10 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, c
         *pf_progress = kb;
         mbar_arrive_expect_tx(bf, SM::kTxBytes);
         tma_load_2d(st, mapA, bf, kc, m0);
-        if (Epi::kDual) {
+        if constexpr (PAIR) {  // this CTA's half of the B k-block: BN/2 rows (dual: rank 0 takes b[0], rank 1 takes b[1])
+          if (Epi::kDual) tma_load_2d(st + SM::kABytes, &maps.b[crank], bf, kc, nb0);
+          else tma_load_2d(st + SM::kABytes, mapB0, bf, kc, tile_n * BN + (int)crank * (BN / 2));
+        } else if (Epi::kDual) {
           tma_load_2d(st + SM::kABytes, &maps.b[0], bf, kc, nb0);
           tma_load_2d(st + SM::kABytes + kBoxN * BK * 4, &maps.b[1], bf, kc, nb0);
         } else {
@@ -408,8 +479,8 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, c
     // ===== MMA issuer =====
     // One thread feeds the tensor core, so its instruction stream is on the critical path: descriptors are
     // (constant high word, base low word + a small offset) — one 32-bit add per operand.
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_tf32<BN>();
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = PAIR ? umma_idesc_tf32<BN, 2 * kGemmBM>() : umma_idesc_tf32<BN>();
       constexpr uint32_t idesc2 = umma_idesc_tf32<2 * BN <= 256 ? 2 * BN : BN>();  // PS: A_hi · [B_hi | B_lo]
       const uint64_t d0 = umma_smem_desc<BK>(stage0 + SM::kBOff);  // B hi of stage 0, k-step 0
       const uint32_t d_hi32 = (uint32_t)(d0 >> 32), d_lo32 = (uint32_t)d0;
@@ -421,16 +492,25 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, c
         const int ab = NACC == 2 ? (ch & 1) : 0;  // accumulator of this chunk
         const uint32_t acc = tmem + ab * AN;
         if (first && ch >= NACC) {  // it still holds chunk ch-NACC until the workers have drained it
-          mbar_wait(bar_accfree + 8 * ab, (NACC == 2 ? (ch >> 1) - 1 : ch - 1) & 1);  // (the fence after the `ready` wait below covers this one too)
+          if constexpr (PAIR) mbar_wait_cluster(bar_accfree + 8 * ab, ((ch >> 1) - 1) & 1);
+          else mbar_wait(bar_accfree + 8 * ab, (NACC == 2 ? (ch >> 1) - 1 : ch - 1) & 1);  // (the fence after the `ready` wait below covers this one too)
           RAMA_GEMM_TR(kb, 7);
         }
-        mbar_wait(bar_ready + 8 * s, ph);
+        if constexpr (PAIR) mbar_wait_cluster(bar_ready + 8 * s, ph);
+        else mbar_wait(bar_ready + 8 * s, ph);
         tc_fence_after();
         RAMA_GEMM_TR(kb, 3);
         const uint32_t bh = d_lo32 + s * (SM::kStageBytes >> 4), bl = bh + (SM::kBBytes >> 4);
         const uint32_t a_hi = tmem_a + 64 * s, a_lo = a_hi + 32;
         // 8 tf32 = 32 bytes = 2 descriptor units inside the swizzle row; TMEM A: 8 columns per k-step
-        if constexpr (PS) {
+        if constexpr (PAIR) {
+#pragma unroll
+          for (int ks = 0; ks < BK / 8; ++ks) {
+            umma_tf32_ts_pair(acc, a_lo + 8 * ks, desc(bh + 2 * ks), idesc, !(first && ks == 0));  // small terms first
+            umma_tf32_ts_pair(acc, a_hi + 8 * ks, desc(bl + 2 * ks), idesc, 1);
+            umma_tf32_ts_pair(acc, a_hi + 8 * ks, desc(bh + 2 * ks), idesc, 1);
+          }
+        } else if constexpr (PS) {
           // Measured (role timeline, 8 MMAs per k-block): alternating N = 128 / N = 64 instructions issue at ≈82 clk each — a
           // change of instruction shape costs a bubble.  So the four wide products go first, then the narrow ones (PS = 1), or
           // every product is wide (PS = 2: A_lo · [B_hi | B_lo] also adds the lo·lo term — 64 clk instead of 55, one shape).
@@ -464,8 +544,13 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, c
           XA(0, kb != 0); MM(0, !first); XB(0); MM(1, 1); XA(1, 1); MM(2, 1); XB(1); MM(3, 1);
           XA(2, 1); XB(2); XA(3, 1); XB(3);
         }
-        umma_commit(bar_empty + 8 * s);  // smem stage + TMEM A stage reusable once these MMAs have read them
-        if (last) umma_commit(bar_accfull + 8 * ab);
+        if constexpr (PAIR) {  // both CTAs' stages / accumulators
+          umma_commit_pair(bar_empty + 8 * s);
+          if (last) umma_commit_pair(bar_accfull + 8 * ab);
+        } else {
+          umma_commit(bar_empty + 8 * s);  // smem stage + TMEM A stage reusable once these MMAs have read them
+          if (last) umma_commit(bar_accfull + 8 * ab);
+        }
         RAMA_GEMM_TR(kb, 4);
         if (++s == STAGES) { s = 0; ph ^= 1; }
         if (++in_ch == CH) { in_ch = 0; ++ch; }
@@ -505,7 +590,10 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, c
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_accfree + 8 * b);
+      if (lane == 0) {
+        if (PAIR && !leader) mbar_arrive_cluster(bar_accfree + 8 * b, 0);  // the leader's issuer counts both CTAs' drains
+        else mbar_arrive(bar_accfree + 8 * b);
+      }
     };
 
     // The two groups of four worker warps (half = 0 / 1) take alternate k-blocks, so the latency chain of one
@@ -583,7 +671,10 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, c
       tmem_st_wait();            // A halves have landed in TMEM
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_ready + 8 * s);
+      if (lane == 0) {
+        if (PAIR && !leader) mbar_arrive_cluster(bar_ready + 8 * s, 0);  // the leader's MMA reads both CTAs' halves
+        else mbar_arrive(bar_ready + 8 * s);
+      }
       if (quarter == 0 && lane == 0) RAMA_GEMM_TR(kb, 2);
       s += 2;
       if (s >= STAGES) { s -= STAGES; ph ^= 1; }
@@ -611,6 +702,8 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, c
     }
 
     Epi epi = epi_in;
+    // (every MMA has completed — the last chunk's commit fired — so the pipeline stages are free: 4 KB of stage 0 per warp)
+    if constexpr (epi_has_scratch<Epi>::value) epi.scratch = reinterpret_cast<float*>(gen_base + SM::kARingBytes + (warp - 2) * 4096);
     const int m = m0 + quarter * 32 + lane;
     const bool valid = m < shp.M;
     if constexpr (Epi::kDual) {
@@ -620,10 +713,19 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shp, c
       for (int j = 0; j < NSEG; ++j) epi(m, tile_n * BN + seg_col(j), acc[j], group, split, valid);
     }
   }
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc<SM::kTmemCols>(tmem);
+  if constexpr (PAIR) {
+    tc_fence_before();
+    cluster_sync_all();  // neither CTA leaves (or frees tensor memory) while the other may still signal it or read its B half
+    if (warp == 1) {
+      tc_fence_after();
+      tmem_dealloc_pair<SM::kTmemCols>(tmem);
+    }
+  } else {
+    __syncthreads();
+    if (warp == 1) {
+      tc_fence_after();
+      tmem_dealloc<SM::kTmemCols>(tmem);
+    }
   }
 }
 

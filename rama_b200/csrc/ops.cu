@@ -285,6 +285,9 @@ extern "C" int rama_op_matmul_nt(rama_ctx* c, float* out, const float* a, const 
       case 1: e = launch_gemm_tf32x3<128, 4, 4, 0>(c->op_stream, &A, 1, &B, 1, m, n, k, hi_round, 1, epi); break;
       case 2: e = launch_gemm_tf32x3<128, 2, 2, 1>(c->op_stream, &A, 1, &B, 1, m, n, k, hi_round, 1, epi); break;
       case 3: e = launch_gemm_tf32x3<64, 4, 2, 2>(c->op_stream, &A, 1, &B, 1, m, n, k, hi_round, 1, epi); break;
+      // CTA pair (tcgen05.mma.cta_group::2): 256×128 tile over two SMs, each holding half of the B k-block
+      case 4: e = launch_gemm_tf32x3<128, 4, 4, 0, 0, 0, 2, 1>(c->op_stream, &A, 1, &B, 1, m, n, k, hi_round, 1, epi); break;
+      case 5: e = launch_gemm_tf32x3<128, 4, 2, 0, 0, 0, 2, 1>(c->op_stream, &A, 1, &B, 1, m, n, k, hi_round, 1, epi); break;
       default: return fail(RAMA_E_INVALID, "matmul_nt: unknown variant %d", variant);
     }
   }

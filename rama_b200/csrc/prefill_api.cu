@@ -8,6 +8,19 @@
 
 constexpr int kPrefillChunk = 512;
 
+// The prefill GEMM tile: 128×128 per CTA, or (RAMA_PREFILL_PAIR=1, chunks of more than 128 rows) a CTA pair on the two SMs of a
+// TPC computing 256×128 with tcgen05.mma.cta_group::2 — each CTA holds half of the weight k-block (gemm_tf32x3.cuh PAIR).
+// The pair is parity-green and measured SLOWER (420 vs 552 TFLOP/s tf32 issued at 512×4096×4096): with K = 8 per tf32
+// instruction each SM must pull 2 KB of the peer's B half per MMA through the SM-to-SM path (≈21 B/clk), 97 clk against the
+// 64 clk of the math — the operand sharing that pays for 16-bit kinds does not for 3xTF32.  Off by default.
+static int prefill_pair() {
+  static const int v = env_int("RAMA_PREFILL_PAIR", 0);
+  return v;
+}
+#define PREFILL_GEMM(st, A, nA, B, nB, M, N, K, epi, pdl)                                                       \
+  ((prefill_pair() && (M) > kGemmBM) ? launch_gemm_tf32x3<128, 4, 4, 0, 0, 0, 2, 1>(st, A, nA, B, nB, M, N, K, 0, 1, epi, pdl) \
+                                     : launch_gemm_tf32x3<128, 4, 4, 0>(st, A, nA, B, nB, M, N, K, 0, 1, epi, pdl))
+
 // Allocations of the prefill workspace.  Under the peer exchange the normalised activations (every rank stores its rows
 // into every rank's copy) and the inbox of partial rows live in a peer-addressable block: collective between processes;
 // a single-process group allocates on all ranks first and cross-wires the blocks (prefill_prepare_group).
@@ -135,7 +148,7 @@ static int prefill_chunk(rama_session* s, const int32_t* tokens, int M, int pos0
                           {W[RAMA_T_WK] + (size_t)l * Dq * D, (size_t)Dq, (size_t)D},
                           {W[RAMA_T_WV] + (size_t)l * Dq * D, (size_t)Dq, (size_t)D}};
       EpiQKVPrefill epi{s->pf_q, kc, vc, W[RAMA_T_FREQ_REAL], W[RAMA_T_FREQ_IMAG], pos0, Dq, hs / 2};
-      GK(RAMA_PK_GEMM, (launch_gemm_tf32x3<128, 4, 4, 0>(st, &A, 1, B, 3, M, Dq, D, 0, 1, epi, pdl)));
+      GK(RAMA_PK_GEMM, PREFILL_GEMM(st, &A, 1, B, 3, M, Dq, D, epi, pdl));
     }
     // causal attention of every prompt row over the cache   (infer.rs:34)
     {
@@ -166,10 +179,10 @@ static int prefill_chunk(rama_session* s, const int32_t* tokens, int M, int pos0
       GemmOperand A{s->pf_att, (size_t)M, (size_t)Dq};
       GemmOperand B{W[RAMA_T_WO] + (size_t)l * D * Dq, (size_t)D, (size_t)Dq};
       if (xchg) {
-        GK(RAMA_PK_GEMM, (launch_gemm_tf32x3<128, 4, 4, 0>(st, &A, 1, &B, 1, M, D, Dq, 0, 1, push, pdl)));
+        GK(RAMA_PK_GEMM, PREFILL_GEMM(st, &A, 1, &B, 1, M, D, Dq, push, pdl));
       } else {
         EpiStoreNT epi{s->pf_y, D, D, 0};
-        GK(RAMA_PK_GEMM, (launch_gemm_tf32x3<128, 4, 4, 0>(st, &A, 1, &B, 1, M, D, Dq, 0, 1, epi, pdl)));
+        GK(RAMA_PK_GEMM, PREFILL_GEMM(st, &A, 1, &B, 1, M, D, Dq, epi, pdl));
       }
     }
     if (xchg) {
@@ -189,17 +202,17 @@ static int prefill_chunk(rama_session* s, const int32_t* tokens, int M, int pos0
       GemmOperand B[2] = {{W[RAMA_T_W1] + (size_t)l * Fl * D, (size_t)Fl, (size_t)D},
                           {W[RAMA_T_W3] + (size_t)l * Fl * D, (size_t)Fl, (size_t)D}};
       EpiSwiGLUPrefill epi{s->pf_h, Fl};
-      GK(RAMA_PK_GEMM, (launch_gemm_tf32x3<128, 4, 4, 0>(st, &A, 1, B, 2, M, Fl, D, 0, 1, epi, pdl)));
+      GK(RAMA_PK_GEMM, PREFILL_GEMM(st, &A, 1, B, 2, M, Fl, D, epi, pdl));
     }
     // w2   (infer.rs:46)
     {
       GemmOperand A{s->pf_h, (size_t)M, (size_t)Fl};
       GemmOperand B{W[RAMA_T_W2] + (size_t)l * D * Fl, (size_t)D, (size_t)Fl};
       if (xchg) {
-        GK(RAMA_PK_GEMM, (launch_gemm_tf32x3<128, 4, 4, 0>(st, &A, 1, &B, 1, M, D, Fl, 0, 1, push, pdl)));
+        GK(RAMA_PK_GEMM, PREFILL_GEMM(st, &A, 1, &B, 1, M, D, Fl, push, pdl));
       } else {
         EpiStoreNT epi{s->pf_y, D, D, 0};
-        GK(RAMA_PK_GEMM, (launch_gemm_tf32x3<128, 4, 4, 0>(st, &A, 1, &B, 1, M, D, Fl, 0, 1, epi, pdl)));
+        GK(RAMA_PK_GEMM, PREFILL_GEMM(st, &A, 1, &B, 1, M, D, Fl, epi, pdl));
       }
     }
     if (P > 1 && !xchg) {

@@ -186,46 +186,66 @@ __device__ __forceinline__ float* tp_sel(float* const (&tbl)[kMaxPeers], int r) 
   return f;
 }
 
-// ---- GEMM epilogues that push the partial to the row owners (gemm_tf32x3.cuh epilogue interface) ----------------------
+// ---- pushing the partial rows to their owners ------------------------------------------------------------------------------
 
-// prefill: C row m (prompt row), columns n..n+31 → inbox of rank m / rpr, slab `me`
+// prefill: C row m (prompt row), columns n..n+31 → inbox of rank m / rpr, slab `me`.
+// A thread of the GEMM epilogue holds 32 columns of ONE row, so a warp-wide store would scatter 32 × 16 bytes over 32 rows —
+// harmless into local L2, but over NVLink every 16-byte piece travels as its own write (measured: the pushing wo / w2 GEMMs
+// of a TP = 4 prefill ran 22 % slower than the storing ones).  The 32×32 block therefore goes through 4 KB of shared memory
+// private to the warp (`scratch`, set by the kernel — the pipeline stages are idle by then) and leaves as whole 128-byte row
+// segments: 8 lanes per row, 4 rows per store instruction.
 struct EpiPushNT {
   static constexpr bool kDual = false;
   float* inbox[kMaxPeers];
   int rpr, me, ldc, N;
+  float* scratch;
   __device__ __forceinline__ void operator()(int m, int n, const float (&v)[32], int, int, bool valid) const {
-    if (!valid) return;
-    const int q = m / rpr;
-    float* row = tp_sel(inbox, q) + ((size_t)me * rpr + (m - q * rpr)) * ldc + n;
-    if (n + 32 <= N) {
+    const int lane = threadIdx.x & 31;
+    float4* s4 = reinterpret_cast<float4*>(scratch);
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        reinterpret_cast<float4*>(row)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-    } else {
+    for (int c = 0; c < 8; ++c)  // row `lane`, 16-byte chunk c, XOR-swizzled: conflict-free both ways
+      s4[lane * 8 + (c ^ (lane & 7))] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+    __syncwarp();
+    const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+    const int m_base = m - lane;
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (n + j < N) row[j] = v[j];
+    for (int i = 0; i < 8; ++i) {
+      const int r = 4 * i + (lane >> 3), c = lane & 7;
+      if ((vmask >> r) & 1u) {
+        const float4 x = s4[r * 8 + (c ^ (r & 7))];
+        const int mr = m_base + r, q = mr / rpr, col = n + 4 * c;
+        float* dst = tp_sel(inbox, q) + ((size_t)me * rpr + (mr - q * rpr)) * ldc + col;
+        if (col + 3 < N) {
+          *reinterpret_cast<float4*>(dst) = x;
+        } else {
+          const float xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (col + e < N) dst[e] = xv[e];
+        }
+      }
     }
+    __syncwarp();
   }
 };
 
-// batched decode (Cᵀ: tile rows are weight rows r = m, columns are sequences b): partial (split) of sequence b →
-// inbox of rank b / bpr, slab (me · ksplit + split); consecutive lanes hold consecutive r ⇒ 128-byte remote stores
-struct EpiPushT {
-  static constexpr bool kDual = false;
-  float* inbox[kMaxPeers];
-  int bpr, me, ldc, N, ksplit;
-  __device__ __forceinline__ void operator()(int m, int n, const float (&v)[32], int, int split, bool valid) const {
-    if (!valid) return;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int b = n + j;
-      if (b < N) {
-        const int q = b / bpr;
-        tp_sel(inbox, q)[(((size_t)me * ksplit + split) * bpr + (b - q * bpr)) * ldc + m] = v[j];
-      }
-    }
+// batched decode: Σ over the split-K partials of this rank, then ONE store of every reduced row into its owner's inbox
+// (slab `me`) — pushing the S partials themselves would put S times the bytes on NVLink.  Grid (ceil(D/4/256), n).
+struct TpInboxes { float* p[kMaxPeers]; };
+static __global__ void __launch_bounds__(256) tp_sum_push_kernel(const float* __restrict__ part, int S, size_t slab, const TpInboxes inbox,
+                                                          int bpr, int me, int D) {
+  pdl_launch_dependents(); pdl_wait();  // (no-ops unless launched with programmatic stream serialization)
+  const int b = blockIdx.y, i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= (D >> 2)) return;
+  const float4* src = reinterpret_cast<const float4*>(part + (size_t)b * D) + i;
+  const size_t slab4 = slab >> 2;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s = 0; s < S; ++s) {  // split order: deterministic
+    const float4 t = src[(size_t)s * slab4];
+    a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
   }
-};
+  const int q = b / bpr;
+  reinterpret_cast<float4*>(tp_sel(inbox.p, q) + ((size_t)me * bpr + (b - q * bpr)) * D)[i] = a;
+}
 
 }  // namespace rama

@@ -38,7 +38,7 @@ SHAPES = [(128, 256, 64), (128, 256, 4096), (512, 4096, 4096), (512, 1024, 11008
           (1, 32, 16), (130, 520, 1000), (512, 768, 768), (512, 11008, 1024)]  # the last one: more tiles than SMs
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])  # 4, 5: CTA pair (tcgen05.mma.cta_group::2, 256×128 tile over two SMs)
 @pytest.mark.parametrize("shape", SHAPES)
 def test_matmul_nt_f32_accuracy(gpu, shape, variant):
     M, N, K = shape

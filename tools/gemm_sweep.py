@@ -15,7 +15,8 @@ L = _lib.lib()
 PREFILL = [(512, 4096, 4096), (512, 11008, 4096), (512, 4096, 11008), (512, 32000, 4096), (2048, 4096, 4096)]
 DECODE = [(4096, 64, 4096), (11008, 64, 4096), (4096, 64, 11008), (32000, 64, 4096), (12288, 64, 4096), (22016, 64, 4096)]
 MODE = sys.argv[1] if len(sys.argv) > 1 else "all"
-SETS = ((PREFILL, [0, 1, 2, 3], 0), (DECODE, [0, 1, 2, 3], 2)) if MODE == "all" else ((DECODE, [4, 6, 7, 8, 9], 2),)
+SETS = (((PREFILL, [0, 1, 2, 3], 0), (DECODE, [0, 1, 2, 3], 2)) if MODE == "all" else
+        ((PREFILL, [1, 4, 5], 0),) if MODE == "prefill" else ((DECODE, [4, 6, 7, 8, 9], 2),))
 for shapes, variants, flags in SETS:
     for (M, N, K) in shapes:
         a = DeviceBuffer(gpu, M * K); b = DeviceBuffer(gpu, N * K); o = DeviceBuffer(gpu, M * N)
