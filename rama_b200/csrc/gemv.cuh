@@ -537,14 +537,17 @@ struct EpiCls {
 
 // ---- the streaming core ---------------------------------------------------------------------
 
-template <int WK, int RP, int U, class Rows>
-__device__ __forceinline__ void gemv_pairs(const Rows& rows, int K4, int p0, int np,
-                                           const float4* __restrict__ xs, float* __restrict__ part) {
-  constexpr int WR = kGemvWarps / WK;
+// WK (warps that split K) is a run-time argument of the core so that the persistent step kernel can use ONE instantiation per
+// phase type (gemv_pairs_rt); the per-variant kernels pass a constant through the force-inlined wrapper and get the same code
+// as a template parameter would give.
+template <int RP, int U, class Rows>
+__device__ __forceinline__ void gemv_pairs_core(const Rows& rows, int K4, int p0, int np, const float4* __restrict__ xs,
+                                                float* __restrict__ part, const int WK) {
+  const int WR = kGemvWarps / WK;
   constexpr int R = 2 * RP;
-  constexpr int stride = kWarp * WK;
+  const int stride = kWarp * WK;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int wr = warp / WK, wk = warp % WK;
+  const int wr = warp / WK, wk = warp - wr * WK;
 
   for (int base = wr * RP; base < np; base += WR * RP) {
     const float4* rp[R];
@@ -591,6 +594,12 @@ __device__ __forceinline__ void gemv_pairs(const Rows& rows, int K4, int p0, int
       }
     }
   }
+}
+
+template <int WK, int RP, int U, class Rows>
+__device__ __forceinline__ void gemv_pairs(const Rows& rows, int K4, int p0, int np,
+                                           const float4* __restrict__ xs, float* __restrict__ part) {
+  gemv_pairs_core<RP, U>(rows, K4, p0, np, xs, part, WK);
 }
 
 // Shared memory: float4 xs[K4] | float part[max_pairs_per_cta * 2 * WK]
@@ -754,57 +763,7 @@ gemv_smem_kernel(const Pro pro, const Rows rows, const Epi epi_in, int K4, int n
 template <class Rows>
 __device__ __forceinline__ void gemv_pairs_rt(const Rows& rows, int K4, int p0, int np, const float4* __restrict__ xs,
                                               float* __restrict__ part, int WK) {
-  constexpr int RP = 2, U = 4, R = 2 * RP;
-  const int WR = kGemvWarps / WK;
-  const int stride = kWarp * WK;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int wr = warp / WK, wk = warp - wr * WK;
-
-  for (int base = wr * RP; base < np; base += WR * RP) {
-    const float4* rp[R];
-#pragma unroll
-    for (int j = 0; j < RP; ++j) {
-      const int p = min(base + j, np - 1);  // clamp: a duplicate is computed but never stored
-      rows(p0 + p, rp[2 * j], rp[2 * j + 1]);
-    }
-    float acc[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) acc[r] = 0.f;
-
-    int c = wk * kWarp + lane;
-    for (; c + (U - 1) * stride < K4; c += U * stride) {
-      float4 w[U][R];
-#pragma unroll
-      for (int u = 0; u < U; ++u)
-#pragma unroll
-        for (int r = 0; r < R; ++r) w[u][r] = ldg_stream(rp[r] + c + u * stride);
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const float4 xv = xs[c + u * stride];
-#pragma unroll
-        for (int r = 0; r < R; ++r) acc[r] = dot4(w[u][r], xv, acc[r]);
-      }
-    }
-    for (; c < K4; c += stride) {
-      float4 w[R];
-#pragma unroll
-      for (int r = 0; r < R; ++r) w[r] = ldg_stream(rp[r] + c);
-      const float4 xv = xs[c];
-#pragma unroll
-      for (int r = 0; r < R; ++r) acc[r] = dot4(w[r], xv, acc[r]);
-    }
-#pragma unroll
-    for (int r = 0; r < R; ++r) acc[r] = warp_sum(acc[r]);
-    if (lane == 0) {
-#pragma unroll
-      for (int j = 0; j < RP; ++j) {
-        if (base + j < np) {
-          part[((base + j) * 2 + 0) * WK + wk] = acc[2 * j];
-          part[((base + j) * 2 + 1) * WK + wk] = acc[2 * j + 1];
-        }
-      }
-    }
-  }
+  gemv_pairs_core<2, 4>(rows, K4, p0, np, xs, part, WK);
 }
 
 // L2 prefetch of the head of this CTA's slab of a coming phase (weights never depend on activations)

@@ -255,7 +255,8 @@ inline cudaError_t launch_gemv_t(int grid, cudaStream_t st, int pdl, const Pro& 
     cfg.attrs = at; cfg.numAttrs = 1;
     int n_active = 0;
     if (cudaOccupancyMaxActiveClusters(&n_active, kern, &cfg) != cudaSuccess) { cudaGetLastError(); continue; }
-    if ((double)n_active * c >= 0.97 * g) {
+    static const double min_frac = env_int("RAMA_TP_CLUSTER_MINPCT", 97) / 100.0;  // share of the CTAs that must fit one wave
+    if ((double)n_active * c >= min_frac * g) {
       cs = c;
       grid = std::min(g, n_active * c);
       na = 1;
