@@ -89,7 +89,7 @@ extern "C" int rama_ctx_create(int device, const rama_tp* tp, rama_ctx** out) {
   c->tp_nowait = env_int("RAMA_TP_NOWAIT", 0);
   c->variant_override = env_int("RAMA_GEMV_VARIANT", -1);
   c->staged = env_int("RAMA_GEMV_STAGED", 1);
-  c->tp_cluster = env_int("RAMA_TP_CLUSTER", 4);
+  c->tp_cluster = env_int("RAMA_TP_CLUSTER", -1);
   c->tp_reduce = env_int("RAMA_TP_REDUCE", -1);
   c->embed_kernel = env_int("RAMA_EMBED_KERNEL", 1);  // the fold measured +0.3 % (stories15M 10173 → 10201 tok/s): a tiny kernel in a PDL chain is almost free
   c->stage_max_kb = std::max(0, std::min((int)(kGemvSmemStageMaxSolo / 1024), env_int("RAMA_GEMV_STAGE_KB", 110)));

@@ -23,7 +23,7 @@ namespace rama {
 constexpr int kGemvThreads = 512;
 constexpr int kGemvWarps = kGemvThreads / kWarp;
 constexpr int kPdlPrefetchBytes = 192 * 1024;  // per CTA: ≈ what HBM delivers to one SM in ~4 µs
-constexpr int kMaxClusterShare = 4;            // cluster size of the shared peer reduction (ProNorm)
+constexpr int kMaxClusterShare = 8;            // cluster size of the shared peer reduction (ProNorm)
 
 struct ArgPart {  // greedy partial: best value and its global vocabulary index
   float v;

@@ -109,7 +109,7 @@ struct rama_ctx {
   int tp_sim = 0;
   int tp_reduce = -1;  // RAMA_TP_REDUCE: how a norm prologue reduces the P peer partials — 0 every CTA reads all of them, 1 the CTAs
                        // of a cluster share the reads (tp_cluster), 2 two-phase through a local LL buffer; -1 (default): 1
-  int tp_cluster = 4;  // RAMA_TP_CLUSTER: cluster size of the shared peer reduction in the norm prologues (0/1: off)
+  int tp_cluster = -1;  // RAMA_TP_CLUSTER: largest cluster size of the shared peer reduction in the norm prologues (0/1: off; -1: 8 at P = 8, else 4)
   int persistent = 0;  // RAMA_STEP=persistent: the decode step as one persistent cooperative kernel (step_kernel.cuh);
                        // default: one fused kernel per op group in a CUDA graph (measured faster)
   std::mutex mu;
@@ -255,7 +255,10 @@ inline cudaError_t launch_gemv_t(int grid, cudaStream_t st, int pdl, const Pro& 
     cfg.attrs = at; cfg.numAttrs = 1;
     int n_active = 0;
     if (cudaOccupancyMaxActiveClusters(&n_active, kern, &cfg) != cudaSuccess) { cudaGetLastError(); continue; }
-    static const double min_frac = env_int("RAMA_TP_CLUSTER_MINPCT", 97) / 100.0;  // share of the CTAs that must fit one wave
+    // share of the SM-filling grid that must fit ONE wave of clusters (clusters cannot span GPCs, and a CTA of this kernel owns an
+    // SM: 8-CTA clusters leave 128 of 148 CTAs).  Measured on one rank's share of a TP = 8 step (RAMA_TP_SIM, tok/s): clusters of
+    // 2 (all 148 CTAs) 863, of 4 (136) 879–908, of 8 (128) 921 — the shared reduction saves more than the lost SMs cost
+    static const double min_frac = env_int("RAMA_TP_CLUSTER_MINPCT", 80) / 100.0;
     if ((double)n_active * c >= min_frac * g) {
       cs = c;
       grid = std::min(g, n_active * c);
@@ -408,6 +411,8 @@ inline cudaError_t launch_k(bool pdl, void (*kern)(P...), dim3 grid, dim3 block,
   return cudaLaunchKernelEx(&cfg, kern, std::forward<A>(args)...);
 }
 
+
+inline int tp_cluster_size(const rama_ctx* c) { return c->tp_cluster >= 0 ? c->tp_cluster : (c->world >= 8 ? 8 : 4); }
 
 // how this session's norm prologues reduce the peer partials (rama_ctx::tp_reduce)
 inline int tp_reduce_mode(const rama_session* s) {

@@ -449,7 +449,7 @@ static int enqueue_step(rama_session* s, cudaStream_t st, int mode, StepTrace* t
       ProNorm pro{s->x0, l == 0 ? nullptr : s->w2out, s->x1, W[RAMA_T_RMS_ATT] + (size_t)l * D, nullptr, peer_in(s, 1, l - 1)};
       if (l == 0 && !embed_kernel) { pro.emb = W[RAMA_T_TOKEN_EMBEDDING]; pro.ctrl = s->ctrl; pro.seq = s->seq; pro.vocab = c->V; }
       const int nowait = l > 0 ? set_peer_reduce(s, pro, 1, q.pdl) : 0;
-      const int want_cluster = (s->p2p && l > 0 && tp_reduce_mode(s) == 1) ? c->tp_cluster : 0;
+      const int want_cluster = (s->p2p && l > 0 && tp_reduce_mode(s) == 1) ? tp_cluster_size(c) : 0;
       RowsQKV rows{W[RAMA_T_WQ] + (size_t)l * Dq * D, W[RAMA_T_WK] + (size_t)l * Dq * D,
                    W[RAMA_T_WV] + (size_t)l * Dq * D, D, Dq / 2};
       EpiQKV epi{s->q, s->k, s->v, s->key_cache + (size_t)l * T * Dq, s->value_cache + (size_t)l * T * Dq,
@@ -543,7 +543,7 @@ static int enqueue_step(rama_session* s, cudaStream_t st, int mode, StepTrace* t
       EpiSwiGLU epi{s->hb, s->hb2};
       const int np = Fl, var = pick_variant(c, D / 4, np);
       q.pre(RAMA_K_W13);
-      q.post(launch_gemv(var, pick_grid(c, var, np), st, q.pdl | nowait, pro, rows, epi, D / 4, np, (s->p2p && tp_reduce_mode(s) == 1) ? c->tp_cluster : 0, q.slot(RAMA_K_W13)));
+      q.post(launch_gemv(var, pick_grid(c, var, np), st, q.pdl | nowait, pro, rows, epi, D / 4, np, (s->p2p && tp_reduce_mode(s) == 1) ? tp_cluster_size(c) : 0, q.slot(RAMA_K_W13)));
     }
     // ---- w2 (infer.rs:46); residual add (:47) folded into the next prologue ----
     {
