@@ -409,6 +409,15 @@ def main():
         for k, (ms, n) in sess.profile_step(int(toks[pos - 1]) if pos else 1, pos).items():
             a = prof.setdefault(k, [0.0, 0])
             a[0] += ms; a[1] += n
+    # ---- in-graph timeline (collective under TP): where a token's time goes INSIDE the captured graph — %globaltimer stamps in
+    # every kernel of the production step, programmatic dependent launch included (the event pairs above serialise the kernels and
+    # add launch latency: they overstate each kernel by ~20 %)
+    from rama_b200.engine import step_timeline, summarize_timeline
+    tl_pos = tokens // 2
+    tl = step_timeline(sess, int(toks[tl_pos - 1]) if tl_pos else 1, tl_pos, 1, 5)
+    tl_sum = summarize_timeline(tl)
+    tl_step_us = (tl[-1]["end"] - tl[0]["ready"]) * 1e-3
+
     def teardown():
         # symmetric on every rank: the library's communicator is destroyed collectively
         sess.close(); gpu.close()
@@ -493,6 +502,20 @@ def main():
                 "step_frac_of_nominal_8TBs": round(step_bytes * value / 1e9 / 8000.0, 4),
                 "step_bytes_per_token_per_gpu": step_bytes}
     kernels = {k: {"ms_per_token": round(v[0] / 5, 4), "launches_per_token": v[1] // 5} for k, v in prof.items() if v[1]}
+    w13_tl = tl_sum.get("w13")
+    if w13_tl:
+        w13_us = w13_tl["chain"] / w13_tl["n"]
+        roofline["in_graph"] = {"avg_launch_us": round(w13_us, 2), "achieved": round(w13_bytes / (w13_us * 1e-6) / 1e9, 1),
+                                "frac": round(w13_bytes / (w13_us * 1e-6) / 1e9 / peak, 4),
+                                "kernel_share_of_step": round(w13_tl["chain"] / tl_step_us, 4),
+                                "what": "the same kernel inside the production CUDA graph: its dependency resolved -> the next kernel's "
+                                        "dependency resolved (%globaltimer stamps, position %d)" % tl_pos}
+    timeline = {"pos": tl_pos, "step_us": round(tl_step_us, 1),
+                "by_kind": {k: {"launches": a["n"], "us_per_token": round(a["chain"], 1), "prologue_us_per_launch": round(a["prologue"] / a["n"], 2),
+                                "body_us_per_launch": round(a["body"] / a["n"], 2), "tail_us_per_launch": round(a["tail"] / a["n"], 2)}
+                            for k, a in tl_sum.items()},
+                "what": "rama_step_timeline: CTA 0 of every kernel of the captured step stamps entry / dependency resolved / prologue done "
+                        "(under TP: peer partials arrived) / end; us_per_token = the kernel kind's share of the step's critical path"}
 
     line = {"metric": METRIC, "value": round(value, 3), "unit": "tok/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(dev_ms / args.steps, 4), "higher_is_better": True,
@@ -510,7 +533,7 @@ def main():
                     "what": "forward(token,pos)+sample() per token through the C ABI; 32 B ctrl H2D from pinned "
                             "memory and 8 B D2H per token inside the timed region"},
             "gpu_launches": args.steps * tokens * sess.launches_per_step(),
-            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu}
+            "roofline": roofline, "kernels": kernels, "timeline": timeline, "cpu_baseline": cpu}
     if pf is not None:
         pf["speedup_vs_per_token_steps"] = round(pf["tok_per_s"] / value, 1)
         bf16, _ = measured_tensor_peak()
