@@ -352,12 +352,24 @@ def main():
             if world > 1:
                 dist.all_reduce(bt, op=dist.ReduceOp.MAX)
             b_s = float(bt.item())
+            # the same batch with the loop on the device (rama_generate_batch): one graph replay per step, no PCIe traffic
+            n_loop = b_warm + b_steps
+            batch.generate(bsess, [PROMPT] * nb, n_loop, 0.0, 0.9)
+            barrier()
+            _, loop_ms = batch.generate(bsess, [PROMPT] * nb, n_loop, 0.0, 0.9)
+            lt = torch.tensor([loop_ms], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(lt, op=dist.ReduceOp.MAX)
+            loop_ms = float(lt.item())
             step_ms = b_s / b_steps * 1e3
             avg_pos = b_warm + (b_steps - 1) / 2
             wbytes = cfg.weight_bytes_per_token() / world   # per GPU
             kvb = nb * (2 * cfg.n_layers * (avg_pos + 1) * cfg.dim * 4 + 2 * cfg.n_layers * cfg.dim * 4) / world
             bd = {"sequences": nb, "steps": b_steps, "ms_per_step": round(step_ms, 3),
                   "tok_per_s": round(nb / (step_ms * 1e-3), 1), "speedup_vs_batch1": None,
+                  "device_loop": {"ms_per_step": round(loop_ms / n_loop, 3), "tok_per_s": round(nb * n_loop / (loop_ms * 1e-3), 1),
+                                  "steps": n_loop, "what": "rama_generate_batch: token feedback on the device, CUDA-event time of the "
+                                                           "step loop from position 0, max over ranks"},
                   "launches_per_step": batch.launches_per_step(),
                   "hbm_gbs_algorithmic_per_gpu": round((wbytes + kvb) / (step_ms * 1e-3) / 1e9, 1),
                   "tensor_tf32_tflops_issued_per_gpu": round(3 * nb * 2.0 * (wbytes / 4) / (step_ms * 1e-3) / 1e12, 1),
@@ -509,7 +521,7 @@ def main():
                                 "frac": round(w13_bytes / (w13_us * 1e-6) / 1e9 / peak, 4),
                                 "kernel_share_of_step": round(w13_tl["chain"] / tl_step_us, 4),
                                 "what": "the same kernel inside the production CUDA graph: its dependency resolved -> the next kernel's "
-                                        "dependency resolved (%globaltimer stamps, position %d)" % tl_pos}
+                                        f"dependency resolved (globaltimer stamps, position {tl_pos})"}
     timeline = {"pos": tl_pos, "step_us": round(tl_step_us, 1),
                 "by_kind": {k: {"launches": a["n"], "us_per_token": round(a["chain"], 1), "prologue_us_per_launch": round(a["prologue"] / a["n"], 2),
                                 "body_us_per_launch": round(a["body"] / a["n"], 2), "tail_us_per_launch": round(a["tail"] / a["n"], 2)}

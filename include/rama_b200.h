@@ -173,6 +173,13 @@ int rama_forward_batch(rama_batch* b, rama_session* const* sessions, const int32
 /* ≙ Device::sample for each of the n sessions (same temperature/topp), one launch; synchronous */
 int rama_sample_batch(rama_batch* b, rama_session* const* sessions, int32_t n, float temperature, float topp,
                       int32_t* next);
+/* ≙ n generate() loops (mod.rs:169-206) advanced together with the token feedback on the device: every sequence starts at
+ * BOS / position 0, prompts[i][0..n_prompt[i]) is forced, `steps` tokens per sequence are written to out_tokens[i*steps + t]
+ * (same temperature / topp for all, as rama_sample_batch).  One captured graph per batch size holds the batched step and the n
+ * samplers; nothing crosses PCIe between steps.  elapsed_ms = device time of the step loop.  Synchronous. */
+int rama_generate_batch(rama_batch* b, rama_session* const* sessions, int32_t n, const int32_t* const* prompts,
+                        const int32_t* n_prompt, int32_t steps, float temperature, float topp, int32_t* out_tokens,
+                        float* elapsed_ms);
 int rama_batch_sync(rama_batch* b);
 int rama_batch_launches_per_step(const rama_batch* b, int32_t* n);
 

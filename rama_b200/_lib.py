@@ -68,6 +68,7 @@ _SIGS = {
     "rama_batch_destroy": ([vp], C.c_int),
     "rama_forward_batch": ([vp, C.POINTER(vp), ip, ip, C.c_int32], C.c_int),
     "rama_sample_batch": ([vp, C.POINTER(vp), C.c_int32, C.c_float, C.c_float, ip], C.c_int),
+    "rama_generate_batch": ([vp, C.POINTER(vp), C.c_int32, C.POINTER(ip), ip, C.c_int32, C.c_float, C.c_float, ip, fp], C.c_int),
     "rama_batch_sync": ([vp], C.c_int),
     "rama_batch_launches_per_step": ([vp, ip], C.c_int),
     "rama_prefill": ([vp, ip, C.c_int32, C.c_int32, fp, fp, ip], C.c_int),

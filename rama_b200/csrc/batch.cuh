@@ -32,17 +32,26 @@ static __global__ void sum_partials_kernel(float* __restrict__ out, const float*
 }
 
 // x[b] = token_embedding_table[token_b] (infer.rs:13); mirrors (token,pos) into the session's control block
-static __global__ void __launch_bounds__(256) batch_embed_kernel(const BatchSeq* __restrict__ seqs, const float* __restrict__ emb,
-                                                          float* __restrict__ x, int D, int vocab, unsigned* step_counter) {
+// chained (rama_generate_batch: the loop stays on the device): the step's (token, pos) come from the sequence's control block,
+// where the sampler of the previous step left them, and are copied into the table the other kernels of the step read.
+static __global__ void __launch_bounds__(256) batch_embed_kernel(BatchSeq* __restrict__ seqs, const float* __restrict__ emb,
+                                                          float* __restrict__ x, int D, int vocab, unsigned* step_counter,
+                                                          int chained) {
   pdl_launch_dependents(); pdl_wait();  // (no-ops unless launched with programmatic stream serialization)
   if (step_counter && blockIdx.x == 0 && threadIdx.x == 0) *step_counter += 1u;  // epoch source of the step's TP exchanges
   const BatchSeq sq = seqs[blockIdx.x];
-  int token = sq.token;
+  int token = chained ? sq.ctrl->token : sq.token;
   if (threadIdx.x == 0) {
-    // the error flag describes THIS step (rama_sample_batch reads it per step): a session handed back to a pool and reused
-    // must not carry an earlier request's error
-    sq.ctrl->pos = sq.pos; sq.ctrl->token = token; sq.ctrl->chained = 0;
-    sq.ctrl->error = (token < 0 || token >= vocab) ? 1 : 0;
+    if (chained) {
+      seqs[blockIdx.x].pos = sq.ctrl->pos;
+      seqs[blockIdx.x].token = token;
+      if (token < 0 || token >= vocab) sq.ctrl->error = 1;
+    } else {
+      // the error flag describes THIS step (rama_sample_batch reads it per step): a session handed back to a pool and reused
+      // must not carry an earlier request's error
+      sq.ctrl->pos = sq.pos; sq.ctrl->token = token; sq.ctrl->chained = 0;
+      sq.ctrl->error = (token < 0 || token >= vocab) ? 1 : 0;
+    }
   }
   if (token < 0 || token >= vocab) token = 0;
   const float4* src = reinterpret_cast<const float4*>(emb + (size_t)token * D);

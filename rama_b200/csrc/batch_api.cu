@@ -42,6 +42,7 @@ struct rama_batch {
   int32_t* h_next = nullptr;         // pinned [2·cap]
   int ring_i = 0;
   std::vector<cudaGraphExec_t> graphs;  // by batch size
+  std::vector<cudaGraphExec_t> graphs_chained;  // by batch size: step + samplers of the device-resident loop (rama_generate_batch)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int launches = 0;
   std::shared_ptr<BatchFence> fence;    // re-recorded after every step; the sessions of the step hold a reference
@@ -129,6 +130,7 @@ static int batch_create_rank(rama_ctx* c, int32_t max_seqs, rama_batch** out, bo
     b->xn = reinterpret_cast<float*>(b->blk.local + b->off_xn);
   }
   b->graphs.assign(max_seqs + 1, nullptr);
+  b->graphs_chained.assign(max_seqs + 1, nullptr);
   b->fence = std::make_shared<BatchFence>();
   if (cudaEventCreateWithFlags(&b->fence->ev, cudaEventDisableTiming) != cudaSuccess) {
     rama_batch_destroy(b);
@@ -178,6 +180,7 @@ extern "C" int rama_batch_destroy(rama_batch* b) {
   if (b->stream) cudaStreamSynchronize(b->stream);
   std::lock_guard<std::mutex> cap_lk(b->ctx->cap_mu);
   for (auto g : b->graphs) if (g) cudaGraphExecDestroy(g);
+  for (auto g : b->graphs_chained) if (g) cudaGraphExecDestroy(g);
   if (b->p2p) {
     peer_block_free(b->ctx, &b->blk, b->stream, b->x);
     b->xn = nullptr;  // lived inside the block
@@ -197,7 +200,7 @@ extern "C" int rama_batch_destroy(rama_batch* b) {
 
 // enqueue one batched step for n sequences (everything per-sequence is read from b->d_seqs on the device,
 // so the captured graph of a batch size serves every step)
-static int enqueue_batch_step(rama_batch* b, int n, int* n_launch) {
+static int enqueue_batch_step(rama_batch* b, int n, int* n_launch, bool chained = false) {
   rama_ctx* c = b->ctx;
   cudaStream_t st = b->stream;
   const int D = c->D, Dq = c->Dq, Fl = c->Fl, T = c->T, hs = c->hs, L = c->L, Vl = c->Vl;
@@ -214,7 +217,7 @@ static int enqueue_batch_step(rama_batch* b, int n, int* n_launch) {
   } while (0)
   const bool xchg = b->p2p;
   unsigned* step_counter = xchg ? reinterpret_cast<unsigned*>(b->blk.local + b->off_step) : nullptr;
-  LK(launch_k(pdl, batch_embed_kernel, dim3(n), dim3(256), st, b->d_seqs, W[RAMA_T_TOKEN_EMBEDDING], b->x, D, c->V, step_counter));
+  LK(launch_k(pdl, batch_embed_kernel, dim3(n), dim3(256), st, b->d_seqs, W[RAMA_T_TOKEN_EMBEDDING], b->x, D, c->V, step_counter, chained ? 1 : 0));
   const bool ps = batch_ps(c) != 0;
   // the batch's activation operands: n rows, or (pre-split) the [128][K] matrix of activations + remainder plane
   const size_t brows = ps ? 2 * kBatchPlane : (size_t)n;
@@ -473,6 +476,101 @@ extern "C" int rama_sample_batch(rama_batch* b, rama_session* const* sessions, i
     if (b->h_next[2 * i + 1] == 1) return fail(RAMA_E_STATE, "token id outside the vocabulary reached the device step (sequence %d)", i);
     if (b->h_next[2 * i + 1] == 2) return fail(RAMA_E_STATE, "top-p candidate list is empty (the reference panics here, infer.rs:66) (sequence %d)", i);
     next[i] = b->h_next[2 * i];
+  }
+  return RAMA_OK;
+}
+
+// ≙ n generate() loops (mod.rs:169-206) advanced together with the token feedback on the device: every sequence starts at
+// BOS / position 0, its prompt is forced, `steps` tokens each (out_tokens[i·steps + t]).  One captured graph per batch size
+// holds the batched step and the n samplers; nothing crosses PCIe between steps.  Collective under tensor parallelism.
+extern "C" int rama_generate_batch(rama_batch* b, rama_session* const* sessions, int32_t n, const int32_t* const* prompts,
+                                   const int32_t* n_prompt, int32_t steps, float temperature, float topp, int32_t* out_tokens,
+                                   float* elapsed_ms) {
+  if (!b || !sessions || !n_prompt || !out_tokens) return fail(RAMA_E_INVALID, "NULL argument");
+  if (!b->ranks.empty()) {
+    std::vector<std::vector<rama_session*>> pr;
+    RK(group_sessions(b, sessions, n, pr));
+    std::vector<std::vector<int32_t>> scratch(b->ranks.size());
+    return group_run(b->ctx, [&](int r) {
+      if (r == 0) return rama_generate_batch(b->ranks[0], pr[0].data(), n, prompts, n_prompt, steps, temperature, topp, out_tokens, elapsed_ms);
+      scratch[r].resize((size_t)std::max(1, n * steps));
+      return rama_generate_batch(b->ranks[r], pr[r].data(), n, prompts, n_prompt, steps, temperature, topp, scratch[r].data(), nullptr);
+    });
+  }
+  rama_ctx* c = b->ctx;
+  RK(batch_check_sessions(b, sessions, n));
+  if (steps < 0 || steps > c->T) return fail(RAMA_E_STATE, "steps %d exceeds seq_len %d", steps, c->T);  // the reference panics past seq_len
+  for (int i = 0; i < n; ++i) {
+    if (n_prompt[i] < 0 || (n_prompt[i] > 0 && (!prompts || !prompts[i]))) return fail(RAMA_E_INVALID, "prompt %d is NULL", i);
+    for (int j = 0; j < n_prompt[i]; ++j)
+      if (prompts[i][j] < 0 || prompts[i][j] >= c->V) return fail(RAMA_E_INVALID, "prompt token %d of sequence %d outside the vocabulary", prompts[i][j], i);
+  }
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(b->stream));  // h_sp and the pinned rings are reused below
+  BatchSeq* hs = b->h_seqs + (size_t)b->ring_i * b->cap;
+  if (++b->ring_i == kBatchRing) b->ring_i = 0;
+  for (int i = 0; i < n; ++i) {
+    rama_session* s = sessions[i];
+    CK(session_enter(s));
+    CK(cudaStreamSynchronize(s->stream));
+    s->async_pending = false;
+    hs[i] = BatchSeq{s->key_cache, s->value_cache, s->logits, s->ctrl, 0, 1, {nullptr}};
+    if (b->p2p) {
+      if (!s->p2p) return fail(RAMA_E_STATE, "session %d was not created for the peer exchange", i);
+      for (int r = 0; r < c->world; ++r) hs[i].logits_peer[r] = reinterpret_cast<float*>(s->blk.base[r] + s->off_logits);
+    }
+    b->h_sp[i] = SampleParams{s->logits, nullptr, 0, 0, c->V, s->ctrl, s->d_prompt, s->d_out, s->sort_keys, 0.f, 0.f, 1, PeerIn{}};
+    const int np = std::min<int>(n_prompt[i], c->T);
+    if (np) CK(cudaMemcpyAsync(s->d_prompt, prompts[i], (size_t)np * sizeof(int32_t), cudaMemcpyHostToDevice, b->stream));
+    StepCtrl* h = &s->h_ring[s->ring_i];
+    if (++s->ring_i == kRing) s->ring_i = 0;
+    memset(h, 0, sizeof(*h));
+    h->pos = 0; h->token = 1;  // BOS (mod.rs:182)
+    h->chained = 1; h->n_prompt = n_prompt[i]; h->temperature = temperature; h->topp = topp;
+    CK(cudaMemcpyAsync(s->ctrl, h, sizeof(StepCtrl), cudaMemcpyHostToDevice, b->stream));
+    s->logits_gathered = true;
+    s->parts_valid = false;
+    s->fence = b->fence;
+  }
+  CK(cudaMemcpyAsync(b->d_seqs, hs, (size_t)n * sizeof(BatchSeq), cudaMemcpyHostToDevice, b->stream));
+  CK(cudaMemcpyAsync(b->d_sp, b->h_sp, (size_t)n * sizeof(SampleParams), cudaMemcpyHostToDevice, b->stream));
+  if (!b->graphs_chained[n]) {
+    std::lock_guard<std::mutex> cap_lk(c->cap_mu);
+    cudaGraph_t g = nullptr;
+    CK(cudaStreamBeginCapture(b->stream, cudaStreamCaptureModeRelaxed));
+    int nl = 0;
+    int rc = enqueue_batch_step(b, n, &nl, true);
+    if (rc == RAMA_OK) {
+      sample_batch_kernel<<<n, kSampleThreads, 0, b->stream>>>(b->d_sp);
+      if (cudaGetLastError() != cudaSuccess) rc = fail(RAMA_E_CUDA, "sampler launch in the batched loop");
+    }
+    cudaError_t e = cudaStreamEndCapture(b->stream, &g);
+    if (rc != RAMA_OK) { if (g) cudaGraphDestroy(g); return rc; }
+    if (e != cudaSuccess) return fail(RAMA_E_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&b->graphs_chained[n], g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) return fail(RAMA_E_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+    b->launches = nl;
+  }
+  CK(cudaEventRecord(b->ev0, b->stream));
+  for (int t = 0; t < steps; ++t) CK(cudaGraphLaunch(b->graphs_chained[n], b->stream));
+  CK(cudaEventRecord(b->ev1, b->stream));
+  batch_collect_kernel<<<1, 64, 0, b->stream>>>(b->d_seqs, b->d_next, n);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(b->h_next, b->d_next, (size_t)2 * n * sizeof(int32_t), cudaMemcpyDeviceToHost, b->stream));
+  for (int i = 0; i < n && steps > 0; ++i)
+    CK(cudaMemcpyAsync(out_tokens + (size_t)i * steps, sessions[i]->d_out, (size_t)steps * sizeof(int32_t), cudaMemcpyDeviceToHost, b->stream));
+  CK(cudaEventRecord(b->fence->ev, b->stream));
+  CK(cudaStreamSynchronize(b->stream));
+  if (elapsed_ms) CK(cudaEventElapsedTime(elapsed_ms, b->ev0, b->ev1));
+  if (b->p2p) {
+    int32_t xerr = 0;
+    CK(cudaMemcpy(&xerr, b->d_err, sizeof(xerr), cudaMemcpyDeviceToHost));
+    if (xerr == 3) return fail(RAMA_E_NCCL, "timed out waiting for a tensor-parallel peer in the batched loop");
+  }
+  for (int i = 0; i < n; ++i) {
+    if (b->h_next[2 * i + 1] == 1) return fail(RAMA_E_STATE, "token id outside the vocabulary reached the device step (sequence %d)", i);
+    if (b->h_next[2 * i + 1] == 2) return fail(RAMA_E_STATE, "top-p candidate list is empty (the reference panics here, infer.rs:66) (sequence %d)", i);
   }
   return RAMA_OK;
 }

@@ -521,6 +521,21 @@ class Batch:
         check(_lib.lib().rama_sample_batch(self.h, self._handles(sessions), n, temperature, topp, out.ctypes.data_as(ip)))
         return [int(x) for x in out]
 
+    def generate(self, sessions: Sequence["Session"], prompts: Sequence[Sequence[int]], steps: int, temperature: float = 0.0,
+                 topp: float = 0.9):
+        """≙ generate() (mod.rs:169-206) for every session at once, token feedback on the device (rama_generate_batch).
+        Returns (tokens[n][steps], elapsed_ms of the step loop)."""
+        n = len(sessions)
+        assert len(prompts) == n
+        keep = [np.asarray(list(p), dtype=np.int32) for p in prompts]
+        ptrs = (ip * n)(*[k.ctypes.data_as(ip) if k.size else ip() for k in keep])
+        lens = np.asarray([k.size for k in keep], dtype=np.int32)
+        out = np.zeros((n, max(steps, 1)), dtype=np.int32)
+        ms = C.c_float()
+        check(_lib.lib().rama_generate_batch(self.h, self._handles(sessions), n, ptrs, lens.ctypes.data_as(ip), steps, temperature,
+                                             topp, out.ctypes.data_as(ip), C.byref(ms)))
+        return out[:, :steps] if steps else out[:, :0], ms.value
+
     def sync(self):
         check(_lib.lib().rama_batch_sync(self.h))
 

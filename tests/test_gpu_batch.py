@@ -70,6 +70,42 @@ def test_batched_steps_equal_per_session_forward(name, B):
     gpu.close()
 
 
+@pytest.mark.parametrize("name", ["tiny", "tiny-sep"])
+@pytest.mark.parametrize("temperature", [0.0, 0.8])
+def test_generate_batch_equals_every_sequences_own_generate(name, temperature):
+    """rama_generate_batch: the device-resident loop for several sequences at once — every row is the token stream the oracle's
+    generate() (mod.rs:169-206) produces for that prompt, greedy and top-p, prompts of different lengths (one empty, one longer
+    than the run), and the sessions are afterwards where their own loops would have left them."""
+    cfg, tensors, gpu, om = _pair(name)
+    rng = np.random.default_rng(17)
+    steps = cfg.seq_len
+    prompts = [[], [5], [int(t) for t in rng.integers(2, cfg.vocab_size, 7)], [int(t) for t in rng.integers(2, cfg.vocab_size, 19)],
+               [int(t) for t in rng.integers(2, cfg.vocab_size, steps + 3)]]
+    B = len(prompts)
+    sess = [Session(gpu) for _ in range(B)]
+    batch = Batch(gpu, 8)
+    got, ms = batch.generate(sess, prompts, steps, temperature, 0.9)
+    assert got.shape == (B, steps) and ms > 0
+    for i, p in enumerate(prompts):
+        want, _, _, _ = ref.generate(om, ref.State(om), p, steps, temperature, 0.9)
+        assert [int(t) for t in got[i]] == [int(t) for t in want], (name, temperature, i)
+    again, _ = batch.generate(sess, prompts, steps, temperature, 0.9)          # reusable, bit-reproducible
+    assert (again == got).all()
+    # the sessions hold their own caches: a per-session forward continues from there like after generate()
+    st = ref.State(om)
+    want0, _, _, _ = ref.generate(om, st, prompts[2], 10, 0.0, 0.9)
+    g2, _ = batch.generate(sess[:3], prompts[:3], 10, 0.0, 0.9)
+    assert [int(t) for t in g2[2]] == [int(t) for t in want0]
+    sess[2].forward(int(want0[9]), 10); ref.forward(om, st, int(want0[9]), 10)
+    assert rel_err(sess[2].logits(), st.logits) < LOGIT_TOL
+    with pytest.raises(RamaError):
+        batch.generate(sess, prompts, cfg.seq_len + 1)                         # the reference panics past seq_len
+    batch.close()
+    for s in sess:
+        s.close()
+    gpu.close()
+
+
 def test_batch_errors():
     cfg, tensors, gpu, om = _pair("tiny")
     a, b = Session(gpu), Session(gpu)

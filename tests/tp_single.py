@@ -96,6 +96,12 @@ def run(world: int):
         for i in range(B):
             assert rel(bs[i].logits(), sts[i].logits) < 1e-3, (world, name, "batch", i)
         assert batch.sample(bs, 0.0, 0.9) == [argmax_last(st.logits) for st in sts], (world, name, "batch sample")
+        prompts_b = [[], [9, 8, 7], [4], [3, 3, 3, 3, 3, 3], [11]]
+        for temp in (0.0, 0.8):                                               # device-resident batched loop
+            gb, _ = batch.generate(bs, prompts_b, 16, temp, 0.9)
+            for i, pb in enumerate(prompts_b):
+                wb, _, _, _ = ref.generate(om, ref.State(om), pb, 16, temp, 0.9)
+                assert [int(t) for t in gb[i]] == [int(t) for t in wb], (world, name, "generate_batch", temp, i)
         batch.close()
         for x in bs:
             x.close()

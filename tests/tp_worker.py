@@ -98,6 +98,12 @@ def main():
                 assert eb < 1e-3, ("batch", name, rank, i, eb)
             nb = batch.sample(bs, 0.0, 0.9)
             assert nb == [int(np.flatnonzero(st.logits == st.logits.max())[-1]) for st in sts], ("batch sample", name, rank)
+            # device-resident batched loop under TP
+            prompts_b = [[], [9, 8, 7], [4]]
+            gb, _ = batch.generate(bs, prompts_b, 16, 0.0, 0.9)
+            for i, pb in enumerate(prompts_b):
+                wb, _, _, _ = ref.generate(om, ref.State(om), pb, 16, 0.0, 0.9)
+                assert [int(t) for t in gb[i]] == [int(t) for t in wb], ("generate_batch", name, rank, i)
             batch.close()
             for x in bs:
                 x.close()
