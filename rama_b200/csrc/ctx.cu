@@ -100,6 +100,8 @@ extern "C" int rama_ctx_create(int device, const rama_tp* tp, rama_ctx** out) {
   {
     const char* m = getenv("RAMA_STEP");
     c->persistent = m && strcmp(m, "persistent") == 0;
+    c->cluster_step = m && strcmp(m, "cluster") == 0 ? 1 : (m && strcmp(m, "kernels") == 0 ? 0 : -1);
+    c->cluster_step_ctas = std::max(2, std::min(16, env_int("RAMA_STEP_CLUSTER", 16)));
   }
   {
     const char* m = getenv("RAMA_TP_COMM");

@@ -110,6 +110,8 @@ struct rama_ctx {
   int tp_reduce = -1;  // RAMA_TP_REDUCE: how a norm prologue reduces the P peer partials — 0 every CTA reads all of them, 1 the CTAs
                        // of a cluster share the reads (tp_cluster), 2 two-phase through a local LL buffer; -1 (default): 1
   int tp_cluster = -1;  // RAMA_TP_CLUSTER: largest cluster size of the shared peer reduction in the norm prologues (0/1: off; -1: 8 at P = 8, else 4)
+  int cluster_step = -1;  // RAMA_STEP=cluster / kernels: the layers of a tiny model as ONE cluster-scope kernel (step_kernel.cuh); -1: by size
+  int cluster_step_ctas = 16;  // RAMA_STEP_CLUSTER: CTAs of that cluster (16 needs the non-portable cluster size attribute)
   int persistent = 0;  // RAMA_STEP=persistent: the decode step as one persistent cooperative kernel (step_kernel.cuh);
                        // default: one fused kernel per op group in a CUDA graph (measured faster)
   std::mutex mu;
@@ -162,6 +164,7 @@ struct rama_session {
   unsigned* seq = nullptr;      // device step counter (epoch source of the fused TP exchange)
   unsigned long long* bar = nullptr;  // persistent step kernel: [0] grid-barrier arrivals, [1] steps completed
   bool persistent = false;
+  bool cluster_step = false;    // the layers run as one cluster-scope kernel (tiny models on one GPU)
   int cls_grid = 0;             // CTAs of the classifier launch (slots that get written)
   // fused TP exchange: one peer-addressable block per session
   //   parts[P][SMs][2] (LL) | inbox[2][P][D] (LL) | logits[V] | x0[D] | bulk flags[3][P] | bulk done counter

@@ -156,6 +156,14 @@ static int session_create_rank(rama_ctx* c, rama_session** out, bool connect) {
   A(dalloc(&s->tickets, (size_t)c->Hl));
   s->persistent = c->persistent && !c->group && (c->world == 1 || s->p2p);
   if (s->persistent) s->cls_grid = c->sm_count;  // every CTA of the persistent kernel writes a classifier partial
+  // Tiny models on one GPU: the whole stack of layers fits L2 several times over and a token is ~30 dependent kernels of ~3 µs
+  // each for ~1 µs of streaming.  The layers then run as ONE kernel whose CTAs form a single cluster (step_kernel.cuh, cluster
+  // mode).  Worth it only while a handful of SMs can stream the layers from L2 faster than the kernel chain runs.
+  {
+    const size_t layer_bytes = (size_t)c->L * (4 * D * D + 3 * D * c->F) * sizeof(float);
+    const bool fits = c->world == 1 && !s->persistent && layer_bytes <= ((size_t)env_int("RAMA_STEP_CLUSTER_MAX_MB", 32) << 20);
+    s->cluster_step = fits && c->cluster_step != 0 && (c->cluster_step == 1 || env_int("RAMA_STEP_CLUSTER_AUTO", 0));
+  }
   A(dalloc(&s->part, (size_t)c->world * c->sm_count));
   if (s->p2p) A(dalloc(&s->red_ll, (size_t)2 * D));
   A(dalloc(&s->seq, 1));
@@ -353,7 +361,7 @@ static void launch_plain(StepEnq& q, int kind, F&& f) {
 static int wk_for(int K4) { return K4 >= 1024 ? 8 : (K4 >= 512 ? 4 : (K4 >= 128 ? 2 : 1)); }
 
 // The step as ONE persistent cooperative launch (step_kernel.cuh); mode as enqueue_step.
-static int enqueue_step_persistent(rama_session* s, cudaStream_t st, int mode, int* n_launch, long long* trace = nullptr) {
+static StepParams step_params(rama_session* s, int mode, long long* trace) {
   rama_ctx* c = s->ctx;
   StepParams p{};
   p.trace = trace;
@@ -371,6 +379,57 @@ static int enqueue_step_persistent(rama_session* s, cudaStream_t st, int mode, i
   p.rank = c->rank; p.world = s->p2p ? c->world : 1;
   for (int r = 0; r < kMaxPeers; ++r) p.peer_base[r] = r < c->world ? s->blk.base[r] : nullptr;
   p.off_inbox = s->off_inbox; p.off_parts = s->off_parts;
+  return p;
+}
+
+// The LAYERS of the step as one cluster-scope launch (tiny models); the classifier and the sampler stay separate kernels.
+static cudaError_t launch_cluster_layers(rama_session* s, cudaStream_t st, int pdl) {
+  rama_ctx* c = s->ctx;
+  StepParams p = step_params(s, 0, nullptr);
+  p.cluster = 1;
+  int cs = c->cluster_step_ctas;
+  static std::atomic<unsigned long long> attr_done{0}, np_done{0};
+  cudaError_t e = ensure_dyn_smem((const void*)decode_step_kernel, (int)kMaxDynSmem, attr_done);
+  if (e != cudaSuccess) return e;
+  if (cs > 8) {  // non-portable cluster size: opt in once per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!(np_done.load() & (1ull << dev))) {
+      if (cudaFuncSetAttribute(decode_step_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) np_done.fetch_or(1ull << dev);
+      else { cudaGetLastError(); cs = 8; }
+    }
+  }
+  for (;; cs /= 2) {  // largest cluster the device can co-schedule
+    size_t smem = 0;
+    auto need = [&](int K4, int n_pairs, int wk) { smem = std::max(smem, gemv_smem_bytes(K4, n_pairs, cs, wk)); };
+    need(c->D / 4, 3 * c->Dq / 2, p.wk_d); need(c->Dq / 4, c->D / 2, p.wk_wo); need(c->D / 4, c->Fl, p.wk_d);
+    need(c->Fl / 4, c->D / 2, p.wk_w2);
+    if (smem > kMaxDynSmem) return cudaErrorInvalidValue;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(cs);
+    cfg.blockDim = dim3(kGemvThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    int na = 0;
+    at[na].id = cudaLaunchAttributeClusterDimension;
+    at[na].val.clusterDim.x = cs; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+    ++na;
+    int n_active = 0;
+    cfg.attrs = at; cfg.numAttrs = na;
+    if (cudaOccupancyMaxActiveClusters(&n_active, decode_step_kernel, &cfg) != cudaSuccess || n_active < 1) {
+      cudaGetLastError();
+      if (cs > 2) continue;
+      return cudaErrorInvalidConfiguration;
+    }
+    (void)pdl;  // (the kernel reads ctrl at entry: it keeps a full stream dependency on the previous step's sampler)
+    return cudaLaunchKernelEx(&cfg, decode_step_kernel, p);
+  }
+}
+
+static int enqueue_step_persistent(rama_session* s, cudaStream_t st, int mode, int* n_launch, long long* trace = nullptr) {
+  rama_ctx* c = s->ctx;
+  StepParams p = step_params(s, mode, trace);
   const int grid = c->sm_count;
   size_t smem = 0;
   auto need = [&](int K4, int n_pairs, int wk) { smem = std::max(smem, gemv_smem_bytes(K4, n_pairs, grid, wk)); };
@@ -428,7 +487,14 @@ static int enqueue_step(rama_session* s, cudaStream_t st, int mode, StepTrace* t
   // x ← embedding row of ctrl->token (infer.rs:13): a gather kernel of its own, or (RAMA_EMBED_KERNEL=0) folded into the
   // layer-0 QKV prologue (ProNorm::emb)
   const bool embed_kernel = c->embed_kernel != 0;
-  if (embed_kernel) {
+  // tiny models: embedding gather + every layer in ONE cluster-scope kernel (launch_cluster_layers); not for the event-timed /
+  // stamped variants of the step, which describe the multi-kernel chain
+  const bool cluster_layers = s->cluster_step && !tr && !tl && !s->keep_att;
+  if (cluster_layers) {
+    q.pre(RAMA_K_QKV);
+    q.post(launch_cluster_layers(s, st, q.pdl));
+  }
+  if (embed_kernel && !cluster_layers) {
     q.pre(RAMA_K_EMBED);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(std::max(1, std::min(8, D / 4 / 256)));
@@ -443,7 +509,7 @@ static int enqueue_step(rama_session* s, cudaStream_t st, int mode, StepTrace* t
     q.post(cudaLaunchKernelEx(&cfg, step_begin_kernel, s->ctrl, s->seq, W[RAMA_T_TOKEN_EMBEDDING], s->x0, D, c->V, q.pdl, q.slot(RAMA_K_EMBED)));
   }
 
-  for (int l = 0; l < L; ++l) {
+  for (int l = 0; l < (cluster_layers ? 0 : L); ++l) {
     // ---- rmsnorm → [wq|wk|wv] → RoPE → KV write (infer.rs:19-33) ----
     {
       ProNorm pro{s->x0, l == 0 ? nullptr : s->w2out, s->x1, W[RAMA_T_RMS_ATT] + (size_t)l * D, nullptr, peer_in(s, 1, l - 1)};
@@ -662,6 +728,7 @@ extern "C" int rama_session_launches_per_step(const rama_session* s, int* n) {
   if (!s->ranks.empty()) return rama_session_launches_per_step(s->ranks[0], n);
   const rama_ctx* c = s->ctx;
   if (s->persistent) { *n = 1; return RAMA_OK; }  // the whole greedy step is one persistent cooperative launch
+  if (s->cluster_step && !s->keep_att) { *n = 3; return RAMA_OK; }  // layers (one cluster-scope kernel) + classifier + sampler
   // embed + L·(qkv, attn, wo, w13, w2) + cls + sample (+ collectives under TP); attention + wo are one launch
   // for the small models at positions < 256
   *n = (c->embed_kernel ? 1 : 0) + (s->wo_part ? 4 : 5) * c->L + 1 + 1 + (c->world > 1 && !s->p2p ? 2 * c->L + 1 : 0);

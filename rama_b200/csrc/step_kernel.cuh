@@ -43,6 +43,10 @@ struct StepParams {
   char* peer_base[kMaxPeers];
   size_t off_inbox, off_parts;
   long long* trace;           // optional: CTA 0 stamps clock64() at kernel entry, before and after every barrier
+  // Cluster mode (tiny models, RAMA_STEP=cluster): the grid is ONE thread-block cluster and the phases of the LAYERS are separated
+  // by barrier.cluster (hardware, ≈0.2–0.4 µs) instead of the L2-counter grid barrier (≈2 µs) or a kernel boundary (≈3 µs); the
+  // kernel ends after the last w2 and the classifier runs as the usual full-grid GEMV (16 SMs cannot stream a 37 MB classifier).
+  int cluster;
 };
 
 constexpr int kStepAttnWarps = kGemvWarps;  // 16 warps × 4 timesteps = 64 per attention work item
@@ -217,7 +221,8 @@ static __global__ void __launch_bounds__(kGemvThreads, 1) decode_step_kernel(con
   auto barrier = [&]() {
     target += gridDim.x;
     stamp();
-    grid_barrier(&p.bar[0], target, &p.ctrl->error);
+    if (p.cluster) cluster_sync_all();  // release / acquire at cluster scope: covers the global-memory activations too
+    else grid_barrier(&p.bar[0], target, &p.ctrl->error);
     stamp();
   };
   constexpr size_t kPrefetch = 192 * 1024;
@@ -270,6 +275,8 @@ static __global__ void __launch_bounds__(kGemvThreads, 1) decode_step_kernel(con
     if (l + 1 < L) {
       RowsQKV nxt{p.wq + (size_t)(l + 1) * Dq * D, p.wk + (size_t)(l + 1) * Dq * D, p.wv + (size_t)(l + 1) * Dq * D, D, Dq / 2};
       gemv_prefetch_slab(nxt, 3 * Dq / 2, kPrefetch);
+    } else if (p.cluster) {
+      return;  // the classifier GEMV and the sampler follow as kernels of their own (stream order: this kernel's w2 is complete)
     } else {
       RowsPlain nxt{p.wcls, D, p.Vl};
       gemv_prefetch_slab(nxt, (p.Vl + 1) / 2, kPrefetch);

@@ -103,8 +103,12 @@ def _greedy_case(name, steps, prompt, seed=1234):
     return cfg, want, got_dev, got_host, gap, worst
 
 
-def test_stories15M_256_greedy_tokens_identical():
-    """BASELINE.json configs[0]: stories15M, f32, greedy, 256 tokens — identical token sequence."""
+@pytest.mark.parametrize("step", ["default", "cluster", "kernels"])
+def test_stories15M_256_greedy_tokens_identical(step, monkeypatch):
+    """BASELINE.json configs[0]: stories15M, f32, greedy, 256 tokens — identical token sequence; with the layers as one
+    cluster-scope kernel (RAMA_STEP=cluster) and as the chain of kernels."""
+    if step != "default":
+        monkeypatch.setenv("RAMA_STEP", step)
     cfg, want, got_dev, got_host, gap, worst = _greedy_case("stories15M", 256, PROMPT)
     assert gap > 1e-4, f"seed gives a top-2 gap of {gap}: argmax not stable under f32 reordering"
     assert list(want[: len(PROMPT)]) == PROMPT
@@ -199,7 +203,9 @@ def test_long_context_attention_with_live_cache():
 
 
 @pytest.mark.parametrize("env", [{"RAMA_ATTN": "split"}, {"RAMA_ATTN_WO": "1"}, {"RAMA_ATTN_WO": "2"}, {"RAMA_PDL": "0"},
-                                 {"RAMA_GEMV_STAGED": "0"}, {"RAMA_GEMV_STAGE_KB": "208"}, {"RAMA_EMBED_KERNEL": "0"}])
+                                 {"RAMA_GEMV_STAGED": "0"}, {"RAMA_GEMV_STAGE_KB": "208"}, {"RAMA_EMBED_KERNEL": "0"},
+                                 {"RAMA_STEP": "cluster"}, {"RAMA_STEP": "cluster", "RAMA_STEP_CLUSTER": "8"},
+                                 {"RAMA_STEP": "kernels"}])
 def test_kernel_variants_kept_as_options_agree_with_the_oracle(env, monkeypatch):
     """Every measured alternative that stays selectable at run time is held to the same parity
     bar as the default path: teacher-forced logits and the greedy stream on the tiny models."""
