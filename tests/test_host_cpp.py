@@ -101,6 +101,39 @@ def test_engine_cli_prints_the_oracles_greedy_text(tmp_path):
             assert text == "".join("" if int(t) == 1 else pieces[int(t)] for t in want)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("gpus", [2, 4])
+def test_engine_cli_on_several_gpus_of_one_process(tmp_path, gpus):
+    """`engine --gpus N` / `RAMA_GPUS=N engine …`: the one `GPU` handle of main.rs:70-98 becomes a tensor-parallel context over
+    N devices of the same process (rama_ctx_create_multi) and prints the oracle's greedy text."""
+    import torch
+    from oracle import ref
+    from rama_b200 import checkpoint as ck
+    if torch.cuda.device_count() < gpus:
+        pytest.skip(f"needs {gpus} GPUs")
+    _build()
+    model = os.path.join(GOLDEN, "ref_untied.bin")
+    cfg, tensors = ck.read_checkpoint(model)
+    if cfg.n_heads % gpus or cfg.vocab_size % gpus or cfg.hidden_dim % (4 * gpus):
+        pytest.skip("golden model not divisible")
+    pieces = ["<unk>", "<s>", "</s>"] + [f"w{i:02d}." for i in range(3, cfg.vocab_size)]
+    tok = tmp_path / "tokenizer.bin"
+    with open(tok, "wb") as f:
+        f.write(struct.pack("<I", max(len(p) for p in pieces)))
+        for p in pieces:
+            b = p.encode()
+            f.write(struct.pack("<fi", 0.0, len(b)) + b)
+    steps = cfg.seq_len
+    want, _, _, _ = ref.generate(ref.Model(cfg, tensors), ref.State(ref.Model(cfg, tensors)), [], steps, 0.0, 0.9)
+    expect = "".join("" if int(t) == 1 else pieces[int(t)] for t in want)
+    for how in ("flag", "env"):
+        cmd = [ENGINE, "-m", model, "-t", str(tok), "-s", str(steps), "-r", "0.0"] + (["--gpus", str(gpus)] if how == "flag" else [])
+        env = dict(os.environ, RAMA_GPUS=str(gpus)) if how == "env" else os.environ
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert r.stdout.split("\n--------------------------------\n")[0] == expect, how
+
+
 def _letter_tokenizer(path, vocab_size):
     """llama2.c tokenizer.bin (bpe.rs:27-43) whose pieces are the specials, the lower-case letters, the space, a few merges and
     fillers: enough for Tokenizer::encode of plain prompts and a printable piece for every id the model may emit."""
