@@ -317,7 +317,8 @@ def main():
               "attn_f32_tflops_per_gpu": round(attn_flops / max(pf_kinds["attn"], 1e-6) / 1e9, 2),
               "ms_by_kind": {k: round(v, 3) for k, v in pf_kinds.items()},
               "what": "rama_prefill: tcgen05 kind::tf32 GEMMs with in-kernel hi/lo split (3 MMAs per k-step, f32-accurate), "
-                      "fused RoPE/KV-write and SwiGLU epilogues, causal f32 attention; ms_by_kind from CUDA events "
+                      "fused RoPE/KV-write and SwiGLU epilogues, causal attention on the warp-level tensor path (mma.sync m16n8k8 "
+                      "tf32, the same 3-term split; RAMA_PREFILL_ATTN=cuda: f32 CUDA cores); ms_by_kind from CUDA events "
                       "around every launch"}
 
     # ---- batched decode (BASELINE config 5): 64 concurrent sequences, one tensor-core pass per step ----

@@ -290,6 +290,265 @@ __global__ void __launch_bounds__(kPfThreads) prefill_attn_kernel(const PrefillA
   }  // pass
 }
 
+// ---- the same attention on the tensor cores ----------------------------------------------------------------
+// mma.sync m16n8k8 tf32 with the 3xTF32 split of both operands (x = hi + lo, hi = the 19 bits the tensor core reads;
+// lo·hi + hi·lo + hi·hi, small terms first), f32 accumulation: products are exact to ≈2^-21, the same arithmetic the
+// prefill GEMMs use.  A CTA of NW × KS warps owns a block of BQ = 16·NW queries and walks the causal range in 64-key tiles;
+// warp (wq, ks) owns queries 16wq..16wq+15 against keys [ks·64/KS, (ks+1)·64/KS) of every tile:
+//   S = Q·Kᵀ   A = Q rows (shared memory, split on load), B = K rows (K[key][d] IS the "col" operand), 8 keys per n-tile
+//   online softmax on the accumulator fragments (a thread holds 2 rows × 2 keys per n-tile; row statistics over the quad)
+//   O += P·V   the S accumulators ARE the A operand: with the k index of the MMA mapped to keys (t → 8j+2t, t+4 → 8j+2t+1) the
+//              accumulator fragment of n-tile j is exactly the A fragment of k-step j — no shuffle, no shared-memory round trip;
+//              B = V[key][col] read with the same key mapping.
+// KS > 1 (keys of a tile split over warps) is what puts two or more warps on every scheduler when the grid has only one CTA
+// per SM (512 rows × 32 heads = 128 paired blocks): mma.sync chains are latency-bound with one warp per scheduler.  The KS
+// partial (m, l, O) triples of a query row meet in shared memory after the last tile and are merged by the ks = 0 warp, share by share.
+// K and V tiles arrive by cp.async (zero-filled beyond the causal range): K of tile i+1 lands under the softmax and P·V of
+// tile i, V of tile i+1 under the next Q·Kᵀ.  n-tiles / k-steps wholly above a warp's last query are skipped (the diagonal
+// tile costs about half).  Row pitch HS+4 words: every fragment load of Q, K and V is bank-conflict free.
+// Query blocks are paired (x, nq−1−x) like the CUDA-core kernel: one balanced wave.
+__device__ __forceinline__ void cp_async16_zfill(float* smem_dst, const float* gsrc, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  const int n = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void tf32_split(float x, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(x) & 0xFFFFE000u;
+  lo = __float_as_uint(x - __uint_as_float(hi)) & 0xFFFFE000u;   // (x − hi is exact; its own 13 low bits are dropped)
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// G independent accumulator tiles against one A fragment, term by term (lo·hi of every tile, then hi·lo, then hi·hi): consecutive
+// MMAs never depend on each other; a tile's three terms sit G instructions apart.  b(i, half) returns the f32 B element of tile i.
+template <int G, typename BF>
+__device__ __forceinline__ void mma_tf32x3_group(float (*d)[4], const uint32_t (&ahi)[4], const uint32_t (&alo)[4], BF b) {
+  uint32_t bh[G][2], bl[G][2];
+#pragma unroll
+  for (int i = 0; i < G; ++i) {
+    tf32_split(b(i, 0), bh[i][0], bl[i][0]);
+    tf32_split(b(i, 1), bh[i][1], bl[i][1]);
+  }
+#pragma unroll
+  for (int i = 0; i < G; ++i) mma_tf32(d[i], alo, bh[i][0], bh[i][1]);
+#pragma unroll
+  for (int i = 0; i < G; ++i) mma_tf32(d[i], ahi, bl[i][0], bl[i][1]);
+#pragma unroll
+  for (int i = 0; i < G; ++i) mma_tf32(d[i], ahi, bh[i][0], bh[i][1]);
+}
+
+// 2^x on the special-function unit (ex2.approx: relative error ≤ 2^-22; 2^-inf = +0)
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+constexpr int kPfMmaBK = 64;
+__host__ __device__ constexpr size_t prefill_attn_mma_smem_bytes(int hs, int nw) {
+  return (size_t)(16 * nw + 2 * kPfMmaBK) * (hs + 4) * sizeof(float);
+}
+
+template <int HS, int NW, int KS>
+__global__ void __launch_bounds__(32 * NW * KS) prefill_attn_mma_kernel(const PrefillAttnParams p) {
+  pdl_launch_dependents(); pdl_wait();  // (no-ops unless launched with programmatic stream serialization)
+  static_assert(HS % 16 == 0 && HS <= kPfMaxHs, "head size: a multiple of 16 (pairs of 8-wide MMA tiles)");
+  constexpr int BQ = 16 * NW, BK = kPfMmaBK, LD = HS + 4, KT = HS / 8, HS4 = HS / 4, NTHR = 32 * NW * KS;
+  constexpr int KW = BK / KS, NT = KW / 8;   // keys, key n-tiles of a tile per warp
+  static_assert(NT >= 2 && BQ <= BK, "at least one pair of key tiles per warp; the merge buffers live in the K / V tiles");
+  constexpr int GS = NT >= 8 ? 8 : NT, GO = KT % 8 == 0 ? 8 : (KT % 4 == 0 ? 4 : 2);   // independent MMA chains per group
+  extern __shared__ __align__(16) float pf_smem[];
+  float* Qs = pf_smem;           // [BQ][LD]
+  float* Ks = Qs + BQ * LD;      // [BK][LD]   (after the last tile: a ks > 0 share's O partial, [BQ][LD])
+  float* Vs = Ks + BK * LD;      // [BK][LD]   (after the last tile: its (m, l) pairs, [BQ][2])
+
+  const int h = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int wq = warp % NW, ksp = warp / NW, kof = ksp * KW;
+  const size_t col = (size_t)h * HS;
+  // softmax in base 2: exp(s/√hs − m) = 2^(s·c − m'), c = log2(e)/√hs — one multiply per score and one MUFU per exponential
+  const float sc = 1.4426950408889634f / sqrtf((float)HS);
+  const int nq = (p.M + BQ - 1) / BQ;
+
+  for (int pass = 0; pass < 2; ++pass) {
+    const int qb = pass == 0 ? (int)blockIdx.x : nq - 1 - (int)blockIdx.x;
+    if (pass == 1 && qb <= (int)blockIdx.x) break;
+    const int q0 = qb * BQ;
+    const int n_keys = p.pos0 + min(q0 + BQ, p.M);   // keys 0 .. position of the block's last query
+    const int nkb = (n_keys + BK - 1) / BK;
+    auto issue_tile = [&](float* tile, const float* cache, int kb) {
+      if (kb < nkb) {
+        const int k0 = kb * BK;
+        for (int i = tid; i < BK * HS4; i += NTHR) {
+          const int r = i / HS4, c = i - r * HS4;
+          const bool valid = k0 + r < n_keys;
+          cp_async16_zfill(tile + r * LD + 4 * c, cache + (size_t)(valid ? k0 + r : 0) * p.Dq + col + 4 * c, valid);
+        }
+      }
+      cp_async_commit();   // (always: the wait counts below assume one group per call)
+    };
+    __syncthreads();  // the previous pass is done with Qs / Ks / Vs
+    for (int i = tid; i < BQ * HS4; i += NTHR) {   // the query block rides in the first K tile's copy group (rows ≥ M: zeros)
+      const int r = i / HS4, c = i - r * HS4;
+      const bool valid = q0 + r < p.M;
+      cp_async16_zfill(Qs + r * LD + 4 * c, p.q + (size_t)(valid ? q0 + r : 0) * p.Dq + col + 4 * c, valid);
+    }
+    issue_tile(Ks, p.key_cache, 0);
+    issue_tile(Vs, p.value_cache, 0);
+
+    float o[KT][4];
+#pragma unroll
+    for (int n = 0; n < KT; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+    const int qpos0 = p.pos0 + q0 + 16 * wq + g, qpos1 = qpos0 + 8;   // this thread's two query positions
+    const int wlast = p.pos0 + q0 + 16 * wq + 15;                     // the warp's last query position
+    const float* qrow0 = Qs + (16 * wq + g) * LD + t;
+    const float* qrow1 = qrow0 + 8 * LD;
+
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int k0 = kb * BK + kof;   // first key of this warp's share of the tile
+      const int nlive = wlast >= k0 ? min(NT, (wlast - k0) / 8 + 1) : 0;   // key n-tiles with any unmasked entry for this warp
+      cp_async_wait<1>();   // K of this tile (V may still be in flight)
+      __syncthreads();      // … from every thread (first tile: the query block too)
+      float s[NT][4];
+#pragma unroll
+      for (int n = 0; n < NT; ++n) s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
+      if (nlive > 0) {
+#pragma unroll 2
+        for (int ks = 0; ks < KT; ++ks) {
+          uint32_t ahi[4], alo[4];
+          tf32_split(qrow0[8 * ks], ahi[0], alo[0]);
+          tf32_split(qrow1[8 * ks], ahi[1], alo[1]);
+          tf32_split(qrow0[8 * ks + 4], ahi[2], alo[2]);
+          tf32_split(qrow1[8 * ks + 4], ahi[3], alo[3]);
+          const float* kp = Ks + (kof + g) * LD + 8 * ks + t;
+#pragma unroll
+          for (int n0 = 0; n0 < NT; n0 += GS)   // (a group with any live tile is computed whole)
+            if (n0 < nlive)
+              mma_tf32x3_group<GS>(&s[n0], ahi, alo, [&](int i, int half) { return kp[8 * (n0 + i) * LD + 4 * half]; });
+        }
+      }
+      __syncthreads();   // every warp is done with Ks
+      issue_tile(Ks, p.key_cache, kb + 1);
+
+      if (nlive > 0) {
+        // scale (cpu.rs:41 divides by √hs; here folded into the base-2 constant), causal mask, online softmax on the fragments
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+          if (n < nlive) {
+            const int key = k0 + 8 * n + 2 * t;
+            s[n][0] = key <= qpos0 ? s[n][0] * sc : -INFINITY;
+            s[n][1] = key + 1 <= qpos0 ? s[n][1] * sc : -INFINITY;
+            s[n][2] = key <= qpos1 ? s[n][2] * sc : -INFINITY;
+            s[n][3] = key + 1 <= qpos1 ? s[n][3] * sc : -INFINITY;
+            mx0 = fmaxf(mx0, fmaxf(s[n][0], s[n][1]));
+            mx1 = fmaxf(mx1, fmaxf(s[n][2], s[n][3]));
+          }
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        // a row may have seen no key yet (KS > 1: the upper key shares of the first tile): keep its statistics at (−inf, 0)
+        // and subtract 0 instead of −inf, so that every power below is 2^(−inf) = 0 rather than 2^NaN
+        const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+        const float sub0 = mn0 == -INFINITY ? 0.f : mn0, sub1 = mn1 == -INFINITY ? 0.f : mn1;
+        const float f0 = fast_exp2(m0 - sub0), f1 = fast_exp2(m1 - sub1);
+        float ps0 = 0.f, ps1 = 0.f;
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+          if (n < nlive) {
+            s[n][0] = fast_exp2(s[n][0] - sub0); s[n][1] = fast_exp2(s[n][1] - sub0);   // 2^(−inf) = 0 for masked keys
+            s[n][2] = fast_exp2(s[n][2] - sub1); s[n][3] = fast_exp2(s[n][3] - sub1);
+            ps0 += s[n][0] + s[n][1];
+            ps1 += s[n][2] + s[n][3];
+          }
+        }
+        ps0 += __shfl_xor_sync(0xffffffffu, ps0, 1); ps0 += __shfl_xor_sync(0xffffffffu, ps0, 2);
+        ps1 += __shfl_xor_sync(0xffffffffu, ps1, 1); ps1 += __shfl_xor_sync(0xffffffffu, ps1, 2);
+        l0 = l0 * f0 + ps0; l1 = l1 * f1 + ps1;
+        m0 = mn0; m1 = mn1;
+#pragma unroll
+        for (int n = 0; n < KT; ++n) { o[n][0] *= f0; o[n][1] *= f0; o[n][2] *= f1; o[n][3] *= f1; }
+      }
+
+      cp_async_wait<1>();   // V of this tile (the next K may still be in flight)
+      __syncthreads();
+      if (nlive > 0) {
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          if (j < nlive) {
+            // A fragment of k-step j = accumulator fragment of n-tile j under the key mapping above: (row g, key 8j+2t), (row g+8, same),
+            // (row g, key 8j+2t+1), (row g+8, same)
+            uint32_t ahi[4], alo[4];
+            tf32_split(s[j][0], ahi[0], alo[0]);
+            tf32_split(s[j][2], ahi[1], alo[1]);
+            tf32_split(s[j][1], ahi[2], alo[2]);
+            tf32_split(s[j][3], ahi[3], alo[3]);
+            const float* vp = Vs + (kof + 8 * j + 2 * t) * LD + g;
+#pragma unroll
+            for (int n0 = 0; n0 < KT; n0 += GO)
+              mma_tf32x3_group<GO>(&o[n0], ahi, alo, [&](int i, int half) { return vp[half * LD + 8 * (n0 + i)]; });
+          }
+        }
+      }
+      __syncthreads();   // every warp is done with Vs
+      issue_tile(Vs, p.value_cache, kb + 1);
+    }
+    cp_async_wait<0>();
+
+    const int r0 = q0 + 16 * wq + g, r1 = r0 + 8;
+    if (KS > 1) {
+      // merge the key shares, one share per round: warp ks = k publishes (m, l, O) in the K / V tile space, the ks = 0 warp (finite m:
+      // it holds key 0) rescales and adds — fixed order.  The loop's last barrier already retired every reader of the tiles, and no
+      // copy is in flight.
+      float* Os = Ks;   // [BQ][LD]
+      float* Ms = Vs;   // [BQ][2]
+      const int row = 16 * wq + g;
+      for (int k = 1; k < KS; ++k) {
+        if (ksp == k) {
+#pragma unroll
+          for (int n = 0; n < KT; ++n) {
+            *reinterpret_cast<float2*>(Os + row * LD + 8 * n + 2 * t) = make_float2(o[n][0], o[n][1]);
+            *reinterpret_cast<float2*>(Os + (row + 8) * LD + 8 * n + 2 * t) = make_float2(o[n][2], o[n][3]);
+          }
+          if (t == 0) {
+            Ms[2 * row] = m0; Ms[2 * row + 1] = l0;
+            Ms[2 * (row + 8)] = m1; Ms[2 * (row + 8) + 1] = l1;
+          }
+        }
+        __syncthreads();
+        if (ksp == 0) {
+          const float pm0 = Ms[2 * row], pl0 = Ms[2 * row + 1], pm1 = Ms[2 * (row + 8)], pl1 = Ms[2 * (row + 8) + 1];
+          const float mn0 = fmaxf(m0, pm0), mn1 = fmaxf(m1, pm1);
+          const float a0 = fast_exp2(m0 - mn0), b0 = fast_exp2(pm0 - mn0), a1 = fast_exp2(m1 - mn1), b1 = fast_exp2(pm1 - mn1);   // (pm = −inf → b = 0)
+          l0 = l0 * a0 + pl0 * b0; l1 = l1 * a1 + pl1 * b1;
+          m0 = mn0; m1 = mn1;
+#pragma unroll
+          for (int n = 0; n < KT; ++n) {
+            const float2 u0 = *reinterpret_cast<const float2*>(Os + row * LD + 8 * n + 2 * t);
+            const float2 u1 = *reinterpret_cast<const float2*>(Os + (row + 8) * LD + 8 * n + 2 * t);
+            o[n][0] = o[n][0] * a0 + u0.x * b0; o[n][1] = o[n][1] * a0 + u0.y * b0;
+            o[n][2] = o[n][2] * a1 + u1.x * b1; o[n][3] = o[n][3] * a1 + u1.y * b1;
+          }
+        }
+        if (k + 1 < KS) __syncthreads();   // the next share overwrites the buffers
+      }
+    }
+    if (ksp == 0) {
+#pragma unroll
+      for (int n = 0; n < KT; ++n) {
+        if (r0 < p.M) *reinterpret_cast<float2*>(p.out + (size_t)r0 * p.Dq + col + 8 * n + 2 * t) = make_float2(o[n][0] / l0, o[n][1] / l0);
+        if (r1 < p.M) *reinterpret_cast<float2*>(p.out + (size_t)r1 * p.Dq + col + 8 * n + 2 * t) = make_float2(o[n][2] / l1, o[n][3] / l1);
+      }
+    }
+  }  // pass
+}
+
 // last prompt row → the decode path's residual buffer: x0 = x[M-1] + y[M-1]
 static __global__ void prefill_last_row_kernel(const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ x0,
                                         int D) {

@@ -65,6 +65,47 @@ static int ensure_prefill_ws(rama_session* s) {
   return RAMA_OK;
 }
 
+// Prefill attention on the tensor cores (prefill.cuh, prefill_attn_mma_kernel): one instantiation per head size × (query warps NW,
+// key shares KS).  RAMA_PREFILL_ATTN=cuda keeps the f32 CUDA-core kernel (the only path for head sizes outside the table below);
+// mma41 / mma42 / mma44 / mma22 / mma14 force one shape (tests, A/B runs).
+static int prefill_attn_mode() {   // (read per call: a getenv next to a multi-millisecond prefill, and the tests switch it)
+  const char* e = getenv("RAMA_PREFILL_ATTN");
+  if (!e || !*e || !strcmp(e, "mma")) return 1;
+  if (!strcmp(e, "cuda")) return 0;
+  if (!strcmp(e, "mma41")) return 41;
+  if (!strcmp(e, "mma42")) return 42;
+  if (!strcmp(e, "mma44")) return 44;
+  if (!strcmp(e, "mma22")) return 22;
+  if (!strcmp(e, "mma14")) return 14;
+  return 1;
+}
+
+template <int HS, int NW, int KS>
+static cudaError_t launch_attn_mma(cudaLaunchConfig_t cfg, int M, int heads, const PrefillAttnParams& ap) {
+  static std::atomic<unsigned long long> done{0};
+  cudaError_t e = ensure_dyn_smem((const void*)prefill_attn_mma_kernel<HS, NW, KS>, (int)prefill_attn_mma_smem_bytes(HS, NW), done);
+  if (e != cudaSuccess) return e;
+  const int nq = (M + 16 * NW - 1) / (16 * NW);
+  cfg.gridDim = dim3((nq + 1) / 2, heads);
+  cfg.blockDim = dim3(32 * NW * KS);
+  cfg.dynamicSmemBytes = prefill_attn_mma_smem_bytes(HS, NW);
+  return cudaLaunchKernelEx(&cfg, prefill_attn_mma_kernel<HS, NW, KS>, ap);
+}
+
+template <int NW, int KS>
+static cudaError_t launch_attn_mma_hs(const cudaLaunchConfig_t& cfg, int M, int heads, const PrefillAttnParams& ap) {
+  switch (ap.hs) {
+    case 16: return launch_attn_mma<16, NW, KS>(cfg, M, heads, ap);
+    case 32: return launch_attn_mma<32, NW, KS>(cfg, M, heads, ap);
+    case 48: return launch_attn_mma<48, NW, KS>(cfg, M, heads, ap);
+    case 64: return launch_attn_mma<64, NW, KS>(cfg, M, heads, ap);
+    case 96: return launch_attn_mma<96, NW, KS>(cfg, M, heads, ap);
+    case 128: return launch_attn_mma<128, NW, KS>(cfg, M, heads, ap);
+    default: return cudaErrorInvalidValue;
+  }
+}
+static bool attn_mma_has(int hs) { return hs == 16 || hs == 32 || hs == 48 || hs == 64 || hs == 96 || hs == 128; }
+
 struct PfTrace {  // optional per-launch CUDA-event timing by kind (rama_prefill's ms_kind)
   cudaStream_t st;
   bool on;
@@ -164,7 +205,21 @@ static int prefill_chunk(rama_session* s, const int32_t* tokens, int M, int pos0
         at[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
       }
-      if (((nq64 + 1) / 2) * c->Hl >= 96) {
+      // tensor-core kernel: the largest query block whose paired grid still covers most of the SMs; eight warps per CTA either way
+      int amode = attn_mma_has(hs) ? prefill_attn_mode() : 0;
+      const int nq32 = (M + 31) / 32;
+      if (amode == 1) amode = ((nq64 + 1) / 2) * c->Hl >= 96 ? 42 : ((nq32 + 1) / 2) * c->Hl >= 96 ? 22 : ((nq16 + 1) / 2) * c->Hl >= 48 ? 14 : 0;
+      if (amode == 44) {
+        GK(RAMA_PK_ATTN, (launch_attn_mma_hs<4, 4>(cfg, M, c->Hl, ap)));
+      } else if (amode == 42) {
+        GK(RAMA_PK_ATTN, (launch_attn_mma_hs<4, 2>(cfg, M, c->Hl, ap)));
+      } else if (amode == 41) {
+        GK(RAMA_PK_ATTN, (launch_attn_mma_hs<4, 1>(cfg, M, c->Hl, ap)));
+      } else if (amode == 22) {
+        GK(RAMA_PK_ATTN, (launch_attn_mma_hs<2, 2>(cfg, M, c->Hl, ap)));
+      } else if (amode == 14) {
+        GK(RAMA_PK_ATTN, (launch_attn_mma_hs<1, 4>(cfg, M, c->Hl, ap)));
+      } else if (((nq64 + 1) / 2) * c->Hl >= 96) {
         cfg.gridDim = dim3((nq64 + 1) / 2, c->Hl);
         cfg.dynamicSmemBytes = prefill_attn_smem_bytes(hs, 4);
         GK(RAMA_PK_ATTN, cudaLaunchKernelEx(&cfg, prefill_attn_kernel<4>, ap));

@@ -28,10 +28,15 @@ def _kv(sess, cfg, n):
     return k, v
 
 
-@pytest.mark.parametrize("name", ["tiny", "tiny-sep"])
+# f32 CUDA-core kernel / tensor-core kernel as (query warps, key shares) = (4,1) (4,2) (4,4) (2,2) (1,4)
+@pytest.mark.parametrize("attn", ["cuda", "mma41", "mma42", "mma44", "mma22", "mma14"])
+@pytest.mark.parametrize("name", ["tiny", "tiny-sep", "tiny-long"])   # head sizes 16, 48, 32
 @pytest.mark.parametrize("n,pos0", [(1, 0), (7, 0), (33, 0), (None, 0), (20, 5), (1, 9)])
-def test_prefill_equals_sequential_forward_and_oracle(name, n, pos0):
+def test_prefill_equals_sequential_forward_and_oracle(name, n, pos0, attn, monkeypatch):
+    monkeypatch.setenv("RAMA_PREFILL_ATTN", attn)
     cfg, tensors, gpu, om = _pair(name)
+    if n is None and cfg.seq_len > 256:
+        n = 200 - pos0   # (tiny-long: 2048 positions; 200 rows = four 64-key tiles with a ragged last one)
     n = cfg.seq_len - pos0 if n is None else n
     rng = np.random.default_rng(11)
     toks = [1] + [int(t) for t in rng.integers(0, cfg.vocab_size, pos0 + n - 1)]
@@ -87,7 +92,13 @@ def test_prefill_errors():
     s.close(); gpu.close()
 
 
-def test_prefill_512_at_7b_layer_shapes():
+@pytest.mark.parametrize("attn", ["mma", "cuda"])
+def test_prefill_512_at_7b_layer_shapes(attn, monkeypatch):
+    monkeypatch.setenv("RAMA_PREFILL_ATTN", attn)   # mma: the default — at this geometry the 8-warp tensor-core kernel (4 query warps × 2 key shares)
+    _prefill_512_at_7b_layer_shapes(attn)
+
+
+def _prefill_512_at_7b_layer_shapes(attn):
     """BASELINE config 4 geometry (dim 4096, ffn 11008, 32 heads, 512 prompt tokens) on 2 layers: the tensor-core
     prefill against the CPU ORACLE run token by token over the same 512 rows (K = 4096 / 11008 contractions — where a
     tcgen05 accumulation drift would show), and against 512 per-token steps of the decode path."""
@@ -105,7 +116,7 @@ def test_prefill_512_at_7b_layer_shapes():
         a.forward(t, pos)
         ref.forward(om, os_, t, pos)
     ms, kinds, launches = b.prefill(toks, 0, profile=True)
-    print("prefill-512 l7-2layer ms", ms, kinds, launches)
+    print("prefill-512 l7-2layer attn", attn, "ms", ms, kinds, launches)
     ka, va = _kv(a, cfg, n)
     kb, vb = _kv(b, cfg, n)
     ko = os_.key_cache.reshape(cfg.n_layers, cfg.seq_len, -1)[:, :n]
@@ -116,6 +127,31 @@ def test_prefill_512_at_7b_layer_shapes():
     assert rel_err(b.logits(), a.logits()) < LOGIT_TOL
     want = int(np.flatnonzero(os_.logits == os_.logits.max())[-1])    # later index wins (cpu.rs:165)
     assert b.sample(0.0, 0.9) == want == a.sample(0.0, 0.9)
+    a.close(); b.close(); gpu.close()
+
+
+@pytest.mark.parametrize("attn", ["mma41", "mma42", "mma44", "mma22", "mma14", "cuda"])
+def test_prefill_chunk_at_head_size_128_ragged(attn, monkeypatch):
+    """Head size 128 (the 7B head) with a ragged chunk: 150 rows appended at position 70 — query blocks and key tiles both end
+    mid-tile, and the first key tiles lie wholly below every query of the chunk."""
+    monkeypatch.setenv("RAMA_PREFILL_ATTN", attn)
+    cfg = ck.CONFIGS["mid-4layer"]
+    gpu = GPU(0)
+    gpu.load_synthetic(cfg, ck.SynthSpec())
+    rng = np.random.default_rng(17)
+    pos0, n = 70, 150
+    toks = [1] + [int(t) for t in rng.integers(0, cfg.vocab_size, pos0 + n - 1)]
+    a, b = Session(gpu), Session(gpu)
+    for pos, t in enumerate(toks):
+        a.forward(t, pos)
+    for pos in range(pos0):
+        b.forward(toks[pos], pos)
+    b.prefill(toks[pos0:], pos0)
+    ka, va = _kv(a, cfg, pos0 + n)
+    kb, vb = _kv(b, cfg, pos0 + n)
+    assert rel_err(kb, ka) < 1e-4 and rel_err(vb, va) < 1e-4
+    assert rel_err(b.logits(), a.logits()) < LOGIT_TOL
+    assert b.sample(0.0, 0.9) == a.sample(0.0, 0.9)
     a.close(); b.close(); gpu.close()
 
 
