@@ -303,8 +303,8 @@ __global__ void __launch_bounds__(kPfThreads) prefill_attn_kernel(const PrefillA
 // KS > 1 (keys of a tile split over warps) is what puts two or more warps on every scheduler when the grid has only one CTA
 // per SM (512 rows × 32 heads = 128 paired blocks): mma.sync chains are latency-bound with one warp per scheduler.  The KS
 // partial (m, l, O) triples of a query row meet in shared memory after the last tile and are merged by the ks = 0 warp, share by share.
-// K and V tiles arrive by cp.async (zero-filled beyond the causal range): K of tile i+1 lands under the softmax and P·V of
-// tile i, V of tile i+1 under the next Q·Kᵀ.  n-tiles / k-steps wholly above a warp's last query are skipped (the diagonal
+// K and V tiles arrive by cp.async (zero-filled beyond the causal range).  Single-buffered (NW < 4): K of tile i+1 lands under the
+// softmax and P·V of tile i, V of tile i+1 under the next Q·Kᵀ; double-buffered (NW = 4): tile i+1 lands under the whole of tile i.  n-tiles / k-steps wholly above a warp's last query are skipped (the diagonal
 // tile costs about half).  Row pitch HS+4 words: every fragment load of Q, K and V is bank-conflict free.
 // Query blocks are paired (x, nq−1−x) like the CUDA-core kernel: one balanced wave.
 __device__ __forceinline__ void cp_async16_zfill(float* smem_dst, const float* gsrc, bool valid) {
@@ -351,8 +351,12 @@ __device__ __forceinline__ float fast_exp2(float x) {
 }
 
 constexpr int kPfMmaBK = 64;
+// 64-query blocks (NW = 4: at most one CTA per SM fits anyway) double-buffer the K / V tiles: the copy of tile i+1 runs under the
+// whole of tile i and ONE barrier per tile is left, so the warps of a CTA drift apart and one warp's softmax overlaps another's MMAs.
+// The smaller blocks keep single tiles (two CTAs per SM is what overlaps their phases).
+__host__ __device__ constexpr int prefill_attn_mma_bufs(int nw) { return nw >= 4 ? 2 : 1; }
 __host__ __device__ constexpr size_t prefill_attn_mma_smem_bytes(int hs, int nw) {
-  return (size_t)(16 * nw + 2 * kPfMmaBK) * (hs + 4) * sizeof(float);
+  return (size_t)(16 * nw + 2 * prefill_attn_mma_bufs(nw) * kPfMmaBK) * (hs + 4) * sizeof(float);
 }
 
 template <int HS, int NW, int KS>
@@ -365,8 +369,10 @@ __global__ void __launch_bounds__(32 * NW * KS) prefill_attn_mma_kernel(const Pr
   constexpr int GS = NT >= 8 ? 8 : NT, GO = KT % 8 == 0 ? 8 : (KT % 4 == 0 ? 4 : 2);   // independent MMA chains per group
   extern __shared__ __align__(16) float pf_smem[];
   float* Qs = pf_smem;           // [BQ][LD]
-  float* Ks = Qs + BQ * LD;      // [BK][LD]   (after the last tile: a ks > 0 share's O partial, [BQ][LD])
-  float* Vs = Ks + BK * LD;      // [BK][LD]   (after the last tile: its (m, l) pairs, [BQ][2])
+  constexpr int NBUF = prefill_attn_mma_bufs(NW);
+  constexpr bool DB = NBUF == 2;
+  float* Ks = Qs + BQ * LD;          // [NBUF][BK][LD]   (after the last tile: a ks > 0 share's O partial, [BQ][LD])
+  float* Vs = Ks + NBUF * BK * LD;   // [NBUF][BK][LD]   (after the last tile: its (m, l) pairs, [BQ][2])
 
   const int h = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int wq = warp % NW, ksp = warp / NW, kof = ksp * KW;
@@ -381,7 +387,7 @@ __global__ void __launch_bounds__(32 * NW * KS) prefill_attn_mma_kernel(const Pr
     const int q0 = qb * BQ;
     const int n_keys = p.pos0 + min(q0 + BQ, p.M);   // keys 0 .. position of the block's last query
     const int nkb = (n_keys + BK - 1) / BK;
-    auto issue_tile = [&](float* tile, const float* cache, int kb) {
+    auto issue_tile = [&](float* tile, const float* cache, int kb, bool commit = true) {
       if (kb < nkb) {
         const int k0 = kb * BK;
         for (int i = tid; i < BK * HS4; i += NTHR) {
@@ -390,7 +396,11 @@ __global__ void __launch_bounds__(32 * NW * KS) prefill_attn_mma_kernel(const Pr
           cp_async16_zfill(tile + r * LD + 4 * c, cache + (size_t)(valid ? k0 + r : 0) * p.Dq + col + 4 * c, valid);
         }
       }
-      cp_async_commit();   // (always: the wait counts below assume one group per call)
+      if (commit) cp_async_commit();   // (also for an empty tile: the wait counts below assume one group per call)
+    };
+    auto issue_pair = [&](int kb) {   // double-buffered: K and V of tile kb as ONE group into buffer kb & 1
+      issue_tile(Ks + (kb & 1) * BK * LD, p.key_cache, kb, false);
+      issue_tile(Vs + (kb & 1) * BK * LD, p.value_cache, kb, true);
     };
     __syncthreads();  // the previous pass is done with Qs / Ks / Vs
     for (int i = tid; i < BQ * HS4; i += NTHR) {   // the query block rides in the first K tile's copy group (rows ≥ M: zeros)
@@ -398,8 +408,12 @@ __global__ void __launch_bounds__(32 * NW * KS) prefill_attn_mma_kernel(const Pr
       const bool valid = q0 + r < p.M;
       cp_async16_zfill(Qs + r * LD + 4 * c, p.q + (size_t)(valid ? q0 + r : 0) * p.Dq + col + 4 * c, valid);
     }
-    issue_tile(Ks, p.key_cache, 0);
-    issue_tile(Vs, p.value_cache, 0);
+    if (DB) {
+      issue_pair(0);
+    } else {
+      issue_tile(Ks, p.key_cache, 0);
+      issue_tile(Vs, p.value_cache, 0);
+    }
 
     float o[KT][4];
 #pragma unroll
@@ -413,8 +427,16 @@ __global__ void __launch_bounds__(32 * NW * KS) prefill_attn_mma_kernel(const Pr
     for (int kb = 0; kb < nkb; ++kb) {
       const int k0 = kb * BK + kof;   // first key of this warp's share of the tile
       const int nlive = wlast >= k0 ? min(NT, (wlast - k0) / 8 + 1) : 0;   // key n-tiles with any unmasked entry for this warp
-      cp_async_wait<1>();   // K of this tile (V may still be in flight)
-      __syncthreads();      // … from every thread (first tile: the query block too)
+      if (DB) {
+        cp_async_wait<0>();   // this tile's K and V (the only group in flight)
+        __syncthreads();      // … from every thread; and every warp has left tile kb−1, whose buffers the next copy overwrites
+        issue_pair(kb + 1);
+      } else {
+        cp_async_wait<1>();   // K of this tile (V may still be in flight)
+        __syncthreads();      // … from every thread (first tile: the query block too)
+      }
+      const float* Kt = Ks + (DB ? (kb & 1) * BK * LD : 0);
+      const float* Vt = Vs + (DB ? (kb & 1) * BK * LD : 0);
       float s[NT][4];
 #pragma unroll
       for (int n = 0; n < NT; ++n) s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
@@ -426,15 +448,17 @@ __global__ void __launch_bounds__(32 * NW * KS) prefill_attn_mma_kernel(const Pr
           tf32_split(qrow1[8 * ks], ahi[1], alo[1]);
           tf32_split(qrow0[8 * ks + 4], ahi[2], alo[2]);
           tf32_split(qrow1[8 * ks + 4], ahi[3], alo[3]);
-          const float* kp = Ks + (kof + g) * LD + 8 * ks + t;
+          const float* kp = Kt + (kof + g) * LD + 8 * ks + t;
 #pragma unroll
           for (int n0 = 0; n0 < NT; n0 += GS)   // (a group with any live tile is computed whole)
             if (n0 < nlive)
               mma_tf32x3_group<GS>(&s[n0], ahi, alo, [&](int i, int half) { return kp[8 * (n0 + i) * LD + 4 * half]; });
         }
       }
-      __syncthreads();   // every warp is done with Ks
-      issue_tile(Ks, p.key_cache, kb + 1);
+      if (!DB) {
+        __syncthreads();   // every warp is done with Ks
+        issue_tile(Ks, p.key_cache, kb + 1);
+      }
 
       if (nlive > 0) {
         // scale (cpu.rs:41 divides by √hs; here folded into the base-2 constant), causal mask, online softmax on the fragments
@@ -476,8 +500,10 @@ __global__ void __launch_bounds__(32 * NW * KS) prefill_attn_mma_kernel(const Pr
         for (int n = 0; n < KT; ++n) { o[n][0] *= f0; o[n][1] *= f0; o[n][2] *= f1; o[n][3] *= f1; }
       }
 
-      cp_async_wait<1>();   // V of this tile (the next K may still be in flight)
-      __syncthreads();
+      if (!DB) {
+        cp_async_wait<1>();   // V of this tile (the next K may still be in flight)
+        __syncthreads();
+      }
       if (nlive > 0) {
 #pragma unroll
         for (int j = 0; j < NT; ++j) {
@@ -489,22 +515,25 @@ __global__ void __launch_bounds__(32 * NW * KS) prefill_attn_mma_kernel(const Pr
             tf32_split(s[j][2], ahi[1], alo[1]);
             tf32_split(s[j][1], ahi[2], alo[2]);
             tf32_split(s[j][3], ahi[3], alo[3]);
-            const float* vp = Vs + (kof + 8 * j + 2 * t) * LD + g;
+            const float* vp = Vt + (kof + 8 * j + 2 * t) * LD + g;
 #pragma unroll
             for (int n0 = 0; n0 < KT; n0 += GO)
               mma_tf32x3_group<GO>(&o[n0], ahi, alo, [&](int i, int half) { return vp[half * LD + 8 * (n0 + i)]; });
           }
         }
       }
-      __syncthreads();   // every warp is done with Vs
-      issue_tile(Vs, p.value_cache, kb + 1);
+      if (!DB) {
+        __syncthreads();   // every warp is done with Vs
+        issue_tile(Vs, p.value_cache, kb + 1);
+      }
     }
     cp_async_wait<0>();
+    if (DB && KS > 1) __syncthreads();   // (single tiles: the loop's last barrier) every warp is done with the tiles the merge re-uses
 
     const int r0 = q0 + 16 * wq + g, r1 = r0 + 8;
     if (KS > 1) {
       // merge the key shares, one share per round: warp ks = k publishes (m, l, O) in the K / V tile space, the ks = 0 warp (finite m:
-      // it holds key 0) rescales and adds — fixed order.  The loop's last barrier already retired every reader of the tiles, and no
+      // it holds key 0) rescales and adds — fixed order.  The barrier above / the loop's last barrier retired every reader of the tiles, and no
       // copy is in flight.
       float* Os = Ks;   // [BQ][LD]
       float* Ms = Vs;   // [BQ][2]
