@@ -138,7 +138,7 @@ int rama_session_sync(rama_session* s);
 
 /* Prompt prefill on the tensor cores: processes tokens[0..n) at positions [pos0, pos0+n) in one pass —
  * every weight matrix is read once per prompt, the contractions run as tcgen05 3xTF32 GEMMs, attention is
- * causal over the KV cache.  The reference has no such entry point: generate() feeds the prompt through
+ * causal over the KV cache (a 3xTF32 mma.sync flash kernel; RAMA_PREFILL_ATTN=cuda selects the f32 CUDA-core one).  The reference has no such entry point: generate() feeds the prompt through
  * forward() one token at a time and discards the logits (mod.rs:187-192).  Afterwards the session is in the
  * state those n forward() calls would have left: KV-cache rows pos0..pos0+n-1 of every layer (infer.rs:31-33)
  * and the logits of the last position (infer.rs:51), so rama_sample / rama_forward(token, pos0+n) continue
