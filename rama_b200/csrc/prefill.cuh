@@ -1,6 +1,7 @@
 // prefill.cuh — prompt prefill: the M prompt tokens at positions [pos0, pos0+M) go through the layers
 // together, so every weight matrix is read once per prompt instead of once per token and the
-// contractions run on the tensor cores (gemm_tf32x3.cuh).
+// contractions run on the tensor cores (gemm_tf32x3.cuh for the weight products, prefill_attn_mma_kernel
+// below for Q·Kᵀ and P·V).
 //
 // The reference has no such function: generate() feeds the prompt one token at a time through
 // forward() and discards the logits (mod.rs:187-192).  What prefill must leave behind is therefore
@@ -129,8 +130,8 @@ struct EpiSwiGLUPrefill {
 // Query row m (position pos0+m) attends to cache rows 0..pos0+m of its head: exactly what
 // multi_head_attention computes for that position (cpu.rs:23-52), with an online softmax.
 // Grid (ceil(ceil(M/64)/2), heads), each CTA two query blocks (see below); 256 threads as 16×16: thread (ty,tx) owns score rows 4ty..4ty+3 × key columns
-// tx+16j, and output rows 4ty..4ty+3 × head columns 4tx+64j.  f32 CUDA-core math: attention is ~1 % of the
-// prefill flops, the GEMMs own the tensor cores.
+// tx+16j, and output rows 4ty..4ty+3 × head columns 4tx+64j.  f32 CUDA-core math: since round 2 the fallback of the
+// tensor-core kernel below (head sizes outside its table, grids too small for it, RAMA_PREFILL_ATTN=cuda).
 constexpr int kPfBK = 64, kPfThreads = 256, kPfMaxHs = 128;
 // query rows per thread RQ ∈ {4, 1} → 64 or 16 queries per block: the small block keeps the SMs busy when a rank
 // holds few heads (tensor parallelism) or the prompt is short
